@@ -1,0 +1,160 @@
+/* zdr_b200.h — C ABI of the B200-native differentiable ray-tracer core.
+ *
+ * This is the drop-in boundary for the ONE hot path of 111116/zdr: the per-pixel render
+ * kernels (forward + adjoint) that the reference launches through LuisaCompute from
+ *   render.py:168-171  (forward kernel launch, 11-argument operator signature)
+ *   render.py:193-196  (backward kernel launch, 12-argument operator signature, seed+1)
+ * and the scene assembly those kernels read (render.py:73-128, :130-148, :150-156).
+ * Every entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *  - plain C types only; no torch/ATen types cross this boundary.
+ *  - every function returns 0 on success, a negative zdr_status on failure, never throws;
+ *    zdr_last_error() returns a thread-local human readable message for the last failure.
+ *  - *_dev pointers are CUDA device pointers owned by the caller (torch owns them in the
+ *    Python surface, borrowed for the duration of the call, as the reference borrows them
+ *    through DLPack at render.py:162-164,179-181).
+ *  - *_host pointers are ordinary host memory.
+ *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it, no device-wide sync
+ *    (the reference does two full barriers per call, render.py:165,172 — we do none).
+ *  - there is NO CPU fallback: with no usable CUDA device every compute entry fails with
+ *    ZDR_ERR_CUDA.
+ */
+#ifndef ZDR_B200_H
+#define ZDR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZDR_ABI_VERSION 1
+
+typedef enum zdr_status {
+    ZDR_OK = 0,
+    ZDR_ERR_ARG = -1,     /* bad argument (NULL, negative size, unknown integrator ...) */
+    ZDR_ERR_STATE = -2,   /* call order violated (render before commit, tables not set ...) */
+    ZDR_ERR_CUDA = -3,    /* CUDA runtime failure / no device */
+    ZDR_ERR_LIMIT = -4    /* reference limits exceeded (render.py:114: > 10000 instances) */
+} zdr_status;
+
+/* integrator ids == the keys of the dict at render.py:65-69 */
+typedef enum zdr_integrator {
+    ZDR_COLLOCATED = 0,   /* collocated.py:10-57 */
+    ZDR_DIRECT = 1,       /* direct.py:20-167    */
+    ZDR_PATH = 2          /* prb.py:18-187       */
+} zdr_integrator;
+
+/* prb_mode (SURVEY.md §8a "PRB defects"): how the path adjoint is weighted */
+#define ZDR_PRB_LITERAL 0    /* prb.py:162 cotangent beta/pdf*Le, no inst>0 break in bwd    */
+#define ZDR_PRB_CORRECTED 1  /* textbook PRB: cotangent Le_remaining/f; fwd/bwd control flow equal */
+
+/* Camera == luisa.StructType(fov, origin, target, up) at render.py:28; plus every scalar the
+ * reference passes to the kernel (render.py:168-171) and the module-level constants that
+ * LuisaCompute bakes in at JIT time (direct.py:14, prb.py:15-16, interaction.py:33). */
+typedef struct zdr_params {
+    float cam_fov;            /* full horizontal field of view, radians (camera.py:15) */
+    float cam_origin[3];
+    float cam_target[3];
+    float cam_up[3];
+    int32_t width, height;    /* dispatch_size=res (render.py:171): res=(W,H) */
+    int32_t tex_res_x;        /* texture_res.x == material.shape[0] (render.py:161,170) */
+    int32_t tex_res_y;        /* texture_res.y == material.shape[1] */
+    int32_t spp;
+    int32_t seed;             /* forward: seed; backward: caller passes seed+1 (render.py:196) */
+    int32_t use_tent_filter;  /* render.py:71 */
+    int32_t max_depth;        /* prb.py:15 (16 upstream; BASELINE configs use 8 and 16) */
+    int32_t rr_depth;         /* prb.py:16 */
+    int32_t use_mis;          /* direct.py:14 */
+    int32_t bilinear;         /* interaction.py:33 */
+    int32_t prb_mode;         /* ZDR_PRB_* */
+    /* data-parallel shard of the dispatch grid (multi-GPU): rows
+     * [row0,row1) of the image and samples [it0,it1) of every pixel. Full job: 0,H,0,spp. */
+    int32_t row0, row1;
+    int32_t it0, it1;
+    int32_t reserved[4];
+} zdr_params;
+
+typedef struct zdr_scene zdr_scene;
+
+/* --- library-wide ---------------------------------------------------------------------- */
+int zdr_abi_version(void);
+const char* zdr_last_error(void);
+
+/* Sampler tables: replaces the module-level uploads at pmj02bn.py:9-16.
+ * pmj:  [sets][n][2] uint32 (pbrt-v4 PMJ02bnSamples), converted as pmj02bn.py:9 does
+ *       (round-to-nearest u32->f32, times 2^-32).
+ * bn:   [ntex][res][res] uint16 (pbrt-v4 BlueNoiseTextures), /65536 (pmj02bn.py:14).
+ * Uploaded to `device`; must be called once per device before any render. */
+int zdr_set_sampler_tables(int device, const uint32_t* pmj_host, int sets, int n,
+                           const uint16_t* bn_host, int ntex, int res);
+
+/* --- scene assembly: replaces Scene.load_geometry (render.py:73-128) ------------------- */
+int zdr_scene_create(zdr_scene** out, int device);           /* luisa.Accel()+BindlessArray(), render.py:74-75 */
+void zdr_scene_destroy(zdr_scene* s);
+/* accel.add(vertex_buffer, triangle_buffer, transform=) + heap.emplace(2i / 2i+1), render.py:96-111.
+ * verts: nv rows of the 32-byte Vertex (vertex.py:4): px py pz  u v  nx ny nz.
+ * tris: nt*3 int32 indices (load_obj.py:63-68). xform: float4x4, column-major (16 floats).
+ * Instance id = order of calls (render.py:81). */
+int zdr_scene_add_mesh(zdr_scene* s, const float* verts_nx8_host, int nv,
+                       const int32_t* tris_host, int nt,
+                       const float xform_colmajor[16], const float emission[3]);
+/* accel.update(); heap.update() (render.py:127-128): flattens instances to world space and
+ * builds the BVH on the GPU. */
+int zdr_scene_commit(zdr_scene* s);
+/* Scene.update_lights (render.py:130-148): n must equal the instance count. */
+int zdr_scene_set_emissions(zdr_scene* s, const float* emission_nx3_host, int n);
+/* Scene.add_envmap -> load_envmap (render.py:150-156, envmap.py:116-202). rgba float, h rows. */
+int zdr_scene_set_envmap(zdr_scene* s, const float* rgba_host, int w, int h, int compensate_mis);
+int zdr_scene_instance_count(const zdr_scene* s);
+int zdr_scene_light_count(const zdr_scene* s);
+int zdr_scene_triangle_count(const zdr_scene* s);
+
+/* --- the hot path: replaces the kernel launches at render.py:168-171 / :193-196 -------- */
+/* image_dev: (H,W,4) f32, written for rows [row0,row1). material_dev: (tex_res_x*tex_res_y*4) f32. */
+int zdr_render_forward(zdr_scene* s, int integrator, const zdr_params* p,
+                       const float* material_dev, float* image_dev, void* stream);
+/* d_image_dev: (H,W,4) f32 cotangent; d_material_dev: same shape as material, ACCUMULATED into
+ * (the reference zero-fills it first at render.py:220; callers here do the same). */
+int zdr_render_backward(zdr_scene* s, int integrator, const zdr_params* p,
+                        const float* material_dev, const float* d_image_dev,
+                        float* d_material_dev, void* stream);
+
+/* Same operators with HOST buffers: the call a non-torch embedder (or bench.py's e2e leg)
+ * makes; performs H2D of the inputs and D2H of the result inside the call, then syncs. */
+int zdr_render_forward_host(zdr_scene* s, int integrator, const zdr_params* p,
+                            const float* material_host, float* image_host);
+int zdr_render_backward_host(zdr_scene* s, int integrator, const zdr_params* p,
+                             const float* material_host, const float* d_image_host,
+                             float* d_material_host);
+
+/* --- instrumentation ------------------------------------------------------------------ */
+/* counters accumulated by the render kernels since the last reset (flushed once per block):
+ * [0] closest-hit rays  [1] any-hit rays  [2] BVH nodes visited  [3] triangles tested
+ * [4] gradient scatters (write_bsdf_grad calls)  [5] red.v4 issued  [6] shaded vertices
+ * [7] camera samples.  Blocks until the scene's last launch finished. */
+#define ZDR_NUM_COUNTERS 8
+int zdr_get_counters(zdr_scene* s, uint64_t out[ZDR_NUM_COUNTERS]);
+int zdr_reset_counters(zdr_scene* s);
+
+/* --- probes (parity tests only; small n). All pointers HOST. ---------------------------- */
+/* closest hit for n rays (o.xyz, d.xyz, tmin, tmax) -> inst, prim, bary u, v, t (inst=-1: miss) */
+int zdr_probe_trace_closest(zdr_scene* s, const float* rays_nx8_host, int n,
+                            int32_t* inst_prim_nx2_host, float* uvt_nx3_host);
+int zdr_probe_trace_any(zdr_scene* s, const float* rays_nx8_host, int n, int32_t* occluded_host);
+/* sampler: for each of n (px,py,seed,spp,sample_index) run the draw program `prog`
+ * (string of '1' = next(), '2' = next2f()) and write one float per '1', two per '2'. */
+int zdr_probe_sampler(int device, const int32_t* state_nx5_host, int n, const char* prog,
+                      float* out_host);
+/* per-sample (unclamped) radiance of the forward estimator: out (H,W,spp,3) f32 */
+int zdr_probe_render_samples(zdr_scene* s, int integrator, const zdr_params* p,
+                             const float* material_host, float* out_host);
+/* ggx_brdf value and its analytic adjoint wrt (diffuse.xyz, roughness), cotangent g:
+ * in  n x 13: wo.xyz wi.xyz diffuse.xyz roughness g.xyz ; out n x 7: f.xyz dmat.xyzw */
+int zdr_probe_ggx(int device, const float* in_nx13_host, int n, float* out_nx7_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZDR_B200_H */
