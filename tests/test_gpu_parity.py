@@ -1,0 +1,327 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Bars (BASELINE.json north_star): sampler values and primitive ids bit-exact,
+images rel-L2 <= 1e-4, gradients rel-L2 <= 1e-3.  The forward pass shares the oracle's numeric
+contract, so per-sample radiance is additionally compared bit-for-bit."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from zdr_b200 import _abi
+from zdr_b200._abi import ZDR_COLLOCATED, ZDR_DIRECT, ZDR_PATH, make_params, np_ptr
+
+from . import scenes
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-4      # relative L2, images
+GRAD_TOL = 1e-3     # relative L2, texture gradients
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    d = np.linalg.norm(b.ravel())
+    return np.linalg.norm((a - b).ravel()) / (d if d > 0 else 1.0)
+
+
+class GpuScene:
+    """Thin ctypes driver of the C ABI with HOST buffers (no torch): what a cgo/JNI-style embedder does."""
+
+    def __init__(self, models, device=0):
+        from zdr_b200.load_obj import load_mesh
+        from zdr_b200.mathtypes import float4x4
+        from zdr_b200.tables import get_tables
+        self.lib = _abi.load_library()
+        pmj, bn, _ = get_tables()
+        _abi.check(self.lib.zdr_set_sampler_tables(device, np_ptr(pmj, C.c_uint32), pmj.shape[0], pmj.shape[1],
+                                                    np_ptr(bn, C.c_uint16), bn.shape[0], bn.shape[1]))
+        self.h = C.c_void_p()
+        _abi.check(self.lib.zdr_scene_create(C.byref(self.h), device))
+        cache = {}
+        for obj, xf, em in models:
+            if obj not in cache:
+                cache[obj] = load_mesh(obj)
+            verts, tris = cache[obj]
+            xfa = np.asarray((xf if xf is not None else float4x4(1.0)).flat(), np.float32)
+            ema = np.asarray(list(em), np.float32)
+            _abi.check(self.lib.zdr_scene_add_mesh(self.h, np_ptr(verts, C.c_float), verts.shape[0], np_ptr(tris, C.c_int32),
+                                                    tris.shape[0] // 3, np_ptr(xfa, C.c_float), np_ptr(ema, C.c_float)))
+        _abi.check(self.lib.zdr_scene_commit(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.zdr_scene_destroy(self.h)
+            self.h = None
+
+    def set_emissions(self, e):
+        e = np.ascontiguousarray(e, np.float32)
+        _abi.check(self.lib.zdr_scene_set_emissions(self.h, np_ptr(e, C.c_float), e.shape[0]))
+
+    def set_envmap(self, img, compensate=True):
+        img = np.ascontiguousarray(img, np.float32)
+        _abi.check(self.lib.zdr_scene_set_envmap(self.h, np_ptr(img, C.c_float), img.shape[1], img.shape[0], int(compensate)))
+
+    def forward(self, integ, p, mat):
+        mat = np.ascontiguousarray(mat, np.float32)
+        img = np.zeros((p.height, p.width, 4), np.float32)
+        _abi.check(self.lib.zdr_render_forward_host(self.h, integ, C.byref(p), np_ptr(mat, C.c_float), np_ptr(img, C.c_float)))
+        return img
+
+    def backward(self, integ, p, mat, dimg):
+        mat, dimg = np.ascontiguousarray(mat, np.float32), np.ascontiguousarray(dimg, np.float32)
+        dm = np.zeros_like(mat)
+        _abi.check(self.lib.zdr_render_backward_host(self.h, integ, C.byref(p), np_ptr(mat, C.c_float), np_ptr(dimg, C.c_float),
+                                                      np_ptr(dm, C.c_float)))
+        return dm
+
+    def samples(self, integ, p, mat):
+        mat = np.ascontiguousarray(mat, np.float32)
+        out = np.zeros((p.height, p.width, p.spp, 3), np.float32)
+        _abi.check(self.lib.zdr_probe_render_samples(self.h, integ, C.byref(p), np_ptr(mat, C.c_float), np_ptr(out, C.c_float)))
+        return out
+
+    def trace_closest(self, rays):
+        r = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        ip, uvt = np.empty((r.shape[0], 2), np.int32), np.empty((r.shape[0], 3), np.float32)
+        _abi.check(self.lib.zdr_probe_trace_closest(self.h, np_ptr(r, C.c_float), r.shape[0], np_ptr(ip, C.c_int32), np_ptr(uvt, C.c_float)))
+        return ip, uvt
+
+    def trace_any(self, rays):
+        r = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        occ = np.empty(r.shape[0], np.int32)
+        _abi.check(self.lib.zdr_probe_trace_any(self.h, np_ptr(r, C.c_float), r.shape[0], np_ptr(occ, C.c_int32)))
+        return occ
+
+    def counters(self):
+        out = (C.c_uint64 * _abi.ZDR_NUM_COUNTERS)()
+        _abi.check(self.lib.zdr_get_counters(self.h, out))
+        return dict(zip(_abi.COUNTER_NAMES, (int(x) for x in out)))
+
+    def reset_counters(self):
+        _abi.check(self.lib.zdr_reset_counters(self.h))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+# ----------------------------------------------------------------------------- sampler (bit-exact)
+@pytest.mark.parametrize("spp", [1, 4, 64, 256, 1024])
+def test_sampler_bit_exact(oracle, spp):
+    rng = np.random.default_rng(spp)
+    n = 4096
+    st = np.stack([rng.integers(0, 4096, n), rng.integers(0, 4096, n),
+                   rng.choice([0, 1, 12345, 853402567, 19260817, 948377263, 2147483647, -5], n),
+                   np.full(n, spp), rng.integers(0, spp, n)], axis=1).astype(np.int32)
+    prog = "2" + "112" + "12" + "1" + ("11212" * 12)     # camera, light, bsdf, rr, ... up to dimension > 64
+    ref = oracle.sampler_draws(st, prog)
+    out = np.empty_like(ref)
+    lib = _abi.load_library()
+    from zdr_b200.tables import get_tables
+    pmj, bn, _ = get_tables()
+    _abi.check(lib.zdr_set_sampler_tables(0, np_ptr(pmj, C.c_uint32), pmj.shape[0], pmj.shape[1], np_ptr(bn, C.c_uint16), bn.shape[0], bn.shape[1]))
+    _abi.check(lib.zdr_probe_sampler(0, np_ptr(st, C.c_int32), n, prog.encode(), np_ptr(out, C.c_float)))
+    assert np.array_equal(bits(out), bits(ref))
+    assert (ref >= 0).all() and (ref < 1).all()
+
+
+def test_sampler_test_sampler_py_inputs(oracle):
+    """test_sampler.py:23-30: pixel (24,345), seed 0, n=32, second next2f()."""
+    st = np.array([[24, 345, 0, 32, i] for i in range(32)], np.int32)
+    ref = oracle.sampler_draws(st, "22")
+    out = np.empty_like(ref)
+    lib = _abi.load_library()
+    _abi.check(lib.zdr_probe_sampler(0, np_ptr(st, C.c_int32), 32, b"22", np_ptr(out, C.c_float)))
+    assert np.array_equal(bits(out), bits(ref))
+
+
+# --------------------------------------------------------------------------- intersection (exact ids)
+def _random_rays(n, seed, lo, hi):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(lo, hi, (n, 3))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([o, d, np.zeros((n, 1)), np.full((n, 1), 1e30)], axis=1).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["cbox", "spheres"])
+def test_trace_prim_ids_exact(oracle, name):
+    if name == "cbox":
+        models, lo, hi, n = scenes.cbox_path_models(), (-3.5, -0.5, -3.5), (3.5, 6.0, 6.5), 20000
+    else:
+        models, lo, hi, n = scenes.sphere_grid_models(12, seed=1), (-1, -1, -1), (4, 4, 2), 4000
+    g, o = GpuScene(models), oracle.OracleScene(models)
+    rays = _random_rays(n, 7, lo, hi)
+    # axis-aligned and edge-grazing rays too: shared edges are where tie-breaking matters
+    rays[:64, 3:6] = np.eye(3, dtype=np.float32)[np.arange(64) % 3] * np.where(np.arange(64) % 2, 1, -1)[:, None]
+    ip_g, uvt_g = g.trace_closest(rays)
+    ip_o, uvt_o = o.trace_closest(rays)
+    assert np.array_equal(ip_g, ip_o)
+    hit = ip_o[:, 0] >= 0
+    assert hit.sum() > n // 20
+    assert np.array_equal(bits(uvt_g[hit]), bits(uvt_o[hit]))
+    # shadow rays: bounded segments
+    seg = rays.copy()
+    seg[:, 6] = 1e-4
+    seg[:, 7] = np.random.default_rng(3).uniform(0.1, 6.0, n)
+    assert np.array_equal(g.trace_any(seg), o.trace_any(seg))
+    g.close()
+
+
+def test_trace_shared_edge_rays(oracle):
+    """Rays aimed exactly at mesh vertices / edge midpoints of the Cornell box: watertightness and
+    the lowest-id tie-break must agree with the oracle's in-order scan."""
+    from zdr_b200.load_obj import load_mesh
+    models = scenes.cbox_path_models()
+    verts, tris = load_mesh(models[0][0])
+    P = verts[:, :3][tris.reshape(-1, 3)]                       # (T,3,3)
+    targets = np.concatenate([P.reshape(-1, 3), (P[:, 0] + P[:, 1]) / 2, (P[:, 1] + P[:, 2]) / 2, (P[:, 0] + P[:, 2]) / 2])
+    origin = np.array([-0.2, 2.6, 6.0], np.float32)
+    d = targets - origin
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([np.broadcast_to(origin, d.shape), d, np.zeros((len(d), 1)), np.full((len(d), 1), 1e30)], axis=1).astype(np.float32)
+    g, o = GpuScene(models), oracle.OracleScene(models)
+    ip_g, uvt_g = g.trace_closest(rays)
+    ip_o, uvt_o = o.trace_closest(rays)
+    assert np.array_equal(ip_g, ip_o)
+    assert np.array_equal(bits(uvt_g[ip_o[:, 0] >= 0]), bits(uvt_o[ip_o[:, 0] >= 0]))
+    g.close()
+
+
+# ------------------------------------------------------------------------------- BRDF + adjoint
+def test_ggx_value_and_adjoint(oracle):
+    rng = np.random.default_rng(5)
+    n = 20000
+
+    def hemi(k):
+        v = rng.normal(size=(k, 3))
+        v[:, 2] = np.abs(v[:, 2]) + 1e-3
+        return v / np.linalg.norm(v, axis=1, keepdims=True)
+
+    inp = np.concatenate([hemi(n), hemi(n), rng.uniform(0, 1, (n, 3)), rng.uniform(0.02, 1, (n, 1)), rng.normal(size=(n, 3))], axis=1).astype(np.float32)
+    ref = oracle.ggx(inp)
+    out = np.empty_like(ref)
+    _abi.check(_abi.load_library().zdr_probe_ggx(0, np_ptr(inp, C.c_float), n, np_ptr(out, C.c_float)))
+    assert np.array_equal(bits(out), bits(ref))
+
+
+# ------------------------------------------------------------------ per-sample radiance + image + grads
+CASES = {
+    # name: (models, integrator, res, spp, material, kwargs)
+    "c1_collocated": (scenes.cbox_collocated_models, ZDR_COLLOCATED, (256, 256), 1, lambda: scenes.random_material((1024, 1024), 0), {}),
+    "collocated_spp4_box": (scenes.cbox_collocated_models, ZDR_COLLOCATED, (96, 64), 4, lambda: scenes.random_material((64, 64), 1), {"use_tent_filter": False}),
+    "c2_direct_small": (scenes.cbox_direct_models, ZDR_DIRECT, (128, 128), 8, lambda: scenes.random_material((1024, 1024), 0), {}),
+    "direct_uv_nomis": (scenes.cbox_path_models, ZDR_DIRECT, (96, 96), 4, lambda: scenes.random_material((256, 256), 2), {"use_mis": False}),
+    "direct_uv_nearest": (scenes.cbox_path_models, ZDR_DIRECT, (64, 64), 4, lambda: scenes.random_material((32, 32), 3), {"bilinear": False}),
+    "c3_path_small": (scenes.cbox_path_models, ZDR_PATH, (96, 96), 8, lambda: scenes.random_material((1024, 1024), 0), {"max_depth": 8}),
+    "path_literal": (scenes.cbox_path_models, ZDR_PATH, (64, 64), 4, lambda: scenes.random_material((128, 128), 4), {"max_depth": 5, "prb_mode": _abi.ZDR_PRB_LITERAL}),
+    "path_depth16": (scenes.cbox_path_models, ZDR_PATH, (48, 48), 4, lambda: scenes.random_material((128, 128), 5), {"max_depth": 16}),
+}
+
+
+@pytest.fixture(scope="module")
+def case_cache():
+    return {}
+
+
+def _run_case(oracle, name, cache):
+    if name in cache:
+        return cache[name]
+    models_fn, integ, res, spp, mat_fn, kw = CASES[name]
+    models, mat = models_fn(), mat_fn()
+    g, o = GpuScene(models), oracle.OracleScene(models)
+    out = {"integ": integ, "mat": mat, "g": g, "o": o, "res": res, "spp": spp, "kw": kw}
+    cache[name] = out
+    return out
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_parity(oracle, case_cache, name):
+    c = _run_case(oracle, name, case_cache)
+    p = make_params(scenes.CBOX_CAMERA, c["res"], c["mat"].shape, c["spp"], 0, **c["kw"])
+    s_g, s_o = c["g"].samples(c["integ"], p, c["mat"]), c["o"].render_samples(c["integ"], p, c["mat"])
+    same = bits(s_g) == bits(s_o)
+    assert same.all(), f"{(~same).sum()} of {same.size} per-sample radiance values differ; max abs {np.nanmax(np.abs(s_g - s_o))}"
+    img_g, img_o = c["g"].forward(c["integ"], p, c["mat"]), c["o"].render_forward(c["integ"], p, c["mat"])
+    assert np.array_equal(bits(img_g), bits(img_o))
+    assert rel_l2(img_g, img_o) <= IMG_TOL
+    assert (img_o[..., 3] == 1).all() and img_o[..., :3].max() > 0
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_backward_parity(oracle, case_cache, name):
+    c = _run_case(oracle, name, case_cache)
+    p = make_params(scenes.CBOX_CAMERA, c["res"], c["mat"].shape, c["spp"], 1, **c["kw"])      # seed+1, render.py:196
+    rng = np.random.default_rng(11)
+    dimg = rng.normal(size=(c["res"][1], c["res"][0], 4)).astype(np.float32)
+    c["g"].reset_counters()
+    c["o"].reset_ray_counters()
+    dm_g, dm_o = c["g"].backward(c["integ"], p, c["mat"], dimg), c["o"].render_backward(c["integ"], p, c["mat"], dimg)
+    assert np.abs(dm_o).max() > 0
+    assert rel_l2(dm_g, dm_o) <= GRAD_TOL, rel_l2(dm_g, dm_o)
+    # the same texels are touched
+    assert np.array_equal(dm_g != 0, dm_o != 0) or rel_l2(dm_g, dm_o) < 1e-5
+    # ray counts identical (the metric's numerator)
+    cg, (oc, oa) = c["g"].counters(), c["o"].ray_counters()
+    assert (cg["closest_rays"], cg["any_rays"]) == (oc, oa)
+
+
+def test_shard_rows_and_samples(oracle, case_cache):
+    """Row tiles are bit-identical to the full render; sample-range shards sum to it (§8e)."""
+    c = _run_case(oracle, "c3_path_small", case_cache)
+    W, H = c["res"]
+    full = c["g"].forward(c["integ"], make_params(scenes.CBOX_CAMERA, c["res"], c["mat"].shape, c["spp"], 0, **c["kw"]), c["mat"])
+    acc = np.zeros_like(full)
+    for r0, r1 in [(0, 17), (17, 64), (64, H)]:
+        p = make_params(scenes.CBOX_CAMERA, c["res"], c["mat"].shape, c["spp"], 0, rows=(r0, r1), **c["kw"])
+        part = c["g"].forward(c["integ"], p, c["mat"])
+        assert not part[:r0].any() and not part[r1:].any()
+        acc += part
+    assert np.array_equal(bits(acc), bits(full))
+    dimg = np.ones((H, W, 4), np.float32)
+    pf = make_params(scenes.CBOX_CAMERA, c["res"], c["mat"].shape, c["spp"], 1, **c["kw"])
+    g_full = c["g"].backward(c["integ"], pf, c["mat"], dimg)
+    g_sum = np.zeros_like(g_full)
+    for r0, r1 in [(0, 40), (40, H)]:
+        for i0, i1 in [(0, 3), (3, c["spp"])]:
+            p = make_params(scenes.CBOX_CAMERA, c["res"], c["mat"].shape, c["spp"], 1, rows=(r0, r1), its=(i0, i1), **c["kw"])
+            g_sum += c["g"].backward(c["integ"], p, c["mat"], dimg)
+    assert rel_l2(g_sum, g_full) < 1e-5
+
+
+def test_transformed_instances_and_update_lights(oracle):
+    """test_lightstage.py shape: transformed instances, lights toggled with update_lights."""
+    models = scenes.sphere_grid_models(6, seed=2)
+    models[3] = (models[3][0], models[3][1], scenes.float3(9.0, 7.0, 5.0))
+    models[5] = (models[5][0], models[5][1], scenes.float3(0.0))
+    g, o = GpuScene(models), oracle.OracleScene(models)
+    mat = scenes.random_material((64, 64), 9)
+    cam = scenes.Camera(fov=0.9, origin=scenes.float3(-2.0, 2.5, -4.0), target=scenes.float3(1.0, 0.3, 0.3), up=scenes.float3(0, 1, 0))
+    for emis in [None, [(0, 0, 0), (0, 0, 0), (3, 3, 3), (0, 0, 0), (0, 0, 0), (5, 1, 1)]]:
+        if emis is not None:
+            g.set_emissions(np.asarray(emis, np.float32))
+            o.update_lights(emis)
+        for integ in (ZDR_DIRECT, ZDR_PATH):
+            p = make_params(cam, (80, 60), mat.shape, 4, 0, max_depth=4)
+            assert np.array_equal(bits(g.samples(integ, p, mat)), bits(o.render_samples(integ, p, mat)))
+            dimg = np.ones((60, 80, 4), np.float32)
+            assert rel_l2(g.backward(integ, p, mat, dimg), o.render_backward(integ, p, mat, dimg)) <= GRAD_TOL
+    g.close()
+
+
+def test_envmap_path(oracle):
+    """C5 shape, small: instanced spheres + procedural envmap, path depth 6."""
+    models = scenes.sphere_grid_models(8, seed=4)
+    env = scenes.procedural_envmap(128, 64, seed=1)
+    g, o = GpuScene(models), oracle.OracleScene(models)
+    g.set_envmap(env)
+    o.set_envmap(env)
+    mat = scenes.random_material((64, 64), 10)
+    cam = scenes.Camera(fov=0.9, origin=scenes.float3(-2.0, 2.5, -4.0), target=scenes.float3(1.0, 0.3, 0.3), up=scenes.float3(0, 1, 0))
+    for integ in (ZDR_DIRECT, ZDR_PATH):
+        p = make_params(cam, (64, 48), mat.shape, 8, 0, max_depth=6)
+        img_g, img_o = g.forward(integ, p, mat), o.render_forward(integ, p, mat)
+        assert rel_l2(img_g, img_o) <= IMG_TOL, rel_l2(img_g, img_o)     # acosf/atan2f are libm vs CUDA: tolerance, not bits
+        dimg = np.ones((48, 64, 4), np.float32)
+        assert rel_l2(g.backward(integ, p, mat, dimg), o.render_backward(integ, p, mat, dimg)) <= GRAD_TOL
+    g.close()

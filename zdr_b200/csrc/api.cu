@@ -1,0 +1,545 @@
+// api.cu — the C ABI of include/zdr_b200.h: scene assembly (render.py:73-148), sampler-table
+// upload (pmj02bn.py:9-16), the forward / adjoint operator launches (render.py:168-171,
+// 193-196) and the parity probes.  Nothing here has a CPU fallback: every compute entry needs a
+// CUDA device and returns ZDR_ERR_CUDA without one.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "bvh_build.h"
+#include "envmap.cuh"
+#include "render.cuh"
+
+#define ZDR_EXPORT extern "C" __attribute__((visibility("default")))
+
+using namespace zdr;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(ZDR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ---- sampler tables, one immutable copy per device (pmj02bn.py:9-16) ---------------------------
+constexpr int kMaxDevices = 64;
+struct Tables {
+    float2* pmj = nullptr;
+    float* bn = nullptr;
+    int sets = 0, n = 0, ntex = 0, res = 0;
+};
+Tables g_tables[kMaxDevices];
+std::mutex g_tables_mu;
+
+struct Mesh {
+    std::vector<float> verts;     // nv x 8 (vertex.py:4)
+    std::vector<int32_t> tris;    // nt x 3
+    float M[16];
+    float N[9];
+    float emission[3];
+    int tri_base = 0;
+};
+
+// inverse(transpose(M3x3)), interaction.py:28 — cofactor expansion, plain binary32 operations
+void normal_matrix(const float* M, float* N) {
+    const float a00 = M[0], a01 = M[1], a02 = M[2];
+    const float a10 = M[4], a11 = M[5], a12 = M[6];
+    const float a20 = M[8], a21 = M[9], a22 = M[10];
+    const float c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+    const float c10 = a02 * a21 - a01 * a22, c11 = a00 * a22 - a02 * a20, c12 = a01 * a20 - a00 * a21;
+    const float c20 = a01 * a12 - a02 * a11, c21 = a02 * a10 - a00 * a12, c22 = a00 * a11 - a01 * a10;
+    const float det = a00 * c00 + a01 * c01 + a02 * c02;
+    const float id = 1.0f / det;
+    N[0] = c00 * id; N[1] = c01 * id; N[2] = c02 * id;
+    N[3] = c10 * id; N[4] = c11 * id; N[5] = c12 * id;
+    N[6] = c20 * id; N[7] = c21 * id; N[8] = c22 * id;
+}
+
+template <typename T>
+struct DevBuf {   // grow-only device scratch
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, sizeof(T) * n);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct zdr_scene {
+    int device = 0;
+    std::vector<Mesh> meshes;
+    bool committed = false;
+    BvhResult bvh = {};
+    InstData* d_inst = nullptr;
+    int* d_lights = nullptr;
+    int light_count = 0;
+    int num_tris = 0;
+    EnvMap env = {};
+    unsigned long long* d_counters = nullptr;
+    cudaStream_t own_stream = nullptr;       // for the *_host entry points and the probes
+    DevBuf<float> s_mat, s_img, s_dimg, s_dmat, s_misc, s_misc2;
+    DevBuf<int> s_int, s_int2;
+};
+
+namespace {
+
+int use_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(ZDR_ERR_CUDA, "no CUDA device (%s); zdr_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= count || device >= kMaxDevices) return fail(ZDR_ERR_ARG, "bad device %d", device);
+    CK(cudaSetDevice(device));
+    return ZDR_OK;
+}
+
+int upload_lights(zdr_scene* s) {   // render.py:116-126, :141-148
+    const int n = (int)s->meshes.size();
+    std::vector<InstData> inst(n);
+    std::vector<int> lights;
+    for (int i = 0; i < n; ++i) {
+        const Mesh& m = s->meshes[i];
+        memset(&inst[i], 0, sizeof(InstData));
+        memcpy(inst[i].N, m.N, sizeof(m.N));
+        memcpy(inst[i].emission, m.emission, sizeof(m.emission));
+        inst[i].tri_base = m.tri_base;
+        inst[i].tri_count = (int)(m.tris.size() / 3);
+        if (m.emission[0] > 0.f || m.emission[1] > 0.f || m.emission[2] > 0.f) lights.push_back(i);   // render.py:89-90
+    }
+    s->light_count = (int)lights.size();
+    if (lights.empty()) lights.push_back(0);
+    lights.resize(n > 0 ? n : 1, 0);
+    // the kernels of an in-flight launch may still read the old tables
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(s->d_inst, inst.data(), sizeof(InstData) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_lights, lights.data(), sizeof(int) * lights.size(), cudaMemcpyHostToDevice));
+    return ZDR_OK;
+}
+
+int scene_view(zdr_scene* s, SceneView* v) {
+    if (!s->committed) return fail(ZDR_ERR_STATE, "scene not committed (zdr_scene_commit)");
+    const Tables& t = g_tables[s->device];
+    if (!t.pmj || !t.bn) return fail(ZDR_ERR_STATE, "sampler tables not set for device %d (zdr_set_sampler_tables)", s->device);
+    memset(v, 0, sizeof(*v));
+    v->nodes = s->bvh.nodes; v->tris = s->bvh.tris; v->shade = s->bvh.shade; v->slot_of_gid = s->bvh.slot_of_gid;
+    v->inst = s->d_inst; v->lights = s->d_lights;
+    v->root_link = s->bvh.root_link;
+    v->num_tris = s->num_tris; v->num_nodes = s->bvh.num_nodes; v->num_inst = (int)s->meshes.size();
+    v->light_count = s->light_count;
+    v->env_count = s->env.valid ? 1 : 0;
+    v->pmj = t.pmj; v->bn = t.bn; v->pmj_sets = t.sets; v->pmj_n = t.n; v->bn_ntex = t.ntex; v->bn_res = t.res;
+    v->env_tex = s->env.tex; v->env_alias = s->env.alias; v->env_pdf = s->env.pdf; v->env_w = s->env.w; v->env_h = s->env.h;
+    return ZDR_OK;
+}
+
+int check_params(const zdr_scene* s, int integrator, const zdr_params* p) {
+    if (!s || !p) return fail(ZDR_ERR_ARG, "null scene/params");
+    if (integrator < ZDR_COLLOCATED || integrator > ZDR_PATH) return fail(ZDR_ERR_ARG, "unknown integrator %d", integrator);
+    if (p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->tex_res_x <= 0 || p->tex_res_y <= 0)
+        return fail(ZDR_ERR_ARG, "non-positive width/height/spp/texture size");
+    if (p->row0 < 0 || p->row1 > p->height || p->row0 > p->row1 || p->it0 < 0 || p->it1 > p->spp || p->it0 > p->it1)
+        return fail(ZDR_ERR_ARG, "bad shard rows [%d,%d) its [%d,%d)", p->row0, p->row1, p->it0, p->it1);
+    if (p->max_depth < 0 || p->rr_depth < 0) return fail(ZDR_ERR_ARG, "negative depth");
+    return ZDR_OK;
+}
+
+int make_args(zdr_scene* s, const zdr_params* p, RenderArgs* a) {
+    memset(a, 0, sizeof(*a));
+    int rc = scene_view(s, &a->sc);
+    if (rc) return rc;
+    // camera.py:7-10, evaluated once per launch (pure function of the camera)
+    const float3 origin = f3(p->cam_origin[0], p->cam_origin[1], p->cam_origin[2]);
+    const float3 target = f3(p->cam_target[0], p->cam_target[1], p->cam_target[2]);
+    const float3 up = f3(p->cam_up[0], p->cam_up[1], p->cam_up[2]);
+    a->cam_o = origin;
+    a->cam_fwd = normalize(target - origin);
+    a->cam_right = normalize(cross(a->cam_fwd, up));
+    a->cam_up = cross(a->cam_right, a->cam_fwd);
+    a->tan_half_fov = tanf(0.5f * p->cam_fov);
+    a->W = p->width; a->H = p->height; a->spp = p->spp; a->seed = p->seed;
+    a->use_tent = p->use_tent_filter; a->max_depth = p->max_depth; a->rr_depth = p->rr_depth;
+    a->use_mis = p->use_mis; a->prb_mode = p->prb_mode;
+    a->row0 = p->row0; a->row1 = p->row1; a->it0 = p->it0; a->it1 = p->it1;
+    a->tex.rx = p->tex_res_x; a->tex.ry = p->tex_res_y; a->tex.bilinear = p->bilinear;
+    a->counters = s->d_counters;
+    return ZDR_OK;
+}
+
+inline bool want_stats(const zdr_params* p) { return (p->reserved[0] & 1) != 0; }
+
+}  // namespace
+
+// ---- library-wide ---------------------------------------------------------------------------
+ZDR_EXPORT int zdr_abi_version(void) { return ZDR_ABI_VERSION; }
+ZDR_EXPORT const char* zdr_last_error(void) { return g_err; }
+
+ZDR_EXPORT int zdr_set_sampler_tables(int device, const uint32_t* pmj_host, int sets, int n, const uint16_t* bn_host,
+                                      int ntex, int res) {
+    if (!pmj_host || !bn_host || sets <= 0 || n <= 0 || ntex <= 0 || res <= 0) return fail(ZDR_ERR_ARG, "bad sampler tables");
+    int rc = use_device(device);
+    if (rc) return rc;
+    const size_t np = (size_t)sets * n * 2, nb = (size_t)ntex * res * res;
+    std::vector<float> pf(np), bf(nb);
+    for (size_t i = 0; i < np; ++i) pf[i] = (float)pmj_host[i] * 0x1p-32f;   // pmj02bn.py:9: RN(u32->f32) * 2^-32
+    for (size_t i = 0; i < nb; ++i) bf[i] = (float)bn_host[i] * 0x1p-16f;    // pmj02bn.py:14
+    std::lock_guard<std::mutex> lock(g_tables_mu);
+    Tables& t = g_tables[device];
+    CK(cudaDeviceSynchronize());
+    if (t.pmj) cudaFree(t.pmj);
+    if (t.bn) cudaFree(t.bn);
+    t = Tables();
+    CK(cudaMalloc(&t.pmj, sizeof(float) * np));
+    CK(cudaMalloc(&t.bn, sizeof(float) * nb));
+    CK(cudaMemcpy(t.pmj, pf.data(), sizeof(float) * np, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t.bn, bf.data(), sizeof(float) * nb, cudaMemcpyHostToDevice));
+    t.sets = sets; t.n = n; t.ntex = ntex; t.res = res;
+    return ZDR_OK;
+}
+
+// ---- scene assembly -------------------------------------------------------------------------
+ZDR_EXPORT int zdr_scene_create(zdr_scene** out, int device) {
+    if (!out) return fail(ZDR_ERR_ARG, "null out");
+    *out = nullptr;
+    int rc = use_device(device);
+    if (rc) return rc;
+    zdr_scene* s = new (std::nothrow) zdr_scene();
+    if (!s) return fail(ZDR_ERR_ARG, "out of host memory");
+    s->device = device;
+    cudaError_t e = cudaMalloc(&s->d_counters, sizeof(unsigned long long) * C_NUM);
+    if (e == cudaSuccess) e = cudaMemset(s->d_counters, 0, sizeof(unsigned long long) * C_NUM);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(ZDR_ERR_CUDA, "scene_create: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return ZDR_OK;
+}
+
+ZDR_EXPORT void zdr_scene_destroy(zdr_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    free_bvh(&s->bvh);
+    free_envmap(&s->env);
+    cudaFree(s->d_inst); cudaFree(s->d_lights); cudaFree(s->d_counters);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    s->s_mat.release(); s->s_img.release(); s->s_dimg.release(); s->s_dmat.release(); s->s_misc.release();
+    s->s_misc2.release(); s->s_int.release(); s->s_int2.release();
+    delete s;
+}
+
+ZDR_EXPORT int zdr_scene_add_mesh(zdr_scene* s, const float* verts, int nv, const int32_t* tris, int nt,
+                                  const float xform[16], const float emission[3]) {
+    if (!s || !verts || !tris || nv <= 0 || nt <= 0) return fail(ZDR_ERR_ARG, "add_mesh: bad arguments");
+    if (s->meshes.size() >= 10000) return fail(ZDR_ERR_LIMIT, "too many instances (render.py:114: 10000)");
+    for (int i = 0; i < 3 * nt; ++i)
+        if (tris[i] < 0 || tris[i] >= nv) return fail(ZDR_ERR_ARG, "add_mesh: index %d out of range", tris[i]);
+    static const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    s->meshes.emplace_back();
+    Mesh& m = s->meshes.back();
+    m.verts.assign(verts, verts + 8 * (size_t)nv);
+    m.tris.assign(tris, tris + 3 * (size_t)nt);
+    memcpy(m.M, xform ? xform : I16, sizeof(m.M));
+    normal_matrix(m.M, m.N);
+    for (int k = 0; k < 3; ++k) m.emission[k] = emission ? emission[k] : 0.0f;
+    s->committed = false;
+    return ZDR_OK;
+}
+
+ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
+    if (!s || s->meshes.empty()) return fail(ZDR_ERR_STATE, "commit: empty scene");
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    size_t nt = 0;
+    for (Mesh& m : s->meshes) { m.tri_base = (int)nt; nt += m.tris.size() / 3; }
+    if (nt >= (1u << 29)) return fail(ZDR_ERR_LIMIT, "too many triangles");
+    // flatten the instances to world space: p = (M * float4(v,1)).xyz as interaction.py:19-21
+    std::vector<float4> tri(3 * nt), shade(4 * nt);
+    float3 lo = f3(INFINITY, INFINITY, INFINITY), hi = f3(-INFINITY, -INFINITY, -INFINITY);
+    for (size_t i = 0; i < s->meshes.size(); ++i) {
+        const Mesh& m = s->meshes[i];
+        const size_t mt = m.tris.size() / 3;
+        for (size_t t = 0; t < mt; ++t) {
+            const size_t g = m.tri_base + t;
+            const float* v[3];
+            float3 p[3];
+            for (int k = 0; k < 3; ++k) {
+                v[k] = m.verts.data() + 8 * (size_t)m.tris[3 * t + k];
+                p[k] = xform_point(m.M, f3(v[k][0], v[k][1], v[k][2]));
+                lo = f3(fminf(lo.x, p[k].x), fminf(lo.y, p[k].y), fminf(lo.z, p[k].z));
+                hi = f3(fmaxf(hi.x, p[k].x), fmaxf(hi.y, p[k].y), fmaxf(hi.z, p[k].z));
+            }
+            tri[3 * g + 0] = make_float4(p[0].x, p[0].y, p[0].z, __builtin_bit_cast(float, (int)g));
+            tri[3 * g + 1] = make_float4(p[1].x, p[1].y, p[1].z, __builtin_bit_cast(float, (int)i));
+            tri[3 * g + 2] = make_float4(p[2].x, p[2].y, p[2].z, __builtin_bit_cast(float, (int)t));
+            for (int k = 0; k < 3; ++k) shade[4 * g + k] = make_float4(v[k][5], v[k][6], v[k][7], v[k][3]);
+            shade[4 * g + 3] = make_float4(v[0][4], v[1][4], v[2][4], 0.0f);
+        }
+    }
+    if (!(lo.x <= hi.x)) return fail(ZDR_ERR_ARG, "commit: non-finite geometry");
+    CK(cudaDeviceSynchronize());
+    free_bvh(&s->bvh);
+    cudaFree(s->d_inst); cudaFree(s->d_lights);
+    s->d_inst = nullptr; s->d_lights = nullptr;
+    float4 *d_tri = nullptr, *d_shade = nullptr;
+    CK(cudaMalloc(&d_tri, sizeof(float4) * tri.size()));
+    cudaError_t e = cudaMalloc(&d_shade, sizeof(float4) * shade.size());
+    if (e == cudaSuccess) e = cudaMemcpy(d_tri, tri.data(), sizeof(float4) * tri.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_shade, shade.data(), sizeof(float4) * shade.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = build_bvh(d_tri, d_shade, (int)nt, lo, hi, s->own_stream, &s->bvh);
+    cudaFree(d_tri); cudaFree(d_shade);
+    if (e != cudaSuccess) return fail(ZDR_ERR_CUDA, "commit/build_bvh: %s", cudaGetErrorString(e));
+    if (s->bvh.max_depth + 2 > kStackSize) return fail(ZDR_ERR_LIMIT, "BVH depth %d exceeds the traversal stack", s->bvh.max_depth);
+    s->num_tris = (int)nt;
+    CK(cudaMalloc(&s->d_inst, sizeof(InstData) * s->meshes.size()));
+    CK(cudaMalloc(&s->d_lights, sizeof(int) * s->meshes.size()));
+    rc = upload_lights(s);
+    if (rc) return rc;
+    s->committed = true;
+    return ZDR_OK;
+}
+
+ZDR_EXPORT int zdr_scene_set_emissions(zdr_scene* s, const float* e3, int n) {   // render.py:130-148
+    if (!s || !e3) return fail(ZDR_ERR_ARG, "set_emissions: null");
+    if (n != (int)s->meshes.size()) return fail(ZDR_ERR_ARG, "set_emissions: %d emissions for %d instances (render.py:141)", n, (int)s->meshes.size());
+    for (int i = 0; i < n; ++i) memcpy(s->meshes[i].emission, e3 + 3 * i, sizeof(float) * 3);
+    if (!s->committed) return ZDR_OK;
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    return upload_lights(s);
+}
+
+ZDR_EXPORT int zdr_scene_set_envmap(zdr_scene* s, const float* rgba, int w, int h, int compensate_mis) {
+    if (!s || !rgba || w <= 0 || h <= 0) return fail(ZDR_ERR_ARG, "set_envmap: bad arguments");
+    if (h != w && w != 2 * h) return fail(ZDR_ERR_ARG, "set_envmap: image must be 1:1 or 2:1 (envmap.py:122-128)");
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    cudaError_t e = build_envmap(rgba, w, h, compensate_mis != 0, s->own_stream, &s->env);
+    if (e != cudaSuccess) return fail(ZDR_ERR_CUDA, "set_envmap: %s", cudaGetErrorString(e));
+    return ZDR_OK;
+}
+
+ZDR_EXPORT int zdr_scene_instance_count(const zdr_scene* s) { return s ? (int)s->meshes.size() : 0; }
+ZDR_EXPORT int zdr_scene_light_count(const zdr_scene* s) {
+    if (!s) return 0;
+    int n = 0;
+    for (const Mesh& m : s->meshes) n += (m.emission[0] > 0.f || m.emission[1] > 0.f || m.emission[2] > 0.f) ? 1 : 0;
+    return n;
+}
+ZDR_EXPORT int zdr_scene_triangle_count(const zdr_scene* s) {
+    if (!s) return 0;
+    size_t n = 0;
+    for (const Mesh& m : s->meshes) n += m.tris.size() / 3;
+    return (int)n;
+}
+
+// ---- the hot path ---------------------------------------------------------------------------
+ZDR_EXPORT int zdr_render_forward(zdr_scene* s, int integrator, const zdr_params* p, const float* material_dev,
+                                  float* image_dev, void* stream) {
+    int rc = check_params(s, integrator, p);
+    if (rc) return rc;
+    if (!material_dev || !image_dev) return fail(ZDR_ERR_ARG, "render_forward: null buffer");
+    if ((rc = use_device(s->device))) return rc;
+    RenderArgs a;
+    if ((rc = make_args(s, p, &a))) return rc;
+    a.tex.mat = reinterpret_cast<const float4*>(material_dev);
+    a.image = reinterpret_cast<float4*>(image_dev);
+    CK(launch_forward(integrator, a, want_stats(p), (cudaStream_t)stream));
+    return ZDR_OK;
+}
+
+ZDR_EXPORT int zdr_render_backward(zdr_scene* s, int integrator, const zdr_params* p, const float* material_dev,
+                                   const float* d_image_dev, float* d_material_dev, void* stream) {
+    int rc = check_params(s, integrator, p);
+    if (rc) return rc;
+    if (!material_dev || !d_image_dev || !d_material_dev) return fail(ZDR_ERR_ARG, "render_backward: null buffer");
+    if ((rc = use_device(s->device))) return rc;
+    RenderArgs a;
+    if ((rc = make_args(s, p, &a))) return rc;
+    a.tex.mat = reinterpret_cast<const float4*>(material_dev);
+    a.tex.dmat = reinterpret_cast<float4*>(d_material_dev);
+    a.d_image = reinterpret_cast<const float4*>(d_image_dev);
+    CK(launch_backward(integrator, a, want_stats(p), (cudaStream_t)stream));
+    return ZDR_OK;
+}
+
+ZDR_EXPORT int zdr_render_forward_host(zdr_scene* s, int integrator, const zdr_params* p, const float* material_host,
+                                       float* image_host) {
+    int rc = check_params(s, integrator, p);
+    if (rc) return rc;
+    if (!material_host || !image_host) return fail(ZDR_ERR_ARG, "render_forward_host: null buffer");
+    if ((rc = use_device(s->device))) return rc;
+    const size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4, nimg = (size_t)p->width * p->height * 4;
+    CK(s->s_mat.reserve(nmat));
+    CK(s->s_img.reserve(nimg));
+    cudaStream_t st = s->own_stream;
+    CK(cudaMemcpyAsync(s->s_mat.p, material_host, sizeof(float) * nmat, cudaMemcpyHostToDevice, st));
+    if ((rc = zdr_render_forward(s, integrator, p, s->s_mat.p, s->s_img.p, st))) return rc;
+    const size_t off = (size_t)p->row0 * p->width * 4, cnt = (size_t)(p->row1 - p->row0) * p->width * 4;
+    CK(cudaMemcpyAsync(image_host + off, s->s_img.p + off, sizeof(float) * cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ZDR_OK;
+}
+
+ZDR_EXPORT int zdr_render_backward_host(zdr_scene* s, int integrator, const zdr_params* p, const float* material_host,
+                                        const float* d_image_host, float* d_material_host) {
+    int rc = check_params(s, integrator, p);
+    if (rc) return rc;
+    if (!material_host || !d_image_host || !d_material_host) return fail(ZDR_ERR_ARG, "render_backward_host: null buffer");
+    if ((rc = use_device(s->device))) return rc;
+    const size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4, nimg = (size_t)p->width * p->height * 4;
+    CK(s->s_mat.reserve(nmat));
+    CK(s->s_dmat.reserve(nmat));
+    CK(s->s_dimg.reserve(nimg));
+    cudaStream_t st = s->own_stream;
+    CK(cudaMemcpyAsync(s->s_mat.p, material_host, sizeof(float) * nmat, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->s_dimg.p, d_image_host, sizeof(float) * nimg, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(s->s_dmat.p, 0, sizeof(float) * nmat, st));                                  // render.py:220
+    if ((rc = zdr_render_backward(s, integrator, p, s->s_mat.p, s->s_dimg.p, s->s_dmat.p, st))) return rc;
+    CK(cudaMemcpyAsync(d_material_host, s->s_dmat.p, sizeof(float) * nmat, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ZDR_OK;
+}
+
+// ---- instrumentation ------------------------------------------------------------------------
+ZDR_EXPORT int zdr_get_counters(zdr_scene* s, uint64_t out[ZDR_NUM_COUNTERS]) {
+    if (!s || !out) return fail(ZDR_ERR_ARG, "get_counters: null");
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    static_assert(C_NUM == ZDR_NUM_COUNTERS, "counter count");
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, s->d_counters, sizeof(uint64_t) * C_NUM, cudaMemcpyDeviceToHost));
+    return ZDR_OK;
+}
+ZDR_EXPORT int zdr_reset_counters(zdr_scene* s) {
+    if (!s) return fail(ZDR_ERR_ARG, "reset_counters: null");
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(s->d_counters, 0, sizeof(uint64_t) * C_NUM));
+    return ZDR_OK;
+}
+
+// ---- probes ---------------------------------------------------------------------------------
+ZDR_EXPORT int zdr_probe_trace_closest(zdr_scene* s, const float* rays, int n, int32_t* inst_prim, float* uvt) {
+    if (!s || !rays || !inst_prim || !uvt || n < 0) return fail(ZDR_ERR_ARG, "probe_trace_closest: bad arguments");
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    SceneView sc;
+    if ((rc = scene_view(s, &sc))) return rc;
+    if (n == 0) return ZDR_OK;
+    CK(s->s_misc.reserve(8 * (size_t)n));
+    CK(s->s_misc2.reserve(3 * (size_t)n));
+    CK(s->s_int.reserve(2 * (size_t)n));
+    cudaStream_t st = s->own_stream;
+    CK(cudaMemcpyAsync(s->s_misc.p, rays, sizeof(float) * 8 * n, cudaMemcpyHostToDevice, st));
+    CK(launch_probe_trace(sc, s->s_misc.p, n, false, s->s_int.p, s->s_misc2.p, nullptr, st));
+    CK(cudaMemcpyAsync(inst_prim, s->s_int.p, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(uvt, s->s_misc2.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ZDR_OK;
+}
+
+ZDR_EXPORT int zdr_probe_trace_any(zdr_scene* s, const float* rays, int n, int32_t* occluded) {
+    if (!s || !rays || !occluded || n < 0) return fail(ZDR_ERR_ARG, "probe_trace_any: bad arguments");
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    SceneView sc;
+    if ((rc = scene_view(s, &sc))) return rc;
+    if (n == 0) return ZDR_OK;
+    CK(s->s_misc.reserve(8 * (size_t)n));
+    CK(s->s_int.reserve((size_t)n));
+    cudaStream_t st = s->own_stream;
+    CK(cudaMemcpyAsync(s->s_misc.p, rays, sizeof(float) * 8 * n, cudaMemcpyHostToDevice, st));
+    CK(launch_probe_trace(sc, s->s_misc.p, n, true, nullptr, nullptr, s->s_int.p, st));
+    CK(cudaMemcpyAsync(occluded, s->s_int.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ZDR_OK;
+}
+
+ZDR_EXPORT int zdr_probe_sampler(int device, const int32_t* state, int n, const char* prog, float* out) {
+    if (!state || !prog || !out || n < 0) return fail(ZDR_ERR_ARG, "probe_sampler: bad arguments");
+    int rc = use_device(device);
+    if (rc) return rc;
+    const Tables& t = g_tables[device];
+    if (!t.pmj || !t.bn) return fail(ZDR_ERR_STATE, "sampler tables not set for device %d", device);
+    if (n == 0) return ZDR_OK;
+    SceneView sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.pmj = t.pmj; sc.bn = t.bn; sc.pmj_sets = t.sets; sc.pmj_n = t.n; sc.bn_ntex = t.ntex; sc.bn_res = t.res;
+    const int len = (int)strlen(prog);
+    int per = 0;
+    for (int k = 0; k < len; ++k) per += prog[k] == '2' ? 2 : 1;
+    int* d_state = nullptr; char* d_prog = nullptr; float* d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_state, sizeof(int) * 5 * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_prog, (size_t)len + 1);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(float) * (size_t)per * n + 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_state, state, sizeof(int) * 5 * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_prog, prog, (size_t)len + 1, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_probe_sampler(sc, d_state, n, d_prog, len, per, d_out, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(float) * (size_t)per * n, cudaMemcpyDeviceToHost);
+    cudaFree(d_state); cudaFree(d_prog); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(ZDR_ERR_CUDA, "probe_sampler: %s", cudaGetErrorString(e));
+    return ZDR_OK;
+}
+
+ZDR_EXPORT int zdr_probe_render_samples(zdr_scene* s, int integrator, const zdr_params* p, const float* material_host,
+                                        float* out_host) {
+    int rc = check_params(s, integrator, p);
+    if (rc) return rc;
+    if (!material_host || !out_host) return fail(ZDR_ERR_ARG, "probe_render_samples: null buffer");
+    if ((rc = use_device(s->device))) return rc;
+    const size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4, nout = (size_t)p->width * p->height * p->spp * 3;
+    CK(s->s_mat.reserve(nmat));
+    CK(s->s_misc.reserve(nout));
+    RenderArgs a;
+    if ((rc = make_args(s, p, &a))) return rc;
+    cudaStream_t st = s->own_stream;
+    CK(cudaMemcpyAsync(s->s_mat.p, material_host, sizeof(float) * nmat, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(s->s_misc.p, 0, sizeof(float) * nout, st));
+    a.tex.mat = reinterpret_cast<const float4*>(s->s_mat.p);
+    a.samples_out = s->s_misc.p;
+    CK(launch_forward(integrator, a, want_stats(p), st));
+    CK(cudaMemcpyAsync(out_host, s->s_misc.p, sizeof(float) * nout, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ZDR_OK;
+}
+
+ZDR_EXPORT int zdr_probe_ggx(int device, const float* in, int n, float* out) {
+    if (!in || !out || n < 0) return fail(ZDR_ERR_ARG, "probe_ggx: bad arguments");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (n == 0) return ZDR_OK;
+    float *d_in = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_in, sizeof(float) * 13 * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(float) * 7 * (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, in, sizeof(float) * 13 * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_probe_ggx(d_in, n, d_out, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(float) * 7 * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(ZDR_ERR_CUDA, "probe_ggx: %s", cudaGetErrorString(e));
+    return ZDR_OK;
+}

@@ -1,0 +1,24 @@
+// bvh_build.h — interface of the GPU LBVH builder (bvh_build.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace zdr {
+
+struct BvhResult {
+    float4* nodes;        // 4 float4 per inner node (traverse.cuh layout)
+    float4* tris;         // 3 float4 per triangle, leaf order
+    float4* shade;        // 4 float4 per triangle, leaf order
+    int* slot_of_gid;     // scene-order triangle id -> leaf-order slot
+    int root_link;
+    int num_nodes;
+    int max_depth;        // of the un-collapsed radix tree (upper bound for the traversal stack)
+};
+
+// tri_in / shade_in: device arrays in scene order (3 resp. 4 float4 per triangle).
+// lo/hi: bounds of all vertices. Synchronises `stream` before returning.
+cudaError_t build_bvh(const float4* tri_in, const float4* shade_in, int n, float3 lo, float3 hi,
+                      cudaStream_t stream, BvhResult* out);
+void free_bvh(BvhResult* r);
+
+}  // namespace zdr

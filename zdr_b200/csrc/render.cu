@@ -1,0 +1,411 @@
+// render.cu — per-pixel render kernels (forward + adjoint) for the collocated, direct and path
+// integrators.  Replaces the LuisaCompute kernels derived at integrator.py:8-53 from
+// collocated.py / direct.py / prb.py and dispatched at render.py:168-171,193-196.
+#include "render.cuh"
+
+namespace zdr {
+
+namespace {
+
+// per-thread tallies, reduced per warp and flushed with one atomic per counter per warp
+struct Tally {
+    unsigned closest, any, scatter, shaded, samples;
+    TraceStats ts;
+};
+
+template <bool STATS>
+struct Ctx {
+    const RenderArgs& a;
+    Tally& tl;
+    ZDR_DEV Hit closest(const Ray& r) { tl.closest++; return trace<false, STATS>(a.sc, r, tl.ts); }
+    ZDR_DEV bool occluded(const Ray& r) { tl.any++; return trace<true, STATS>(a.sc, r, tl.ts).inst >= 0; }
+    ZDR_DEV void scatter(float2 uv, float4 g) { tl.scatter++; write_bsdf_grad(a.tex, uv, g); }
+};
+
+ZDR_DEV Ray make_ray(float3 o, float3 d, float tmin, float tmax) { Ray r; r.o = o; r.d = d; r.tmin = tmin; r.tmax = tmax; return r; }
+
+// ------------------------------------------------------------------------------ collocated.py
+template <bool STATS>
+ZDR_DEV float3 collocated_estimator(Ctx<STATS>& c, const Ray& ray) {               // collocated.py:10-31
+    const Hit hit = c.closest(ray);
+    if (hit.inst < 0) return f3(0.f, 0.f, 0.f);
+    const Interaction it = surface_interact(c.a.sc, hit);
+    if (backfacing(ray.d, it)) return f3(0.f, 0.f, 0.f);
+    c.tl.shaded++;
+    const float4 mat = read_bsdf(c.a.tex, it.uv);
+    const Onb onb = make_onb(it.ns);
+    const float3 wo_local = to_local(onb, -ray.d);
+    const float3 beta = ggx_brdf(wo_local, wo_local, f3(mat.x, mat.y, mat.z), 0.04f, mat.w);
+    const float inv = 1.0f / hit.t;
+    const float li = 1.0f * (inv * inv);
+    return beta * li;
+}
+template <bool STATS>
+ZDR_DEV void collocated_estimator_backward(Ctx<STATS>& c, const Ray& ray, float3 le_grad) {   // collocated.py:34-57
+    const Hit hit = c.closest(ray);
+    if (hit.inst < 0) return;
+    const Interaction it = surface_interact(c.a.sc, hit);
+    if (backfacing(ray.d, it)) return;
+    c.tl.shaded++;
+    const float4 mat = read_bsdf(c.a.tex, it.uv);
+    const Onb onb = make_onb(it.ns);
+    const float3 wo_local = to_local(onb, -ray.d);
+    const float inv = 1.0f / hit.t;
+    const float li = 1.0f * (inv * inv);
+    c.scatter(it.uv, ggx_brdf_grad(wo_local, wo_local, 0.04f, mat.w, le_grad * li));
+}
+
+ZDR_DEV float3 env_emission(const SceneView& sc, float3 dir) {                     // direct.py:24
+    return sc.env_count > 0 ? env_texture(sc, direction_to_uv(dir)) : f3(0.f, 0.f, 0.f);
+}
+
+// ---------------------------------------------------------------------------------- direct.py
+// Shared walk of direct_estimator (direct.py:20-85) and direct_estimator_backward (:88-167):
+// BWD=false returns radiance; BWD=true accumulates the BRDF adjoints and scatters once.
+template <bool BWD, bool STATS>
+ZDR_DEV float3 direct_walk(Ctx<STATS>& c, const Ray& ray, Sampler& sampler, float3 le_grad) {
+    const SceneView& sc = c.a.sc;
+    const float3 zero = f3(0.f, 0.f, 0.f);
+    const Hit hit = c.closest(ray);
+    if (hit.inst < 0) return BWD ? zero : env_emission(sc, ray.d);
+    const Interaction it = surface_interact(sc, hit);
+    if (backfacing(ray.d, it)) return zero;
+    float3 emission = inst_emission(sc, hit.inst);
+    if (hit.inst > 0) return BWD ? zero : emission;                                // direct.py:30-32
+    c.tl.shaded++;
+    const float4 mat = read_bsdf(c.a.tex, it.uv);
+    const float3 diffuse = f3(mat.x, mat.y, mat.z);
+    const float roughness = mat.w;
+    const float specular = 0.04f;
+    float3 radiance = zero;
+    float4 mat_grad = make_float4(0.f, 0.f, 0.f, 0.f);
+    const LightSample light = sample_light(sc, it.p, sampler);
+    const bool occluded = c.occluded(make_ray(it.p, light.wi, 1e-4f, light.dist));
+    const Onb onb = make_onb(it.ns);
+    const float3 wo_local = to_local(onb, -ray.d);
+    const float3 wi_light_local = to_local(onb, light.wi);
+    if (!occluded && wi_light_local.z > 0.0f) {
+        float mis_weight = 1.0f;
+        if (c.a.use_mis) mis_weight = balanced_heuristic(light.pdf, ggx_sample_pdf(wo_local, wi_light_local, roughness));
+        const float dn = fmaxf(light.pdf, 1e-4f);
+        if (BWD) {
+            const float3 cot = le_grad * ((light.eval * mis_weight) / dn);
+            mat_grad = mat_grad + ggx_brdf_grad(wo_local, wi_light_local, specular, roughness, cot);
+        } else {
+            const float3 bsdf = ggx_brdf(wo_local, wi_light_local, diffuse, specular, roughness);
+            radiance = radiance + ((bsdf * mis_weight) * light.eval) / dn;
+        }
+    }
+    if (c.a.use_mis) {
+        const float3 wi_local = ggx_sample(sc, wo_local, roughness, sampler);
+        const float3 wi = to_world(onb, wi_local);
+        if (dot(wi, it.ng) < 1e-4f || wi_local.z < 1e-4f) {
+            if (BWD) c.scatter(it.uv, mat_grad);                                   // direct.py:138
+            return radiance;
+        }
+        const Ray r2 = make_ray(offset_ray_origin(it.p, it.ng), wi, 0.0f, 1e30f);
+        const Hit hit2 = c.closest(r2);
+        float pdf_light;
+        if (hit2.inst < 0) {
+            emission = env_emission(sc, r2.d);
+            pdf_light = sc.env_count > 0 ? env_sampled_light_pdf(sc, r2.d) : 0.0f;
+        } else {
+            const Interaction it2 = surface_interact(sc, hit2);
+            if (backfacing(r2.d, it2)) {
+                // direct.py:152 scatters at `it.uv` after `it` was rebound to the second hit
+                if (BWD) c.scatter(it2.uv, mat_grad);
+                return radiance;
+            }
+            emission = inst_emission(sc, hit2.inst);
+            pdf_light = sample_light_pdf(sc, it.p, hit2, it2.p);
+        }
+        if (any_pos(emission)) {
+            const float pdf_bsdf = ggx_sample_pdf(wo_local, wi_local, roughness);
+            const float mis_weight = balanced_heuristic(pdf_bsdf, pdf_light);
+            if (BWD) {
+                const float3 cot = (le_grad * (emission * mis_weight)) / pdf_bsdf;
+                mat_grad = mat_grad + ggx_brdf_grad(wo_local, wi_local, specular, roughness, cot);
+            } else {
+                const float3 beta = ggx_brdf(wo_local, wi_local, diffuse, specular, roughness) / pdf_bsdf;
+                return radiance + (beta * mis_weight) * emission;
+            }
+        }
+    }
+    if (BWD) c.scatter(it.uv, mat_grad);                                           // direct.py:167
+    return radiance;
+}
+
+// ------------------------------------------------------------------------------------- prb.py
+// One walk serves path_estimator (prb.py:18-88; MODE 0), and the adjoint pass of
+// path_estimator_backward (prb.py:102-187; MODE 1) which needs Le from a MODE 0 replay.
+template <int MODE, bool STATS>
+ZDR_DEV float3 path_walk(Ctx<STATS>& c, Ray ray, Sampler& sampler, float3 Le, float3 le_grad) {
+    const SceneView& sc = c.a.sc;
+    const bool corrected = c.a.prb_mode == ZDR_PRB_CORRECTED;
+    float3 radiance = f3(0.f, 0.f, 0.f), beta = f3(1.f, 1.f, 1.f);
+    float pdf_bsdf = 1e30f;
+    const float specular = 0.04f;
+    for (int depth = 0; depth < c.a.max_depth; ++depth) {
+        const Hit hit = c.closest(ray);
+        if (hit.inst < 0) {
+            if (MODE == 0 && sc.env_count > 0) {
+                const float3 tex = env_texture(sc, direction_to_uv(ray.d));
+                const float3 emission = corrected ? tex : beta * tex;              // prb.py:28
+                const float mis_weight = balanced_heuristic(pdf_bsdf, env_sampled_light_pdf(sc, ray.d));
+                radiance = radiance + (beta * mis_weight) * emission;
+            }
+            break;
+        }
+        const Interaction it = surface_interact(sc, hit);
+        if (backfacing(ray.d, it)) break;
+        const float3 emission = inst_emission(sc, hit.inst);
+        if (any_pos(emission)) {
+            const float mis_weight = balanced_heuristic(pdf_bsdf, sample_light_pdf(sc, ray.o, hit, it.p));
+            if (MODE == 0) radiance = radiance + (beta * mis_weight) * emission;
+            else Le = Le - (beta * mis_weight) * emission;
+            break;
+        }
+        if ((MODE == 0 || corrected) && hit.inst > 0) break;                       // prb.py:45-46 (fwd only upstream)
+        c.tl.shaded++;
+        float4 mat_grad = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 mat = read_bsdf(c.a.tex, it.uv);
+        const float3 diffuse = f3(mat.x, mat.y, mat.z);
+        const float roughness = mat.w;
+        const Onb onb = make_onb(it.ns);
+        const float3 wo_local = to_local(onb, -ray.d);
+        const LightSample light = sample_light(sc, it.p, sampler);
+        const bool occluded = c.occluded(make_ray(it.p, light.wi, 1e-4f, light.dist));
+        const float3 wi_light_local = to_local(onb, light.wi);
+        if (!occluded && wi_light_local.z >= 1e-4f) {
+            const float3 bsdf = ggx_brdf(wo_local, wi_light_local, diffuse, specular, roughness);
+            pdf_bsdf = ggx_sample_pdf(wo_local, wi_light_local, roughness);
+            const float mis_weight = balanced_heuristic(light.pdf, pdf_bsdf);
+            const float dn = fmaxf(light.pdf, 1e-4f);
+            const float3 contrib = (((beta * bsdf) * mis_weight) * light.eval) / dn;
+            if (MODE == 0) radiance = radiance + contrib;
+            else {
+                const float3 cot = (((beta * mis_weight) * light.eval) / dn) * le_grad;   // prb.py:145
+                mat_grad = mat_grad + ggx_brdf_grad(wo_local, wi_light_local, specular, roughness, cot);
+                Le = Le - contrib;
+            }
+        }
+        bool done = false;
+        const float3 wi_local = ggx_sample(sc, wo_local, roughness, sampler);
+        pdf_bsdf = ggx_sample_pdf(wo_local, wi_local, roughness);
+        const float3 wi = to_world(onb, wi_local);
+        if (dot(wi, it.ng) < 1e-4f || wi_local.z < 1e-4f) done = true;
+        if (!done) {
+            ray = make_ray(offset_ray_origin(it.p, it.ng), wi, 0.0f, 1e30f);
+            const float3 bsdf = ggx_brdf(wo_local, wi_local, diffuse, specular, roughness);
+            if (MODE == 1) {
+                float3 cot;
+                if (corrected)
+                    cot = f3(bsdf.x != 0.0f ? Le.x / bsdf.x * le_grad.x : 0.0f, bsdf.y != 0.0f ? Le.y / bsdf.y * le_grad.y : 0.0f,
+                             bsdf.z != 0.0f ? Le.z / bsdf.z * le_grad.z : 0.0f);
+                else
+                    cot = ((beta / pdf_bsdf) * Le) * le_grad;                      // prb.py:162
+                mat_grad = mat_grad + ggx_brdf_grad(wo_local, wi_local, specular, roughness, cot);
+            }
+            beta = beta * (bsdf / pdf_bsdf);
+            if (depth >= c.a.rr_depth) {                                           // prb.py:78-87
+                const float l = luminance(beta);
+                if (l == 0.0f) done = true;
+                else {
+                    const float q = fmaxf(l, 0.05f);
+                    const float r = sampler_next(sc, sampler);
+                    if (r >= q) done = true;
+                    else beta = beta / q;
+                }
+            }
+        }
+        if (MODE == 1) {                                                           // prb.py:178-187
+            if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad))
+                c.scatter(it.uv, mat_grad);
+        }
+        if (done) break;
+    }
+    return radiance;
+}
+
+// --------------------------------------------------------------------- camera.py, integrator.py
+ZDR_DEV float tent_warp1(float u) {                                                // camera.py:20-31
+    return u < 0.5f ? 1.0f * (sqrtf(2.0f * u) - 1.0f) : 1.0f * (1.0f - sqrtf(2.0f - 2.0f * u));
+}
+ZDR_DEV Ray camera_sample(const RenderArgs& a, int x, int y, Sampler& sampler) {    // integrator.py:17-25, camera.py:5-17
+    float2 off = sampler_next2f(a.sc, sampler);
+    if (a.use_tent) { off.x = tent_warp1(off.x) + 0.5f; off.y = tent_warp1(off.y) + 0.5f; }
+    float px = 2.0f / (float)a.W * ((float)x + off.x) - 1.0f;
+    float py = 2.0f / (float)a.H * ((float)y + off.y) - 1.0f;
+    py *= (float)a.H / (float)a.W;
+    const float sx = px * a.tan_half_fov, sy = py * a.tan_half_fov;
+    const float3 d = f3(sx * a.cam_right.x - sy * a.cam_up.x + a.cam_fwd.x, sx * a.cam_right.y - sy * a.cam_up.y + a.cam_fwd.y,
+                        sx * a.cam_right.z - sy * a.cam_up.z + a.cam_fwd.z);
+    return make_ray(a.cam_o, normalize(d), 0.0f, 1e30f);
+}
+
+ZDR_DEV unsigned warp_sum(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+ZDR_DEV void flush_tally(const RenderArgs& a, const Tally& t) {
+    const unsigned v[C_NUM] = {t.closest, t.any, t.ts.nodes, t.ts.tris, t.scatter, t.scatter * 4u, t.shaded, t.samples};
+#pragma unroll
+    for (int i = 0; i < C_NUM; ++i) {
+        const unsigned s = warp_sum(v[i]);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(a.counters + i, (unsigned long long)s);
+    }
+}
+
+// block = 128 threads = 4 warps; each warp owns an 8x4 pixel tile, the block a 16x8 tile
+constexpr int kBlockThreads = 128;
+ZDR_DEV void pixel_of_thread(const RenderArgs& a, int& x, int& y) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    x = blockIdx.x * 16 + (w & 1) * 8 + (l & 7);
+    y = a.row0 + blockIdx.y * 8 + (w >> 1) * 4 + (l >> 3);
+}
+
+template <int INTEGRATOR, bool STATS>
+__global__ void __launch_bounds__(kBlockThreads) k_forward(const __grid_constant__ RenderArgs a) {
+    int x, y;
+    pixel_of_thread(a, x, y);
+    Tally tl = {};
+    Ctx<STATS> c{a, tl};
+    if (x < a.W && y < a.row1) {
+        float3 s = f3(0.f, 0.f, 0.f);
+        for (int it = a.it0; it < a.it1; ++it) {                                   // integrator.py:15
+            Sampler sampler = make_sampler(x, y, a.seed, a.spp, it);
+            const Ray ray = camera_sample(a, x, y, sampler);
+            tl.samples++;
+            float3 radiance;
+            if (INTEGRATOR == ZDR_COLLOCATED) radiance = collocated_estimator(c, ray);
+            else if (INTEGRATOR == ZDR_DIRECT) radiance = direct_walk<false>(c, ray, sampler, f3(0.f, 0.f, 0.f));
+            else radiance = path_walk<0>(c, ray, sampler, f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f));
+            if (a.samples_out) {
+                float* o = a.samples_out + (((size_t)y * a.W + x) * a.spp + it) * 3;
+                o[0] = radiance.x; o[1] = radiance.y; o[2] = radiance.z;
+            }
+            if (!any_nan(radiance))                                                // integrator.py:27-28
+                s = s + f3(clampf(radiance.x, 0.0f, 100000.0f), clampf(radiance.y, 0.0f, 100000.0f),
+                           clampf(radiance.z, 0.0f, 100000.0f));
+        }
+        if (a.image) a.image[(size_t)x + (size_t)y * a.W] = make_float4(s.x / (float)a.spp, s.y / (float)a.spp, s.z / (float)a.spp, 1.0f);
+    }
+    flush_tally(a, tl);
+}
+
+template <int INTEGRATOR, bool STATS>
+__global__ void __launch_bounds__(kBlockThreads) k_backward(const __grid_constant__ RenderArgs a) {
+    int x, y;
+    pixel_of_thread(a, x, y);
+    Tally tl = {};
+    Ctx<STATS> c{a, tl};
+    if (x < a.W && y < a.row1) {
+        const float4 g = __ldg(a.d_image + ((size_t)x + (size_t)y * a.W));          // integrator.py:38-40
+        float3 le_grad = f3(g.x / (float)a.spp, g.y / (float)a.spp, g.z / (float)a.spp);
+        if (any_nan(le_grad)) le_grad = f3(0.f, 0.f, 0.f);
+        for (int it = a.it0; it < a.it1; ++it) {
+            Sampler sampler = make_sampler(x, y, a.seed, a.spp, it);
+            const Ray ray = camera_sample(a, x, y, sampler);
+            tl.samples++;
+            if (INTEGRATOR == ZDR_COLLOCATED) collocated_estimator_backward(c, ray, le_grad);
+            else if (INTEGRATOR == ZDR_DIRECT) direct_walk<true>(c, ray, sampler, le_grad);
+            else {
+                Sampler twin = sampler;                                            // prb.py:97-99
+                const float3 Le = path_walk<0>(c, ray, twin, f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f));
+                if (!any_nan(Le)) path_walk<1>(c, ray, sampler, Le, le_grad);
+            }
+        }
+    }
+    flush_tally(a, tl);
+}
+
+__global__ void k_probe_trace(const SceneView sc, const float* __restrict__ rays, int n, int any, int* __restrict__ ip,
+                              float* __restrict__ uvt, int* __restrict__ occ) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = rays + 8 * (size_t)i;
+    const Ray ray = make_ray(f3(r[0], r[1], r[2]), f3(r[3], r[4], r[5]), r[6], r[7]);
+    TraceStats ts = {};
+    if (any) { occ[i] = trace<true, false>(sc, ray, ts).inst >= 0 ? 1 : 0; return; }
+    const Hit h = trace<false, false>(sc, ray, ts);
+    ip[2 * i] = h.inst; ip[2 * i + 1] = h.prim;
+    uvt[3 * i] = h.u; uvt[3 * i + 1] = h.v; uvt[3 * i + 2] = h.t;
+}
+
+__global__ void k_probe_sampler(const SceneView sc, const int* __restrict__ state, int n, const char* __restrict__ prog,
+                                int prog_len, int per, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int* st = state + 5 * (size_t)i;
+    Sampler sm = make_sampler(st[0], st[1], st[2], st[3], st[4]);
+    float* o = out + (size_t)per * i;
+    for (int k = 0; k < prog_len; ++k) {
+        if (prog[k] == '2') { const float2 u = sampler_next2f(sc, sm); *o++ = u.x; *o++ = u.y; }
+        else *o++ = sampler_next(sc, sm);
+    }
+}
+
+__global__ void k_probe_ggx(const float* __restrict__ in, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* a = in + 13 * (size_t)i;
+    const float3 wo = f3(a[0], a[1], a[2]), wi = f3(a[3], a[4], a[5]), d = f3(a[6], a[7], a[8]), g = f3(a[10], a[11], a[12]);
+    const float3 f = ggx_brdf(wo, wi, d, 0.04f, a[9]);
+    const float4 dm = ggx_brdf_grad(wo, wi, 0.04f, a[9], g);
+    float* o = out + 7 * (size_t)i;
+    o[0] = f.x; o[1] = f.y; o[2] = f.z; o[3] = dm.x; o[4] = dm.y; o[5] = dm.z; o[6] = dm.w;
+}
+
+dim3 render_grid(const RenderArgs& a) { return dim3((a.W + 15) / 16, (a.row1 - a.row0 + 7) / 8); }
+
+template <int I>
+cudaError_t launch_fwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
+    if (stats) k_forward<I, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+    else k_forward<I, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+template <int I>
+cudaError_t launch_bwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
+    if (stats) k_backward<I, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+    else k_backward<I, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_forward(int integrator, const RenderArgs& a, bool stats, cudaStream_t s) {
+    if (a.row1 <= a.row0 || a.it1 <= a.it0) return cudaSuccess;
+    switch (integrator) {
+        case ZDR_COLLOCATED: return launch_fwd_i<ZDR_COLLOCATED>(a, stats, s);
+        case ZDR_DIRECT: return launch_fwd_i<ZDR_DIRECT>(a, stats, s);
+        default: return launch_fwd_i<ZDR_PATH>(a, stats, s);
+    }
+}
+cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cudaStream_t s) {
+    if (a.row1 <= a.row0 || a.it1 <= a.it0) return cudaSuccess;
+    switch (integrator) {
+        case ZDR_COLLOCATED: return launch_bwd_i<ZDR_COLLOCATED>(a, stats, s);
+        case ZDR_DIRECT: return launch_bwd_i<ZDR_DIRECT>(a, stats, s);
+        default: return launch_bwd_i<ZDR_PATH>(a, stats, s);
+    }
+}
+cudaError_t launch_probe_trace(const SceneView& sc, const float* rays, int n, bool any, int* ip, float* uvt, int* occ,
+                               cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    k_probe_trace<<<(n + 127) / 128, 128, 0, s>>>(sc, rays, n, any ? 1 : 0, ip, uvt, occ);
+    return cudaGetLastError();
+}
+cudaError_t launch_probe_sampler(const SceneView& sc, const int* state, int n, const char* prog, int prog_len, int per,
+                                 float* out, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    k_probe_sampler<<<(n + 127) / 128, 128, 0, s>>>(sc, state, n, prog, prog_len, per, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_probe_ggx(const float* in, int n, float* out, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    k_probe_ggx<<<(n + 127) / 128, 128, 0, s>>>(in, n, out);
+    return cudaGetLastError();
+}
+
+}  // namespace zdr

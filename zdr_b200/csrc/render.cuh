@@ -1,0 +1,32 @@
+// render.cuh — kernel argument block shared by render.cu and api.cu.
+#pragma once
+#include "scene.cuh"
+#include "shading.cuh"
+#include "../../include/zdr_b200.h"
+
+namespace zdr {
+
+struct RenderArgs {
+    SceneView sc;
+    TexView tex;
+    // camera basis, computed once per launch on the host exactly as camera.py:7-10 does per ray
+    float3 cam_o, cam_fwd, cam_right, cam_up;
+    float tan_half_fov;
+    int W, H, spp, seed, use_tent, max_depth, rr_depth, use_mis, prb_mode;
+    int row0, row1, it0, it1;
+    float4* image;            // forward: (H,W) float4
+    const float4* d_image;    // backward: (H,W) float4 cotangent
+    float* samples_out;       // probe: (H,W,spp,3) un-clamped per-sample radiance, or null
+    unsigned long long* counters;
+};
+
+// launchers (render.cu)
+cudaError_t launch_forward(int integrator, const RenderArgs& a, bool stats, cudaStream_t stream);
+cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cudaStream_t stream);
+cudaError_t launch_probe_trace(const SceneView& sc, const float* rays_dev, int n, bool any, int* ip_dev,
+                               float* uvt_dev, int* occ_dev, cudaStream_t stream);
+cudaError_t launch_probe_sampler(const SceneView& sc, const int* state_dev, int n, const char* prog_dev, int prog_len,
+                                 int per, float* out_dev, cudaStream_t stream);
+cudaError_t launch_probe_ggx(const float* in_dev, int n, float* out_dev, cudaStream_t stream);
+
+}  // namespace zdr

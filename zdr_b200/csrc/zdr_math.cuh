@@ -1,0 +1,102 @@
+// zdr_math.cuh — float3 algebra of the render kernels.
+//
+// NUMERIC CONTRACT: the library is compiled with -fmad=false, so every
+// float operation below is a single IEEE-754 binary32 operation in source order; fused
+// multiply-adds happen ONLY where fmaf() is written.  dot/cross/lincomb/lerp/mat-vec use the
+// fma chains below; x**2 = x*x, x**5 = (x*x)*(x*x)*x; normalize(v) = v * (1/sqrt(v.v)).
+// LuisaCompute's own lowering of these builtins is not inspectable, so this
+// contract *defines* them for the framework; the CPU oracle states the same contract.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define ZDR_DEV __device__ __forceinline__
+#define ZDR_HD __host__ __device__ __forceinline__
+
+namespace zdr {
+
+constexpr float kPi = 3.14159274101257324f;       // float(math.pi)
+constexpr float kTwoPi = 6.28318548202514648f;    // float(2*math.pi)
+
+ZDR_HD float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+ZDR_HD float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+ZDR_HD float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+ZDR_HD float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+ZDR_HD float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+ZDR_HD float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+ZDR_HD float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+ZDR_HD float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+ZDR_HD float dot(float3 a, float3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+ZDR_HD float3 cross(float3 a, float3 b) {
+    return f3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+ZDR_HD float3 normalize(float3 v) {
+    float inv = 1.0f / sqrtf(dot(v, v));
+    return v * inv;
+}
+ZDR_HD float length(float3 v) { return sqrtf(dot(v, v)); }
+// a*A + b*B + c*C
+ZDR_HD float3 lincomb(float a, float3 A, float b, float3 B, float c, float3 C) {
+    return f3(fmaf(c, C.x, fmaf(b, B.x, a * A.x)), fmaf(c, C.y, fmaf(b, B.y, a * A.y)),
+              fmaf(c, C.z, fmaf(b, B.z, a * A.z)));
+}
+ZDR_HD float lerp(float a, float b, float t) { return fmaf(t, b - a, a); }
+ZDR_HD float4 lerp(float4 a, float4 b, float t) {
+    return make_float4(lerp(a.x, b.x, t), lerp(a.y, b.y, t), lerp(a.z, b.z, t), lerp(a.w, b.w, t));
+}
+ZDR_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+ZDR_HD int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+ZDR_HD bool any_nan(float3 a) { return (a.x != a.x) || (a.y != a.y) || (a.z != a.z); }
+ZDR_HD bool any_nan(float4 a) { return (a.x != a.x) || (a.y != a.y) || (a.z != a.z) || (a.w != a.w); }
+ZDR_HD bool any_pos(float3 a) { return a.x > 0.0f || a.y > 0.0f || a.z > 0.0f; }
+
+// float -> int, saturating, NaN -> 0 (cvt.rzi.s32.f32)
+ZDR_DEV int f2i(float x) { return __float2int_rz(x); }
+
+// (M * float4(v,1)).xyz, M column-major
+ZDR_HD float3 xform_point(const float* M, float3 v) {
+    return f3(fmaf(M[8], v.z, fmaf(M[4], v.y, fmaf(M[0], v.x, M[12]))),
+              fmaf(M[9], v.z, fmaf(M[5], v.y, fmaf(M[1], v.x, M[13]))),
+              fmaf(M[10], v.z, fmaf(M[6], v.y, fmaf(M[2], v.x, M[14]))));
+}
+// 3x3 column-major times vector
+ZDR_HD float3 mat3_mul(const float* N, float3 v) {
+    return f3(fmaf(N[6], v.z, fmaf(N[3], v.y, N[0] * v.x)), fmaf(N[7], v.z, fmaf(N[4], v.y, N[1] * v.x)),
+              fmaf(N[8], v.z, fmaf(N[5], v.y, N[2] * v.x)));
+}
+
+// sin/cos of a binary32 angle evaluated in binary64: Cody-Waite reduction by pi/2 and Taylor
+// polynomials in fma-Horner form, rounded once.  Identical operation sequence on host and
+// device, so the sampled directions do not depend on a vendor libm.
+ZDR_HD void sincos_contract(float phi, float* s_out, float* c_out) {
+    double x = (double)phi;
+    double kd = rint(x * 0.63661977236758134308);
+    double r = fma(-kd, 1.57079632679489655800e+00, x);
+    r = fma(-kd, 6.12323399573676603587e-17, r);
+    double r2 = r * r;
+    double ps = -1.0 / 1307674368000.0;
+    ps = fma(ps, r2, 1.0 / 6227020800.0);
+    ps = fma(ps, r2, -1.0 / 39916800.0);
+    ps = fma(ps, r2, 1.0 / 362880.0);
+    ps = fma(ps, r2, -1.0 / 5040.0);
+    ps = fma(ps, r2, 1.0 / 120.0);
+    ps = fma(ps, r2, -1.0 / 6.0);
+    double sn = fma(ps * r2, r, r);
+    double pc = 1.0 / 20922789888000.0;
+    pc = fma(pc, r2, -1.0 / 87178291200.0);
+    pc = fma(pc, r2, 1.0 / 479001600.0);
+    pc = fma(pc, r2, -1.0 / 3628800.0);
+    pc = fma(pc, r2, 1.0 / 40320.0);
+    pc = fma(pc, r2, -1.0 / 720.0);
+    pc = fma(pc, r2, 1.0 / 24.0);
+    pc = fma(pc, r2, -0.5);
+    double cs = fma(pc, r2, 1.0);
+    int q = (int)((long long)kd & 3);
+    double s = (q == 0) ? sn : (q == 1) ? cs : (q == 2) ? -sn : -cs;
+    double c = (q == 0) ? cs : (q == 1) ? -sn : (q == 2) ? -cs : sn;
+    *s_out = (float)s;
+    *c_out = (float)c;
+}
+
+}  // namespace zdr

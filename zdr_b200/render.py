@@ -1,0 +1,254 @@
+"""PyTorch surface of the B200 ray-tracer core: ``Scene`` / ``Camera`` / ``RenderOperator``.
+
+Drop-in for the reference's ``render.py`` (``Scene`` at ``render.py:31-257``): same constructor,
+same mutable ``camera`` / ``use_tent_filter`` attributes, same ``render`` / ``update_lights`` /
+``add_envmap`` methods, gradients through ``Scene.RenderOperator`` (``render.py:201-223``).
+Instead of LuisaCompute kernels the operator launches the hand-written sm_100a kernels of
+``csrc/`` through the C ABI of ``include/zdr_b200.h``; tensors stay torch-owned, the library
+borrows their device pointers and enqueues on torch's current stream (no device-wide barrier,
+where the reference does two per call at ``render.py:165,172``).
+
+There is no CPU fallback: constructing a ``Scene`` without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import INTEGRATORS, PRB_MODES, ZdrError, check, load_library, make_params, np_ptr, wrap_i32
+from .load_obj import load_mesh
+from .mathtypes import Camera, float3, float4x4
+from .tables import get_tables
+
+_tables_on_device = set()
+
+
+def _ensure_tables(device_index: int):
+    """Uploads the pmj02bn tables once per device (the module-level uploads of pmj02bn.py:9-16)."""
+    if device_index in _tables_on_device:
+        return
+    pmj, bn, _ = get_tables()
+    lib = load_library()
+    check(lib.zdr_set_sampler_tables(device_index, np_ptr(pmj, C.c_uint32), pmj.shape[0], pmj.shape[1],
+                                     np_ptr(bn, C.c_uint16), bn.shape[0], bn.shape[1]), "zdr_set_sampler_tables")
+    _tables_on_device.add(device_index)
+
+
+def _emission3(e) -> float3:
+    """render.py:85-88 / :142: None -> 0, scalar -> broadcast."""
+    if e is None:
+        return float3(0.0)
+    if type(e) in {int, float}:
+        return float3(e)
+    return float3(e)
+
+
+class Scene:
+    """A 3D scene for differentiable rendering (reference: ``render.py:31``).
+
+    Args:
+        models: list of ``(obj_file, transform, emission)``; ``transform`` a ``float4x4`` or None,
+            ``emission`` a ``float3`` / number / None (``render.py:81-91``).  Instance 0 is the
+            textured object, every instance with a positive emission is a light.
+            ``obj_file`` may also be a ``(verts Nx8, tris)`` pair of arrays.
+        integrator: ``'path'`` | ``'direct'`` | ``'collocated'`` (``render.py:65-69``).
+        device: CUDA device index (default: torch's current device).
+
+    Attributes mirroring the reference's JIT-time module constants, settable per scene:
+        ``max_depth``/``rr_depth`` (``prb.py:15-16``), ``use_mis`` (``direct.py:14``),
+        ``bilinear`` (``interaction.py:33``), ``prb_mode`` (``'corrected'`` | ``'literal'``,
+        DESIGN.md "PRB adjoint").
+    """
+
+    def __init__(self, models, integrator: str = "direct", device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("zdr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if integrator not in INTEGRATORS:
+            raise KeyError(integrator)
+        self._lib = load_library()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        _ensure_tables(self.device_index)
+        self._handle = C.c_void_p()
+        check(self._lib.zdr_scene_create(C.byref(self._handle), self.device_index), "zdr_scene_create")
+        self.loaded_obj = {}
+        self.load_geometry(models)
+        self.camera = Camera(fov=40 / 180 * 3.1415926, origin=float3(1.0, 0.5, 0.0), target=float3(0.0, 0.0, 0.0),
+                             up=float3(0.0, 1.0, 0.0))                                 # render.py:57-62
+        self.integrator = integrator
+        self.use_tent_filter = True                                                    # render.py:71
+        self.max_depth = 16
+        self.rr_depth = 2
+        self.use_mis = True
+        self.bilinear = True
+        self.prb_mode = "corrected"
+        self.collect_stats = False
+        # data-parallel shard of the dispatch grid; None = whole image
+        self.shard_rows = None
+
+    # ------------------------------------------------------------------ scene assembly
+    def load_geometry(self, models):
+        """render.py:73-128."""
+        lib = self._lib
+        emissions = []
+        for obj_file, transform, emission in models:
+            if transform is None:
+                transform = float4x4(1.0)
+            emission = _emission3(emission)
+            emissions.append(emission)
+            if isinstance(obj_file, str):
+                if obj_file not in self.loaded_obj:
+                    self.loaded_obj[obj_file] = load_mesh(obj_file)
+                verts, tris = self.loaded_obj[obj_file]
+            else:
+                verts, tris = obj_file
+            verts = np.ascontiguousarray(verts, dtype=np.float32)
+            tris = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1)
+            xf = np.asarray(transform.flat(), dtype=np.float32)
+            em = np.asarray(list(emission), dtype=np.float32)
+            check(lib.zdr_scene_add_mesh(self._handle, np_ptr(verts, C.c_float), verts.shape[0], np_ptr(tris, C.c_int32),
+                                         tris.shape[0] // 3, np_ptr(xf, C.c_float), np_ptr(em, C.c_float)),
+                  "zdr_scene_add_mesh")
+        self.inst_count = len(emissions)
+        if self.inst_count > 10000:
+            raise RuntimeError("exceeding maximum number of mesh instances")          # render.py:114-115
+        check(lib.zdr_scene_commit(self._handle), "zdr_scene_commit")
+        self.env_count = 0
+        self.emissions = emissions
+        self.light_count = lib.zdr_scene_light_count(self._handle)
+
+    def update_lights(self, emissions):
+        """Rewrite the emission of every instance (``render.py:130-148``)."""
+        self.emissions = emissions
+        assert len(emissions) == self.inst_count
+        e = np.asarray([list(_emission3(x)) for x in emissions], dtype=np.float32).reshape(-1, 3)
+        check(self._lib.zdr_scene_set_emissions(self._handle, np_ptr(e, C.c_float), e.shape[0]), "zdr_scene_set_emissions")
+        self.light_count = self._lib.zdr_scene_light_count(self._handle)
+
+    def add_envmap(self, filename, compensate_mis: bool = True):
+        """``render.py:150-156``.  ``filename``: image path (needs ``imageio``), ``.npy`` path, or
+        an ``(H,W,3|4)`` float array."""
+        if isinstance(filename, str):
+            if filename.endswith(".npy"):
+                img = np.load(filename)
+            else:
+                import imageio                                                      # render.py:151
+                img = np.asarray(imageio.imread(filename))
+        else:
+            img = np.asarray(filename)
+        if img.shape[2] == 3:
+            img = np.concatenate([img, np.ones_like(img[..., :1])], axis=-1)
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        check(self._lib.zdr_scene_set_envmap(self._handle, np_ptr(img, C.c_float), img.shape[1], img.shape[0],
+                                             int(bool(compensate_mis))), "zdr_scene_set_envmap")
+        self.env_count = 1
+
+    # ------------------------------------------------------------------ operator launches
+    def _params(self, material, res, spp, seed, rows=None):
+        p = make_params(self.camera, res, material.shape[0:2], spp, seed, use_tent_filter=self.use_tent_filter,
+                        max_depth=self.max_depth, rr_depth=self.rr_depth, use_mis=self.use_mis, bilinear=self.bilinear,
+                        prb_mode=PRB_MODES[self.prb_mode] if isinstance(self.prb_mode, str) else int(self.prb_mode),
+                        rows=rows if rows is not None else self.shard_rows)
+        p.reserved[0] = 1 if self.collect_stats else 0
+        return p
+
+    def _check_material(self, material):
+        assert material.ndim == 3 and material.shape[2] == 4                          # render.py:160
+        if not material.is_cuda or material.device.index != self.device_index:
+            raise ValueError(f"material must live on cuda:{self.device_index}")
+        if material.dtype != torch.float32:
+            raise TypeError("material must be float32")
+
+    def render_forward(self, material, res, spp, seed, integrator: Optional[str] = None, rows=None):
+        """``render.py:159-173``: -> ``(H, W, 4)`` float32 cuda tensor, alpha = 1."""
+        self._check_material(material)
+        material = material.detach().contiguous()
+        image = torch.empty((res[1], res[0], 4), dtype=torch.float32, device=self.device)
+        p = self._params(material, res, spp, seed, rows)
+        if p.row0 > 0 or p.row1 < p.height:
+            image.zero_()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(self._lib.zdr_render_forward(self._handle, INTEGRATORS[integrator or self.integrator], C.byref(p),
+                                           material.data_ptr(), image.data_ptr(), stream), "zdr_render_forward")
+        return image
+
+    def render_backward(self, grad_output, d_material, material, res, spp, seed, integrator: Optional[str] = None,
+                        rows=None):
+        """``render.py:176-199``: accumulates into ``d_material``; the adjoint is estimated with
+        ``seed+1`` (``render.py:196``)."""
+        self._check_material(material)
+        material = material.detach().contiguous()
+        d_image = grad_output.reshape((res[0] * res[1], 4)).contiguous()              # render.py:181
+        if d_image.dtype != torch.float32:
+            d_image = d_image.float()
+        assert d_material.is_contiguous() and d_material.shape == material.shape
+        p = self._params(material, res, spp, wrap_i32(int(seed) + 1), rows)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(self._lib.zdr_render_backward(self._handle, INTEGRATORS[integrator or self.integrator], C.byref(p),
+                                            material.data_ptr(), d_image.data_ptr(), d_material.data_ptr(), stream),
+              "zdr_render_backward")
+        return d_material, None, None, None, None
+
+    class RenderOperator(torch.autograd.Function):
+        """``render.py:201-223``."""
+
+        @staticmethod
+        def forward(ctx, material, self, *args):
+            ctx.save_for_backward(material)
+            ctx.scene = weakref.ref(self)
+            ctx.args = args
+            ctx.camera = self.camera.copy()
+            ctx.emissions = list(self.emissions)
+            return self.render_forward(material.detach(), *args)
+
+        @staticmethod
+        def backward(ctx, grad_output):
+            scene = ctx.scene()
+            if scene is None:
+                raise RuntimeError("the Scene of this render was garbage-collected before backward()")
+            camera_bak = scene.camera                                                 # render.py:216-218
+            scene.camera = ctx.camera
+            scene.update_lights(ctx.emissions)
+            material, = ctx.saved_tensors
+            mat_grad = torch.zeros(material.size(), dtype=material.dtype, device=material.device)
+            try:
+                grads = scene.render_backward(grad_output, mat_grad, material.detach(), *ctx.args)
+            finally:
+                scene.camera = camera_bak
+            return grads
+
+    def render(self, material, *, res, spp, seed=0):
+        """Renders the scene; differentiable w.r.t. ``material`` (``render.py:225-241``).
+
+        material: cuda float32 ``(Ht, Wt, 4)`` = (diffuse rgb, roughness); res = (width, height).
+        Returns a ``(height, width, 4)`` tensor."""
+        return Scene.RenderOperator.apply(material, self, res, spp, seed)
+
+    # ------------------------------------------------------------------ instrumentation
+    def counters(self) -> dict:
+        out = (C.c_uint64 * _abi.ZDR_NUM_COUNTERS)()
+        check(self._lib.zdr_get_counters(self._handle, out), "zdr_get_counters")
+        return dict(zip(_abi.COUNTER_NAMES, (int(x) for x in out)))
+
+    def reset_counters(self):
+        check(self._lib.zdr_reset_counters(self._handle), "zdr_reset_counters")
+
+    @property
+    def triangle_count(self) -> int:
+        return self._lib.zdr_scene_triangle_count(self._handle)
+
+    def close(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            self._lib.zdr_scene_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
