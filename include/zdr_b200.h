@@ -73,8 +73,15 @@ typedef struct zdr_params {
      * [row0,row1) of the image and samples [it0,it1) of every pixel. Full job: 0,H,0,spp. */
     int32_t row0, row1;
     int32_t it0, it1;
-    int32_t reserved[4];
+    /* second sharding level used by the multi-GPU path: the 8-row tiles of [row0,row1) are
+     * dealt round-robin, shard `shard_index` of `shard_count` renders tiles i with
+     * i % shard_count == shard_index (load balance; every pixel keeps its whole sample loop on
+     * one GPU, so the image is bit-identical to the unsharded one). 0 or 1 = no interleave. */
+    int32_t shard_index, shard_count;
+    int32_t flags;            /* ZDR_FLAG_* */
+    int32_t reserved[1];
 } zdr_params;
+#define ZDR_FLAG_STATS 1      /* also count BVH nodes visited / triangles tested (slower) */
 
 typedef struct zdr_scene zdr_scene;
 

@@ -1180,6 +1180,12 @@ static f3 estimate(Ctx* c, int integrator, Ray ray, Sampler* sm) {
     }
 }
 
+/* zdr_params.shard_index/shard_count: 8-row tiles of [row0,row1) dealt round-robin */
+static inline int row_in_shard(const zdr_params* p, int y) {
+    if (p->shard_count <= 1) return 1;
+    return ((y - p->row0) / 8) % p->shard_count == p->shard_index;
+}
+
 static int check_render_args(zo_scene* s, int integrator, const zdr_params* p) {
     if (!s || !p) return ZDR_ERR_ARG;
     if (!s->committed || !g_pmj || !g_bn) return ZDR_ERR_STATE;
@@ -1197,6 +1203,7 @@ static int render_forward_impl(zo_scene* s, int integrator, const zdr_params* p,
     uint64_t nc = 0, na = 0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : nc, na)
     for (int y = p->row0; y < p->row1; ++y) {
+        if (!row_in_shard(p, y)) continue;
         zo_scene local = *s; local.n_closest = 0; local.n_any = 0;
         Ctx c = {&local, {material, NULL, p->tex_res_x, p->tex_res_y, p->bilinear}, p};
         for (int x = 0; x < p->width; ++x) {
@@ -1243,6 +1250,7 @@ ZO_API int zo_render_backward(zo_scene* s, int integrator, const zdr_params* p, 
     uint64_t nc = 0, na = 0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : nc, na)
     for (int y = p->row0; y < p->row1; ++y) {
+        if (!row_in_shard(p, y)) continue;
         zo_scene local = *s; local.n_closest = 0; local.n_any = 0;
         Ctx c = {&local, {material, acc, p->tex_res_x, p->tex_res_y, p->bilinear}, p};
         for (int x = 0; x < p->width; ++x) {

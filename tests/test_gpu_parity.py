@@ -102,7 +102,12 @@ class GpuScene:
 
 
 def bits(a):
-    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+    """bit pattern of float32 data, with every NaN mapped to one canonical pattern (a NaN sample
+    is dropped by integrator.py:27 whatever its payload; x86 and sm_100a differ in NaN sign)."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = a.view(np.uint32).copy()
+    b[np.isnan(a)] = 0x7FC00000
+    return b
 
 
 # ----------------------------------------------------------------------------- sampler (bit-exact)

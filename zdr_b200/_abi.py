@@ -13,6 +13,7 @@ INTEGRATORS = {"collocated": ZDR_COLLOCATED, "direct": ZDR_DIRECT, "path": ZDR_P
 ZDR_PRB_LITERAL, ZDR_PRB_CORRECTED = 0, 1
 PRB_MODES = {"literal": ZDR_PRB_LITERAL, "corrected": ZDR_PRB_CORRECTED}
 ZDR_NUM_COUNTERS = 8
+ZDR_FLAG_STATS = 1
 COUNTER_NAMES = ("closest_rays", "any_rays", "nodes_visited", "tris_tested",
                  "grad_scatters", "red_v4", "shaded_vertices", "camera_samples")
 
@@ -31,7 +32,8 @@ class ZdrParams(C.Structure):
         ("max_depth", C.c_int32), ("rr_depth", C.c_int32),
         ("use_mis", C.c_int32), ("bilinear", C.c_int32), ("prb_mode", C.c_int32),
         ("row0", C.c_int32), ("row1", C.c_int32), ("it0", C.c_int32), ("it1", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("flags", C.c_int32),
+        ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -41,7 +43,8 @@ def wrap_i32(x: int) -> int:
 
 
 def make_params(camera, res, tex_shape, spp, seed, *, use_tent_filter=True, max_depth=16, rr_depth=2,
-                use_mis=True, bilinear=True, prb_mode=ZDR_PRB_CORRECTED, rows=None, its=None) -> ZdrParams:
+                use_mis=True, bilinear=True, prb_mode=ZDR_PRB_CORRECTED, rows=None, its=None, shard=None,
+                stats=False) -> ZdrParams:
     p = ZdrParams()
     p.cam_fov = float(camera.fov)
     p.cam_origin[:] = list(camera.origin)
@@ -55,6 +58,8 @@ def make_params(camera, res, tex_shape, spp, seed, *, use_tent_filter=True, max_
     p.use_mis, p.bilinear, p.prb_mode = int(bool(use_mis)), int(bool(bilinear)), int(prb_mode)
     p.row0, p.row1 = (0, p.height) if rows is None else (int(rows[0]), int(rows[1]))
     p.it0, p.it1 = (0, p.spp) if its is None else (int(its[0]), int(its[1]))
+    p.shard_index, p.shard_count = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
+    p.flags = ZDR_FLAG_STATS if stats else 0
     return p
 
 

@@ -161,6 +161,8 @@ int check_params(const zdr_scene* s, int integrator, const zdr_params* p) {
     if (p->row0 < 0 || p->row1 > p->height || p->row0 > p->row1 || p->it0 < 0 || p->it1 > p->spp || p->it0 > p->it1)
         return fail(ZDR_ERR_ARG, "bad shard rows [%d,%d) its [%d,%d)", p->row0, p->row1, p->it0, p->it1);
     if (p->max_depth < 0 || p->rr_depth < 0) return fail(ZDR_ERR_ARG, "negative depth");
+    if (p->shard_count > 1 && (p->shard_index < 0 || p->shard_index >= p->shard_count))
+        return fail(ZDR_ERR_ARG, "bad shard %d of %d", p->shard_index, p->shard_count);
     return ZDR_OK;
 }
 
@@ -181,12 +183,14 @@ int make_args(zdr_scene* s, const zdr_params* p, RenderArgs* a) {
     a->use_tent = p->use_tent_filter; a->max_depth = p->max_depth; a->rr_depth = p->rr_depth;
     a->use_mis = p->use_mis; a->prb_mode = p->prb_mode;
     a->row0 = p->row0; a->row1 = p->row1; a->it0 = p->it0; a->it1 = p->it1;
+    a->shard_count = p->shard_count > 1 ? p->shard_count : 1;
+    a->shard_index = p->shard_count > 1 ? p->shard_index : 0;
     a->tex.rx = p->tex_res_x; a->tex.ry = p->tex_res_y; a->tex.bilinear = p->bilinear;
     a->counters = s->d_counters;
     return ZDR_OK;
 }
 
-inline bool want_stats(const zdr_params* p) { return (p->reserved[0] & 1) != 0; }
+inline bool want_stats(const zdr_params* p) { return (p->flags & ZDR_FLAG_STATS) != 0; }
 
 }  // namespace
 

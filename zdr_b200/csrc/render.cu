@@ -262,7 +262,7 @@ constexpr int kBlockThreads = 128;
 ZDR_DEV void pixel_of_thread(const RenderArgs& a, int& x, int& y) {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     x = blockIdx.x * 16 + (w & 1) * 8 + (l & 7);
-    y = a.row0 + blockIdx.y * 8 + (w >> 1) * 4 + (l >> 3);
+    y = a.row0 + (blockIdx.y * a.shard_count + a.shard_index) * 8 + (w >> 1) * 4 + (l >> 3);
 }
 
 template <int INTEGRATOR, bool STATS>
@@ -357,7 +357,10 @@ __global__ void k_probe_ggx(const float* __restrict__ in, int n, float* __restri
     o[0] = f.x; o[1] = f.y; o[2] = f.z; o[3] = dm.x; o[4] = dm.y; o[5] = dm.z; o[6] = dm.w;
 }
 
-dim3 render_grid(const RenderArgs& a) { return dim3((a.W + 15) / 16, (a.row1 - a.row0 + 7) / 8); }
+dim3 render_grid(const RenderArgs& a) {
+    const int tiles = (a.row1 - a.row0 + 7) / 8;
+    return dim3((a.W + 15) / 16, (tiles - a.shard_index + a.shard_count - 1) / a.shard_count);
+}
 
 template <int I>
 cudaError_t launch_fwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
@@ -375,7 +378,7 @@ cudaError_t launch_bwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
 }  // namespace
 
 cudaError_t launch_forward(int integrator, const RenderArgs& a, bool stats, cudaStream_t s) {
-    if (a.row1 <= a.row0 || a.it1 <= a.it0) return cudaSuccess;
+    if (a.row1 <= a.row0 || a.it1 <= a.it0 || render_grid(a).y == 0) return cudaSuccess;
     switch (integrator) {
         case ZDR_COLLOCATED: return launch_fwd_i<ZDR_COLLOCATED>(a, stats, s);
         case ZDR_DIRECT: return launch_fwd_i<ZDR_DIRECT>(a, stats, s);
@@ -383,7 +386,7 @@ cudaError_t launch_forward(int integrator, const RenderArgs& a, bool stats, cuda
     }
 }
 cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cudaStream_t s) {
-    if (a.row1 <= a.row0 || a.it1 <= a.it0) return cudaSuccess;
+    if (a.row1 <= a.row0 || a.it1 <= a.it0 || render_grid(a).y == 0) return cudaSuccess;
     switch (integrator) {
         case ZDR_COLLOCATED: return launch_bwd_i<ZDR_COLLOCATED>(a, stats, s);
         case ZDR_DIRECT: return launch_bwd_i<ZDR_DIRECT>(a, stats, s);

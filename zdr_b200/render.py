@@ -90,6 +90,7 @@ class Scene:
         self.collect_stats = False
         # data-parallel shard of the dispatch grid; None = whole image
         self.shard_rows = None
+        self.shard = None          # (index, count): round-robin 8-row tiles, see zdr_params.shard_index
 
     # ------------------------------------------------------------------ scene assembly
     def load_geometry(self, models):
@@ -153,8 +154,7 @@ class Scene:
         p = make_params(self.camera, res, material.shape[0:2], spp, seed, use_tent_filter=self.use_tent_filter,
                         max_depth=self.max_depth, rr_depth=self.rr_depth, use_mis=self.use_mis, bilinear=self.bilinear,
                         prb_mode=PRB_MODES[self.prb_mode] if isinstance(self.prb_mode, str) else int(self.prb_mode),
-                        rows=rows if rows is not None else self.shard_rows)
-        p.reserved[0] = 1 if self.collect_stats else 0
+                        rows=rows if rows is not None else self.shard_rows, shard=self.shard, stats=self.collect_stats)
         return p
 
     def _check_material(self, material):
@@ -170,7 +170,7 @@ class Scene:
         material = material.detach().contiguous()
         image = torch.empty((res[1], res[0], 4), dtype=torch.float32, device=self.device)
         p = self._params(material, res, spp, seed, rows)
-        if p.row0 > 0 or p.row1 < p.height:
+        if p.row0 > 0 or p.row1 < p.height or p.shard_count > 1:
             image.zero_()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         check(self._lib.zdr_render_forward(self._handle, INTEGRATORS[integrator or self.integrator], C.byref(p),
