@@ -135,98 +135,6 @@ ZDR_DEV float3 direct_walk(Ctx<STATS>& c, const Ray& ray, Sampler& sampler, floa
     return radiance;
 }
 
-// ------------------------------------------------------------------------------------- prb.py
-// One walk serves path_estimator (prb.py:18-88; MODE 0), and the adjoint pass of
-// path_estimator_backward (prb.py:102-187; MODE 1) which needs Le from a MODE 0 replay.
-template <int MODE, bool STATS>
-ZDR_DEV float3 path_walk(Ctx<STATS>& c, Ray ray, Sampler& sampler, float3 Le, float3 le_grad) {
-    const SceneView& sc = c.a.sc;
-    const bool corrected = c.a.prb_mode == ZDR_PRB_CORRECTED;
-    float3 radiance = f3(0.f, 0.f, 0.f), beta = f3(1.f, 1.f, 1.f);
-    float pdf_bsdf = 1e30f;
-    const float specular = 0.04f;
-    for (int depth = 0; depth < c.a.max_depth; ++depth) {
-        const Hit hit = c.closest(ray);
-        if (hit.inst < 0) {
-            if (MODE == 0 && sc.env_count > 0) {
-                const float3 tex = env_texture(sc, direction_to_uv(ray.d));
-                const float3 emission = corrected ? tex : beta * tex;              // prb.py:28
-                const float mis_weight = balanced_heuristic(pdf_bsdf, env_sampled_light_pdf(sc, ray.d));
-                radiance = radiance + (beta * mis_weight) * emission;
-            }
-            break;
-        }
-        const Interaction it = surface_interact(sc, hit);
-        if (backfacing(ray.d, it)) break;
-        const float3 emission = inst_emission(sc, hit.inst);
-        if (any_pos(emission)) {
-            const float mis_weight = balanced_heuristic(pdf_bsdf, sample_light_pdf(sc, ray.o, hit, it.p));
-            if (MODE == 0) radiance = radiance + (beta * mis_weight) * emission;
-            else Le = Le - (beta * mis_weight) * emission;
-            break;
-        }
-        if ((MODE == 0 || corrected) && hit.inst > 0) break;                       // prb.py:45-46 (fwd only upstream)
-        c.tl.shaded++;
-        float4 mat_grad = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 mat = read_bsdf(c.a.tex, it.uv);
-        const float3 diffuse = f3(mat.x, mat.y, mat.z);
-        const float roughness = mat.w;
-        const Onb onb = make_onb(it.ns);
-        const float3 wo_local = to_local(onb, -ray.d);
-        const LightSample light = sample_light(sc, it.p, sampler);
-        const bool occluded = c.occluded(make_ray(it.p, light.wi, 1e-4f, light.dist));
-        const float3 wi_light_local = to_local(onb, light.wi);
-        if (!occluded && wi_light_local.z >= 1e-4f) {
-            const float3 bsdf = ggx_brdf(wo_local, wi_light_local, diffuse, specular, roughness);
-            pdf_bsdf = ggx_sample_pdf(wo_local, wi_light_local, roughness);
-            const float mis_weight = balanced_heuristic(light.pdf, pdf_bsdf);
-            const float dn = fmaxf(light.pdf, 1e-4f);
-            const float3 contrib = (((beta * bsdf) * mis_weight) * light.eval) / dn;
-            if (MODE == 0) radiance = radiance + contrib;
-            else {
-                const float3 cot = (((beta * mis_weight) * light.eval) / dn) * le_grad;   // prb.py:145
-                mat_grad = mat_grad + ggx_brdf_grad(wo_local, wi_light_local, specular, roughness, cot);
-                Le = Le - contrib;
-            }
-        }
-        bool done = false;
-        const float3 wi_local = ggx_sample(sc, wo_local, roughness, sampler);
-        pdf_bsdf = ggx_sample_pdf(wo_local, wi_local, roughness);
-        const float3 wi = to_world(onb, wi_local);
-        if (dot(wi, it.ng) < 1e-4f || wi_local.z < 1e-4f) done = true;
-        if (!done) {
-            ray = make_ray(offset_ray_origin(it.p, it.ng), wi, 0.0f, 1e30f);
-            const float3 bsdf = ggx_brdf(wo_local, wi_local, diffuse, specular, roughness);
-            if (MODE == 1) {
-                float3 cot;
-                if (corrected)
-                    cot = f3(bsdf.x != 0.0f ? Le.x / bsdf.x * le_grad.x : 0.0f, bsdf.y != 0.0f ? Le.y / bsdf.y * le_grad.y : 0.0f,
-                             bsdf.z != 0.0f ? Le.z / bsdf.z * le_grad.z : 0.0f);
-                else
-                    cot = ((beta / pdf_bsdf) * Le) * le_grad;                      // prb.py:162
-                mat_grad = mat_grad + ggx_brdf_grad(wo_local, wi_local, specular, roughness, cot);
-            }
-            beta = beta * (bsdf / pdf_bsdf);
-            if (depth >= c.a.rr_depth) {                                           // prb.py:78-87
-                const float l = luminance(beta);
-                if (l == 0.0f) done = true;
-                else {
-                    const float q = fmaxf(l, 0.05f);
-                    const float r = sampler_next(sc, sampler);
-                    if (r >= q) done = true;
-                    else beta = beta / q;
-                }
-            }
-        }
-        if (MODE == 1) {                                                           // prb.py:178-187
-            if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad))
-                c.scatter(it.uv, mat_grad);
-        }
-        if (done) break;
-    }
-    return radiance;
-}
-
 // --------------------------------------------------------------------- camera.py, integrator.py
 ZDR_DEV float tent_warp1(float u) {                                                // camera.py:20-31
     return u < 0.5f ? 1.0f * (sqrtf(2.0f * u) - 1.0f) : 1.0f * (1.0f - sqrtf(2.0f - 2.0f * u));
@@ -274,13 +182,12 @@ __global__ void __launch_bounds__(kBlockThreads) k_forward(const __grid_constant
     if (x < a.W && y < a.row1) {
         float3 s = f3(0.f, 0.f, 0.f);
         for (int it = a.it0; it < a.it1; ++it) {                                   // integrator.py:15
-            Sampler sampler = make_sampler(x, y, a.seed, a.spp, it);
+            Sampler sampler = make_sampler(a.sc, x, y, a.seed, a.spp, it);
             const Ray ray = camera_sample(a, x, y, sampler);
             tl.samples++;
             float3 radiance;
             if (INTEGRATOR == ZDR_COLLOCATED) radiance = collocated_estimator(c, ray);
-            else if (INTEGRATOR == ZDR_DIRECT) radiance = direct_walk<false>(c, ray, sampler, f3(0.f, 0.f, 0.f));
-            else radiance = path_walk<0>(c, ray, sampler, f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f));
+            else radiance = direct_walk<false>(c, ray, sampler, f3(0.f, 0.f, 0.f));
             if (a.samples_out) {
                 float* o = a.samples_out + (((size_t)y * a.W + x) * a.spp + it) * 3;
                 o[0] = radiance.x; o[1] = radiance.y; o[2] = radiance.z;
@@ -305,17 +212,175 @@ __global__ void __launch_bounds__(kBlockThreads) k_backward(const __grid_constan
         float3 le_grad = f3(g.x / (float)a.spp, g.y / (float)a.spp, g.z / (float)a.spp);
         if (any_nan(le_grad)) le_grad = f3(0.f, 0.f, 0.f);
         for (int it = a.it0; it < a.it1; ++it) {
-            Sampler sampler = make_sampler(x, y, a.seed, a.spp, it);
+            Sampler sampler = make_sampler(a.sc, x, y, a.seed, a.spp, it);
             const Ray ray = camera_sample(a, x, y, sampler);
             tl.samples++;
             if (INTEGRATOR == ZDR_COLLOCATED) collocated_estimator_backward(c, ray, le_grad);
-            else if (INTEGRATOR == ZDR_DIRECT) direct_walk<true>(c, ray, sampler, le_grad);
-            else {
-                Sampler twin = sampler;                                            // prb.py:97-99
-                const float3 Le = path_walk<0>(c, ray, twin, f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f));
-                if (!any_nan(Le)) path_walk<1>(c, ray, sampler, Le, le_grad);
+            else direct_walk<true>(c, ray, sampler, le_grad);
+        }
+    }
+    flush_tally(a, tl);
+}
+
+// ------------------------------------------------------------------------------------- prb.py
+// Path integrator (prb.py:18-88) and its Path-Replay-Backprop adjoint (prb.py:91-187) as ONE
+// bounce state machine.  The reference nests `for it in range(spp)` around `while depth <
+// max_depth` in one thread per pixel, so a warp idles until its longest path ends and — with the
+// replay and the adjoint walk inlined as separate copies — the kernel's code does not fit the
+// instruction cache.  Here one loop iteration is one bounce of whatever sample the lane is on:
+// a lane whose path ended regenerates its next sample (or, in the adjoint kernel, switches from
+// the replay phase to the adjoint phase of the same sample) at the top of the loop, so the whole
+// warp executes the single copy of closest-hit / shading / shadow-ray / BSDF-sampling code
+// together.  Every pixel still runs its samples in order in one thread: the image keeps the
+// reference's accumulation order (integrator.py:15-28) and is bit-identical to the oracle's.
+//   phase 0: radiance walk (L accumulates);  phase 1 (BWD only): adjoint walk (L = Le remaining).
+template <bool BWD, bool STATS>
+__global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant__ RenderArgs a) {
+    int x, y;
+    pixel_of_thread(a, x, y);
+    const SceneView& sc = a.sc;
+    Tally tl = {};
+    Ctx<STATS> c{a, tl};
+    const bool corrected = a.prb_mode == ZDR_PRB_CORRECTED;
+    const float specular = 0.04f;
+    const float3 zero = f3(0.f, 0.f, 0.f);
+    if (x < a.W && y < a.row1) {
+        float3 acc = zero, le_grad = zero;
+        if (BWD) {                                                                 // integrator.py:38-40
+            const float4 g = __ldg(a.d_image + ((size_t)x + (size_t)y * a.W));
+            le_grad = f3(g.x / (float)a.spp, g.y / (float)a.spp, g.z / (float)a.spp);
+            if (any_nan(le_grad)) le_grad = zero;
+        }
+        int it = a.it0, depth = 0, phase = 0;
+        bool alive = false;
+        Ray ray = make_ray(zero, zero, 0.f, 0.f);
+        float3 cam_d = zero, beta = zero, L = zero;
+        float pdf_bsdf = 0.f;
+        Sampler sampler = make_sampler(sc, x, y, a.seed, a.spp, 0);
+        for (;;) {
+            if (!alive) {
+                if (it >= a.it1) break;
+                sampler.sample_index = it;                                         // make_pmj02bn_sampler(coord, seed, spp, it)
+                sampler.dimension = 0;
+                ray = camera_sample(a, x, y, sampler);
+                cam_d = ray.d;
+                beta = f3(1.f, 1.f, 1.f); L = zero; pdf_bsdf = 1e30f; depth = 0; phase = 0;   // prb.py:20-22
+                alive = true;
+                tl.samples++;
+            }
+            bool end = false;
+            if (depth >= a.max_depth) {                                            // prb.py:23
+                end = true;
+            } else {
+                const Hit hit = c.closest(ray);                                    // prb.py:25
+                if (hit.inst < 0) {
+                    if (phase == 0 && sc.env_count > 0) {                          // prb.py:26-31
+                        const float3 tex = env_texture(sc, direction_to_uv(ray.d));
+                        const float3 emission = corrected ? tex : beta * tex;     // prb.py:28 applies beta twice
+                        const float mis_weight = balanced_heuristic(pdf_bsdf, env_sampled_light_pdf(sc, ray.d));
+                        L = L + (beta * mis_weight) * emission;
+                    }
+                    end = true;
+                } else {
+                    const Interaction itx = surface_interact(sc, hit);
+                    const float3 emission = inst_emission(sc, hit.inst);
+                    if (backfacing(ray.d, itx)) {                                  // prb.py:35-36
+                        end = true;
+                    } else if (any_pos(emission)) {                                // prb.py:39-44 / :117-121
+                        const float mis_weight = balanced_heuristic(pdf_bsdf, sample_light_pdf(sc, ray.o, hit, itx.p));
+                        const float3 contrib = (beta * mis_weight) * emission;
+                        L = (phase == 0) ? L + contrib : L - contrib;
+                        end = true;
+                    } else if ((phase == 0 || corrected) && hit.inst > 0) {        // prb.py:45-46 (forward only upstream)
+                        end = true;
+                    } else {
+                        tl.shaded++;
+                        float4 mat_grad = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 mat = read_bsdf(a.tex, itx.uv);
+                        const float3 diffuse = f3(mat.x, mat.y, mat.z);
+                        const float roughness = mat.w;
+                        const Onb onb = make_onb(itx.ns);
+                        const float3 wo_local = to_local(onb, -ray.d);
+                        const LightSample light = sample_light(sc, itx.p, sampler);                     // prb.py:57
+                        const bool occluded = c.occluded(make_ray(itx.p, light.wi, 1e-4f, light.dist));  // prb.py:58-59
+                        const float3 wi_light_local = to_local(onb, light.wi);
+                        if (!occluded && wi_light_local.z >= 1e-4f) {                                   // prb.py:61-66
+                            const float4 ev = ggx_eval(wo_local, wi_light_local, diffuse, specular, roughness);
+                            const float3 bsdf = f3(ev.x, ev.y, ev.z);
+                            pdf_bsdf = ev.w;
+                            const float mis_weight = balanced_heuristic(light.pdf, pdf_bsdf);
+                            const float dn = fmaxf(light.pdf, 1e-4f);
+                            const float3 contrib = (((beta * bsdf) * mis_weight) * light.eval) / dn;
+                            if (!BWD || phase == 0) {
+                                L = L + contrib;
+                            } else {
+                                const float3 cot = (((beta * mis_weight) * light.eval) / dn) * le_grad;   // prb.py:145
+                                mat_grad = mat_grad + ggx_brdf_grad_nl(wo_local, wi_light_local, specular, roughness, cot);
+                                L = L - contrib;                                                        // prb.py:147
+                            }
+                        }
+                        const float3 wi_local = ggx_sample(sc, wo_local, roughness, sampler);           // prb.py:69
+                        const float4 ev = ggx_eval(wo_local, wi_local, diffuse, specular, roughness);
+                        pdf_bsdf = ev.w;
+                        const float3 wi = to_world(onb, wi_local);
+                        if (dot(wi, itx.ng) < 1e-4f || wi_local.z < 1e-4f) {                            // prb.py:73-74
+                            end = true;
+                        } else {
+                            ray = make_ray(offset_ray_origin(itx.p, itx.ng), wi, 0.0f, 1e30f);          // prb.py:75
+                            const float3 bsdf = f3(ev.x, ev.y, ev.z);
+                            if (BWD && phase == 1) {
+                                float3 cot;
+                                if (corrected)   // d(Le_remaining)/d(bsdf) = Le_remaining / bsdf per channel
+                                    cot = f3(bsdf.x != 0.0f ? L.x / bsdf.x * le_grad.x : 0.0f, bsdf.y != 0.0f ? L.y / bsdf.y * le_grad.y : 0.0f,
+                                             bsdf.z != 0.0f ? L.z / bsdf.z * le_grad.z : 0.0f);
+                                else
+                                    cot = ((beta / pdf_bsdf) * L) * le_grad;                            // prb.py:162
+                                mat_grad = mat_grad + ggx_brdf_grad_nl(wo_local, wi_local, specular, roughness, cot);
+                            }
+                            beta = beta * (bsdf / pdf_bsdf);                                            // prb.py:76
+                            if (depth >= a.rr_depth) {                                                  // prb.py:78-87
+                                const float l = luminance(beta);
+                                if (l == 0.0f) {
+                                    end = true;
+                                } else {
+                                    const float q = fmaxf(l, 0.05f);
+                                    const float r = sampler_next(sc, sampler);
+                                    if (r >= q) end = true;
+                                    else beta = beta / q;
+                                }
+                            }
+                        }
+                        if (BWD && phase == 1) {                                                        // prb.py:178-187
+                            if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad))
+                                c.scatter(itx.uv, mat_grad);
+                        }
+                        ++depth;
+                    }
+                }
+            }
+            if (end) {
+                if (BWD && phase == 0 && !any_nan(L)) {
+                    // prb.py:97-101: Le is known; walk the same path again with the original sampler state
+                    phase = 1;
+                    ray = make_ray(a.cam_o, cam_d, 0.0f, 1e30f);
+                    sampler.dimension = 2;
+                    beta = f3(1.f, 1.f, 1.f); pdf_bsdf = 1e30f; depth = 0;
+                } else {
+                    if (!BWD) {
+                        if (a.samples_out) {
+                            float* o = a.samples_out + (((size_t)y * a.W + x) * a.spp + it) * 3;
+                            o[0] = L.x; o[1] = L.y; o[2] = L.z;
+                        }
+                        if (!any_nan(L))                                                                // integrator.py:27-28
+                            acc = acc + f3(clampf(L.x, 0.0f, 100000.0f), clampf(L.y, 0.0f, 100000.0f), clampf(L.z, 0.0f, 100000.0f));
+                    }
+                    alive = false;
+                    ++it;
+                }
             }
         }
+        if (!BWD && a.image)
+            a.image[(size_t)x + (size_t)y * a.W] = make_float4(acc.x / (float)a.spp, acc.y / (float)a.spp, acc.z / (float)a.spp, 1.0f);
     }
     flush_tally(a, tl);
 }
@@ -338,7 +403,7 @@ __global__ void k_probe_sampler(const SceneView sc, const int* __restrict__ stat
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int* st = state + 5 * (size_t)i;
-    Sampler sm = make_sampler(st[0], st[1], st[2], st[3], st[4]);
+    Sampler sm = make_sampler(sc, st[0], st[1], st[2], st[3], st[4]);
     float* o = out + (size_t)per * i;
     for (int k = 0; k < prog_len; ++k) {
         if (prog[k] == '2') { const float2 u = sampler_next2f(sc, sm); *o++ = u.x; *o++ = u.y; }
@@ -382,7 +447,10 @@ cudaError_t launch_forward(int integrator, const RenderArgs& a, bool stats, cuda
     switch (integrator) {
         case ZDR_COLLOCATED: return launch_fwd_i<ZDR_COLLOCATED>(a, stats, s);
         case ZDR_DIRECT: return launch_fwd_i<ZDR_DIRECT>(a, stats, s);
-        default: return launch_fwd_i<ZDR_PATH>(a, stats, s);
+        default:
+            if (stats) k_path<false, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+            else k_path<false, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+            return cudaGetLastError();
     }
 }
 cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cudaStream_t s) {
@@ -390,7 +458,10 @@ cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cud
     switch (integrator) {
         case ZDR_COLLOCATED: return launch_bwd_i<ZDR_COLLOCATED>(a, stats, s);
         case ZDR_DIRECT: return launch_bwd_i<ZDR_DIRECT>(a, stats, s);
-        default: return launch_bwd_i<ZDR_PATH>(a, stats, s);
+        default:
+            if (stats) k_path<true, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+            else k_path<true, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+            return cudaGetLastError();
     }
 }
 cudaError_t launch_probe_trace(const SceneView& sc, const float* rays, int n, bool any, int* ip, float* uvt, int* occ,

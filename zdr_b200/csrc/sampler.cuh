@@ -48,62 +48,92 @@ ZDR_HD int permutation_element(int i_in, int l, int w_in, uint32_t p) {
     return ((s % l) + l) % l;
 }
 
-struct Sampler {     // pmj02bn.py:78-85
+struct Sampler {     // pmj02bn.py:78-85, plus per-(pixel,seed) values hoisted out of the draws
     int px, py, sample_index, dimension, seed, spp, w;
+    uint32_t h_xy;      // xxhash32_int4 state after mixing seed, pixel.x, pixel.y (pmj02bn.py:66-69)
+    int bn_k, bn_cy;    // blue-noise index = tex * bn_k + bn_cy with bn_k = (res + cx) * res (pmj02bn.py:20-23)
 };
 
 // pmj02bn.py:87-102
-ZDR_HD Sampler make_sampler(int px, int py, int seed, int spp, int sample_index) {
+ZDR_DEV Sampler make_sampler(const SceneView& sc, int px, int py, int seed, int spp, int sample_index) {
     int w = spp - 1;
     w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
     Sampler s;
     s.px = px; s.py = py; s.sample_index = sample_index; s.dimension = 0; s.seed = seed; s.spp = spp; s.w = w;
+    const uint32_t P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+    uint32_t h = (uint32_t)seed + P5 + (uint32_t)px * P3;
+    h = P4 * ((h << 17) | (h >> 15));
+    h += (uint32_t)py * P3;
+    s.h_xy = P4 * ((h << 17) | (h >> 15));
+    const int qx = px ^ seed, qy = py ^ seed;              // pmj02bn.py:108: pixel ^ seed
+    const int cx = qx % sc.bn_res, cy = qy % sc.bn_res;    // truncating %, as the reference's int2 % lowers
+    s.bn_k = (sc.bn_res + cx) * sc.bn_res;
+    s.bn_cy = cy;
     return s;
 }
-
 // pmj02bn.py:19-24 — literal index formula tex*(res+cx)*res+cy; indices past the table wrap
-// modulo its length (upstream: undefined behaviour from dimension 25 on).
-ZDR_DEV float blue_noise(const SceneView& sc, int tex_id, int px, int py) {
-    int tex_index = tex_id % sc.bn_ntex;
-    int cx = px % sc.bn_res, cy = py % sc.bn_res;
-    long long i = (long long)tex_index * (sc.bn_res + cx) * sc.bn_res + cy;
-    long long len = (long long)sc.bn_ntex * sc.bn_res * sc.bn_res;
-    i %= len;
+// modulo its length (upstream: undefined behaviour from dimension 25 on).  The index is below
+// 2*len + res, so the modulo is at most two conditional subtractions.
+ZDR_DEV float blue_noise(const float* __restrict__ bn, int ntex, int res, int bn_k, int bn_cy, int tex_id) {
+    const int tex_index = (int)((unsigned)tex_id % (unsigned)ntex);   // tex_id >= 0
+    long long i = (long long)tex_index * bn_k + bn_cy;
+    const long long len = (long long)ntex * res * res;
     if (i < 0) i += len;
-    return __ldg(sc.bn + i);
+    if (i >= len) i -= len;
+    if (i >= len) i -= len;
+    return __ldg(bn + i);
 }
 // pmj02bn.py:26-30
-ZDR_DEV float2 pmj02bn_sample(const SceneView& sc, int set_id, int sample_id) {
-    int set_index = set_id % sc.pmj_sets;
-    long long i = (long long)set_index * sc.pmj_n + sample_id;
-    long long len = (long long)sc.pmj_sets * sc.pmj_n;
-    i %= len;
-    if (i < 0) i += len;
-    return __ldg(sc.pmj + i);
+ZDR_DEV float2 pmj02bn_sample(const float2* __restrict__ pmj, int sets, int n, int set_id, int sample_id) {
+    const int set_index = (int)((unsigned)set_id % (unsigned)sets);
+    long long i = (long long)set_index * n + sample_id;
+    const long long len = (long long)sets * n;
+    if (i >= len) i %= len;          // only for spp > table length
+    return __ldg(pmj + i);
 }
+ZDR_DEV uint32_t hash_dim(uint32_t h_xy, int dimension) {
+    const uint32_t P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u;
+    uint32_t h = h_xy + (uint32_t)dimension * P3;
+    h = P4 * ((h << 17) | (h >> 15));
+    h = P2 * (h ^ (h >> 15));
+    h = P3 * (h ^ (h >> 13));
+    return h ^ (h >> 16);
+}
+// The draws are out-of-line, by-value functions: seven call sites per path vertex would
+// otherwise each inline ~100-150 instructions and push the render kernels out of the 32 KB
+// instruction-cache level.
 // pmj02bn.py:104-112
-ZDR_DEV float sampler_next(const SceneView& sc, Sampler& s) {
-    uint32_t h = xxhash32_int4(s.px, s.py, s.dimension, s.seed);
-    int index = permutation_element(s.sample_index, s.spp, s.w, h);
-    float delta = blue_noise(sc, s.dimension, s.px ^ s.seed, s.py ^ s.seed);
-    float u = ((float)index + delta) / (float)s.spp;
-    s.dimension += 1;
+static __device__ __noinline__ float sampler_next_v(const float* __restrict__ bn, int ntex, int res, uint32_t h_xy, int bn_k, int bn_cy,
+                                             int sample_index, int spp, int w, int dimension) {
+    const uint32_t h = hash_dim(h_xy, dimension);
+    const int index = permutation_element(sample_index, spp, w, h);
+    const float delta = blue_noise(bn, ntex, res, bn_k, bn_cy, dimension);
+    const float u = ((float)index + delta) / (float)spp;
     return clampf(u, 0.0f, kOneMinusEps);
 }
 // pmj02bn.py:114-126
-ZDR_DEV float2 sampler_next2f(const SceneView& sc, Sampler& s) {
-    int index = s.sample_index;
-    int pmj_instance = s.dimension / 2;
-    if (pmj_instance >= sc.pmj_sets) {
-        uint32_t h = xxhash32_int4(s.px, s.py, s.dimension, s.seed);
-        index = permutation_element(s.sample_index, s.spp, s.w, h);
-    }
-    float2 u = pmj02bn_sample(sc, pmj_instance, index);
-    u.x = u.x + blue_noise(sc, s.dimension, s.px ^ s.seed, s.py ^ s.seed);
-    u.y = u.y + blue_noise(sc, s.dimension + 1, s.px ^ s.seed, s.py ^ s.seed);
-    s.dimension += 2;
+static __device__ __noinline__ float2 sampler_next2f_v(const float2* __restrict__ pmj, int sets, int n, const float* __restrict__ bn, int ntex,
+                                                int res, uint32_t h_xy, int bn_k, int bn_cy, int sample_index, int spp, int w,
+                                                int dimension) {
+    int index = sample_index;
+    const int pmj_instance = dimension / 2;
+    if (pmj_instance >= sets) index = permutation_element(sample_index, spp, w, hash_dim(h_xy, dimension));
+    float2 u = pmj02bn_sample(pmj, sets, n, pmj_instance, index);
+    u.x = u.x + blue_noise(bn, ntex, res, bn_k, bn_cy, dimension);
+    u.y = u.y + blue_noise(bn, ntex, res, bn_k, bn_cy, dimension + 1);
     u.x = u.x - floorf(u.x);
     u.y = u.y - floorf(u.y);
+    return u;
+}
+ZDR_DEV float sampler_next(const SceneView& sc, Sampler& s) {
+    const float u = sampler_next_v(sc.bn, sc.bn_ntex, sc.bn_res, s.h_xy, s.bn_k, s.bn_cy, s.sample_index, s.spp, s.w, s.dimension);
+    s.dimension += 1;
+    return u;
+}
+ZDR_DEV float2 sampler_next2f(const SceneView& sc, Sampler& s) {
+    const float2 u = sampler_next2f_v(sc.pmj, sc.pmj_sets, sc.pmj_n, sc.bn, sc.bn_ntex, sc.bn_res, s.h_xy, s.bn_k, s.bn_cy,
+                                      s.sample_index, s.spp, s.w, s.dimension);
+    s.dimension += 2;
     return u;
 }
 

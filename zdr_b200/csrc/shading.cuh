@@ -142,6 +142,13 @@ ZDR_DEV float4 ggx_brdf_grad(float3 wo, float3 wi, float specular, float roughne
     const float dk = wi.z / kPi;
     return make_float4(g.x * dk, g.y * dk, g.z * dk, (g.x + g.y + g.z) * common);
 }
+// (ggx_brdf, ggx_sample_pdf) of one direction pair; one out-of-line copy shared by the
+// light-sample and BSDF-sample evaluations (instruction-cache budget, see traverse.cuh)
+static __device__ __noinline__ float4 ggx_eval(float wox, float woy, float woz, float wix, float wiy, float wiz, float dr, float dg, float db,
+                                        float specular, float roughness);
+// out-of-line ggx_brdf_grad (adjoint kernels)
+static __device__ __noinline__ float4 ggx_brdf_grad_nl(float wox, float woy, float woz, float wix, float wiy, float wiz, float specular,
+                                                float roughness, float gx, float gy, float gz);
 ZDR_DEV float3 cosine_sample_hemisphere(float2 u) {                      // microfacet.py:33-37
     const float r = sqrtf(u.x);
     const float phi = kTwoPi * u.y;
@@ -183,6 +190,23 @@ ZDR_DEV float ggx_sample_pdf(float3 wo, float3 wi, float roughness) {    // micr
     const float diffuse_pdf = wi.z / kPi;
     const float glossy_pdf = pdf_wm(wo, wm, alpha) / (4.0f * fabsf(dot(wo, wm)));
     return 0.5f * diffuse_pdf + 0.5f * glossy_pdf;
+}
+
+static __device__ __noinline__ float4 ggx_eval(float wox, float woy, float woz, float wix, float wiy, float wiz, float dr, float dg, float db,
+                                        float specular, float roughness) {
+    const float3 wo = f3(wox, woy, woz), wi = f3(wix, wiy, wiz);
+    const float3 f = ggx_brdf(wo, wi, f3(dr, dg, db), specular, roughness);
+    return make_float4(f.x, f.y, f.z, ggx_sample_pdf(wo, wi, roughness));
+}
+static __device__ __noinline__ float4 ggx_brdf_grad_nl(float wox, float woy, float woz, float wix, float wiy, float wiz, float specular,
+                                                float roughness, float gx, float gy, float gz) {
+    return ggx_brdf_grad(f3(wox, woy, woz), f3(wix, wiy, wiz), specular, roughness, f3(gx, gy, gz));
+}
+ZDR_DEV float4 ggx_eval(float3 wo, float3 wi, float3 diffuse, float specular, float roughness) {
+    return ggx_eval(wo.x, wo.y, wo.z, wi.x, wi.y, wi.z, diffuse.x, diffuse.y, diffuse.z, specular, roughness);
+}
+ZDR_DEV float4 ggx_brdf_grad_nl(float3 wo, float3 wi, float specular, float roughness, float3 g) {
+    return ggx_brdf_grad_nl(wo.x, wo.y, wo.z, wi.x, wi.y, wi.z, specular, roughness, g.x, g.y, g.z);
 }
 
 // luisa.offset_ray_origin (direct.py:64): Waechter & Binder, Ray Tracing Gems ch. 6

@@ -8,6 +8,12 @@
 // numeric contract: the oracle evaluates the same expression per (ray, triangle), so the
 // closest hit (smallest t, ties to the lowest scene-order triangle id) is identical no matter
 // in which order the BVH visits the triangles.  The box test only has to be conservative.
+//
+// Shape of the loop ("while-while"): every lane first descends inner nodes until it holds a leaf,
+// then the warp tests leaf triangles together; with the single-loop "if node / else leaf" form a
+// warp spent most of its issue slots on triangle tests with ~5 of 32 lanes active (ncu,
+// profiles/r01b).  One out-of-line copy serves closest-hit and any-hit queries of every call
+// site: the render kernels must fit the 32 KB instruction cache level (B300_MICROARCH.md).
 #pragma once
 #include "scene.cuh"
 
@@ -17,134 +23,169 @@ namespace zdr {
 //              n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z), n3 = (link0, link1, -, -) as int bits.
 // link >= 0: inner node index; link < 0: leaf, ~link = (first_slot << 2) | (count - 1).
 constexpr int kStackSize = 64;
-constexpr int kLinkSentinel = 0x7fffffff;
+constexpr int kLinkSentinel = (int)0x80000000;   // a "leaf" link no leaf can have (first_slot < 2^29)
 
+struct TraceStats { unsigned nodes, tris; };
+
+// Per-ray constants of the watertight test.  kz = dominant axis of d, (kx,ky) the next two axes in
+// cyclic order.  The reference algorithm also swaps kx,ky when d[kz] < 0 to preserve winding; the
+// swap negates U, V, W, det and T exactly (products commute, a-b = -(b-a), rounding is symmetric),
+// so t = T/det and the barycentrics are bit-identical without it and it is omitted here.
 struct RayPre {
     int kx, ky, kz;
     float Sx, Sy, Sz;
+    float okx, oky, okz;     // ray origin, permuted
 };
 
 ZDR_DEV float comp(float3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
 
-ZDR_DEV RayPre ray_pre(float3 d) {
+ZDR_DEV RayPre ray_pre(float3 o, float3 d) {
     RayPre r;
-    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
     r.kz = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
     r.kx = r.kz + 1; if (r.kx == 3) r.kx = 0;
     r.ky = r.kx + 1; if (r.ky == 3) r.ky = 0;
-    float dz = comp(d, r.kz);
-    if (dz < 0.0f) { int t = r.kx; r.kx = r.ky; r.ky = t; }
+    const float dz = comp(d, r.kz);
     r.Sx = comp(d, r.kx) / dz;
     r.Sy = comp(d, r.ky) / dz;
     r.Sz = 1.0f / dz;
+    r.okx = comp(o, r.kx); r.oky = comp(o, r.ky); r.okz = comp(o, r.kz);
     return r;
 }
 
-// true when the ray's line meets the triangle at t > tmin (t,u,v written; the caller applies the
-// upper bound); watertight on shared edges.
-ZDR_DEV bool tri_test(const RayPre& rp, float3 o, float3 p0, float3 p1, float3 p2, float tmin,
-                      float& t_out, float& u_out, float& v_out) {
-    float3 A = p0 - o, B = p1 - o, C = p2 - o;
-    float Akz = comp(A, rp.kz), Bkz = comp(B, rp.kz), Ckz = comp(C, rp.kz);
-    float Ax = fmaf(-rp.Sx, Akz, comp(A, rp.kx)), Ay = fmaf(-rp.Sy, Akz, comp(A, rp.ky));
-    float Bx = fmaf(-rp.Sx, Bkz, comp(B, rp.kx)), By = fmaf(-rp.Sy, Bkz, comp(B, rp.ky));
-    float Cx = fmaf(-rp.Sx, Ckz, comp(C, rp.kx)), Cy = fmaf(-rp.Sy, Ckz, comp(C, rp.ky));
+// True when the ray's line meets the triangle at t > tmin (t,u,v written; the caller applies the
+// upper bound); watertight on shared edges.  `tp` points at the 48-byte record v0|v1|v2 (float4
+// each); the permuted components are fetched with per-lane offsets instead of being selected
+// out of vector registers (two FSEL per component cost more issue slots than the loads).
+ZDR_DEV bool tri_test(const RayPre& rp, const float* __restrict__ tp, float tmin, float& t_out, float& u_out, float& v_out) {
+    const float Akx = __ldg(tp + rp.kx) - rp.okx, Aky = __ldg(tp + rp.ky) - rp.oky, Akz = __ldg(tp + rp.kz) - rp.okz;
+    const float Bkx = __ldg(tp + 4 + rp.kx) - rp.okx, Bky = __ldg(tp + 4 + rp.ky) - rp.oky, Bkz = __ldg(tp + 4 + rp.kz) - rp.okz;
+    const float Ckx = __ldg(tp + 8 + rp.kx) - rp.okx, Cky = __ldg(tp + 8 + rp.ky) - rp.oky, Ckz = __ldg(tp + 8 + rp.kz) - rp.okz;
+    const float Ax = fmaf(-rp.Sx, Akz, Akx), Ay = fmaf(-rp.Sy, Akz, Aky);
+    const float Bx = fmaf(-rp.Sx, Bkz, Bkx), By = fmaf(-rp.Sy, Bkz, Bky);
+    const float Cx = fmaf(-rp.Sx, Ckz, Ckx), Cy = fmaf(-rp.Sy, Ckz, Cky);
     float U = Cx * By - Cy * Bx;
     float V = Ax * Cy - Ay * Cx;
     float W = Bx * Ay - By * Ax;
     if (U == 0.0f || V == 0.0f || W == 0.0f) {
-        double CxBy = (double)Cx * (double)By, CyBx = (double)Cy * (double)Bx;
+        const double CxBy = (double)Cx * (double)By, CyBx = (double)Cy * (double)Bx;
         U = (float)(CxBy - CyBx);
-        double AxCy = (double)Ax * (double)Cy, AyCx = (double)Ay * (double)Cx;
+        const double AxCy = (double)Ax * (double)Cy, AyCx = (double)Ay * (double)Cx;
         V = (float)(AxCy - AyCx);
-        double BxAy = (double)Bx * (double)Ay, ByAx = (double)By * (double)Ax;
+        const double BxAy = (double)Bx * (double)Ay, ByAx = (double)By * (double)Ax;
         W = (float)(BxAy - ByAx);
     }
-    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-    float det = U + V + W;
+    if (fminf(fminf(U, V), W) < 0.0f && fmaxf(fmaxf(U, V), W) > 0.0f) return false;
+    const float det = U + V + W;
     if (det == 0.0f) return false;
-    float Az = rp.Sz * Akz, Bz = rp.Sz * Bkz, Cz = rp.Sz * Ckz;
-    float T = fmaf(W, Cz, fmaf(V, Bz, U * Az));
-    float rcp = 1.0f / det;
-    float t = T * rcp;
+    const float Az = rp.Sz * Akz, Bz = rp.Sz * Bkz, Cz = rp.Sz * Ckz;
+    const float T = fmaf(W, Cz, fmaf(V, Bz, U * Az));
+    const float rcp = 1.0f / det;
+    const float t = T * rcp;
     if (!(t > tmin)) return false;
     t_out = t; u_out = V * rcp; v_out = W * rcp;
     return true;
 }
 
-struct TraceStats { unsigned nodes, tris; };
-
-// conservative slab test; returns entry distance in tn
-ZDR_DEV bool box_test(float lox, float hix, float loy, float hiy, float loz, float hiz, float3 o, float3 id,
+// Conservative slab test (entry distance in tn).  Not part of the numeric contract: the boxes are
+// inflated at build time and the comparison is widened, so it may fuse (t = lo*id - o*id).
+ZDR_DEV bool box_test(float lox, float hix, float loy, float hiy, float loz, float hiz, float3 id, float3 oid,
                       float tmin, float tmax, float& tn) {
-    float x0 = (lox - o.x) * id.x, x1 = (hix - o.x) * id.x;
-    float y0 = (loy - o.y) * id.y, y1 = (hiy - o.y) * id.y;
-    float z0 = (loz - o.z) * id.z, z1 = (hiz - o.z) * id.z;
-    float tnear = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
-    float tfar = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    const float x0 = fmaf(lox, id.x, -oid.x), x1 = fmaf(hix, id.x, -oid.x);
+    const float y0 = fmaf(loy, id.y, -oid.y), y1 = fmaf(hiy, id.y, -oid.y);
+    const float z0 = fmaf(loz, id.z, -oid.z), z1 = fmaf(hiz, id.z, -oid.z);
+    const float tnear = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+    const float tfar = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
     tn = tnear;
-    return tnear * 0.9999995f <= tfar * 1.0000005f;
+    return tnear * 0.999999f <= tfar * 1.000001f;
 }
 
-// Closest hit (ANY=false) or occlusion query (ANY=true; returns hit.inst >= 0 when occluded).
-template <bool ANY, bool STATS>
-ZDR_DEV Hit trace(const SceneView& sc, const Ray& ray, TraceStats& st) {
-    Hit hit;
-    hit.inst = -1; hit.prim = -1; hit.slot = -1; hit.u = 0.0f; hit.v = 0.0f; hit.t = 0.0f;
-    const RayPre rp = ray_pre(ray.d);
-    const float3 id = f3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
-    float best = ray.tmax;
+// Closest hit (any == 0) or occlusion query (any != 0).  Returns (slot, u, v, t) packed in a
+// float4 (slot as int bits; slot < 0: miss / not occluded); the caller reads inst/prim from the
+// .w words of tris[slot].
+template <bool STATS>
+static __device__ __noinline__ float4 trace_packed(const float4* __restrict__ nodes, const float4* __restrict__ tris, int root_link,
+                                            float ox, float oy, float oz, float dx, float dy, float dz, float tmin, float tmax,
+                                            int any, TraceStats* st) {
+    const float3 o = f3(ox, oy, oz), d = f3(dx, dy, dz);
+    int hit_slot = -1;
+    float hit_u = 0.0f, hit_v = 0.0f, hit_t = 0.0f;
+    const RayPre rp = ray_pre(o, d);
+    // reciprocal direction for the slab test, clamped to +-1e30 so that axis-parallel rays give
+    // finite slab distances (no 0*inf NaN); |error| of lo*id - o*id is ~6e-8*|o| in position units,
+    // far inside the build-time inflation of the boxes
+    float3 id = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    if (!(fabsf(id.x) <= 1e30f)) id.x = copysignf(1e30f, d.x);
+    if (!(fabsf(id.y) <= 1e30f)) id.y = copysignf(1e30f, d.y);
+    if (!(fabsf(id.z) <= 1e30f)) id.z = copysignf(1e30f, d.z);
+    const float3 oid = f3(o.x * id.x, o.y * id.y, o.z * id.z);
+    float best = tmax;
     int best_gid = 0x7fffffff;
     int stack[kStackSize];
     int sp = 0;
     stack[sp++] = kLinkSentinel;
-    int link = sc.root_link;
-    while (link != kLinkSentinel) {
-        if (link >= 0) {
-            const float4* n = sc.nodes + 4 * (size_t)link;
+    int link = root_link;
+    for (;;) {
+        while (link >= 0) {                      // inner nodes
+            const float4* n = nodes + 4 * (size_t)link;
             const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
-            if (STATS) st.nodes++;
+            if (STATS) st->nodes++;
             float t0, t1;
             // ties on t must stay reachable: cull with <= best
-            const bool h0 = box_test(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, ray.o, id, ray.tmin, best, t0);
-            const bool h1 = box_test(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, ray.o, id, ray.tmin, best, t1);
+            const bool h0 = box_test(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, id, oid, tmin, best, t0);
+            const bool h1 = box_test(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, id, oid, tmin, best, t1);
             const int l0 = __float_as_int(n3.x), l1 = __float_as_int(n3.y);
             if (h0 && h1) {
                 const bool swap = t1 < t0;
                 stack[sp++] = swap ? l0 : l1;
                 link = swap ? l1 : l0;
-            } else if (h0) {
-                link = l0;
-            } else if (h1) {
-                link = l1;
+            } else if (h0 || h1) {
+                link = h0 ? l0 : l1;
             } else {
                 link = stack[--sp];
             }
-        } else {
+        }
+        if (link == kLinkSentinel) break;
+        {                                        // leaf
             const int code = ~link;
             const int first = code >> 2, count = (code & 3) + 1;
             for (int k = 0; k < count; ++k) {
-                const float4* tp = sc.tris + 3 * (size_t)(first + k);
-                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                if (STATS) st.tris++;
+                const float* tp = reinterpret_cast<const float*>(tris + 3 * (size_t)(first + k));
+                if (STATS) st->tris++;
                 float t, u, v;
-                if (tri_test(rp, ray.o, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), ray.tmin, t, u, v)) {
-                    if (ANY) {
-                        if (t < ray.tmax) { hit.inst = 0; return hit; }
+                if (tri_test(rp, tp, tmin, t, u, v)) {
+                    if (any) {
+                        if (t < tmax) return make_float4(__int_as_float(first + k), u, v, t);
                         continue;
                     }
-                    const int gid = __float_as_int(a.w);
+                    const int gid = __float_as_int(__ldg(tp + 3));
                     // smallest t wins; equal t goes to the lowest scene-order triangle id, which is
                     // what the oracle's in-order scan with a strict '<' keeps
-                    if (t < best || (hit.inst >= 0 && t == best && gid < best_gid)) {
+                    if (t < best || (hit_slot >= 0 && t == best && gid < best_gid)) {
                         best = t; best_gid = gid;
-                        hit.t = t; hit.u = u; hit.v = v; hit.slot = first + k;
-                        hit.inst = __float_as_int(b.w); hit.prim = __float_as_int(c.w);
+                        hit_t = t; hit_u = u; hit_v = v; hit_slot = first + k;
                     }
                 }
             }
             link = stack[--sp];
         }
+    }
+    return make_float4(__int_as_float(hit_slot), hit_u, hit_v, hit_t);
+}
+
+template <bool ANY, bool STATS>
+ZDR_DEV Hit trace(const SceneView& sc, const Ray& ray, TraceStats& st) {
+    const float4 r = trace_packed<STATS>(sc.nodes, sc.tris, sc.root_link, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z,
+                                         ray.tmin, ray.tmax, ANY ? 1 : 0, &st);
+    Hit hit;
+    hit.slot = __float_as_int(r.x); hit.u = r.y; hit.v = r.z; hit.t = r.w;
+    hit.inst = -1; hit.prim = -1;
+    if (!ANY && hit.slot >= 0) {
+        const float4* tp = sc.tris + 3 * (size_t)hit.slot;
+        hit.inst = __float_as_int(__ldg(tp + 1).w);
+        hit.prim = __float_as_int(__ldg(tp + 2).w);
+    } else if (ANY && hit.slot >= 0) {
+        hit.inst = 0;
     }
     return hit;
 }
