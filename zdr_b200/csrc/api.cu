@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -312,7 +313,12 @@ ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
     cudaError_t e = cudaMalloc(&d_shade, sizeof(float4) * shade.size());
     if (e == cudaSuccess) e = cudaMemcpy(d_tri, tri.data(), sizeof(float4) * tri.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_shade, shade.data(), sizeof(float4) * shade.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = build_bvh(d_tri, d_shade, (int)nt, lo, hi, s->own_stream, &s->bvh);
+    if (e == cudaSuccess) {
+        const char* force = getenv("ZDR_BVH");     // "lbvh" | "sah": builder override for experiments
+        const bool sah = force ? strcmp(force, "sah") == 0 : nt <= (size_t)kSahMaxTris;
+        e = sah ? build_bvh_sah_host(tri.data(), shade.data(), (int)nt, lo, hi, s->own_stream, &s->bvh)
+                : build_bvh(d_tri, d_shade, (int)nt, lo, hi, s->own_stream, &s->bvh);
+    }
     cudaFree(d_tri); cudaFree(d_shade);
     if (e != cudaSuccess) return fail(ZDR_ERR_CUDA, "commit/build_bvh: %s", cudaGetErrorString(e));
     if (s->bvh.max_depth + 2 > kStackSize) return fail(ZDR_ERR_LIMIT, "BVH depth %d exceeds the traversal stack", s->bvh.max_depth);

@@ -21,4 +21,10 @@ cudaError_t build_bvh(const float4* tri_in, const float4* shade_in, int n, float
                       cudaStream_t stream, BvhResult* out);
 void free_bvh(BvhResult* r);
 
+// Scenes up to this many triangles get a full-sweep SAH tree (built on the host in microseconds to
+// milliseconds, uploaded once); larger ones the GPU LBVH.  tri_host / shade_host: scene order.
+constexpr int kSahMaxTris = 1 << 14;
+cudaError_t build_bvh_sah_host(const float4* tri_host, const float4* shade_host, int n, float3 lo, float3 hi,
+                               cudaStream_t stream, BvhResult* out);
+
 }  // namespace zdr

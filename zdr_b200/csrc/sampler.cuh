@@ -45,6 +45,7 @@ ZDR_HD int permutation_element(int i_in, int l, int w_in, uint32_t p) {
         i ^= i >> 5;
     } while (i >= (uint32_t)l);
     int32_t s = (int32_t)(i + p);
+    if ((l & (l - 1)) == 0) return s & (l - 1);      // floor-mod by a power of two (every BASELINE config)
     return ((s % l) + l) % l;
 }
 
