@@ -1,0 +1,961 @@
+"""lc_emu — a small CPU emulator of the LuisaCompute Python DSL.  TEST INFRASTRUCTURE ONLY.
+
+Purpose: execute the reference's OWN source files (/root/reference/*.py, imported unmodified)
+on the CPU, so that golden vectors for the oracle can be generated from the reference itself
+(tests/golden/gen_golden.py).  The reference needs `luisa` (LuisaCompute, un-vendored, not
+installable here), a CUDA device, `imageio`, and two missing table modules; this module supplies
+stand-ins for exactly the DSL surface the hot path uses:
+
+  * scalar float32 (`F`, IEEE binary32 after every operation, with a reverse-mode tape for the
+    `autodiff()` blocks), wrapping uint32 (`U`), vectors float2/3/4, int2/3/4, uint2/3/4, bool
+    vectors with swizzles, float3x3 / float4x4;
+  * `@luisa.func` (re-compiles the function source with `a if c else b` rewritten to a
+    component-wise select, as the DSL defines it for vector conditions), `StructType`,
+    `ArrayType`, `Buffer`, `BindlessArray`, `Accel`, `make_ray`, `offset_ray_origin`,
+    `dispatch_id/dispatch_size`, the math builtins, `luisa.autodiff`.
+
+What the emulator CANNOT pin (the arithmetic lives inside LuisaCompute / OptiX, whose source is
+not on this box) it takes from the oracle's own definitions and says so:
+  ray/triangle intersection + tie-breaking (delegated to oracle/zdr_oracle.c's watertight test),
+  offset_ray_origin constants, sin/cos lowering (oracle's zo_sincos), `**` lowering (repeated
+  multiplication), int/uint promotion (C rules), texture2d_sample filtering (bilinear,
+  REPEAT/CLAMP).  Everything else — control flow, sampler hashing and table indexing, the order
+  of sampler draws, BRDF / pdf / MIS formulae, light sampling, texture fetch and gradient
+  scatter footprints, and the autodiff result — comes from executing the reference source.
+"""
+from __future__ import annotations
+
+import ast
+import ctypes
+import ctypes.util
+import importlib.util
+import inspect
+import math
+import sys
+import textwrap
+import types
+from typing import List
+
+import numpy as np
+
+f32 = np.float32
+_libm = ctypes.CDLL(ctypes.util.find_library("m"))
+for _n in ("tanf", "acosf", "expf"):
+    getattr(_libm, _n).restype = ctypes.c_float
+    getattr(_libm, _n).argtypes = [ctypes.c_float]
+_libm.atan2f.restype = ctypes.c_float
+_libm.atan2f.argtypes = [ctypes.c_float, ctypes.c_float]
+
+_py_max, _py_min, _py_abs, _py_any, _py_all = max, min, abs, any, all
+
+# ------------------------------------------------------------------------------------ AD tape
+_tape = None     # list of (out_id, [(in_id, partial)]) while inside autodiff()
+
+
+class _Tape:
+    def __init__(self):
+        self.n = 0
+        self.ops = []
+
+    def new(self):
+        self.n += 1
+        return self.n - 1
+
+
+def _sincos(x: np.float32):
+    from oracle import oracle as o
+    r = o.sincos(np.asarray([x], dtype=np.float32))
+    return f32(r[0, 0]), f32(r[0, 1])
+
+
+# ------------------------------------------------------------------------------------ scalars
+class F:
+    """binary32 value; every operation rounds to binary32."""
+    __slots__ = ("v", "node")
+
+    def __init__(self, v=0.0, node=None):
+        if isinstance(v, F):
+            self.v, self.node = v.v, v.node
+        elif isinstance(v, U):
+            self.v, self.node = f32(v.v), None
+        else:
+            self.v, self.node = f32(v), node
+
+    @staticmethod
+    def _c(x):
+        return x if isinstance(x, F) else F(x)
+
+    def _un(self, val, d):
+        out = F(val)
+        if _tape is not None and self.node is not None:
+            out.node = _tape.new()
+            _tape.ops.append((out.node, [(self.node, float(d))]))
+        return out
+
+    def _bin(self, o, val, da, db):
+        o = F._c(o)
+        out = F(val)
+        if _tape is not None and (self.node is not None or o.node is not None):
+            out.node = _tape.new()
+            ins = []
+            if self.node is not None:
+                ins.append((self.node, float(da)))
+            if o.node is not None:
+                ins.append((o.node, float(db)))
+            _tape.ops.append((out.node, ins))
+        return out
+
+    def __add__(self, o):
+        if isinstance(o, Vec):
+            return o.__radd__(self)
+        o = F._c(o)
+        return self._bin(o, self.v + o.v, 1.0, 1.0)
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        if isinstance(o, Vec):
+            return o.__rsub__(self)
+        o = F._c(o)
+        return self._bin(o, self.v - o.v, 1.0, -1.0)
+
+    def __rsub__(self, o):
+        return F._c(o).__sub__(self)
+
+    def __mul__(self, o):
+        if isinstance(o, Vec):
+            return o.__rmul__(self)
+        o = F._c(o)
+        return self._bin(o, self.v * o.v, o.v, self.v)
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        if isinstance(o, Vec):
+            return o.__rtruediv__(self)
+        o = F._c(o)
+        with np.errstate(all="ignore"):
+            val = self.v / o.v
+            return self._bin(o, val, 1.0 / float(o.v) if o.v != 0 else 0.0, -float(self.v) / (float(o.v) ** 2) if o.v != 0 else 0.0)
+
+    def __rtruediv__(self, o):
+        return F._c(o).__truediv__(self)
+
+    def __neg__(self):
+        return self._un(-self.v, -1.0)
+
+    def __pos__(self):
+        return self
+
+    def __abs__(self):
+        return self._un(np.abs(self.v), 1.0 if self.v >= 0 else -1.0)
+
+    def __pow__(self, n):
+        # `**` with a small integer literal: repeated multiplication (lowering inside LuisaCompute is
+        # not inspectable; the oracle's numeric contract defines x**2 = x*x, x**5 = (x*x)*(x*x)*x)
+        if isinstance(n, int) and n == 2:
+            return self * self
+        if isinstance(n, int) and n == 5:
+            x2 = self * self
+            return (x2 * x2) * self
+        raise NotImplementedError(f"pow {n}")
+
+    def _cmp(self, o):
+        return F._c(o).v
+
+    def __lt__(self, o): return bool(self.v < self._cmp(o))
+    def __le__(self, o): return bool(self.v <= self._cmp(o))
+    def __gt__(self, o): return bool(self.v > self._cmp(o))
+    def __ge__(self, o): return bool(self.v >= self._cmp(o))
+    def __eq__(self, o): return bool(self.v == self._cmp(o))
+    def __ne__(self, o): return bool(self.v != self._cmp(o))
+    __hash__ = None
+
+    def __float__(self): return float(self.v)
+
+    def __int__(self):
+        # float -> int conversion of the DSL: truncation (cvt.rzi), NaN -> 0, saturating
+        if np.isnan(self.v):
+            return 0
+        return int(_py_max(_py_min(float(self.v), 2147483647.0), -2147483648.0))
+
+    def __repr__(self): return f"F({float(self.v)!r})"
+
+
+class U:
+    """uint32 with wrap-around; int (+) uint promotes to uint (C rules; LuisaCompute's rule for the
+    Python front-end is not inspectable — only matters in _permutation_element's final modulo,
+    identical for power-of-two spp)."""
+    __slots__ = ("v",)
+    M = 0xFFFFFFFF
+
+    def __init__(self, v=0):
+        self.v = (v.v if isinstance(v, U) else int(v)) & U.M
+
+    @staticmethod
+    def _i(o):
+        return o.v if isinstance(o, U) else int(o) & U.M
+
+    def __add__(self, o):
+        if isinstance(o, F):
+            return F(self) + o
+        return U(self.v + U._i(o))
+    __radd__ = __add__
+    def __sub__(self, o): return U(self.v - U._i(o))
+    def __rsub__(self, o): return U(U._i(o) - self.v)
+    def __mul__(self, o):
+        if isinstance(o, F):
+            return F(self) * o
+        return U(self.v * U._i(o))
+    __rmul__ = __mul__
+    def __xor__(self, o): return U(self.v ^ U._i(o))
+    __rxor__ = __xor__
+    def __and__(self, o): return U(self.v & U._i(o))
+    __rand__ = __and__
+    def __or__(self, o): return U(self.v | U._i(o))
+    __ror__ = __or__
+    def __rshift__(self, o): return U(self.v >> int(U._i(o)))
+    def __rrshift__(self, o): return U(U._i(o) >> self.v)
+    def __lshift__(self, o): return U(self.v << int(U._i(o)))
+    def __mod__(self, o): return U(self.v % U._i(o))
+    def __floordiv__(self, o): return U(self.v // U._i(o))
+    def __truediv__(self, o): return F(f32(self.v)) / (F(o) if not isinstance(o, F) else o)
+    def __rtruediv__(self, o): return F(o) / F(f32(self.v))
+    def __lt__(self, o): return self.v < U._i(o)
+    def __le__(self, o): return self.v <= U._i(o)
+    def __gt__(self, o): return self.v > U._i(o)
+    def __ge__(self, o): return self.v >= U._i(o)
+    def __eq__(self, o): return self.v == U._i(o)
+    def __ne__(self, o): return self.v != U._i(o)
+    __hash__ = None
+    def __int__(self): return self.v
+    def __index__(self): return self.v
+    def __repr__(self): return f"U({self.v})"
+
+
+def _trunc_mod(a: int, b: int) -> int:
+    """C `%` on signed ints (truncating), as the DSL lowers int % int."""
+    return int(math.fmod(a, b))
+
+
+# ------------------------------------------------------------------------------------ vectors
+_SWZ = {"x": 0, "y": 1, "z": 2, "w": 3, "r": 0, "g": 1, "b": 2, "a": 3}
+
+
+class Vec:
+    n = 0
+    kind = "f"     # f | i | u | b
+
+    def __init__(self, *args):
+        object.__setattr__(self, "c", self._gather(args))
+
+    @classmethod
+    def _conv(cls, x):
+        if cls.kind == "f":
+            return x if isinstance(x, F) else F(x)
+        if cls.kind == "i":
+            return int(x)       # F.__int__ truncates
+        if cls.kind == "u":
+            return x if isinstance(x, U) else U(int(x))
+        return bool(x)
+
+    @classmethod
+    def _gather(cls, args) -> List:
+        if len(args) == 0:
+            return [cls._conv(0) for _ in range(cls.n)]
+        if len(args) == 1 and not isinstance(args[0], Vec):
+            return [cls._conv(args[0]) for _ in range(cls.n)]
+        vals = []
+        for a in args:
+            if isinstance(a, Vec):
+                vals.extend(a.c)
+            else:
+                vals.append(a)
+        if len(vals) != cls.n:
+            raise TypeError(f"{cls.__name__}: expected {cls.n} components, got {len(vals)}")
+        return [cls._conv(v) for v in vals]
+
+    def copy(self):
+        return type(self)(*self.c)
+
+    def __iter__(self):
+        return iter(self.c)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return self.c[i]
+
+    def __setitem__(self, i, v):
+        self.c[i] = self._conv(v)
+
+    def __getattr__(self, name):
+        if name and _py_all(ch in _SWZ for ch in name):
+            idx = [_SWZ[ch] for ch in name]
+            if _py_max(idx) >= self.n:
+                raise AttributeError(name)
+            if len(idx) == 1:
+                return self.c[idx[0]]
+            return _vec_type(self.kind, len(idx))(*[self.c[i] for i in idx])
+        raise AttributeError(name)
+
+    def __setattr__(self, name, val):
+        if name and _py_all(ch in _SWZ for ch in name):
+            idx = [_SWZ[ch] for ch in name]
+            if len(idx) == 1:
+                self.c[idx[0]] = self._conv(val)
+            else:
+                for i, v in zip(idx, val):
+                    self.c[i] = self._conv(v)
+        else:
+            object.__setattr__(self, name, val)
+
+    def _zip(self, o, fn, kind=None):
+        k = kind or self.kind
+        if isinstance(o, Vec):
+            if o.kind == "f" and self.kind in "iu" and kind is None:
+                k = "f"
+            return _vec_type(k, self.n)(*[fn(a, b) for a, b in zip(self.c, o.c)])
+        if isinstance(o, F) and self.kind in "iu" and kind is None:
+            k = "f"
+        return _vec_type(k, self.n)(*[fn(a, o) for a in self.c])
+
+    def _lift(self, a):
+        return a
+
+    def __add__(self, o): return self._zip(o, lambda a, b: a + b)
+    __radd__ = __add__
+    def __sub__(self, o): return self._zip(o, lambda a, b: a - b)
+    def __rsub__(self, o): return self._zip(o, lambda a, b: b - a)
+    def __mul__(self, o):
+        if isinstance(o, Mat):
+            return NotImplemented
+        return self._zip(o, lambda a, b: a * b)
+    __rmul__ = __mul__
+    def __truediv__(self, o): return self._zip(o, lambda a, b: (F(a) if not isinstance(a, F) else a) / b, "f")
+    def __rtruediv__(self, o): return self._zip(o, lambda a, b: (F(b) if not isinstance(b, F) else b) / a, "f")
+    def __neg__(self): return type(self)(*[-a for a in self.c])
+    def __xor__(self, o): return self._zip(o, lambda a, b: a ^ b)
+    def __mod__(self, o):
+        if self.kind == "i":
+            return self._zip(o, lambda a, b: _trunc_mod(a, int(b)))
+        return self._zip(o, lambda a, b: a % b)
+    def __lt__(self, o): return self._zip(o, lambda a, b: a < b, "b")
+    def __le__(self, o): return self._zip(o, lambda a, b: a <= b, "b")
+    def __gt__(self, o): return self._zip(o, lambda a, b: a > b, "b")
+    def __ge__(self, o): return self._zip(o, lambda a, b: a >= b, "b")
+    def __pow__(self, n): return type(self)(*[a ** n for a in self.c])
+    def __bool__(self):
+        raise TypeError("vector used as a scalar condition")
+    def __repr__(self): return f"{type(self).__name__}({', '.join(repr(a) for a in self.c)})"
+
+
+_VT = {}
+
+
+def _vec_type(kind, n):
+    return _VT[(kind, n)]
+
+
+def _mk(name, kind, n):
+    t = type(name, (Vec,), {"n": n, "kind": kind})
+    _VT[(kind, n)] = t
+    return t
+
+
+float2, float3, float4 = _mk("float2", "f", 2), _mk("float3", "f", 3), _mk("float4", "f", 4)
+int2, int3, int4 = _mk("int2", "i", 2), _mk("int3", "i", 3), _mk("int4", "i", 4)
+uint2, uint3, uint4 = _mk("uint2", "u", 2), _mk("uint3", "u", 3), _mk("uint4", "u", 4)
+bool2, bool3, bool4 = _mk("bool2", "b", 2), _mk("bool3", "b", 3), _mk("bool4", "b", 4)
+make_float2, make_float3, make_float4 = float2, float3, float4
+make_int2, make_int3, make_int4 = int2, int3, int4
+make_uint2, make_uint3, make_uint4 = uint2, uint3, uint4
+
+
+class Mat:
+    """column-major square matrix of F; m[c] is column c."""
+
+    def __init__(self, cols):
+        self.cols = [c.copy() for c in cols]
+        self.n = len(cols)
+
+    def __getitem__(self, c):
+        return self.cols[c]
+
+    def __mul__(self, v):
+        if isinstance(v, Vec):
+            # sum over columns of column * v[c], plain binary32 operations in column order
+            acc = self.cols[0] * v.c[0]
+            for c in range(1, self.n):
+                acc = acc + self.cols[c] * v.c[c]
+            return acc
+        raise NotImplementedError
+
+
+def float4x4(*a):
+    if len(a) == 1:
+        s = float(a[0])
+        return Mat([float4(*[s if r == c else 0.0 for r in range(4)]) for c in range(4)])
+    assert len(a) == 16
+    return Mat([float4(*a[4 * c:4 * c + 4]) for c in range(4)])
+
+
+def make_float3x3(c0, c1, c2):
+    return Mat([float3(c0), float3(c1), float3(c2)])
+
+
+def transpose(m: Mat) -> Mat:
+    n = m.n
+    return Mat([_vec_type("f", n)(*[m.cols[r].c[c] for r in range(n)]) for c in range(n)])
+
+
+def inverse(m: Mat) -> Mat:
+    """3x3 inverse by cofactors / determinant (binary32 operations)."""
+    assert m.n == 3
+    a = [[m.cols[c].c[r] for c in range(3)] for r in range(3)]     # a[r][c]
+    cof = [[None] * 3 for _ in range(3)]
+    for r in range(3):
+        for c in range(3):
+            r1, r2 = (r + 1) % 3, (r + 2) % 3
+            c1, c2 = (c + 1) % 3, (c + 2) % 3
+            cof[r][c] = a[r1][c1] * a[r2][c2] - a[r1][c2] * a[r2][c1]
+    det = a[0][0] * cof[0][0] + a[0][1] * cof[0][1] + a[0][2] * cof[0][2]
+    inv_det = 1.0 / det
+    # inverse[r][c] = cof[c][r] / det
+    return Mat([float3(*[cof[c][r] * inv_det for r in range(3)]) for c in range(3)])
+
+
+# ------------------------------------------------------------------------------------ builtins
+def _map(fn, x):
+    if isinstance(x, Vec):
+        return type(x)(*[fn(a) for a in x.c])
+    return fn(x if isinstance(x, F) else F(x))
+
+
+def sqrt(x):
+    def f(a):
+        with np.errstate(all="ignore"):
+            v = np.sqrt(a.v)
+        return a._un(v, 0.5 / float(v) if v > 0 else 0.0)
+    return _map(f, x)
+
+
+def sin(x): return _map(lambda a: F(_sincos(a.v)[0]), x)
+def cos(x): return _map(lambda a: F(_sincos(a.v)[1]), x)
+def tan(x): return _map(lambda a: F(_libm.tanf(float(a.v))), x)
+def acos(x): return _map(lambda a: F(_libm.acosf(float(a.v))), x)
+def exp(x): return _map(lambda a: F(_libm.expf(float(a.v))), x)
+def atan2(y, x): return F(_libm.atan2f(float(F._c(y).v), float(F._c(x).v)))
+def floor(x): return _map(lambda a: F(np.floor(a.v)), x)
+def fract(x): return _map(lambda a: a - F(np.floor(a.v)), x)
+def isnan(x):
+    if isinstance(x, Vec):
+        return _vec_type("b", x.n)(*[bool(np.isnan(a.v)) for a in x.c])
+    return bool(np.isnan(F._c(x).v))
+
+
+def lc_abs(x):
+    if isinstance(x, Vec):
+        return type(x)(*[_py_abs(a) for a in x.c])
+    return _py_abs(x)
+
+
+def _max2(a, b):
+    if isinstance(a, Vec) or isinstance(b, Vec):
+        v = a if isinstance(a, Vec) else b
+        return v._zip(b if v is a else a, lambda p, q: _max2(p, q))
+    if isinstance(a, (F, float)) or isinstance(b, (F, float)):
+        a, b = F._c(a), F._c(b)
+        # fmaxf: the non-NaN operand wins
+        if np.isnan(a.v):
+            return b
+        if np.isnan(b.v):
+            return a
+        return a if a.v >= b.v else b
+    return a if a >= b else b
+
+
+def _min2(a, b):
+    if isinstance(a, Vec) or isinstance(b, Vec):
+        v = a if isinstance(a, Vec) else b
+        return v._zip(b if v is a else a, lambda p, q: _min2(p, q))
+    if isinstance(a, (F, float)) or isinstance(b, (F, float)):
+        a, b = F._c(a), F._c(b)
+        if np.isnan(a.v):
+            return b
+        if np.isnan(b.v):
+            return a
+        return a if a.v <= b.v else b
+    return a if a <= b else b
+
+
+def lc_max(*a):
+    if len(a) == 1:
+        return _py_max(a[0])
+    r = a[0]
+    for x in a[1:]:
+        r = _max2(r, x)
+    return r
+
+
+def lc_min(*a):
+    if len(a) == 1:
+        return _py_min(a[0])
+    r = a[0]
+    for x in a[1:]:
+        r = _min2(r, x)
+    return r
+
+
+def clamp(x, lo, hi):
+    return _min2(_max2(x, lo), hi)
+
+
+def lerp(a, b, t):
+    return a + (b - a) * t if not isinstance(t, Vec) else a + (b - a) * t
+
+
+def dot(a, b):
+    r = a.c[0] * b.c[0]
+    for i in range(1, a.n):
+        r = r + a.c[i] * b.c[i]
+    return r
+
+
+def cross(a, b):
+    return float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x)
+
+
+def length_squared(a): return dot(a, a)
+def length(a): return sqrt(dot(a, a))
+def normalize(a): return a * (1.0 / sqrt(dot(a, a)))
+def reflect(i, n): return i - n * (2.0 * dot(n, i))
+
+
+def lc_any(x):
+    return _py_any(x.c) if isinstance(x, Vec) else _py_any(x)
+
+
+def lc_all(x):
+    return _py_all(x.c) if isinstance(x, Vec) else _py_all(x)
+
+
+def _select(cond, a_fn, b_fn):
+    """`a if cond else b`: lazy for scalar conditions, component-wise for vector conditions."""
+    if isinstance(cond, Vec):
+        a, b = a_fn(), b_fn()
+        return type(a if isinstance(a, Vec) else b)(*[(a.c[i] if isinstance(a, Vec) else a) if cond.c[i] else (b.c[i] if isinstance(b, Vec) else b)
+                                                     for i in range(cond.n)])
+    return a_fn() if cond else b_fn()
+
+
+# dispatch state
+_dispatch = {"id": (0, 0, 0), "size": (1, 1, 1)}
+def dispatch_id(): return uint3(*_dispatch["id"])
+def dispatch_size(): return uint3(*_dispatch["size"])
+
+
+# ------------------------------------------------------------------------------------ autodiff
+class _ADContext:
+    def __enter__(self):
+        global _tape
+        _tape = _Tape()
+        return self
+
+    def __exit__(self, *a):
+        global _tape
+        _tape = None
+        return False
+
+
+_grads = {}
+
+
+def autodiff():
+    return _ADContext()
+
+
+def requires_grad(*xs):
+    for x in xs:
+        if isinstance(x, Vec):
+            for i in range(x.n):
+                x.c[i] = F(x.c[i].v, node=_tape.new())
+        else:
+            raise NotImplementedError("requires_grad on a scalar needs rebinding")
+
+
+def backward(y, seed):
+    """reverse sweep; accumulation in binary64, rounded once (LuisaCompute accumulates in binary32
+    in an order we cannot see — gradients are compared within tolerance)."""
+    g = np.zeros(_tape.n, dtype=np.float64)
+    ys = y.c if isinstance(y, Vec) else [y]
+    ss = seed.c if isinstance(seed, Vec) else [seed]
+    for a, s in zip(ys, ss):
+        if a.node is not None:
+            g[a.node] += float(F._c(s).v)
+    for out, ins in reversed(_tape.ops):
+        go = g[out]
+        if go != 0.0:
+            for i, d in ins:
+                g[i] += go * d
+    _grads["g"] = g
+
+
+def grad(x):
+    g = _grads["g"]
+    if isinstance(x, Vec):
+        return type(x)(*[F(g[a.node]) if a.node is not None else F(0.0) for a in x.c])
+    return F(g[x.node])
+
+
+def detach(x):
+    if isinstance(x, Vec):
+        return type(x)(*[F(a.v) for a in x.c])
+    return F(x.v)
+
+
+# ------------------------------------------------------------------------------------ DSL objects
+class _Struct:
+    _fields = {}
+    _methods = {}
+
+    def __init__(self, **kw):
+        for k, t in self._fields.items():
+            object.__setattr__(self, k, _zero(t))
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    def __setattr__(self, k, v):
+        object.__setattr__(self, k, v.copy() if isinstance(v, Vec) else v)
+
+    def copy(self):
+        o = type(self)()
+        for k in self._fields:
+            setattr(o, k, getattr(self, k))
+        return o
+
+
+def _zero(t):
+    if isinstance(t, type) and issubclass(t, Vec):
+        return t()
+    if t is float:
+        return F(0.0)
+    if t is int:
+        return 0
+    if isinstance(t, _ArrayT):
+        return [_zero(t.t) for _ in range(t.n)]
+    if isinstance(t, type) and issubclass(t, _Struct):
+        return t()
+    return 0
+
+
+class _ArrayT:
+    def __init__(self, n, t):
+        self.n, self.t = n, t
+
+
+def ArrayType(n, t):
+    return _ArrayT(n, t)
+
+
+def StructType(alignment=None, **fields):
+    cls = type("Struct", (_Struct,), {"_fields": dict(fields)})
+
+    def add_method(fn, name=None):
+        setattr(cls, name or fn.__name__, fn)
+    cls.add_method = staticmethod(add_method)
+    return cls
+
+
+def struct(**kw):
+    return types.SimpleNamespace(**kw)
+
+
+def array(xs):
+    return list(xs)
+
+
+class Buffer:
+    """typed linear buffer over a numpy array (element = scalar, vector or Vertex row)."""
+
+    def __init__(self, dtype=None, size=0, data=None):
+        self.dtype, self.size = dtype, size
+        self.data = data
+
+    def copy_from_array(self, arr):
+        self.data = np.ascontiguousarray(arr)
+
+    @staticmethod
+    def from_dlpack(t):
+        a = t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+        b = Buffer(data=a)
+        if a.ndim == 2 and a.shape[1] == 2:
+            b.dtype = float2
+        elif a.ndim == 2 and a.shape[1] == 4:
+            b.dtype = float4
+        else:
+            b.dtype = float
+        b.size = a.shape[0]
+        return b
+
+    oob_reads = 0       # class-wide count of out-of-range reads (undefined behaviour upstream)
+
+    def read(self, i):
+        i = int(i)
+        if not 0 <= i < len(self.data):
+            # pmj02bn.py:23 indexes past the blue-noise table from dimension 25 on (UB upstream);
+            # defined here, as in the oracle, as index modulo table length
+            Buffer.oob_reads += 1
+            i %= len(self.data)
+        if self.dtype is float:
+            return F(self.data[i])
+        if self.dtype is int:
+            return int(self.data[i])
+        if isinstance(self.dtype, type) and issubclass(self.dtype, Vec):
+            return self.dtype(*[x for x in self.data[i]])
+        if isinstance(self.dtype, type) and issubclass(self.dtype, _Struct):     # Vertex rows: 8 floats
+            row = self.data[i]
+            v = self.dtype()
+            v._v = [F(row[0]), F(row[1]), F(row[2])]
+            v._vt = [F(row[3]), F(row[4])]
+            v._vn = [F(row[5]), F(row[6]), F(row[7])]
+            return v
+        raise TypeError(self.dtype)
+
+    def write(self, i, val):
+        self.data[int(i)] = [float(c.v) for c in val.c] if isinstance(val, Vec) else float(F._c(val).v)
+
+    def atomic_fetch_add(self, i, val):
+        # gradient accumulation: binary64 accumulator (atomics have no defined order)
+        old = self.data[int(i)]
+        self.data[int(i)] = old + float(F._c(val).v)
+        return F(old)
+
+
+def buffer(xs):
+    if len(xs) and isinstance(xs[0], Vec):
+        return Buffer(dtype=type(xs[0]), size=len(xs), data=np.asarray([[float(c.v) for c in v.c] for v in xs], dtype=np.float32))
+    return Buffer(dtype=int, size=len(xs), data=np.asarray(xs, dtype=np.int64))
+
+
+class BindlessArray:
+    def __init__(self):
+        self.slots = {}
+        self.textures = {}
+
+    def emplace(self, slot, obj):
+        self.slots[slot] = obj
+
+    def update(self):
+        pass
+
+    def buffer_read(self, dtype, slot, idx):
+        b = self.slots.get(int(slot))
+        if b is None:                       # direct.py:71 reads the envmap pdf slot without an envmap; value unused
+            return _zero(dtype)
+        if dtype is int:
+            return int(b.data[int(idx)])
+        if dtype is float:
+            return F(b.data[int(idx)])
+        old, b.dtype = b.dtype, dtype
+        try:
+            return b.read(idx)
+        finally:
+            b.dtype = old
+
+    def texture2d_sample(self, slot, uv):
+        raise NotImplementedError("envmap textures are not part of the emulated fixtures")
+
+
+class Ray:
+    def __init__(self, o, d, tmin, tmax):
+        self.o, self.d, self.tmin, self.tmax = float3(o), float3(d), F(tmin), F(tmax)
+
+    def get_origin(self): return self.o.copy()
+    def get_dir(self): return self.d.copy()
+
+
+def make_ray(o, d, tmin, tmax):
+    return Ray(o, d, tmin, tmax)
+
+
+def offset_ray_origin(p, n):
+    """Waechter & Binder, Ray Tracing Gems ch. 6 (LuisaCompute's constants from memory — unpinned;
+    same definition as the oracle)."""
+    from oracle import oracle as o
+    r = o.offset_ray_origin(np.asarray([[float(c.v) for c in p.c] + [float(c.v) for c in n.c]], dtype=np.float32))
+    return float3(*r[0])
+
+
+class Hit:
+    def __init__(self, inst, prim, u, v, t):
+        self.inst, self.prim = int(inst), int(prim)
+        self.bary = float2(u, v)
+        self.ray_t = F(t)
+
+    def miss(self):
+        return self.inst < 0
+
+    def interpolate(self, a, b, c):
+        u, v = self.bary.x, self.bary.y
+        return a * (1.0 - u - v) + b * u + c * v
+
+
+class Accel:
+    """accel.add / trace_closest / trace_any.  Intersection is delegated to the oracle's watertight
+    test (zdr_oracle.c): OptiX's arithmetic inside LuisaCompute is not available to pin."""
+
+    def __init__(self):
+        self.models = []
+        self.xforms = []
+        self._scene = None
+
+    def add(self, vertex_buffer, triangle_buffer, transform=None):
+        self.models.append((vertex_buffer, triangle_buffer))
+        self.xforms.append(transform if transform is not None else float4x4(1.0))
+
+    def update(self):
+        from oracle import oracle as o
+        from zdr_b200.mathtypes import float4x4 as host_m4
+        models = []
+        for (vb, tb), m in zip(self.models, self.xforms):
+            flat = [float(m.cols[c].c[r].v) for c in range(4) for r in range(4)]
+            models.append(((np.asarray(vb.data, np.float32).reshape(-1, 8), np.asarray(tb.data, np.int32)), host_m4(*flat), None))
+        self._scene = o.OracleScene(models)
+
+    def instance_transform(self, inst):
+        return self.xforms[int(inst)]
+
+    def _ray8(self, ray):
+        return np.asarray([[float(c.v) for c in ray.o.c] + [float(c.v) for c in ray.d.c] + [float(ray.tmin.v), float(ray.tmax.v)]], np.float32)
+
+    def trace_closest(self, ray, mask=-1):
+        ip, uvt = self._scene.trace_closest(self._ray8(ray))
+        return Hit(ip[0, 0], ip[0, 1], uvt[0, 0], uvt[0, 1], uvt[0, 2])
+
+    def trace_any(self, ray, mask=-1):
+        return bool(self._scene.trace_any(self._ray8(ray))[0])
+
+
+# ------------------------------------------------------------------------------------ @luisa.func
+class _IfExpToSelect(ast.NodeTransformer):
+    def visit_IfExp(self, node):
+        self.generic_visit(node)
+        lam = lambda body: ast.Lambda(args=ast.arguments(posonlyargs=[], args=[], kwonlyargs=[], kw_defaults=[], defaults=[]), body=body)
+        return ast.copy_location(ast.Call(func=ast.Name(id="__lc_select", ctx=ast.Load()), args=[node.test, lam(node.body), lam(node.orelse)],
+                                          keywords=[]), node)
+
+
+_BUILTINS = {}
+
+
+def func(fn):
+    """Re-compiles the function with the DSL's select semantics; builtins (normalize, dot, ...) and
+    the enclosing function's free variables are bound at first call."""
+    state = {}
+
+    def compiled():
+        if "f" not in state:
+            src = textwrap.dedent(inspect.getsource(fn))
+            tree = ast.parse(src)
+            fdef = tree.body[0]
+            fdef.decorator_list = []
+            tree = ast.fix_missing_locations(_IfExpToSelect().visit(tree))
+            ns = dict(fn.__globals__)
+            ns.update(_BUILTINS)
+            if fn.__closure__:
+                for name, cell in zip(fn.__code__.co_freevars, fn.__closure__):
+                    ns[name] = cell.cell_contents
+            code = compile(tree, inspect.getsourcefile(fn) or "<lc_emu>", "exec")
+            exec(code, ns)
+            state["f"] = ns[fdef.name]
+            state["ns"] = ns
+        return state["f"]
+
+    def wrapper(*a, dispatch_size=None, **kw):
+        f = compiled()
+        if dispatch_size is None:
+            return f(*a, **kw)
+        ds = tuple(dispatch_size) + (1,) * (3 - len(dispatch_size))
+        _dispatch["size"] = ds
+        for z in range(ds[2]):
+            for y in range(ds[1]):
+                for x in range(ds[0]):
+                    _dispatch["id"] = (x, y, z)
+                    f(*a, **kw)
+        return None
+    wrapper.__name__ = fn.__name__
+    wrapper.__wrapped__ = fn
+    return wrapper
+
+
+_BUILTINS.update(dict(
+    __lc_select=_select, sqrt=sqrt, sin=sin, cos=cos, tan=tan, acos=acos, atan2=atan2, exp=exp, floor=floor, fract=fract,
+    isnan=isnan, abs=lc_abs, max=lc_max, min=lc_min, clamp=clamp, lerp=lerp, dot=dot, cross=cross, length=length,
+    length_squared=length_squared, normalize=normalize, reflect=reflect, any=lc_any, all=lc_all,
+    make_float2=float2, make_float3=float3, make_float4=float4, make_int2=int2, make_int3=int3, make_int4=int4,
+    make_uint2=uint2, make_uint3=uint3, make_uint4=uint4, make_float3x3=make_float3x3, inverse=inverse, transpose=transpose,
+    dispatch_id=dispatch_id, dispatch_size=dispatch_size, float2=float2, float3=float3, float4=float4, int2=int2, int3=int3,
+    int4=int4, uint2=uint2, uint3=uint3, uint4=uint4, float4x4=float4x4,
+))
+
+
+# ------------------------------------------------------------------------------------ module install
+def install(pmj: np.ndarray, bn: np.ndarray, ref_dir: str = "/root/reference", pkg: str = "zdr_ref"):
+    """Registers fake `luisa`, `luisa.mathtypes`, `luisa.autodiff`, `imageio` modules and the two
+    missing table modules, then imports the reference directory as package `pkg` (unmodified
+    sources).  Returns the package module."""
+    import torch
+
+    luisa = types.ModuleType("luisa")
+    mt = types.ModuleType("luisa.mathtypes")
+    ad = types.ModuleType("luisa.autodiff")
+    for k in ("float2", "float3", "float4", "int2", "int3", "int4", "uint2", "uint3", "uint4", "bool2", "bool3", "bool4",
+              "make_float2", "make_float3", "make_float4", "make_int2", "make_int3", "make_int4", "make_uint2", "make_uint3",
+              "make_uint4", "float4x4", "make_float3x3"):
+        setattr(mt, k, globals()[k])
+        setattr(luisa, k, globals()[k])
+    mt.__all__ = [k for k in vars(mt) if not k.startswith("_")]
+    luisa.mathtypes = mt
+    for k in ("autodiff", "requires_grad", "backward", "grad", "detach"):
+        setattr(ad, k, globals()[k])
+    luisa.autodiff = ad
+    luisa.func = func
+    luisa.init = lambda *a, **k: None
+    luisa.synchronize = lambda: None
+    luisa.StructType, luisa.ArrayType, luisa.struct, luisa.array = StructType, ArrayType, struct, array
+    luisa.Buffer, luisa.buffer, luisa.BindlessArray, luisa.Accel = Buffer, buffer, BindlessArray, Accel
+    luisa.make_ray, luisa.offset_ray_origin = make_ray, offset_ray_origin
+    luisa.float, luisa.int = float, int
+    luisa.__path__ = []                                   # a package: `from luisa.atomic import ...`
+    at = types.ModuleType("luisa.atomic")
+    at._atomic_access_call = lambda *a, **k: None          # recompute_normal.py:2 (load-time helper, not on the hot path)
+    ut = types.ModuleType("luisa.util")
+    luisa.atomic, luisa.util = at, ut
+    sys.modules["luisa.atomic"], sys.modules["luisa.util"] = at, ut
+    sys.modules["luisa"], sys.modules["luisa.mathtypes"], sys.modules["luisa.autodiff"] = luisa, mt, ad
+    if "imageio" not in sys.modules:
+        try:
+            import imageio  # noqa: F401
+        except ImportError:
+            sys.modules["imageio"] = types.ModuleType("imageio")
+    # the two table modules the checkout lacks (.MISSING_LARGE_BLOBS), with the pbrt-v4 symbol names
+    pm = types.ModuleType(f"{pkg}.pmj02tables")
+    pm.PMJ02bnSamples = np.asarray(pmj, dtype=np.int64)
+    pm.nPMJ02bnSets, pm.nPMJ02bnSamples = int(pmj.shape[0]), int(pmj.shape[1])
+    pm.__all__ = ["PMJ02bnSamples", "nPMJ02bnSets", "nPMJ02bnSamples"]
+    bm = types.ModuleType(f"{pkg}.bluenoise")
+    bm.BlueNoiseTextures = np.asarray(bn, dtype=np.int64)
+    bm.NumBlueNoiseTextures, bm.BlueNoiseResolution = int(bn.shape[0]), int(bn.shape[1])
+    bm.__all__ = ["BlueNoiseTextures", "NumBlueNoiseTextures", "BlueNoiseResolution"]
+    sys.modules[f"{pkg}.pmj02tables"], sys.modules[f"{pkg}.bluenoise"] = pm, bm
+    # pmj02bn.py:9,14 call .cuda() at import; there is no GPU here
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        spec = importlib.util.spec_from_file_location(pkg, f"{ref_dir}/__init__.py", submodule_search_locations=[ref_dir])
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[pkg] = mod
+        spec.loader.exec_module(mod)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    return mod

@@ -1,0 +1,199 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by EXECUTING THE REFERENCE'S OWN SOURCES (/root/reference/*.py,
+imported unmodified) under the LuisaCompute emulator oracle/lc_emu.py.
+
+Run in the build container (needs /root/reference):   python tests/golden/gen_golden.py
+The fixtures travel with the repo; the GPU box never reads /root/reference.
+
+Tables: the reference's pbrt-v4 table modules are missing blobs, so the reference runs on the
+same surrogate tables the framework ships (zdr_b200/tables.py); the fixture therefore pins the
+sampler ALGORITHM (hashing, permutation, index formulae, draw order), not the table contents.
+
+What is recorded
+  sampler.npz     pmj02bn.py draws for a grid of (pixel, seed, spp, sample index, draw program)
+  functions.npz   camera.py / onb.py / microfacet.py / light.py device functions on seeded inputs,
+                  including the LuisaCompute-autodiff gradient of ggx_brdf (emulated tape AD)
+  render_*.npz    integrator.py kernels built from collocated.py / direct.py on the Cornell box:
+                  image, and d_material for a fixed d_image, at fixture sizes
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+from oracle import lc_emu as E  # noqa: E402
+from tests import scenes  # noqa: E402
+from zdr_b200.load_obj import read_obj, concat_triangles, load_mesh  # noqa: E402
+from zdr_b200.tables import get_tables  # noqa: E402
+
+pmj, bn, prov = get_tables()
+assert prov == "surrogate"
+ref = E.install(pmj, bn, "/root/reference", "zdr_ref")
+import zdr_ref.camera as R_camera  # noqa: E402
+import zdr_ref.collocated as R_collocated  # noqa: E402
+import zdr_ref.direct as R_direct  # noqa: E402
+import zdr_ref.light as R_light  # noqa: E402
+import zdr_ref.microfacet as R_mf  # noqa: E402
+import zdr_ref.onb as R_onb  # noqa: E402
+import zdr_ref.pmj02bn as R_pmj  # noqa: E402
+import zdr_ref.render as R_render  # noqa: E402
+from zdr_ref.vertex import Vertex  # noqa: E402
+
+
+def fv(v):
+    return [float(c.v) for c in v.c] if isinstance(v, E.Vec) else float(v.v)
+
+
+# ------------------------------------------------------------------------------------ sampler
+def gen_sampler():
+    rng = np.random.default_rng(0)
+    progs = ["2", "21", "2112", "2112121", "2" + "1121211" * 9]        # up to dimension 65 (past the OOB-wrap region)
+    rows, outs, prog_ids = [], [], []
+    for pi, prog in enumerate(progs):
+        for _ in range(40):
+            spp = int(rng.choice([1, 2, 4, 16, 64, 256, 1024]))
+            st = [int(rng.integers(0, 2048)), int(rng.integers(0, 2048)),
+                  int(rng.choice([0, 1, 12345, 853402567, 19260817, 948377263, 2147483647])), spp, int(rng.integers(0, spp))]
+            s = R_pmj.make_pmj02bn_sampler(E.int2(st[0], st[1]), st[2], st[3], st[4])
+            vals = []
+            for ch in prog:
+                if ch == "2":
+                    vals.extend(fv(s.next2f()))
+                else:
+                    vals.append(fv(s.next()))
+            rows.append(st); outs.append(np.asarray(vals, np.float32)); prog_ids.append(pi)
+    # test_sampler.py:23-30: pixel (24,345), seed 0, n=32, second next2f()
+    ts = []
+    for i in range(32):
+        s = R_pmj.make_pmj02bn_sampler(E.int2(24, 345), 0, 32, i)
+        s.next2f()
+        ts.append(fv(s.next2f()))
+    np.savez_compressed(os.path.join(OUT, "sampler.npz"), progs=np.asarray(progs), state=np.asarray(rows, np.int32),
+                        prog_id=np.asarray(prog_ids, np.int32), values=np.asarray(outs, dtype=object),
+                        test_sampler_py=np.asarray(ts, np.float32), allow_pickle=True)
+    print("sampler.npz:", len(rows), "states")
+
+
+# ------------------------------------------------------------------------------------ functions
+def gen_functions():
+    rng = np.random.default_rng(1)
+    n = 200
+
+    def hemi():
+        v = rng.normal(size=3)
+        v[2] = abs(v[2]) + 1e-3
+        return (v / np.linalg.norm(v)).astype(np.float32)
+
+    ggx_in, ggx_out, pdf_out = [], [], []
+    for _ in range(n):
+        wo, wi = hemi(), hemi()
+        d, r, g = rng.uniform(0, 1, 3).astype(np.float32), np.float32(rng.uniform(0.03, 1)), rng.normal(size=3).astype(np.float32)
+        mat = E.float4(*d, r)
+        with E.autodiff():                                   # the reference's AD pattern, collocated.py:44-56
+            E.requires_grad(mat)
+            f = R_mf.ggx_brdf(E.float3(*wo), E.float3(*wi), mat.xyz, 0.04, mat.w)
+            E.backward(f, E.float3(*g))
+            dm = E.grad(mat)
+        ggx_in.append(np.concatenate([wo, wi, d, [r], g]))
+        ggx_out.append(fv(f) + fv(dm))
+        pdf_out.append(fv(R_mf.ggx_sample_pdf(E.float3(*wo), E.float3(*wi), mat.xyz, 0.04, mat.w)))
+    wm_in, wm_out, cos_in, cos_out = [], [], [], []
+    for _ in range(n):
+        w, a, u = hemi(), np.float32(rng.uniform(0.001, 1)), rng.uniform(0, 1, 2).astype(np.float32)
+        wm_in.append(np.concatenate([w, [a], u]))
+        wm_out.append(fv(R_mf.sample_wm(E.float3(*w), E.F(a), E.float2(*u))))
+        cos_in.append(u)
+        cos_out.append(fv(R_mf.cosine_sample_hemisphere(E.float2(*u))))
+    onb_in = [hemi() * rng.choice([-1, 1]) for _ in range(n)]
+    onb_out = []
+    for nn in onb_in:
+        o = R_onb.make_onb(E.float3(*nn))
+        onb_out.append(fv(o.tangent) + fv(o.binormal) + fv(o.normal))
+    tent_in = rng.uniform(0, 1, n).astype(np.float32)
+    tent_out = [fv(R_camera.tent_warp(E.F(u), 1.0)) for u in tent_in]
+    tent2 = fv(R_camera.tent_warp(E.float2(0.2, 0.8), 1.0))           # component-wise select on a vector
+    tri_in = rng.uniform(0, 1, (n, 2)).astype(np.float32)
+    tri_out = [fv(R_light.sample_uniform_triangle(E.float2(*u))) for u in tri_in]
+    cam = R_render.Camera(fov=50 / 180 * 3.1415926, origin=E.float3(-0.2, 2.6, 6.0), target=E.float3(-0.2, 2.6, -2.5),
+                          up=E.float3(0.0, 1.0, 0.0))
+    ndc = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    rays = []
+    for p in ndc:
+        r = R_camera.generate_ray(cam, E.float2(*p))
+        rays.append(fv(r.get_origin()) + fv(r.get_dir()))
+    np.savez_compressed(os.path.join(OUT, "functions.npz"), ggx_in=np.asarray(ggx_in, np.float32), ggx_out=np.asarray(ggx_out, np.float32),
+                        ggx_pdf=np.asarray(pdf_out, np.float32), wm_in=np.asarray(wm_in, np.float32), wm_out=np.asarray(wm_out, np.float32),
+                        cos_in=np.asarray(cos_in, np.float32), cos_out=np.asarray(cos_out, np.float32), onb_in=np.asarray(onb_in, np.float32),
+                        onb_out=np.asarray(onb_out, np.float32), tent_in=tent_in, tent_out=np.asarray(tent_out, np.float32),
+                        tent_vec=np.asarray(tent2, np.float32), tri_in=tri_in, tri_out=np.asarray(tri_out, np.float32), ndc=ndc,
+                        rays=np.asarray(rays, np.float32))
+    print("functions.npz")
+
+
+# ------------------------------------------------------------------------------------ kernels
+class RefScene:
+    """Scene assembly exactly as render.py:73-128 does it, on the emulated heap / accel."""
+
+    def __init__(self, models):
+        self.accel, self.heap = E.Accel(), E.BindlessArray()
+        inst_metadata, light_insts, inst_trig_count = [], [], []
+        for idx, (obj_file, transform, emission) in enumerate(models):
+            em = E.float3(*[float(c) for c in emission]) if emission is not None else E.float3(0.0)
+            if em.x > 0 or em.y > 0 or em.z > 0:
+                light_insts.append(idx)
+            inst_metadata.append(em)
+            verts, tris = load_mesh(obj_file)                 # same (v,t,n) rows / fan order as load_obj.py (tests/test_host.py)
+            vb = E.Buffer(dtype=Vertex, size=len(verts)); vb.copy_from_array(verts)
+            tb = E.buffer([int(t) for t in tris])
+            inst_trig_count.append(len(tris) // 3)
+            xf = E.float4x4(*transform.flat()) if transform is not None else E.float4x4(1.0)
+            self.accel.add(vb, tb, transform=xf)
+            self.heap.emplace(idx * 2 + 0, tb)
+            self.heap.emplace(idx * 2 + 1, vb)
+        self.inst_count = len(models)
+        self.light_count = len(light_insts)
+        self.heap.emplace(23333, E.buffer(inst_metadata))
+        if self.light_count > 0:
+            self.heap.emplace(23334, E.buffer(light_insts + [0] * (self.inst_count - self.light_count)))
+        self.heap.emplace(23335, E.buffer(inst_trig_count))
+        self.accel.update()
+
+
+def gen_render(name, models, fwd_kernel, bwd_kernel, res, spp, tex, seed, mat_seed):
+    sc = RefScene(models)
+    cam = R_render.Camera(fov=50 / 180 * 3.1415926, origin=E.float3(-0.2, 2.6, 6.0), target=E.float3(-0.2, 2.6, -2.5),
+                          up=E.float3(0.0, 1.0, 0.0))
+    mat = scenes.random_material((tex, tex), mat_seed)
+    W, H = res
+    image = E.Buffer(dtype=E.float4, size=W * H, data=np.zeros((W * H, 4), np.float32))
+    mbuf = E.Buffer(dtype=float, size=mat.size, data=mat.reshape(-1).copy())
+    # render.py:168-171
+    fwd_kernel(image, sc.heap, sc.accel, sc.light_count, 0, mbuf, E.int2(tex, tex), cam, spp, seed, True, dispatch_size=(W, H))
+    rng = np.random.default_rng(7)
+    d_image = rng.normal(size=(H, W, 4)).astype(np.float32)
+    dbuf = E.Buffer(dtype=E.float4, size=W * H, data=d_image.reshape(-1, 4).copy())
+    dmat = E.Buffer(dtype=float, size=mat.size, data=np.zeros(mat.size, np.float64))
+    # render.py:193-196 (seed+1)
+    bwd_kernel(dbuf, sc.heap, sc.accel, sc.light_count, 0, dmat, mbuf, E.int2(tex, tex), cam, spp, seed + 1, True, dispatch_size=(W, H))
+    np.savez_compressed(os.path.join(OUT, f"render_{name}.npz"), res=np.asarray(res), spp=spp, tex=tex, seed=seed, mat_seed=mat_seed,
+                        image=image.data.reshape(H, W, 4).astype(np.float32), d_image=d_image,
+                        d_material=dmat.data.reshape(tex, tex, 4).astype(np.float32))
+    print(f"render_{name}.npz: image mean {image.data[:, :3].mean():.5f}, |d_material| sum {np.abs(dmat.data).sum():.4f}")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct"]
+    if "sampler" in which:
+        gen_sampler()
+    if "functions" in which:
+        gen_functions()
+    if "collocated" in which:
+        gen_render("collocated", scenes.cbox_collocated_models(), R_collocated.render_collocated_kernel,
+                   R_collocated.render_collocated_backward_kernel, (24, 24), 2, 64, 0, 3)
+    if "direct" in which:
+        gen_render("direct", scenes.cbox_path_models(), R_direct.render_direct_kernel, R_direct.render_direct_backward_kernel,
+                   (20, 20), 2, 64, 5, 4)
