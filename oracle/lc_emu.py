@@ -343,6 +343,9 @@ class Vec:
     def __le__(self, o): return self._zip(o, lambda a, b: a <= b, "b")
     def __gt__(self, o): return self._zip(o, lambda a, b: a > b, "b")
     def __ge__(self, o): return self._zip(o, lambda a, b: a >= b, "b")
+    def __eq__(self, o): return self._zip(o, lambda a, b: a == b, "b")
+    def __ne__(self, o): return self._zip(o, lambda a, b: a != b, "b")
+    __hash__ = None
     def __pow__(self, n): return type(self)(*[a ** n for a in self.c])
     def __bool__(self):
         raise TypeError("vector used as a scalar condition")
@@ -772,6 +775,7 @@ class Ray:
 
     def get_origin(self): return self.o.copy()
     def get_dir(self): return self.d.copy()
+    def copy(self): return Ray(self.o, self.d, self.tmin, self.tmax)
 
 
 def make_ray(o, d, tmin, tmax):
@@ -837,7 +841,18 @@ class Accel:
 
 
 # ------------------------------------------------------------------------------------ @luisa.func
+def _copy(x):
+    """value semantics of DSL assignment (`twin = sampler` copies, prb.py:96-98)"""
+    return x.copy() if isinstance(x, (Vec, _Struct, Ray)) else x
+
+
 class _IfExpToSelect(ast.NodeTransformer):
+    def visit_Assign(self, node):
+        self.generic_visit(node)
+        if isinstance(node.value, ast.Name):
+            node.value = ast.copy_location(ast.Call(func=ast.Name(id="__lc_copy", ctx=ast.Load()), args=[node.value], keywords=[]), node.value)
+        return node
+
     def visit_IfExp(self, node):
         self.generic_visit(node)
         lam = lambda body: ast.Lambda(args=ast.arguments(posonlyargs=[], args=[], kwonlyargs=[], kw_defaults=[], defaults=[]), body=body)
@@ -889,7 +904,7 @@ def func(fn):
 
 
 _BUILTINS.update(dict(
-    __lc_select=_select, sqrt=sqrt, sin=sin, cos=cos, tan=tan, acos=acos, atan2=atan2, exp=exp, floor=floor, fract=fract,
+    __lc_select=_select, __lc_copy=_copy, sqrt=sqrt, sin=sin, cos=cos, tan=tan, acos=acos, atan2=atan2, exp=exp, floor=floor, fract=fract,
     isnan=isnan, abs=lc_abs, max=lc_max, min=lc_min, clamp=clamp, lerp=lerp, dot=dot, cross=cross, length=length,
     length_squared=length_squared, normalize=normalize, reflect=reflect, any=lc_any, all=lc_all,
     make_float2=float2, make_float3=float3, make_float4=float4, make_int2=int2, make_int3=int3, make_int4=int4,

@@ -163,11 +163,15 @@ class RefScene:
         self.accel.update()
 
 
-def gen_render(name, models, fwd_kernel, bwd_kernel, res, spp, tex, seed, mat_seed):
+def gen_render(name, models, fwd_kernel, bwd_kernel, res, spp, tex, seed, mat_seed, rough_min=0.0):
     sc = RefScene(models)
     cam = R_render.Camera(fov=50 / 180 * 3.1415926, origin=E.float3(-0.2, 2.6, 6.0), target=E.float3(-0.2, 2.6, -2.5),
                           up=E.float3(0.0, 1.0, 0.0))
     mat = scenes.random_material((tex, tex), mat_seed)
+    # GGX's D term near the specular peak of a very smooth texel is ill-conditioned in binary32 (t = nh^2(a2-1)+1
+    # cancels): two correct float32 implementations differ by percents on such a sample, so the path fixture
+    # keeps roughness >= rough_min; the GPU-vs-oracle tests (identical arithmetic) cover the full range.
+    mat[..., 3] = np.float32(rough_min) + np.float32(1.0 - rough_min) * mat[..., 3]
     W, H = res
     image = E.Buffer(dtype=E.float4, size=W * H, data=np.zeros((W * H, 4), np.float32))
     mbuf = E.Buffer(dtype=float, size=mat.size, data=mat.reshape(-1).copy())
@@ -179,14 +183,49 @@ def gen_render(name, models, fwd_kernel, bwd_kernel, res, spp, tex, seed, mat_se
     dmat = E.Buffer(dtype=float, size=mat.size, data=np.zeros(mat.size, np.float64))
     # render.py:193-196 (seed+1)
     bwd_kernel(dbuf, sc.heap, sc.accel, sc.light_count, 0, dmat, mbuf, E.int2(tex, tex), cam, spp, seed + 1, True, dispatch_size=(W, H))
-    np.savez_compressed(os.path.join(OUT, f"render_{name}.npz"), res=np.asarray(res), spp=spp, tex=tex, seed=seed, mat_seed=mat_seed,
+    np.savez_compressed(os.path.join(OUT, f"render_{name}.npz"), res=np.asarray(res), spp=spp, tex=tex, seed=seed, mat_seed=mat_seed, rough_min=rough_min,
                         image=image.data.reshape(H, W, 4).astype(np.float32), d_image=d_image,
                         d_material=dmat.data.reshape(tex, tex, 4).astype(np.float32))
     print(f"render_{name}.npz: image mean {image.data[:, :3].mean():.5f}, |d_material| sum {np.abs(dmat.data).sum():.4f}")
 
 
+# prb.py does not compile as shipped: its call sites disagree with the callee signatures in
+# interaction.py:9, light.py:23,84 and integrator.py:51-52 (SURVEY.md 8a "PRB defects" item 1).  The
+# textual substitutions below are exactly that list — nothing else is changed — and are applied to an
+# in-memory copy of the source; the result is executed as module zdr_ref.prb_patched.
+PRB_PATCHES = [
+    ("surface_interact(hit, heap)", "surface_interact(hit, heap, accel)"),
+    ("sample_light_pdf(ray.get_origin(), light_count, env_count, heap, hit.inst, hit.prim, it.p)",
+     "sample_light_pdf(ray.get_origin(), light_count, heap, accel, hit.inst, hit.prim, it.p)"),
+    ("sample_light_pdf(ray.get_origin(), light_count, heap, hit.inst, hit.prim, it.p)",
+     "sample_light_pdf(ray.get_origin(), light_count, heap, accel, hit.inst, hit.prim, it.p)"),
+    ("sample_light(it.p, light_count, env_count, heap, sampler)", "sample_light(it.p, light_count, env_count, heap, accel, sampler)"),
+    ("sample_light(it.p, light_count, heap, sampler)", "sample_light(it.p, light_count, env_count, heap, accel, sampler)"),
+    ("def path_estimator_backward(ray, sampler, heap, accel, light_count,\n", "def path_estimator_backward(ray, sampler, heap, accel, light_count, env_count,\n"),
+    ("path_estimator(ray_twin, sampler_twin, heap, accel, light_count, material_buffer, texture_res)",
+     "path_estimator(ray_twin, sampler_twin, heap, accel, light_count, env_count, material_buffer, texture_res)"),
+]
+
+
+def load_patched_prb():
+    import importlib.util
+    import tempfile
+    src = open("/root/reference/prb.py").read()
+    for a, b in PRB_PATCHES:
+        assert a in src, a
+        src = src.replace(a, b)
+    d = tempfile.mkdtemp()
+    path = os.path.join(d, "prb_patched.py")
+    open(path, "w").write(src)
+    spec = importlib.util.spec_from_file_location("zdr_ref.prb_patched", path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["zdr_ref.prb_patched"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct"]
+    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path"]
     if "sampler" in which:
         gen_sampler()
     if "functions" in which:
@@ -197,3 +236,7 @@ if __name__ == "__main__":
     if "direct" in which:
         gen_render("direct", scenes.cbox_path_models(), R_direct.render_direct_kernel, R_direct.render_direct_backward_kernel,
                    (20, 20), 2, 64, 5, 4)
+    if "path" in which:
+        prb = load_patched_prb()
+        assert prb.max_depth == 16 and prb.rr_depth == 2
+        gen_render("path_literal", scenes.cbox_path_models(), prb.render_path_kernel, prb.render_path_backward_kernel, (16, 16), 2, 64, 9, 6, rough_min=0.3)

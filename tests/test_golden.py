@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from zdr_b200._abi import ZDR_COLLOCATED, ZDR_DIRECT, make_params
+from zdr_b200._abi import ZDR_COLLOCATED, ZDR_DIRECT, ZDR_PATH, ZDR_PRB_LITERAL, make_params
 
 from . import scenes
 
@@ -57,17 +57,24 @@ def test_device_functions_vs_reference_source(oracle):
     assert np.allclose(oracle.generate_ray(p, z["ndc"]), z["rays"], rtol=1e-6, atol=1e-7)
 
 
-@pytest.mark.parametrize("name,models,integ", [("collocated", scenes.cbox_collocated_models, ZDR_COLLOCATED),
-                                               ("direct", scenes.cbox_path_models, ZDR_DIRECT)])
-def test_render_kernels_vs_reference_source(oracle, name, models, integ):
+@pytest.mark.parametrize("name,models,integ,kw", [
+    ("collocated", scenes.cbox_collocated_models, ZDR_COLLOCATED, {}),
+    ("direct", scenes.cbox_path_models, ZDR_DIRECT, {}),
+    # prb.py with ONLY the call-arity substitutions listed in gen_golden.py (it cannot compile as shipped):
+    # pins prb_mode=literal, max_depth 16, rr_depth 2 — path_estimator and the PRB adjoint incl. autodiff
+    ("path_literal", scenes.cbox_path_models, ZDR_PATH, {"prb_mode": ZDR_PRB_LITERAL, "max_depth": 16, "rr_depth": 2}),
+])
+def test_render_kernels_vs_reference_source(oracle, name, models, integ, kw):
     """integrator.py kernels derived from collocated.py / direct.py (forward and adjoint with
     LuisaCompute autodiff), run under the emulator, vs the oracle: north-star bars."""
     z = np.load(os.path.join(G, f"render_{name}.npz"))
     res, spp, tex, seed = tuple(int(x) for x in z["res"]), int(z["spp"]), int(z["tex"]), int(z["seed"])
     mat = scenes.random_material((tex, tex), int(z["mat_seed"]))
+    rough_min = float(z["rough_min"]) if "rough_min" in z else 0.0          # see gen_golden.gen_render
+    mat[..., 3] = np.float32(rough_min) + np.float32(1.0 - rough_min) * mat[..., 3]
     sc = oracle.OracleScene(models())
-    img = sc.render_forward(integ, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed), mat)
+    img = sc.render_forward(integ, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed, **kw), mat)
     assert rel_l2(img, z["image"]) <= 1e-4, rel_l2(img, z["image"])
-    dm = sc.render_backward(integ, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed + 1), mat, z["d_image"])
+    dm = sc.render_backward(integ, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed + 1, **kw), mat, z["d_image"])
     assert np.abs(z["d_material"]).max() > 0
     assert rel_l2(dm, z["d_material"]) <= 1e-3, rel_l2(dm, z["d_material"])
