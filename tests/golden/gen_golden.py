@@ -189,6 +189,18 @@ def gen_render(name, models, fwd_kernel, bwd_kernel, res, spp, tex, seed, mat_se
     print(f"render_{name}.npz: image mean {image.data[:, :3].mean():.5f}, |d_material| sum {np.abs(dmat.data).sum():.4f}")
 
 
+def gen_loadobj():
+    """load_obj.py:1-68 on every asset: vertex de-dup order and fan triangulation fix the primitive ids."""
+    import zdr_ref.load_obj as R_obj
+    out = {}
+    for name in ("cboxuv.obj", "cbox-combined.obj", "cbox-light.obj", "quad.obj", "sphere.obj"):
+        vertices, faces = R_obj.read_obj(scenes.asset(name))
+        out[name + ":verts"] = np.array([(*v, *t, *n) for v, t, n in vertices], dtype=np.float32)     # render.py:97
+        out[name + ":tris"] = np.array(R_obj.concat_triangles(faces), dtype=np.int32)
+    np.savez_compressed(os.path.join(OUT, "loadobj.npz"), **out)
+    print("loadobj.npz")
+
+
 # prb.py does not compile as shipped: its call sites disagree with the callee signatures in
 # interaction.py:9, light.py:23,84 and integrator.py:51-52 (SURVEY.md 8a "PRB defects" item 1).  The
 # textual substitutions below are exactly that list — nothing else is changed — and are applied to an
@@ -225,7 +237,9 @@ def load_patched_prb():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path"]
+    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path", "loadobj"]
+    if "loadobj" in which:
+        gen_loadobj()
     if "sampler" in which:
         gen_sampler()
     if "functions" in which:

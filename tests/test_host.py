@@ -1,0 +1,110 @@
+"""Host-side logic and the C-ABI surface, no GPU needed."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from zdr_b200 import _abi
+from zdr_b200.load_obj import concat_triangles, load_mesh, read_obj
+from zdr_b200.mathtypes import Camera, float3, float4x4
+from zdr_b200.tables import get_tables, make_surrogate_tables
+
+from . import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "zdr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(zdr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_matches_ctypes_table():
+    names = header_functions()
+    assert len(names) >= 20
+    assert sorted(_abi.SIGNATURES) == names
+
+
+def test_library_loads_and_exports_every_symbol():
+    lib = _abi.load_library()                     # raises if the in-tree .so is missing: no fallback
+    for name in header_functions():
+        assert hasattr(lib, name), name
+    assert lib.zdr_abi_version() == 1
+
+
+def test_params_struct_layout():
+    """zdr_params is ABI: field order / size must match the header (27 x 4 bytes + 10 floats)."""
+    src = open(os.path.join(ROOT, "include", "zdr_b200.h")).read()
+    body = re.search(r"typedef struct zdr_params \{(.*?)\} zdr_params;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(None, 1)[1]
+        for n in names.split(","):
+            n = n.strip()
+            m = re.match(r"(\w+)\[(\d+)\]", n)
+            fields.append((m.group(1), int(m.group(2))) if m else (n, 1))
+    ct = [(n, (t._length_ if hasattr(t, "_length_") else 1)) for n, t in _abi.ZdrParams._fields_]
+    assert fields == ct
+    assert C.sizeof(_abi.ZdrParams) == 4 * sum(k for _, k in fields)
+
+
+def test_compute_entry_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = _abi.load_library()
+    h = C.c_void_p()
+    assert lib.zdr_scene_create(C.byref(h), 0) == -3            # ZDR_ERR_CUDA
+    assert b"no CPU fallback" in lib.zdr_last_error()
+    with pytest.raises(RuntimeError):
+        from zdr_b200 import Scene
+        Scene(scenes.cbox_collocated_models(), integrator="collocated")
+
+
+def test_load_obj_matches_reference_loader():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "loadobj.npz"))
+    for name in ("cboxuv.obj", "cbox-combined.obj", "cbox-light.obj", "quad.obj", "sphere.obj"):
+        vertices, faces = read_obj(scenes.asset(name))
+        verts = np.array([(*p, *t, *n) for p, t, n in vertices], dtype=np.float32)
+        tris = np.array(concat_triangles(faces), dtype=np.int32)
+        assert np.array_equal(tris, z[name + ":tris"]), name
+        assert np.array_equal(verts, z[name + ":verts"], equal_nan=True), name
+    # quad.obj has no vn: normals are recomputed at load (render.py:101-103)
+    verts, tris = load_mesh(scenes.asset("quad.obj"))
+    assert not np.isnan(verts).any() and np.allclose(np.linalg.norm(verts[:, 5:8], axis=1), 1.0)
+    # cbox-combined.obj has no vt: uv == 0 (load_obj.py:48) — the scatter-contention case
+    verts, _ = load_mesh(scenes.asset("cbox-combined.obj"))
+    assert (verts[:, 3:5] == 0).all()
+
+
+def test_mathtypes():
+    m = float4x4(1.0)
+    assert m.flat() == [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]
+    t = float4x4(*range(16))
+    assert list(t[1]) == [4.0, 5.0, 6.0, 7.0]                    # column-major, test_lightstage.py:44
+    v = float3(1, 2, 3)
+    assert list(v * 2 + float3(1.0)) == [3.0, 5.0, 7.0] and v.y == 2.0
+    c = Camera()
+    assert abs(c.fov - 40 / 180 * 3.1415926) < 1e-12 and list(c.origin) == [1.0, 0.5, 0.0]     # render.py:57-62
+    assert _abi.wrap_i32(2147483647 + 1) == -2147483648                                           # seed+1 wrap
+
+
+def test_sampler_tables_shape_and_provenance():
+    pmj, bn, prov = get_tables()
+    assert pmj.shape == (5, 65536, 2) and pmj.dtype == np.uint32                                  # pmj02bn.py:10
+    assert bn.shape == (48, 128, 128) and bn.dtype == np.uint16                                   # pmj02bn.py:15
+    assert prov in ("surrogate",) or prov.startswith("user:")
+    p2, b2 = make_surrogate_tables()
+    assert np.array_equal(p2, pmj) or prov != "surrogate"
+    if prov == "surrogate":
+        # the surrogate PMJ sets are (0,2)-sequences: every 16x16 elementary interval of the first 256 points holds one
+        pts = pmj[0, :256].astype(np.float64) / 2 ** 32
+        cells = (np.floor(pts[:, 0] * 16) * 16 + np.floor(pts[:, 1] * 16)).astype(int)
+        assert len(set(cells.tolist())) == 256

@@ -91,6 +91,7 @@ class Scene:
         # data-parallel shard of the dispatch grid; None = whole image
         self.shard_rows = None
         self.shard = None          # (index, count): round-robin 8-row tiles, see zdr_params.shard_index
+        self._dist_group = None
 
     # ------------------------------------------------------------------ scene assembly
     def load_geometry(self, models):
@@ -226,8 +227,45 @@ class Scene:
         """Renders the scene; differentiable w.r.t. ``material`` (``render.py:225-241``).
 
         material: cuda float32 ``(Ht, Wt, 4)`` = (diffuse rgb, roughness); res = (width, height).
-        Returns a ``(height, width, 4)`` tensor."""
+        Returns a ``(height, width, 4)`` tensor.  After :meth:`distribute` the call is collective:
+        every rank passes the same arguments and gets the full image and the full gradient."""
+        if self._dist_group is not None:
+            return self._render_distributed(material, res, spp, seed)
         return Scene.RenderOperator.apply(material, self, res, spp, seed)
+
+    # ------------------------------------------------------------------ multi-GPU (distributed.py)
+    def distribute(self, group=None):
+        """Shard every later :meth:`render` over the ranks of ``group`` (default: WORLD): replicated
+        scene, round-robin 8-row tiles, NCCL all-reduce of image and texture gradient."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self._dist_group = group if group is not None else dist.group.WORLD
+        return self
+
+    def _render_distributed(self, material, res, spp, seed):
+        from .distributed import sharded_render
+        camera, emissions = self.camera.copy(), list(self.emissions)
+        scene_ref = weakref.ref(self)
+
+        def fwd(mat, res_, spp_, seed_, shard):
+            sc = scene_ref()
+            old, sc.shard = sc.shard, shard
+            try:
+                return sc.render_forward(mat, res_, spp_, seed_)
+            finally:
+                sc.shard = old
+
+        def bwd(grad_output, d_material, mat, res_, spp_, seed_, shard):
+            sc = scene_ref()
+            old_shard, old_cam = sc.shard, sc.camera
+            sc.shard, sc.camera = shard, camera                    # render.py:216-218: state of the forward call
+            sc.update_lights(emissions)
+            try:
+                sc.render_backward(grad_output, d_material, mat, res_, spp_, seed_)
+            finally:
+                sc.shard, sc.camera = old_shard, old_cam
+        return sharded_render(material, fwd, bwd, res=res, spp=spp, seed=seed, group=self._dist_group)
 
     # ------------------------------------------------------------------ instrumentation
     def counters(self) -> dict:
