@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--tex", type=int, default=1024)
     ap.add_argument("--integrator", default="path", choices=["path", "direct", "collocated"])
     ap.add_argument("--ref-spp", type=int, default=2, help="samples per pixel (of --spp) one reference step renders")
-    ap.add_argument("--cpu-spp", type=int, default=4, help="samples per pixel of the cpu_baseline sample")
+    ap.add_argument("--cpu-spp", type=int, default=32, help="samples per pixel of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -340,7 +340,10 @@ def run_ours(args):
         "config": {"workload": name, "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": f"tile-dp{world}",
                    "rays_per_step": int(rays_total), "paths_per_step": 2 * args.res * args.res * args.spp,
                    "ms_forward": round(t_fwd / args.steps, 3), "ms_backward": round(ms_bwd, 3),
-                   "ms_allreduce": round((t_all - t_fwd - t_bwd) / args.steps, 3)},
+                   "ms_allreduce": round((t_all - t_fwd - t_bwd) / args.steps, 3),
+                   "bvh_nodes_per_ray": round((c_fwd["nodes_visited"] + c_bwd["nodes_visited"]) / max(rays_local, 1), 2),
+                   "tris_per_ray": round((c_fwd["tris_tested"] + c_bwd["tris_tested"]) / max(rays_local, 1), 2),
+                   "red_v4_per_scatter": round(c_bwd["red_v4"] / max(c_bwd["grad_scatters"], 1), 3)},
         "clocks": clock_rec,
         "gpu_launches": 2 * args.steps,
         "roofline": {"bound": "hbm", "kernel": f"k_backward<{args.integrator}> (PRB replay + adjoint + gradient scatter)",

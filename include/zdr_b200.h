@@ -82,6 +82,11 @@ typedef struct zdr_params {
     int32_t reserved[1];
 } zdr_params;
 #define ZDR_FLAG_STATS 1      /* also count BVH nodes visited / triangles tested (slower) */
+/* texture-gradient scatter (replaces the atomic_fetch_add of interaction.py:67-70). Default (neither
+ * bit): chosen per launch from the uv extent of instance 0 in texels — warp-aggregated when the
+ * textured object covers fewer than 64 texels in u or v (uniform / uv-less meshes), plain otherwise. */
+#define ZDR_FLAG_SCATTER_AGGREGATE 2
+#define ZDR_FLAG_SCATTER_PLAIN 4
 
 typedef struct zdr_scene zdr_scene;
 

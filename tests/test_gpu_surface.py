@@ -1,0 +1,158 @@
+"""The torch surface (zdr_b200.Scene) on the GPU: the drop-in contract of render.py:31-257."""
+import numpy as np
+import pytest
+import torch
+
+from zdr_b200._abi import INTEGRATORS, make_params
+
+from . import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def scene():
+    from zdr_b200 import Scene
+    sc = Scene(scenes.cbox_path_models(), integrator="direct")
+    sc.camera = scenes.CBOX_CAMERA.copy()
+    return sc
+
+
+def test_render_shapes_and_alpha(scene):
+    mat = torch.from_numpy(scenes.random_material((128, 128), 0)).cuda()
+    img = scene.render(mat, res=(96, 64), spp=4)
+    assert img.shape == (64, 96, 4) and img.dtype == torch.float32 and img.is_cuda      # (H, W, 4), render.py:163
+    assert bool((img[..., 3] == 1).all()) and float(img[..., :3].max()) > 0
+
+
+@pytest.mark.parametrize("integrator", ["collocated", "direct", "path"])
+def test_autograd_matches_oracle(oracle, integrator):
+    from zdr_b200 import Scene
+    models = scenes.cbox_path_models()
+    sc = Scene(models, integrator=integrator)
+    sc.camera = scenes.CBOX_CAMERA.copy()
+    sc.max_depth = 6
+    mat_np = scenes.random_material((96, 96), 3)
+    mat = torch.from_numpy(mat_np).cuda().requires_grad_()
+    img = sc.render(mat, res=(64, 48), spp=4, seed=5)
+    w = torch.from_numpy(np.random.default_rng(1).uniform(0.5, 1.5, (48, 64, 4)).astype(np.float32)).cuda()
+    (img * w).sum().backward()
+    o = oracle.OracleScene(models)
+    ref_img = o.render_forward(INTEGRATORS[integrator], make_params(scenes.CBOX_CAMERA, (64, 48), mat_np.shape, 4, 5, max_depth=6), mat_np)
+    ref_grad = o.render_backward(INTEGRATORS[integrator], make_params(scenes.CBOX_CAMERA, (64, 48), mat_np.shape, 4, 6, max_depth=6), mat_np,
+                                 w.cpu().numpy())          # seed+1, render.py:196
+    assert np.array_equal(img.detach().cpu().numpy(), ref_img)
+    assert rel_l2(mat.grad.cpu().numpy(), ref_grad) <= 1e-3
+
+
+def test_backward_uses_forward_camera_and_lights(scene, oracle):
+    """render.py:207-218: camera and emissions are snapshotted at forward time."""
+    mat_np = scenes.random_material((64, 64), 2)
+    mat = torch.from_numpy(mat_np).cuda().requires_grad_()
+    img = scene.render(mat, res=(48, 48), spp=2, seed=1)
+    cam_bak = scene.camera
+    moved = scenes.CBOX_CAMERA.copy()
+    moved.origin = scenes.float3(0.5, 2.0, 5.0)
+    scene.camera = moved                                    # changed between forward and backward
+    img[..., :3].sum().backward()
+    assert scene.camera is moved                            # restored after the adjoint render (render.py:222)
+    scene.camera = cam_bak
+    o = oracle.OracleScene(scenes.cbox_path_models())
+    d = np.ones((48, 48, 4), np.float32)
+    d[..., 3] = 0
+    ref = o.render_backward(INTEGRATORS["direct"], make_params(scenes.CBOX_CAMERA, (48, 48), mat_np.shape, 2, 2), mat_np, d)
+    assert rel_l2(mat.grad.cpu().numpy(), ref) <= 1e-3
+
+
+def test_non_contiguous_grad_output_and_stream(scene):
+    mat = torch.from_numpy(scenes.random_material((64, 64), 2)).cuda().requires_grad_()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):                              # the library enqueues on torch's current stream
+        img = scene.render(mat, res=(32, 32), spp=2)
+        loss = img.permute(1, 0, 2).flip(0).sum()           # non-contiguous grad_output (render.py:181)
+        loss.backward()
+    s.synchronize()
+    assert torch.isfinite(mat.grad).all() and float(mat.grad.abs().sum()) > 0
+
+
+def test_uniform_texture_contention_case(oracle):
+    """C2/C4 shape: uv == 0 (cbox-combined.obj has no vt) sends every scatter of the image to one texel;
+    the warp-aggregated scatter must still sum to the oracle's gradient."""
+    from zdr_b200 import Scene
+    models = scenes.cbox_direct_models()
+    sc = Scene(models, integrator="direct")
+    sc.camera = scenes.CBOX_CAMERA.copy()
+    mat_np = scenes.constant_material((8, 8))
+    mat = torch.from_numpy(mat_np).cuda().requires_grad_()
+    sc.reset_counters()
+    img = sc.render(mat, res=(128, 128), spp=8, seed=0)
+    img[..., :3].sum().backward()
+    c = sc.counters()
+    o = oracle.OracleScene(models)
+    d = np.ones((128, 128, 4), np.float32)
+    d[..., 3] = 0
+    ref = o.render_backward(INTEGRATORS["direct"], make_params(scenes.CBOX_CAMERA, (128, 128), mat_np.shape, 8, 1), mat_np, d)
+    g = mat.grad.cpu().numpy()
+    assert (g != 0).sum() == (ref != 0).sum() == 4
+    assert rel_l2(g, ref) <= 1e-3
+    assert c["red_v4"] * 8 < c["grad_scatters"] * 4         # aggregation: far fewer reductions than texel writes
+
+
+def test_scatter_modes_agree(oracle):
+    """plain and warp-aggregated scatter are two schedules of the same sum."""
+    from zdr_b200 import Scene
+    sc = Scene(scenes.cbox_path_models(), integrator="path")
+    sc.camera = scenes.CBOX_CAMERA.copy()
+    sc.max_depth = 5
+    grads = {}
+    for mode in ("plain", "aggregate", "auto"):
+        sc.scatter_mode = mode
+        mat = torch.from_numpy(scenes.random_material((64, 64), 7)).cuda().requires_grad_()
+        sc.render(mat, res=(64, 64), spp=4, seed=3)[..., :3].sum().backward()
+        grads[mode] = mat.grad.cpu().numpy()
+    assert rel_l2(grads["aggregate"], grads["plain"]) < 1e-5
+    assert rel_l2(grads["auto"], grads["plain"]) < 1e-5
+
+
+def test_errors_are_python_exceptions(scene):
+    with pytest.raises(AssertionError):
+        scene.render(torch.zeros((4, 4, 3), device="cuda"), res=(8, 8), spp=1)          # render.py:160
+    with pytest.raises(ValueError):
+        scene.render(torch.zeros((4, 4, 4)), res=(8, 8), spp=1)                           # host tensor
+    with pytest.raises(AssertionError):
+        scene.update_lights([None])                                                      # render.py:141
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_nccl_equals_single(tmp_path):
+    """run with gpurun --gpus 2: Scene.distribute over NCCL vs the single-GPU render."""
+    import subprocess
+    import sys
+    script = tmp_path / "w.py"
+    script.write_text('''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["ZDR_ROOT"])
+from tests import scenes
+from zdr_b200 import Scene
+rank = int(os.environ["RANK"]); torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+sc = Scene(scenes.cbox_path_models(), integrator="path", device=rank); sc.camera = scenes.CBOX_CAMERA.copy(); sc.max_depth = 6
+mat = torch.from_numpy(scenes.random_material((128, 128), 0)).cuda().requires_grad_()
+single = sc.render(mat, res=(96, 80), spp=4, seed=2); single[..., :3].sum().backward(); g1 = mat.grad.clone(); mat.grad = None
+sc.distribute()
+multi = sc.render(mat, res=(96, 80), spp=4, seed=2); multi[..., :3].sum().backward()
+assert torch.equal(single, multi), "image differs"
+err = float((mat.grad - g1).norm() / g1.norm()); assert err < 1e-5, err
+dist.destroy_process_group()
+print("rank", rank, "ok", err)
+''')
+    import os
+    env = dict(os.environ, ZDR_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29671", str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -98,6 +98,7 @@ struct zdr_scene {
     int num_tris = 0;
     EnvMap env = {};
     unsigned long long* d_counters = nullptr;
+    float uv_lo[2] = {0.f, 0.f}, uv_hi[2] = {0.f, 0.f};   // uv bounds of instance 0, the textured object (direct.py:30)
     cudaStream_t own_stream = nullptr;       // for the *_host entry points and the probes
     DevBuf<float> s_mat, s_img, s_dimg, s_dmat, s_misc, s_misc2;
     DevBuf<int> s_int, s_int2;
@@ -188,6 +189,15 @@ int make_args(zdr_scene* s, const zdr_params* p, RenderArgs* a) {
     a->shard_index = p->shard_count > 1 ? p->shard_index : 0;
     a->tex.rx = p->tex_res_x; a->tex.ry = p->tex_res_y; a->tex.bilinear = p->bilinear;
     a->counters = s->d_counters;
+    // gradient scatter strategy: warp aggregation pays when many lanes of a warp share a footprint,
+    // i.e. when the textured object's uv range covers only a few texels (uniform / uv-less meshes)
+    if (p->flags & ZDR_FLAG_SCATTER_AGGREGATE) a->aggregate_scatter = 1;
+    else if (p->flags & ZDR_FLAG_SCATTER_PLAIN) a->aggregate_scatter = 0;
+    else {
+        const float span_x = (s->uv_hi[0] - s->uv_lo[0]) * (float)(p->tex_res_x - 1);
+        const float span_y = (s->uv_hi[1] - s->uv_lo[1]) * (float)(p->tex_res_y - 1);
+        a->aggregate_scatter = !(span_x >= 64.0f && span_y >= 64.0f);
+    }
     return ZDR_OK;
 }
 
@@ -304,6 +314,15 @@ ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
         }
     }
     if (!(lo.x <= hi.x)) return fail(ZDR_ERR_ARG, "commit: non-finite geometry");
+    {
+        const Mesh& m0 = s->meshes[0];
+        s->uv_lo[0] = s->uv_lo[1] = INFINITY; s->uv_hi[0] = s->uv_hi[1] = -INFINITY;
+        for (size_t v = 0; v < m0.verts.size() / 8; ++v)
+            for (int k = 0; k < 2; ++k) {
+                s->uv_lo[k] = fminf(s->uv_lo[k], m0.verts[8 * v + 3 + k]);
+                s->uv_hi[k] = fmaxf(s->uv_hi[k], m0.verts[8 * v + 3 + k]);
+            }
+    }
     CK(cudaDeviceSynchronize());
     free_bvh(&s->bvh);
     cudaFree(s->d_inst); cudaFree(s->d_lights);

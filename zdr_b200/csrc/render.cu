@@ -9,24 +9,27 @@ namespace {
 
 // per-thread tallies, reduced per warp and flushed with one atomic per counter per warp
 struct Tally {
-    unsigned closest, any, scatter, shaded, samples;
+    unsigned closest, any, scatter, red, shaded, samples;
     TraceStats ts;
 };
 
-template <bool STATS>
+template <bool STATS, bool AGG = false>
 struct Ctx {
     const RenderArgs& a;
     Tally& tl;
     ZDR_DEV Hit closest(const Ray& r) { tl.closest++; return trace<false, STATS>(a.sc, r, tl.ts); }
     ZDR_DEV bool occluded(const Ray& r) { tl.any++; return trace<true, STATS>(a.sc, r, tl.ts).inst >= 0; }
-    ZDR_DEV void scatter(float2 uv, float4 g) { tl.scatter++; write_bsdf_grad(a.tex, uv, g); }
+    ZDR_DEV void scatter(float2 uv, float4 g) {
+        tl.scatter++;
+        tl.red += AGG ? write_bsdf_grad_aggregated(a.tex, uv, g) : write_bsdf_grad(a.tex, uv, g);
+    }
 };
 
 ZDR_DEV Ray make_ray(float3 o, float3 d, float tmin, float tmax) { Ray r; r.o = o; r.d = d; r.tmin = tmin; r.tmax = tmax; return r; }
 
 // ------------------------------------------------------------------------------ collocated.py
-template <bool STATS>
-ZDR_DEV float3 collocated_estimator(Ctx<STATS>& c, const Ray& ray) {               // collocated.py:10-31
+template <class CTX>
+ZDR_DEV float3 collocated_estimator(CTX& c, const Ray& ray) {               // collocated.py:10-31
     const Hit hit = c.closest(ray);
     if (hit.inst < 0) return f3(0.f, 0.f, 0.f);
     const Interaction it = surface_interact(c.a.sc, hit);
@@ -40,8 +43,8 @@ ZDR_DEV float3 collocated_estimator(Ctx<STATS>& c, const Ray& ray) {            
     const float li = 1.0f * (inv * inv);
     return beta * li;
 }
-template <bool STATS>
-ZDR_DEV void collocated_estimator_backward(Ctx<STATS>& c, const Ray& ray, float3 le_grad) {   // collocated.py:34-57
+template <class CTX>
+ZDR_DEV void collocated_estimator_backward(CTX& c, const Ray& ray, float3 le_grad) {   // collocated.py:34-57
     const Hit hit = c.closest(ray);
     if (hit.inst < 0) return;
     const Interaction it = surface_interact(c.a.sc, hit);
@@ -62,8 +65,8 @@ ZDR_DEV float3 env_emission(const SceneView& sc, float3 dir) {                  
 // ---------------------------------------------------------------------------------- direct.py
 // Shared walk of direct_estimator (direct.py:20-85) and direct_estimator_backward (:88-167):
 // BWD=false returns radiance; BWD=true accumulates the BRDF adjoints and scatters once.
-template <bool BWD, bool STATS>
-ZDR_DEV float3 direct_walk(Ctx<STATS>& c, const Ray& ray, Sampler& sampler, float3 le_grad) {
+template <bool BWD, class CTX>
+ZDR_DEV float3 direct_walk(CTX& c, const Ray& ray, Sampler& sampler, float3 le_grad) {
     const SceneView& sc = c.a.sc;
     const float3 zero = f3(0.f, 0.f, 0.f);
     const Hit hit = c.closest(ray);
@@ -157,7 +160,7 @@ ZDR_DEV unsigned warp_sum(unsigned v) {
     return v;
 }
 ZDR_DEV void flush_tally(const RenderArgs& a, const Tally& t) {
-    const unsigned v[C_NUM] = {t.closest, t.any, t.ts.nodes, t.ts.tris, t.scatter, t.scatter * 4u, t.shaded, t.samples};
+    const unsigned v[C_NUM] = {t.closest, t.any, t.ts.nodes, t.ts.tris, t.scatter, t.red, t.shaded, t.samples};
 #pragma unroll
     for (int i = 0; i < C_NUM; ++i) {
         const unsigned s = warp_sum(v[i]);
@@ -201,12 +204,12 @@ __global__ void __launch_bounds__(kBlockThreads) k_forward(const __grid_constant
     flush_tally(a, tl);
 }
 
-template <int INTEGRATOR, bool STATS>
+template <int INTEGRATOR, bool STATS, bool AGG>
 __global__ void __launch_bounds__(kBlockThreads) k_backward(const __grid_constant__ RenderArgs a) {
     int x, y;
     pixel_of_thread(a, x, y);
     Tally tl = {};
-    Ctx<STATS> c{a, tl};
+    Ctx<STATS, AGG> c{a, tl};
     if (x < a.W && y < a.row1) {
         const float4 g = __ldg(a.d_image + ((size_t)x + (size_t)y * a.W));          // integrator.py:38-40
         float3 le_grad = f3(g.x / (float)a.spp, g.y / (float)a.spp, g.z / (float)a.spp);
@@ -234,13 +237,13 @@ __global__ void __launch_bounds__(kBlockThreads) k_backward(const __grid_constan
 // together.  Every pixel still runs its samples in order in one thread: the image keeps the
 // reference's accumulation order (integrator.py:15-28) and is bit-identical to the oracle's.
 //   phase 0: radiance walk (L accumulates);  phase 1 (BWD only): adjoint walk (L = Le remaining).
-template <bool BWD, bool STATS>
+template <bool BWD, bool STATS, bool AGG>
 __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant__ RenderArgs a) {
     int x, y;
     pixel_of_thread(a, x, y);
     const SceneView& sc = a.sc;
     Tally tl = {};
-    Ctx<STATS> c{a, tl};
+    Ctx<STATS, AGG> c{a, tl};
     const bool corrected = a.prb_mode == ZDR_PRB_CORRECTED;
     const float specular = 0.04f;
     const float3 zero = f3(0.f, 0.f, 0.f);
@@ -435,8 +438,13 @@ cudaError_t launch_fwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
 }
 template <int I>
 cudaError_t launch_bwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
-    if (stats) k_backward<I, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
-    else k_backward<I, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+    if (a.aggregate_scatter) {
+        if (stats) k_backward<I, true, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+        else k_backward<I, false, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+    } else {
+        if (stats) k_backward<I, true, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+        else k_backward<I, false, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+    }
     return cudaGetLastError();
 }
 
@@ -448,8 +456,8 @@ cudaError_t launch_forward(int integrator, const RenderArgs& a, bool stats, cuda
         case ZDR_COLLOCATED: return launch_fwd_i<ZDR_COLLOCATED>(a, stats, s);
         case ZDR_DIRECT: return launch_fwd_i<ZDR_DIRECT>(a, stats, s);
         default:
-            if (stats) k_path<false, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
-            else k_path<false, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+            if (stats) k_path<false, true, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+            else k_path<false, false, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
             return cudaGetLastError();
     }
 }
@@ -459,8 +467,13 @@ cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cud
         case ZDR_COLLOCATED: return launch_bwd_i<ZDR_COLLOCATED>(a, stats, s);
         case ZDR_DIRECT: return launch_bwd_i<ZDR_DIRECT>(a, stats, s);
         default:
-            if (stats) k_path<true, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
-            else k_path<true, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+            if (a.aggregate_scatter) {
+                if (stats) k_path<true, true, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+                else k_path<true, false, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+            } else {
+                if (stats) k_path<true, true, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+                else k_path<true, false, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+            }
             return cudaGetLastError();
     }
 }

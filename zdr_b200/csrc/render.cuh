@@ -14,7 +14,8 @@ struct RenderArgs {
     float tan_half_fov;
     int W, H, spp, seed, use_tent, max_depth, rr_depth, use_mis, prb_mode;
     int row0, row1, it0, it1;
-    int shard_index, shard_count;   // 8-row CTA tiles of [row0,row1) are dealt round-robin to shard_count shards
+    int shard_index, shard_count;
+    int aggregate_scatter;    // warp-aggregated gradient scatter (shading.cuh) instead of plain red.v4   // 8-row CTA tiles of [row0,row1) are dealt round-robin to shard_count shards
     float4* image;            // forward: (H,W) float4
     const float4* d_image;    // backward: (H,W) float4 cotangent
     float* samples_out;       // probe: (H,W,spp,3) un-clamped per-sample radiance, or null

@@ -73,20 +73,100 @@ ZDR_DEV void red_add_f4(float4* addr, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
-ZDR_DEV void write_single_bsdf_grad(const TexView& t, int cx, int cy, float k, float4 d) {
-    cx = clampi(cx, 0, t.rx - 1); cy = clampi(cy, 0, t.ry - 1);
-    red_add_f4(t.dmat + (cx + t.rx * cy), make_float4(k * d.x, k * d.y, k * d.z, k * d.w));
+// Warp-aggregated scatter (replaces the contended atomic_fetch_add the reference's README flags).
+// Lanes of the warp whose bilinear footprint starts at the SAME texel are found with ONE match.any
+// on the footprint key; a lane that is alone (the common case on a uv-mapped, high-resolution
+// texture) issues its four red.v4 directly, so the uncontended path costs one MATCH.  Lanes that
+// share a footprint — neighbouring pixels' primary hits, and whole warps when the texture is
+// uniform or the mesh has no uv (C2/C4: uv == 0) — sum their contributions in lane order through
+// shuffles and the group's lowest lane issues the reductions: 32 serialised L2 atomics on one
+// address become one.  Exact-zero contributions are not issued (adding 0.0 is the identity).
+// Returns the number of red.v4 this lane issued.
+ZDR_DEV bool is_zero4(float4 v) { return v.x == 0.0f && v.y == 0.0f && v.z == 0.0f && v.w == 0.0f; }
+ZDR_DEV float4 group_sum4(unsigned peers, bool full, float4 v) {
+    if (full) {        // all 32 lanes share the key: butterfly
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+            v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+        }
+        return v;
+    }
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (unsigned m = peers; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        sum.x += __shfl_sync(peers, v.x, src); sum.y += __shfl_sync(peers, v.y, src);
+        sum.z += __shfl_sync(peers, v.z, src); sum.w += __shfl_sync(peers, v.w, src);
+    }
+    return sum;
 }
-ZDR_DEV void write_bsdf_grad(const TexView& t, float2 uv, float4 d) {      // interaction.py:72-89
+ZDR_DEV int texel_index(const TexView& t, int cx, int cy) {                // interaction.py:37-39, address mode CLAMP
+    return clampi(cx, 0, t.rx - 1) + t.rx * clampi(cy, 0, t.ry - 1);
+}
+ZDR_DEV float4 scale4(float k, float4 d) { return make_float4(k * d.x, k * d.y, k * d.z, k * d.w); }
+static __device__ __noinline__ unsigned write_bsdf_grad_agg_nl(float4* __restrict__ dmat, int rx, int ry, int bilinear, float uvx, float uvy,
+                                                            float dx, float dy, float dz, float dw) {  // interaction.py:62-89
+    TexView t;
+    t.mat = nullptr; t.dmat = dmat; t.rx = rx; t.ry = ry; t.bilinear = bilinear;
+    const float2 uv = make_float2(uvx, uvy);
+    const float4 d = make_float4(dx, dy, dz, dw);
     const float px = uv.x * (float)(t.rx - 1), py = (1.0f - uv.y) * (float)(t.ry - 1);
-    if (!t.bilinear) { write_single_bsdf_grad(t, f2i(px + 0.4999f), f2i(py + 0.4999f), 1.0f, d); return; }
+    int idx[4];
+    float4 v[4];
+    int n;
+    if (!t.bilinear) {
+        n = 1;
+        idx[0] = texel_index(t, f2i(px + 0.4999f), f2i(py + 0.4999f));
+        v[0] = d;
+    } else {
+        n = 4;
+        const int ix = f2i(px), iy = f2i(py);
+        const float ox = px - (float)ix, oy = py - (float)iy;
+        idx[0] = texel_index(t, ix, iy);         v[0] = scale4((1.0f - ox) * (1.0f - oy), d);
+        idx[1] = texel_index(t, ix, iy + 1);     v[1] = scale4((1.0f - ox) * oy, d);
+        idx[2] = texel_index(t, ix + 1, iy);     v[2] = scale4(ox * (1.0f - oy), d);
+        idx[3] = texel_index(t, ix + 1, iy + 1); v[3] = scale4(ox * oy, d);
+    }
+    const unsigned active = __activemask();
+    // lanes with equal first texel and equal far-corner texel have identical footprints
+    const unsigned peers = __match_any_sync(active, (unsigned long long)(unsigned)idx[0] << 32 | (unsigned)idx[n - 1]);
+    const int lane = threadIdx.x & 31;
+    unsigned issued = 0;
+    if (peers == (1u << lane)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < n && !is_zero4(v[k])) { red_add_f4(t.dmat + idx[k], v[k]); ++issued; }
+        return issued;
+    }
+    const bool full = peers == 0xffffffffu;
+    const bool leader = lane == __ffs(peers) - 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < n) {
+            const float4 sum = group_sum4(peers, full, v[k]);
+            if (leader && !is_zero4(sum)) { red_add_f4(t.dmat + idx[k], sum); ++issued; }
+        }
+    }
+    return issued;
+}
+
+ZDR_DEV unsigned write_bsdf_grad_aggregated(const TexView& t, float2 uv, float4 d) {
+    return write_bsdf_grad_agg_nl(t.dmat, t.rx, t.ry, t.bilinear, uv.x, uv.y, d.x, d.y, d.z, d.w);
+}
+// Plain scatter: one red.v4 per texel of the footprint (the reference issues four scalar atomics per
+// texel, interaction.py:67-70).  Used when the footprints of a warp are spread over the texture
+// (uv-mapped mesh, high-resolution texture): measured on C3, 3.81 of 4 reductions per scatter
+// survive aggregation, so the match + shuffle work is pure overhead there.
+ZDR_DEV unsigned write_bsdf_grad(const TexView& t, float2 uv, float4 d) {
+    const float px = uv.x * (float)(t.rx - 1), py = (1.0f - uv.y) * (float)(t.ry - 1);
+    if (!t.bilinear) { red_add_f4(t.dmat + texel_index(t, f2i(px + 0.4999f), f2i(py + 0.4999f)), d); return 1u; }
     const int ix = f2i(px), iy = f2i(py);
     const float ox = px - (float)ix, oy = py - (float)iy;
-    const float k00 = (1.0f - ox) * (1.0f - oy), k01 = (1.0f - ox) * oy, k10 = ox * (1.0f - oy), k11 = ox * oy;
-    write_single_bsdf_grad(t, ix, iy, k00, d);
-    write_single_bsdf_grad(t, ix, iy + 1, k01, d);
-    write_single_bsdf_grad(t, ix + 1, iy, k10, d);
-    write_single_bsdf_grad(t, ix + 1, iy + 1, k11, d);
+    red_add_f4(t.dmat + texel_index(t, ix, iy), scale4((1.0f - ox) * (1.0f - oy), d));
+    red_add_f4(t.dmat + texel_index(t, ix, iy + 1), scale4((1.0f - ox) * oy, d));
+    red_add_f4(t.dmat + texel_index(t, ix + 1, iy), scale4(ox * (1.0f - oy), d));
+    red_add_f4(t.dmat + texel_index(t, ix + 1, iy + 1), scale4(ox * oy, d));
+    return 4u;
 }
 
 // ---------------------------------------------------------------------------------------------
