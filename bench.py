@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--integrator", default="path", choices=["path", "direct", "collocated"])
     ap.add_argument("--ref-spp", type=int, default=2, help="samples per pixel (of --spp) one reference step renders")
     ap.add_argument("--cpu-spp", type=int, default=32, help="samples per pixel of the cpu_baseline sample")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "wavefront", "megakernel"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -212,14 +213,15 @@ def run_ours(args):
     scene = Scene(models, integrator=args.integrator, device=local_rank)
     scene.camera = cam.copy()
     scene.max_depth = args.depth
+    scene.schedule = args.schedule
     if world > 1:
         scene.shard = (rank, world)
     lib, h = scene._lib, scene._handle
     integ = INTEGRATORS[args.integrator]
     res = (args.res, args.res)
     shard = (rank, world) if world > 1 else None
-    pf = make_params(cam, res, mat_np.shape, args.spp, 0, max_depth=args.depth, shard=shard)
-    pb = make_params(cam, res, mat_np.shape, args.spp, 1, max_depth=args.depth, shard=shard)
+    pf = make_params(cam, res, mat_np.shape, args.spp, 0, max_depth=args.depth, shard=shard, schedule=args.schedule)
+    pb = make_params(cam, res, mat_np.shape, args.spp, 1, max_depth=args.depth, shard=shard, schedule=args.schedule)
     material = torch.from_numpy(mat_np).to(dev)
     image = torch.zeros((args.res, args.res, 4), dtype=torch.float32, device=dev)
     d_image = torch.ones_like(image)
@@ -250,8 +252,8 @@ def run_ours(args):
 
     # one instrumented pass (untimed): rays per step and the algorithmic bytes of each kernel
     scene.reset_counters()
-    pfs = make_params(cam, res, mat_np.shape, args.spp, 0, max_depth=args.depth, shard=shard, stats=True)
-    pbs = make_params(cam, res, mat_np.shape, args.spp, 1, max_depth=args.depth, shard=shard, stats=True)
+    pfs = make_params(cam, res, mat_np.shape, args.spp, 0, max_depth=args.depth, shard=shard, stats=True, schedule=args.schedule)
+    pbs = make_params(cam, res, mat_np.shape, args.spp, 1, max_depth=args.depth, shard=shard, stats=True, schedule=args.schedule)
     check(lib.zdr_render_forward(h, integ, C.byref(pfs), material.data_ptr(), image.data_ptr(), stream.cuda_stream))
     c_fwd = scene.counters()
     scene.reset_counters()

@@ -87,6 +87,11 @@ typedef struct zdr_params {
  * textured object covers fewer than 64 texels in u or v (uniform / uv-less meshes), plain otherwise. */
 #define ZDR_FLAG_SCATTER_AGGREGATE 2
 #define ZDR_FLAG_SCATTER_PLAIN 4
+/* schedule of the path integrator / PRB adjoint. Default (neither bit): wavefront kernels (path state
+ * in HBM, compacted live lists) from 2^21 camera samples per launch on, the one-kernel bounce state
+ * machine below that. Both produce bit-identical images. */
+#define ZDR_FLAG_WAVEFRONT 8
+#define ZDR_FLAG_MEGAKERNEL 16
 
 typedef struct zdr_scene zdr_scene;
 

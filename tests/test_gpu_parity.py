@@ -221,6 +221,10 @@ CASES = {
     "c3_path_small": (scenes.cbox_path_models, ZDR_PATH, (96, 96), 8, lambda: scenes.random_material((1024, 1024), 0), {"max_depth": 8}),
     "path_literal": (scenes.cbox_path_models, ZDR_PATH, (64, 64), 4, lambda: scenes.random_material((128, 128), 4), {"max_depth": 5, "prb_mode": _abi.ZDR_PRB_LITERAL}),
     "path_depth16": (scenes.cbox_path_models, ZDR_PATH, (48, 48), 4, lambda: scenes.random_material((128, 128), 5), {"max_depth": 16}),
+    # the wavefront schedule of the same integrator (default from 2^21 camera samples per launch on)
+    "c3_path_small_wavefront": (scenes.cbox_path_models, ZDR_PATH, (96, 96), 8, lambda: scenes.random_material((1024, 1024), 0), {"max_depth": 8, "schedule": "wavefront"}),
+    "path_literal_wavefront": (scenes.cbox_path_models, ZDR_PATH, (64, 64), 4, lambda: scenes.random_material((128, 128), 4), {"max_depth": 5, "prb_mode": _abi.ZDR_PRB_LITERAL, "schedule": "wavefront"}),
+    "path_depth1_wavefront": (scenes.cbox_path_models, ZDR_PATH, (40, 24), 3, lambda: scenes.random_material((64, 64), 6), {"max_depth": 1, "schedule": "wavefront"}),
 }
 
 
@@ -271,9 +275,10 @@ def test_backward_parity(oracle, case_cache, name):
     assert (cg["closest_rays"], cg["any_rays"]) == (oc, oa)
 
 
-def test_shard_rows_and_samples(oracle, case_cache):
+@pytest.mark.parametrize("case", ["c3_path_small", "c3_path_small_wavefront"])
+def test_shard_rows_and_samples(oracle, case_cache, case):
     """Row tiles are bit-identical to the full render; sample-range shards sum to it (§8e)."""
-    c = _run_case(oracle, "c3_path_small", case_cache)
+    c = _run_case(oracle, case, case_cache)
     W, H = c["res"]
     full = c["g"].forward(c["integ"], make_params(scenes.CBOX_CAMERA, c["res"], c["mat"].shape, c["spp"], 0, **c["kw"]), c["mat"])
     acc = np.zeros_like(full)
@@ -282,6 +287,11 @@ def test_shard_rows_and_samples(oracle, case_cache):
         part = c["g"].forward(c["integ"], p, c["mat"])
         assert not part[:r0].any() and not part[r1:].any()
         acc += part
+    assert np.array_equal(bits(acc), bits(full))
+    acc = np.zeros_like(full)
+    for k in range(3):                                   # round-robin 8-row tiles (multi-GPU sharding)
+        p = make_params(scenes.CBOX_CAMERA, c["res"], c["mat"].shape, c["spp"], 0, shard=(k, 3), **c["kw"])
+        acc += c["g"].forward(c["integ"], p, c["mat"])
     assert np.array_equal(bits(acc), bits(full))
     dimg = np.ones((H, W, 4), np.float32)
     pf = make_params(scenes.CBOX_CAMERA, c["res"], c["mat"].shape, c["spp"], 1, **c["kw"])

@@ -15,6 +15,8 @@ PRB_MODES = {"literal": ZDR_PRB_LITERAL, "corrected": ZDR_PRB_CORRECTED}
 ZDR_NUM_COUNTERS = 8
 ZDR_FLAG_STATS = 1
 ZDR_FLAG_SCATTER_AGGREGATE, ZDR_FLAG_SCATTER_PLAIN = 2, 4
+ZDR_FLAG_WAVEFRONT, ZDR_FLAG_MEGAKERNEL = 8, 16
+SCHEDULES = {"auto": 0, "wavefront": ZDR_FLAG_WAVEFRONT, "megakernel": ZDR_FLAG_MEGAKERNEL}
 SCATTER_MODES = {"auto": 0, "aggregate": ZDR_FLAG_SCATTER_AGGREGATE, "plain": ZDR_FLAG_SCATTER_PLAIN}
 COUNTER_NAMES = ("closest_rays", "any_rays", "nodes_visited", "tris_tested",
                  "grad_scatters", "red_v4", "shaded_vertices", "camera_samples")
@@ -46,7 +48,7 @@ def wrap_i32(x: int) -> int:
 
 def make_params(camera, res, tex_shape, spp, seed, *, use_tent_filter=True, max_depth=16, rr_depth=2,
                 use_mis=True, bilinear=True, prb_mode=ZDR_PRB_CORRECTED, rows=None, its=None, shard=None,
-                stats=False, scatter="auto") -> ZdrParams:
+                stats=False, scatter="auto", schedule="auto") -> ZdrParams:
     p = ZdrParams()
     p.cam_fov = float(camera.fov)
     p.cam_origin[:] = list(camera.origin)
@@ -61,7 +63,7 @@ def make_params(camera, res, tex_shape, spp, seed, *, use_tent_filter=True, max_
     p.row0, p.row1 = (0, p.height) if rows is None else (int(rows[0]), int(rows[1]))
     p.it0, p.it1 = (0, p.spp) if its is None else (int(its[0]), int(its[1]))
     p.shard_index, p.shard_count = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
-    p.flags = (ZDR_FLAG_STATS if stats else 0) | SCATTER_MODES[scatter]
+    p.flags = (ZDR_FLAG_STATS if stats else 0) | SCATTER_MODES[scatter] | SCHEDULES[schedule]
     return p
 
 

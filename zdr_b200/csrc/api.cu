@@ -101,6 +101,8 @@ struct zdr_scene {
     float uv_lo[2] = {0.f, 0.f}, uv_hi[2] = {0.f, 0.f};   // uv bounds of instance 0, the textured object (direct.py:30)
     cudaStream_t own_stream = nullptr;       // for the *_host entry points and the probes
     DevBuf<float> s_mat, s_img, s_dimg, s_dmat, s_misc, s_misc2;
+    DevBuf<char> s_wf;                       // wavefront path state (render.cuh WfState)
+    int num_sms = 148;
     DevBuf<int> s_int, s_int2;
 };
 
@@ -201,6 +203,42 @@ int make_args(zdr_scene* s, const zdr_params* p, RenderArgs* a) {
     return ZDR_OK;
 }
 
+// Path integrator schedule: the wavefront kernels pay a fixed ~20 launches per batch, the one-kernel
+// state machine does not; small jobs stay on the latter.  Returns 1 and fills a->wf when the
+// wavefront path is to be used.
+int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArgs* a, bool* use) {
+    *use = false;
+    if (integrator != ZDR_PATH) return ZDR_OK;
+    const long long rows = (long long)(p->row1 - p->row0 + a->shard_count - 1) / a->shard_count + 8;
+    const long long pixels = (long long)p->width * rows;
+    const long long samples = pixels * (p->it1 - p->it0);
+    if (p->flags & ZDR_FLAG_MEGAKERNEL) return ZDR_OK;
+    if (!(p->flags & ZDR_FLAG_WAVEFRONT) && samples < (1ll << 21)) return ZDR_OK;
+    const long long target_slots = 1ll << 24;                                   // ~1.7 GB of path state
+    long long S = target_slots / (pixels > 0 ? pixels : 1);
+    if (S < 1) S = 1;
+    if (S > p->it1 - p->it0) S = p->it1 - p->it0;
+    const size_t slots = (size_t)(pixels * S);
+    const size_t bytes = slots * wf_bytes_per_slot() + 256;
+    cudaError_t e = s->s_wf.reserve(bytes);
+    if (e != cudaSuccess) return fail(ZDR_ERR_CUDA, "wavefront state (%zu MiB): %s", bytes >> 20, cudaGetErrorString(e));
+    char* base = s->s_wf.p;
+    WfState& w = a->wf;
+    w.A = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
+    w.B = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
+    w.C = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
+    w.D = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
+    w.H = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
+    w.R = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
+    w.list[0] = reinterpret_cast<int*>(base); base += slots * sizeof(int);
+    w.list[1] = reinterpret_cast<int*>(base); base += slots * sizeof(int);
+    w.counts = reinterpret_cast<int*>(base);
+    w.S = (int)S;
+    w.num_sms = s->num_sms;
+    *use = true;
+    return ZDR_OK;
+}
+
 inline bool want_stats(const zdr_params* p) { return (p->flags & ZDR_FLAG_STATS) != 0; }
 
 }  // namespace
@@ -248,6 +286,7 @@ ZDR_EXPORT int zdr_scene_create(zdr_scene** out, int device) {
         delete s;
         return fail(ZDR_ERR_CUDA, "scene_create: %s", cudaGetErrorString(e));
     }
+    cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, device);
     *out = s;
     return ZDR_OK;
 }
@@ -261,7 +300,7 @@ ZDR_EXPORT void zdr_scene_destroy(zdr_scene* s) {
     cudaFree(s->d_inst); cudaFree(s->d_lights); cudaFree(s->d_counters);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     s->s_mat.release(); s->s_img.release(); s->s_dimg.release(); s->s_dmat.release(); s->s_misc.release();
-    s->s_misc2.release(); s->s_int.release(); s->s_int2.release();
+    s->s_misc2.release(); s->s_int.release(); s->s_int2.release(); s->s_wf.release();
     delete s;
 }
 
@@ -396,7 +435,10 @@ ZDR_EXPORT int zdr_render_forward(zdr_scene* s, int integrator, const zdr_params
     if ((rc = make_args(s, p, &a))) return rc;
     a.tex.mat = reinterpret_cast<const float4*>(material_dev);
     a.image = reinterpret_cast<float4*>(image_dev);
-    CK(launch_forward(integrator, a, want_stats(p), (cudaStream_t)stream));
+    bool wavefront;
+    if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;
+    if (wavefront) CK(launch_path_wavefront(false, a, want_stats(p), (cudaStream_t)stream));
+    else CK(launch_forward(integrator, a, want_stats(p), (cudaStream_t)stream));
     return ZDR_OK;
 }
 
@@ -411,7 +453,10 @@ ZDR_EXPORT int zdr_render_backward(zdr_scene* s, int integrator, const zdr_param
     a.tex.mat = reinterpret_cast<const float4*>(material_dev);
     a.tex.dmat = reinterpret_cast<float4*>(d_material_dev);
     a.d_image = reinterpret_cast<const float4*>(d_image_dev);
-    CK(launch_backward(integrator, a, want_stats(p), (cudaStream_t)stream));
+    bool wavefront;
+    if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;
+    if (wavefront) CK(launch_path_wavefront(true, a, want_stats(p), (cudaStream_t)stream));
+    else CK(launch_backward(integrator, a, want_stats(p), (cudaStream_t)stream));
     return ZDR_OK;
 }
 
@@ -426,6 +471,7 @@ ZDR_EXPORT int zdr_render_forward_host(zdr_scene* s, int integrator, const zdr_p
     CK(s->s_img.reserve(nimg));
     cudaStream_t st = s->own_stream;
     CK(cudaMemcpyAsync(s->s_mat.p, material_host, sizeof(float) * nmat, cudaMemcpyHostToDevice, st));
+    if (p->shard_count > 1) CK(cudaMemsetAsync(s->s_img.p, 0, sizeof(float) * nimg, st));      // rows of the other shards
     if ((rc = zdr_render_forward(s, integrator, p, s->s_mat.p, s->s_img.p, st))) return rc;
     const size_t off = (size_t)p->row0 * p->width * 4, cnt = (size_t)(p->row1 - p->row0) * p->width * 4;
     CK(cudaMemcpyAsync(image_host + off, s->s_img.p + off, sizeof(float) * cnt, cudaMemcpyDeviceToHost, st));
@@ -551,7 +597,10 @@ ZDR_EXPORT int zdr_probe_render_samples(zdr_scene* s, int integrator, const zdr_
     CK(cudaMemsetAsync(s->s_misc.p, 0, sizeof(float) * nout, st));
     a.tex.mat = reinterpret_cast<const float4*>(s->s_mat.p);
     a.samples_out = s->s_misc.p;
-    CK(launch_forward(integrator, a, want_stats(p), st));
+    bool wavefront;
+    if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;
+    if (wavefront) CK(launch_path_wavefront(false, a, want_stats(p), st));
+    else CK(launch_forward(integrator, a, want_stats(p), st));
     CK(cudaMemcpyAsync(out_host, s->s_misc.p, sizeof(float) * nout, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return ZDR_OK;

@@ -388,6 +388,257 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
     flush_tally(a, tl);
 }
 
+// ------------------------------------------------------------------------------ wavefront path tracer
+// The same path integrator / PRB adjoint as k_path, cut at the closest-hit query into two small
+// kernels per bounce that run over compacted lists of live paths kept in HBM:
+//   k_wf_generate : camera samples of a batch of S samples x P pixels -> path state, list of all slots
+//   k_wf_extend   : closest-hit traversal of every live path             (ray -> hit record)
+//   k_wf_shade    : everything between two closest-hit queries: emitter / miss / backface tests,
+//                   texture fetch, light sample + shadow ray, BSDF sample, Russian roulette, and in the
+//                   adjoint the BRDF adjoints + gradient scatter; survivors are appended to the
+//                   next list with one warp-aggregated atomic per warp
+//   k_wf_accumulate: per pixel, adds the batch's finished samples IN SAMPLE ORDER (integrator.py:15-28)
+// Why: in the one-kernel form only ~15 of 32 lanes are active (finished lanes idle through
+// shading, traversal trip counts diverge), 128 registers cap occupancy at 16 warps/SM and the
+// code overflows the 32 KB instruction-cache level (profiles/r01d).  Here every warp of the shade
+// stage starts with 32 live paths, each kernel is small, and the state traffic (~190 B per
+// bounce) is what the 7.7 TB/s of HBM3e are for.  Arithmetic per sample is unchanged (same device
+// functions), so images stay bit-identical to the oracle.
+constexpr int kWfThreads = 128;
+constexpr unsigned kWfPhaseBit = 1u << 8;
+
+ZDR_DEV unsigned wf_pack(int depth, int phase, int dimension) { return (unsigned)depth | (phase ? kWfPhaseBit : 0u) | ((unsigned)dimension << 12); }
+ZDR_DEV void wf_pixel(const RenderArgs& a, int pix, int& x, int& y) {
+    const int lr = pix / a.W;
+    x = pix - lr * a.W;
+    y = a.row0 + ((lr >> 3) * a.shard_count + a.shard_index) * 8 + (lr & 7);
+}
+ZDR_DEV int wf_stride() { return gridDim.x * blockDim.x; }
+
+template <bool BWD>
+__global__ void __launch_bounds__(kWfThreads) k_wf_generate(const __grid_constant__ RenderArgs a) {
+    const WfState& w = a.wf;
+    Tally tl = {};
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < w.nslots; slot += wf_stride()) {
+        const int j = slot / w.P, pix = slot - j * w.P;
+        int x, y;
+        wf_pixel(a, pix, x, y);
+        Sampler sampler = make_sampler(a.sc, x, y, a.seed, a.spp, w.it_base + j);
+        const Ray ray = camera_sample(a, x, y, sampler);
+        tl.samples++;
+        w.A[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, 1e30f);                              // prb.py:22
+        w.B[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(wf_pack(0, 0, sampler.dimension)));
+        w.C[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+        w.D[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!BWD) w.R[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w.list[0][slot] = slot;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { w.counts[0] = a.max_depth > 0 ? w.nslots : 0; w.counts[1] = 0; }
+    flush_tally(a, tl);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(kWfThreads) k_wf_extend(const __grid_constant__ RenderArgs a, int in) {
+    const WfState& w = a.wf;
+    const int n = *(volatile int*)(w.counts + in);
+    if (blockIdx.x == 0 && threadIdx.x == 0) w.counts[in ^ 1] = 0;      // the shade stage appends to it
+    Tally tl = {};
+    const int* __restrict__ list = w.list[in];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += wf_stride()) {
+        const int slot = list[i];
+        const float4 A = w.A[slot], B = w.B[slot];
+        tl.closest++;
+        w.H[slot] = trace_packed<STATS>(a.sc.nodes, a.sc.tris, a.sc.root_link, A.x, A.y, A.z, B.x, B.y, B.z, 0.0f, 1e30f, 0, &tl.ts);
+    }
+    flush_tally(a, tl);
+}
+
+template <bool BWD, bool STATS, bool AGG>
+__global__ void __launch_bounds__(kWfThreads) k_wf_shade(const __grid_constant__ RenderArgs a, int in) {
+    const WfState& w = a.wf;
+    const SceneView& sc = a.sc;
+    const int n = *(volatile int*)(w.counts + in);
+    const int n_round = (n + 31) & ~31;
+    const int* __restrict__ list = w.list[in];
+    int* __restrict__ out_list = w.list[in ^ 1];
+    Tally tl = {};
+    Ctx<STATS, AGG> c{a, tl};
+    const bool corrected = a.prb_mode == ZDR_PRB_CORRECTED;
+    const float specular = 0.04f;
+    const float3 zero = f3(0.f, 0.f, 0.f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += wf_stride()) {
+        bool survive = false;
+        int slot = 0;
+        if (i < n) {
+            slot = list[i];
+            const int j = slot / w.P, pix = slot - j * w.P;
+            int x, y;
+            wf_pixel(a, pix, x, y);
+            const int it = w.it_base + j;
+            const float4 A = w.A[slot], B = w.B[slot], C4 = w.C[slot], D4 = w.D[slot], H = w.H[slot];
+            Ray ray = make_ray(f3(A.x, A.y, A.z), f3(B.x, B.y, B.z), 0.0f, 1e30f);
+            float pdf_bsdf = A.w;
+            const unsigned packed = __float_as_uint(B.w);
+            int depth = (int)(packed & 0xffu), phase = (packed & kWfPhaseBit) ? 1 : 0;
+            Sampler sampler = make_sampler(sc, x, y, a.seed, a.spp, it);
+            sampler.dimension = (int)(packed >> 12);
+            float3 beta = f3(C4.x, C4.y, C4.z), L = f3(D4.x, D4.y, D4.z);
+            float3 le_grad = zero;
+            if (BWD) {                                                             // integrator.py:38-40
+                const float4 g = __ldg(a.d_image + ((size_t)x + (size_t)y * a.W));
+                le_grad = f3(g.x / (float)a.spp, g.y / (float)a.spp, g.z / (float)a.spp);
+                if (any_nan(le_grad)) le_grad = zero;
+            }
+            Hit hit;
+            hit.slot = __float_as_int(H.x); hit.u = H.y; hit.v = H.z; hit.t = H.w; hit.inst = -1; hit.prim = -1;
+            if (hit.slot >= 0) {
+                const float4* tp = sc.tris + 3 * (size_t)hit.slot;
+                hit.inst = __float_as_int(__ldg(tp + 1).w);
+                hit.prim = __float_as_int(__ldg(tp + 2).w);
+            }
+            bool end = false;
+            if (hit.inst < 0) {
+                if (phase == 0 && sc.env_count > 0) {                              // prb.py:26-31
+                    const float3 tex = env_texture(sc, direction_to_uv(ray.d));
+                    const float3 emission = corrected ? tex : beta * tex;
+                    const float mis_weight = balanced_heuristic(pdf_bsdf, env_sampled_light_pdf(sc, ray.d));
+                    L = L + (beta * mis_weight) * emission;
+                }
+                end = true;
+            } else {
+                const Interaction itx = surface_interact(sc, hit);
+                const float3 emission = inst_emission(sc, hit.inst);
+                if (backfacing(ray.d, itx)) {                                      // prb.py:35-36
+                    end = true;
+                } else if (any_pos(emission)) {                                    // prb.py:39-44 / :117-121
+                    const float mis_weight = balanced_heuristic(pdf_bsdf, sample_light_pdf(sc, ray.o, hit, itx.p));
+                    const float3 contrib = (beta * mis_weight) * emission;
+                    L = (phase == 0) ? L + contrib : L - contrib;
+                    end = true;
+                } else if ((phase == 0 || corrected) && hit.inst > 0) {            // prb.py:45-46
+                    end = true;
+                } else {
+                    tl.shaded++;
+                    float4 mat_grad = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 mat = read_bsdf(a.tex, itx.uv);
+                    const float3 diffuse = f3(mat.x, mat.y, mat.z);
+                    const float roughness = mat.w;
+                    const Onb onb = make_onb(itx.ns);
+                    const float3 wo_local = to_local(onb, -ray.d);
+                    const LightSample light = sample_light(sc, itx.p, sampler);                     // prb.py:57
+                    const bool occluded = c.occluded(make_ray(itx.p, light.wi, 1e-4f, light.dist));  // prb.py:58-59
+                    const float3 wi_light_local = to_local(onb, light.wi);
+                    if (!occluded && wi_light_local.z >= 1e-4f) {                                   // prb.py:61-66
+                        const float4 ev = ggx_eval(wo_local, wi_light_local, diffuse, specular, roughness);
+                        const float3 bsdf = f3(ev.x, ev.y, ev.z);
+                        pdf_bsdf = ev.w;
+                        const float mis_weight = balanced_heuristic(light.pdf, pdf_bsdf);
+                        const float dn = fmaxf(light.pdf, 1e-4f);
+                        const float3 contrib = (((beta * bsdf) * mis_weight) * light.eval) / dn;
+                        if (!BWD || phase == 0) {
+                            L = L + contrib;
+                        } else {
+                            const float3 cot = (((beta * mis_weight) * light.eval) / dn) * le_grad;   // prb.py:145
+                            mat_grad = mat_grad + ggx_brdf_grad_nl(wo_local, wi_light_local, specular, roughness, cot);
+                            L = L - contrib;                                                        // prb.py:147
+                        }
+                    }
+                    const float3 wi_local = ggx_sample(sc, wo_local, roughness, sampler);           // prb.py:69
+                    const float4 ev = ggx_eval(wo_local, wi_local, diffuse, specular, roughness);
+                    pdf_bsdf = ev.w;
+                    const float3 wi = to_world(onb, wi_local);
+                    if (dot(wi, itx.ng) < 1e-4f || wi_local.z < 1e-4f) {                            // prb.py:73-74
+                        end = true;
+                    } else {
+                        ray = make_ray(offset_ray_origin(itx.p, itx.ng), wi, 0.0f, 1e30f);          // prb.py:75
+                        const float3 bsdf = f3(ev.x, ev.y, ev.z);
+                        if (BWD && phase == 1) {
+                            float3 cot;
+                            if (corrected)
+                                cot = f3(bsdf.x != 0.0f ? L.x / bsdf.x * le_grad.x : 0.0f, bsdf.y != 0.0f ? L.y / bsdf.y * le_grad.y : 0.0f,
+                                         bsdf.z != 0.0f ? L.z / bsdf.z * le_grad.z : 0.0f);
+                            else
+                                cot = ((beta / pdf_bsdf) * L) * le_grad;                            // prb.py:162
+                            mat_grad = mat_grad + ggx_brdf_grad_nl(wo_local, wi_local, specular, roughness, cot);
+                        }
+                        beta = beta * (bsdf / pdf_bsdf);                                            // prb.py:76
+                        if (depth >= a.rr_depth) {                                                  // prb.py:78-87
+                            const float l = luminance(beta);
+                            if (l == 0.0f) {
+                                end = true;
+                            } else {
+                                const float q = fmaxf(l, 0.05f);
+                                const float r = sampler_next(sc, sampler);
+                                if (r >= q) end = true;
+                                else beta = beta / q;
+                            }
+                        }
+                    }
+                    if (BWD && phase == 1) {                                                        // prb.py:178-187
+                        if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad))
+                            c.scatter(itx.uv, mat_grad);
+                    }
+                    ++depth;
+                    if (depth >= a.max_depth) end = true;                                           // prb.py:23
+                }
+            }
+            if (end) {
+                if (BWD && phase == 0 && !any_nan(L)) {
+                    // prb.py:97-101: Le is known; walk the same path again from the camera with the original sampler state
+                    Sampler cam = make_sampler(sc, x, y, a.seed, a.spp, it);
+                    ray = camera_sample(a, x, y, cam);
+                    sampler.dimension = cam.dimension;
+                    beta = f3(1.f, 1.f, 1.f); pdf_bsdf = 1e30f; depth = 0; phase = 1;
+                    survive = true;
+                } else if (!BWD) {
+                    if (a.samples_out) {
+                        float* o = a.samples_out + (((size_t)y * a.W + x) * a.spp + it) * 3;
+                        o[0] = L.x; o[1] = L.y; o[2] = L.z;
+                    }
+                    if (!any_nan(L))                                                                // integrator.py:27-28
+                        w.R[slot] = make_float4(clampf(L.x, 0.0f, 100000.0f), clampf(L.y, 0.0f, 100000.0f), clampf(L.z, 0.0f, 100000.0f), 0.f);
+                }
+            } else {
+                survive = true;
+            }
+            if (survive) {
+                w.A[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, pdf_bsdf);
+                w.B[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(wf_pack(depth, phase, sampler.dimension)));
+                w.C[slot] = make_float4(beta.x, beta.y, beta.z, 0.f);
+                w.D[slot] = make_float4(L.x, L.y, L.z, 0.f);
+            }
+        }
+        // append the survivors of this warp with one atomic
+        const unsigned alive = __ballot_sync(0xffffffffu, survive);
+        if (alive) {
+            const int lane = threadIdx.x & 31;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(w.counts + (in ^ 1), __popc(alive));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (survive) out_list[base + __popc(alive & ((1u << lane) - 1u))] = slot;
+        }
+    }
+    flush_tally(a, tl);
+}
+
+// integrator.py:15-29: s += clamp(radiance) for it ascending; image = s / spp.  The running sum
+// lives in the image buffer between batches.
+__global__ void __launch_bounds__(kWfThreads) k_wf_accumulate(const __grid_constant__ RenderArgs a) {
+    const WfState& w = a.wf;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < w.P; pix += wf_stride()) {
+        int x, y;
+        wf_pixel(a, pix, x, y);
+        float4* px = a.image + ((size_t)x + (size_t)y * a.W);
+        float3 s = f3(0.f, 0.f, 0.f);
+        if (!w.first) { const float4 v = *px; s = f3(v.x, v.y, v.z); }
+        for (int j = 0; j < w.S; ++j) {
+            const float4 r = w.R[(size_t)j * w.P + pix];
+            s = s + f3(r.x, r.y, r.z);
+        }
+        *px = w.last ? make_float4(s.x / (float)a.spp, s.y / (float)a.spp, s.z / (float)a.spp, 1.0f) : make_float4(s.x, s.y, s.z, 0.f);
+    }
+}
+
 __global__ void k_probe_trace(const SceneView sc, const float* __restrict__ rays, int n, int any, int* __restrict__ ip,
                               float* __restrict__ uvt, int* __restrict__ occ) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -477,6 +728,50 @@ cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cud
             return cudaGetLastError();
     }
 }
+size_t wf_bytes_per_slot() { return 6 * sizeof(float4) + 2 * sizeof(int); }
+
+// Host side of the wavefront path tracer: batches of S consecutive samples of every pixel of the
+// shard; per batch generate, then max_depth (forward) or 2*max_depth (adjoint: replay + adjoint
+// walk) rounds of extend + shade, then the ordered accumulation.  No host synchronisation: list
+// lengths stay on the device, the grids are persistent (grid-stride over the live list).
+cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaStream_t s) {
+    const int tiles = (a.row1 - a.row0 + 7) / 8;
+    int rows = 0;
+    for (int t = a.shard_index; t < tiles; t += a.shard_count) rows += min(8, a.row1 - (a.row0 + 8 * t));
+    if (rows <= 0 || a.it1 <= a.it0) return cudaSuccess;
+    WfState& w = a.wf;
+    w.P = a.W * rows;
+    const int grid = w.num_sms * 16;
+    const int rounds = backward ? 2 * a.max_depth : a.max_depth;
+    const int smax = w.S;      // capacity in samples per batch (buffers hold P * smax slots)
+    for (int base = a.it0; base < a.it1; base += smax) {
+        w.S = min(smax, a.it1 - base);
+        w.it_base = base;
+        w.nslots = w.P * w.S;
+        w.first = base == a.it0;
+        w.last = base + smax >= a.it1;
+        if (backward) k_wf_generate<true><<<grid, kWfThreads, 0, s>>>(a);
+        else k_wf_generate<false><<<grid, kWfThreads, 0, s>>>(a);
+        for (int r = 0; r < rounds; ++r) {
+            const int in = r & 1;
+            if (stats) k_wf_extend<true><<<grid, kWfThreads, 0, s>>>(a, in);
+            else k_wf_extend<false><<<grid, kWfThreads, 0, s>>>(a, in);
+            if (!backward) {
+                if (stats) k_wf_shade<false, true, false><<<grid, kWfThreads, 0, s>>>(a, in);
+                else k_wf_shade<false, false, false><<<grid, kWfThreads, 0, s>>>(a, in);
+            } else if (a.aggregate_scatter) {
+                if (stats) k_wf_shade<true, true, true><<<grid, kWfThreads, 0, s>>>(a, in);
+                else k_wf_shade<true, false, true><<<grid, kWfThreads, 0, s>>>(a, in);
+            } else {
+                if (stats) k_wf_shade<true, true, false><<<grid, kWfThreads, 0, s>>>(a, in);
+                else k_wf_shade<true, false, false><<<grid, kWfThreads, 0, s>>>(a, in);
+            }
+        }
+        if (!backward && a.image) k_wf_accumulate<<<grid, kWfThreads, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_probe_trace(const SceneView& sc, const float* rays, int n, bool any, int* ip, float* uvt, int* occ,
                                cudaStream_t s) {
     if (n <= 0) return cudaSuccess;

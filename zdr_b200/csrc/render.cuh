@@ -6,6 +6,25 @@
 
 namespace zdr {
 
+// Global-memory path state of the wavefront path tracer (render.cu, k_wf_*): one slot per
+// (sample-in-batch j, pixel pix), slot = j * P + pix, so a warp works on 32 neighbouring pixels.
+struct WfState {
+    float4* A;        // ray origin.xyz | pdf_bsdf
+    float4* B;        // ray direction.xyz | packed (depth, phase, sampler dimension)
+    float4* C;        // beta.xyz | -
+    float4* D;        // L.xyz (radiance accumulated / Le remaining) | -
+    float4* H;        // closest hit: slot | u | v | t
+    float4* R;        // finished sample: clamped radiance.xyz | -   (forward only)
+    int* list[2];     // ping-pong lists of live slots
+    int* counts;      // counts[0], counts[1]
+    int P;            // pixels of this launch (width * rows of the shard)
+    int S;            // samples of the current batch
+    int it_base;      // first sample index of the batch
+    int nslots;       // P * S
+    int first, last;  // first / last batch of the launch
+    int num_sms;
+};
+
 struct RenderArgs {
     SceneView sc;
     TexView tex;
@@ -20,11 +39,15 @@ struct RenderArgs {
     const float4* d_image;    // backward: (H,W) float4 cotangent
     float* samples_out;       // probe: (H,W,spp,3) un-clamped per-sample radiance, or null
     unsigned long long* counters;
+    WfState wf;
 };
 
 // launchers (render.cu)
 cudaError_t launch_forward(int integrator, const RenderArgs& a, bool stats, cudaStream_t stream);
 cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cudaStream_t stream);
+// wavefront variant of the path integrator / PRB adjoint; `wf` buffers sized for wf_slot_capacity() slots
+size_t wf_bytes_per_slot();
+cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaStream_t stream);
 cudaError_t launch_probe_trace(const SceneView& sc, const float* rays_dev, int n, bool any, int* ip_dev,
                                float* uvt_dev, int* occ_dev, cudaStream_t stream);
 cudaError_t launch_probe_sampler(const SceneView& sc, const int* state_dev, int n, const char* prog_dev, int prog_len,

@@ -88,6 +88,7 @@ class Scene:
         self.bilinear = True
         self.prb_mode = "corrected"
         self.collect_stats = False
+        self.schedule = "auto"          # path integrator: 'auto' | 'wavefront' | 'megakernel' (ZDR_FLAG_*)
         self.scatter_mode = "auto"      # 'auto' | 'aggregate' | 'plain' (ZDR_FLAG_SCATTER_*)
         # data-parallel shard of the dispatch grid; None = whole image
         self.shard_rows = None
@@ -156,7 +157,7 @@ class Scene:
         p = make_params(self.camera, res, material.shape[0:2], spp, seed, use_tent_filter=self.use_tent_filter,
                         max_depth=self.max_depth, rr_depth=self.rr_depth, use_mis=self.use_mis, bilinear=self.bilinear,
                         prb_mode=PRB_MODES[self.prb_mode] if isinstance(self.prb_mode, str) else int(self.prb_mode),
-                        rows=rows if rows is not None else self.shard_rows, shard=self.shard, stats=self.collect_stats, scatter=self.scatter_mode)
+                        rows=rows if rows is not None else self.shard_rows, shard=self.shard, stats=self.collect_stats, scatter=self.scatter_mode, schedule=self.schedule)
         return p
 
     def _check_material(self, material):
