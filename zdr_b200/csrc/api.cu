@@ -209,7 +209,10 @@ int make_args(zdr_scene* s, const zdr_params* p, RenderArgs* a) {
 int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArgs* a, bool* use) {
     *use = false;
     if (integrator != ZDR_PATH) return ZDR_OK;
-    const long long rows = (long long)(p->row1 - p->row0 + a->shard_count - 1) / a->shard_count + 8;
+    long long rows = 0;
+    for (int t = a->shard_index, tiles = (p->row1 - p->row0 + 7) / 8; t < tiles; t += a->shard_count)
+        rows += (p->row1 - (p->row0 + 8 * t)) < 8 ? (p->row1 - (p->row0 + 8 * t)) : 8;
+    if (rows <= 0) return ZDR_OK;
     const long long pixels = (long long)p->width * rows;
     const long long samples = pixels * (p->it1 - p->it0);
     if (p->flags & ZDR_FLAG_MEGAKERNEL) return ZDR_OK;

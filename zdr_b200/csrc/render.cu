@@ -155,13 +155,13 @@ ZDR_DEV Ray camera_sample(const RenderArgs& a, int x, int y, Sampler& sampler) {
 }
 
 ZDR_DEV unsigned warp_sum(unsigned v) {
-#pragma unroll
+#pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 ZDR_DEV void flush_tally(const RenderArgs& a, const Tally& t) {
     const unsigned v[C_NUM] = {t.closest, t.any, t.ts.nodes, t.ts.tris, t.scatter, t.red, t.shaded, t.samples};
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < C_NUM; ++i) {
         const unsigned s = warp_sum(v[i]);
         if ((threadIdx.x & 31) == 0 && s) atomicAdd(a.counters + i, (unsigned long long)s);
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_backward(const __grid_constan
 // together.  Every pixel still runs its samples in order in one thread: the image keeps the
 // reference's accumulation order (integrator.py:15-28) and is bit-identical to the oracle's.
 //   phase 0: radiance walk (L accumulates);  phase 1 (BWD only): adjoint walk (L = Le remaining).
-template <bool BWD, bool STATS, bool AGG>
+template <bool BWD, bool STATS, bool AGG, bool ENV>
 __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant__ RenderArgs a) {
     int x, y;
     pixel_of_thread(a, x, y);
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
             } else {
                 const Hit hit = c.closest(ray);                                    // prb.py:25
                 if (hit.inst < 0) {
-                    if (phase == 0 && sc.env_count > 0) {                          // prb.py:26-31
+                    if (ENV && phase == 0 && sc.env_count > 0) {                          // prb.py:26-31
                         const float3 tex = env_texture(sc, direction_to_uv(ray.d));
                         const float3 emission = corrected ? tex : beta * tex;     // prb.py:28 applies beta twice
                         const float mis_weight = balanced_heuristic(pdf_bsdf, env_sampled_light_pdf(sc, ray.d));
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
                         const float roughness = mat.w;
                         const Onb onb = make_onb(itx.ns);
                         const float3 wo_local = to_local(onb, -ray.d);
-                        const LightSample light = sample_light(sc, itx.p, sampler);                     // prb.py:57
+                        const LightSample light = sample_light<ENV>(sc, itx.p, sampler);                     // prb.py:57
                         const bool occluded = c.occluded(make_ray(itx.p, light.wi, 1e-4f, light.dist));  // prb.py:58-59
                         const float3 wi_light_local = to_local(onb, light.wi);
                         if (!occluded && wi_light_local.z >= 1e-4f) {                                   // prb.py:61-66
@@ -404,6 +404,15 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
 // stage starts with 32 live paths, each kernel is small, and the state traffic (~190 B per
 // bounce) is what the 7.7 TB/s of HBM3e are for.  Arithmetic per sample is unchanged (same device
 // functions), so images stay bit-identical to the oracle.
+#ifndef ZDR_WF_SHADE_MINB
+#define ZDR_WF_SHADE_MINB 8
+#endif
+#ifndef ZDR_WF_EXTEND_MINB
+#define ZDR_WF_EXTEND_MINB 8
+#endif
+#ifndef ZDR_WF_GRID_MULT
+#define ZDR_WF_GRID_MULT 64
+#endif
 constexpr int kWfThreads = 128;
 constexpr unsigned kWfPhaseBit = 1u << 8;
 
@@ -438,7 +447,7 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_generate(const __grid_constan
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(kWfThreads) k_wf_extend(const __grid_constant__ RenderArgs a, int in) {
+__global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_extend(const __grid_constant__ RenderArgs a, int in) {
     const WfState& w = a.wf;
     const int n = *(volatile int*)(w.counts + in);
     if (blockIdx.x == 0 && threadIdx.x == 0) w.counts[in ^ 1] = 0;      // the shade stage appends to it
@@ -453,8 +462,8 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_extend(const __grid_constant_
     flush_tally(a, tl);
 }
 
-template <bool BWD, bool STATS, bool AGG>
-__global__ void __launch_bounds__(kWfThreads) k_wf_shade(const __grid_constant__ RenderArgs a, int in) {
+template <bool BWD, bool STATS, bool AGG, bool ENV>
+__global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_MINB) k_wf_shade(const __grid_constant__ RenderArgs a, int in) {
     const WfState& w = a.wf;
     const SceneView& sc = a.sc;
     const int n = *(volatile int*)(w.counts + in);
@@ -498,7 +507,7 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_shade(const __grid_constant__
             }
             bool end = false;
             if (hit.inst < 0) {
-                if (phase == 0 && sc.env_count > 0) {                              // prb.py:26-31
+                if (ENV && phase == 0 && sc.env_count > 0) {                              // prb.py:26-31
                     const float3 tex = env_texture(sc, direction_to_uv(ray.d));
                     const float3 emission = corrected ? tex : beta * tex;
                     const float mis_weight = balanced_heuristic(pdf_bsdf, env_sampled_light_pdf(sc, ray.d));
@@ -525,7 +534,7 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_shade(const __grid_constant__
                     const float roughness = mat.w;
                     const Onb onb = make_onb(itx.ns);
                     const float3 wo_local = to_local(onb, -ray.d);
-                    const LightSample light = sample_light(sc, itx.p, sampler);                     // prb.py:57
+                    const LightSample light = sample_light<ENV>(sc, itx.p, sampler);                     // prb.py:57
                     const bool occluded = c.occluded(make_ray(itx.p, light.wi, 1e-4f, light.dist));  // prb.py:58-59
                     const float3 wi_light_local = to_local(onb, light.wi);
                     if (!occluded && wi_light_local.z >= 1e-4f) {                                   // prb.py:61-66
@@ -701,14 +710,32 @@ cudaError_t launch_bwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
 
 }  // namespace
 
+namespace {
+template <bool BWD, bool STATS, bool AGG>
+void launch_wf_shade3(bool env, int grid, cudaStream_t s, const RenderArgs& a, int in) {
+    if (env) k_wf_shade<BWD, STATS, AGG, true><<<grid, kWfThreads, 0, s>>>(a, in);
+    else k_wf_shade<BWD, STATS, AGG, false><<<grid, kWfThreads, 0, s>>>(a, in);
+}
+void launch_wf_shade(bool bwd, bool stats, bool agg, bool env, int grid, cudaStream_t s, const RenderArgs& a, int in) {
+    if (!bwd) { if (stats) launch_wf_shade3<false, true, false>(env, grid, s, a, in); else launch_wf_shade3<false, false, false>(env, grid, s, a, in); }
+    else if (agg) { if (stats) launch_wf_shade3<true, true, true>(env, grid, s, a, in); else launch_wf_shade3<true, false, true>(env, grid, s, a, in); }
+    else { if (stats) launch_wf_shade3<true, true, false>(env, grid, s, a, in); else launch_wf_shade3<true, false, false>(env, grid, s, a, in); }
+}
+template <bool BWD, bool STATS, bool AGG>
+void launch_path3(bool env, const RenderArgs& a, cudaStream_t s) {
+    if (env) k_path<BWD, STATS, AGG, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+    else k_path<BWD, STATS, AGG, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+}
+}  // namespace
+
 cudaError_t launch_forward(int integrator, const RenderArgs& a, bool stats, cudaStream_t s) {
     if (a.row1 <= a.row0 || a.it1 <= a.it0 || render_grid(a).y == 0) return cudaSuccess;
     switch (integrator) {
         case ZDR_COLLOCATED: return launch_fwd_i<ZDR_COLLOCATED>(a, stats, s);
         case ZDR_DIRECT: return launch_fwd_i<ZDR_DIRECT>(a, stats, s);
         default:
-            if (stats) k_path<false, true, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
-            else k_path<false, false, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+            if (stats) launch_path3<false, true, false>(a.sc.env_count > 0, a, s);
+            else launch_path3<false, false, false>(a.sc.env_count > 0, a, s);
             return cudaGetLastError();
     }
 }
@@ -719,11 +746,11 @@ cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cud
         case ZDR_DIRECT: return launch_bwd_i<ZDR_DIRECT>(a, stats, s);
         default:
             if (a.aggregate_scatter) {
-                if (stats) k_path<true, true, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
-                else k_path<true, false, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+                if (stats) launch_path3<true, true, true>(a.sc.env_count > 0, a, s);
+                else launch_path3<true, false, true>(a.sc.env_count > 0, a, s);
             } else {
-                if (stats) k_path<true, true, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
-                else k_path<true, false, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+                if (stats) launch_path3<true, true, false>(a.sc.env_count > 0, a, s);
+                else launch_path3<true, false, false>(a.sc.env_count > 0, a, s);
             }
             return cudaGetLastError();
     }
@@ -741,7 +768,7 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
     if (rows <= 0 || a.it1 <= a.it0) return cudaSuccess;
     WfState& w = a.wf;
     w.P = a.W * rows;
-    const int grid = w.num_sms * 16;
+    const int grid = w.num_sms * ZDR_WF_GRID_MULT;
     const int rounds = backward ? 2 * a.max_depth : a.max_depth;
     const int smax = w.S;      // capacity in samples per batch (buffers hold P * smax slots)
     for (int base = a.it0; base < a.it1; base += smax) {
@@ -756,16 +783,7 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
             const int in = r & 1;
             if (stats) k_wf_extend<true><<<grid, kWfThreads, 0, s>>>(a, in);
             else k_wf_extend<false><<<grid, kWfThreads, 0, s>>>(a, in);
-            if (!backward) {
-                if (stats) k_wf_shade<false, true, false><<<grid, kWfThreads, 0, s>>>(a, in);
-                else k_wf_shade<false, false, false><<<grid, kWfThreads, 0, s>>>(a, in);
-            } else if (a.aggregate_scatter) {
-                if (stats) k_wf_shade<true, true, true><<<grid, kWfThreads, 0, s>>>(a, in);
-                else k_wf_shade<true, false, true><<<grid, kWfThreads, 0, s>>>(a, in);
-            } else {
-                if (stats) k_wf_shade<true, true, false><<<grid, kWfThreads, 0, s>>>(a, in);
-                else k_wf_shade<true, false, false><<<grid, kWfThreads, 0, s>>>(a, in);
-            }
+            launch_wf_shade(backward, stats, backward && a.aggregate_scatter, a.sc.env_count > 0, grid, s, a, in);
         }
         if (!backward && a.image) k_wf_accumulate<<<grid, kWfThreads, 0, s>>>(a);
     }

@@ -396,9 +396,10 @@ ZDR_DEV float3 inst_emission(const SceneView& sc, int inst) {
     return f3(d.emission[0], d.emission[1], d.emission[2]);
 }
 // light.py:22-81 (point_light_count = 0, light.py:7)
+template <bool ENV = true>
 ZDR_DEV LightSample sample_light(const SceneView& sc, float3 origin, Sampler& sampler) {
     const float u = sampler_next(sc, sampler);
-    const int n = sc.env_count + 0 + sc.light_count;
+    const int n = (ENV ? sc.env_count : 0) + 0 + sc.light_count;
     LightSample t;
     if (n == 0) {   // upstream indexes lights[-1]; defined: consume the mesh-light dims, null sample
         (void)sampler_next(sc, sampler);
@@ -407,8 +408,10 @@ ZDR_DEV LightSample sample_light(const SceneView& sc, float3 origin, Sampler& sa
         return t;
     }
     int idx = clampi(f2i(u * (float)n), 0, n - 1);
-    if (idx < sc.env_count) return sample_envmap(sc, sampler_next2f(sc, sampler));
-    idx -= sc.env_count;
+    if (ENV) {
+        if (idx < sc.env_count) return sample_envmap(sc, sampler_next2f(sc, sampler));
+        idx -= sc.env_count;
+    }
     const int inst = __ldg(sc.lights + idx);
     const int trig_count = sc.inst[inst].tri_count;
     const int prim = clampi(f2i(sampler_next(sc, sampler) * (float)trig_count), 0, trig_count - 1);

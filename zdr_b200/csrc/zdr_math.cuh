@@ -31,10 +31,18 @@ ZDR_HD float dot(float3 a, float3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x 
 ZDR_HD float3 cross(float3 a, float3 b) {
     return f3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
 }
+// v * (1/sqrt(v.v)).  On the device the IEEE sqrt + divide expand to ~45 instructions with their slow
+// paths; ~20 call sites per path vertex made this the largest single contributor to the render
+// kernels' code size (ncu source page, profiles/r01g), so the device version is ONE out-of-line copy.
+#ifdef __CUDA_ARCH__
+static __device__ __noinline__ float rcp_length(float x, float y, float z) { return 1.0f / sqrtf(fmaf(z, z, fmaf(y, y, x * x))); }
+ZDR_HD float3 normalize(float3 v) { return v * rcp_length(v.x, v.y, v.z); }
+#else
 ZDR_HD float3 normalize(float3 v) {
     float inv = 1.0f / sqrtf(dot(v, v));
     return v * inv;
 }
+#endif
 ZDR_HD float length(float3 v) { return sqrtf(dot(v, v)); }
 // a*A + b*B + c*C
 ZDR_HD float3 lincomb(float a, float3 A, float b, float3 B, float c, float3 C) {
@@ -69,7 +77,12 @@ ZDR_HD float3 mat3_mul(const float* N, float3 v) {
 // sin/cos of a binary32 angle evaluated in binary64: Cody-Waite reduction by pi/2 and Taylor
 // polynomials in fma-Horner form, rounded once.  Identical operation sequence on host and
 // device, so the sampled directions do not depend on a vendor libm.
-ZDR_HD void sincos_contract(float phi, float* s_out, float* c_out) {
+#ifdef __CUDA_ARCH__
+static __device__ __noinline__
+#else
+inline
+#endif
+void sincos_contract(float phi, float* s_out, float* c_out) {
     double x = (double)phi;
     double kd = rint(x * 0.63661977236758134308);
     double r = fma(-kd, 1.57079632679489655800e+00, x);
