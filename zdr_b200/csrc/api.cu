@@ -233,6 +233,9 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
     w.D = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
     w.H = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
     w.R = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
+    w.SA = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
+    w.SB = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
+    w.SC = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
     w.list[0] = reinterpret_cast<int*>(base); base += slots * sizeof(int);
     w.list[1] = reinterpret_cast<int*>(base); base += slots * sizeof(int);
     w.counts = reinterpret_cast<int*>(base);

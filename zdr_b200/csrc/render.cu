@@ -447,12 +447,12 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_generate(const __grid_constan
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_extend(const __grid_constant__ RenderArgs a, int in) {
+__global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_extend(const __grid_constant__ RenderArgs a) {
     const WfState& w = a.wf;
-    const int n = *(volatile int*)(w.counts + in);
-    if (blockIdx.x == 0 && threadIdx.x == 0) w.counts[in ^ 1] = 0;      // the shade stage appends to it
+    const int n = *(volatile int*)(w.counts + 0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) w.counts[1] = 0;           // shade A appends to list[1]
     Tally tl = {};
-    const int* __restrict__ list = w.list[in];
+    const int* __restrict__ list = w.list[0];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += wf_stride()) {
         const int slot = list[i];
         const float4 A = w.A[slot], B = w.B[slot];
@@ -462,14 +462,169 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_extend(co
     flush_tally(a, tl);
 }
 
-template <bool BWD, bool STATS, bool AGG, bool ENV>
-__global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_MINB) k_wf_shade(const __grid_constant__ RenderArgs a, int in) {
+// survivors of a warp are appended to `list` with one atomic
+ZDR_DEV void wf_append(int* __restrict__ list, int* counter, bool keep, int value) {
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+struct WfPath {        // registers of one path inside a stage
+    int slot, x, y, it, depth, phase;
+    Ray ray;
+    float pdf_bsdf;
+    float3 beta, L;
+    Sampler sampler;
+};
+ZDR_DEV WfPath wf_load(const RenderArgs& a, int slot, bool with_throughput) {
+    const WfState& w = a.wf;
+    WfPath p;
+    p.slot = slot;
+    const int j = slot / w.P, pix = slot - j * w.P;
+    wf_pixel(a, pix, p.x, p.y);
+    p.it = w.it_base + j;
+    const float4 A = w.A[slot], B = w.B[slot];
+    p.ray = make_ray(f3(A.x, A.y, A.z), f3(B.x, B.y, B.z), 0.0f, 1e30f);
+    p.pdf_bsdf = A.w;
+    const unsigned packed = __float_as_uint(B.w);
+    p.depth = (int)(packed & 0xffu);
+    p.phase = (packed & kWfPhaseBit) ? 1 : 0;
+    p.sampler = make_sampler(a.sc, p.x, p.y, a.seed, a.spp, p.it);
+    p.sampler.dimension = (int)(packed >> 12);
+    if (with_throughput) {
+        const float4 C4 = w.C[slot], D4 = w.D[slot];
+        p.beta = f3(C4.x, C4.y, C4.z); p.L = f3(D4.x, D4.y, D4.z);
+    } else {
+        p.beta = f3(0.f, 0.f, 0.f); p.L = f3(0.f, 0.f, 0.f);
+    }
+    return p;
+}
+ZDR_DEV Hit wf_hit(const RenderArgs& a, int slot) {
+    const float4 H = a.wf.H[slot];
+    Hit hit;
+    hit.slot = __float_as_int(H.x); hit.u = H.y; hit.v = H.z; hit.t = H.w; hit.inst = -1; hit.prim = -1;
+    if (hit.slot >= 0) {
+        const float4* tp = a.sc.tris + 3 * (size_t)hit.slot;
+        hit.inst = __float_as_int(__ldg(tp + 1).w);
+        hit.prim = __float_as_int(__ldg(tp + 2).w);
+    }
+    return hit;
+}
+// end of a path: forward -> finished sample; adjoint replay (phase 0) -> restart as the adjoint walk
+// (prb.py:97-101); adjoint walk -> dead.  Returns true when the slot stays live.
+template <bool BWD>
+ZDR_DEV bool wf_finish(const RenderArgs& a, WfPath& p) {
+    const WfState& w = a.wf;
+    if (BWD) {
+        if (p.phase != 0 || any_nan(p.L) || a.max_depth <= 0) return false;
+        Sampler cam = make_sampler(a.sc, p.x, p.y, a.seed, a.spp, p.it);
+        const Ray ray = camera_sample(a, p.x, p.y, cam);
+        w.A[p.slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, 1e30f);
+        w.B[p.slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(wf_pack(0, 1, cam.dimension)));
+        w.C[p.slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+        w.D[p.slot] = make_float4(p.L.x, p.L.y, p.L.z, 0.f);
+        return true;
+    }
+    if (a.samples_out) {
+        float* o = a.samples_out + (((size_t)p.y * a.W + p.x) * a.spp + p.it) * 3;
+        o[0] = p.L.x; o[1] = p.L.y; o[2] = p.L.z;
+    }
+    if (!any_nan(p.L))                                                             // integrator.py:27-28
+        w.R[p.slot] = make_float4(clampf(p.L.x, 0.0f, 100000.0f), clampf(p.L.y, 0.0f, 100000.0f), clampf(p.L.z, 0.0f, 100000.0f), 0.f);
+    return false;
+}
+constexpr int kWfPassThrough = (int)0x80000000;     // list[1] entry that skips shadow + shade B (restarted path)
+
+// Stage A: classify the closest hit (prb.py:26-46); paths that go on get their light sample
+// (prb.py:57) and a shadow-ray record.  list[0] -> list[1].
+template <bool BWD, bool ENV>
+__global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_MINB) k_wf_shade_a(const __grid_constant__ RenderArgs a) {
     const WfState& w = a.wf;
     const SceneView& sc = a.sc;
-    const int n = *(volatile int*)(w.counts + in);
+    const int n = *(volatile int*)(w.counts + 0);
     const int n_round = (n + 31) & ~31;
-    const int* __restrict__ list = w.list[in];
-    int* __restrict__ out_list = w.list[in ^ 1];
+    const bool corrected = a.prb_mode == ZDR_PRB_CORRECTED;
+    Tally tl = {};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += wf_stride()) {
+        bool keep = false;
+        int entry = 0;
+        if (i < n) {
+            WfPath p = wf_load(a, w.list[0][i], true);
+            const Hit hit = wf_hit(a, p.slot);
+            bool end = false;
+            if (hit.inst < 0) {
+                if (ENV && p.phase == 0 && sc.env_count > 0) {                     // prb.py:26-31
+                    const float3 tex = env_texture(sc, direction_to_uv(p.ray.d));
+                    const float3 emission = corrected ? tex : p.beta * tex;
+                    const float mis_weight = balanced_heuristic(p.pdf_bsdf, env_sampled_light_pdf(sc, p.ray.d));
+                    p.L = p.L + (p.beta * mis_weight) * emission;
+                }
+                end = true;
+            } else {
+                const Interaction itx = surface_interact(sc, hit);
+                const float3 emission = inst_emission(sc, hit.inst);
+                if (backfacing(p.ray.d, itx)) {                                    // prb.py:35-36
+                    end = true;
+                } else if (any_pos(emission)) {                                    // prb.py:39-44 / :117-121
+                    const float mis_weight = balanced_heuristic(p.pdf_bsdf, sample_light_pdf(sc, p.ray.o, hit, itx.p));
+                    const float3 contrib = (p.beta * mis_weight) * emission;
+                    p.L = (p.phase == 0) ? p.L + contrib : p.L - contrib;
+                    end = true;
+                } else if ((p.phase == 0 || corrected) && hit.inst > 0) {          // prb.py:45-46
+                    end = true;
+                } else {
+                    tl.shaded++;
+                    const LightSample light = sample_light<ENV>(sc, itx.p, p.sampler);                 // prb.py:57
+                    w.SA[p.slot] = make_float4(itx.p.x, itx.p.y, itx.p.z, light.dist);
+                    w.SB[p.slot] = make_float4(light.wi.x, light.wi.y, light.wi.z, light.pdf);
+                    w.SC[p.slot] = make_float4(light.eval.x, light.eval.y, light.eval.z, 0.f);
+                    w.B[p.slot].w = __uint_as_float(wf_pack(p.depth, p.phase, p.sampler.dimension));
+                    keep = true;
+                    entry = p.slot;
+                }
+            }
+            if (end) {
+                keep = wf_finish<BWD>(a, p);
+                entry = p.slot | kWfPassThrough;
+            }
+        }
+        wf_append(w.list[1], w.counts + 1, keep, entry);
+    }
+    flush_tally(a, tl);
+}
+
+// Shadow stage: any-hit query of every path to shade (prb.py:58-59).  list[1] (read only).
+template <bool STATS>
+__global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_shadow(const __grid_constant__ RenderArgs a) {
+    const WfState& w = a.wf;
+    const int n = *(volatile int*)(w.counts + 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) w.counts[0] = 0;          // shade B appends the survivors to list[0]
+    Tally tl = {};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += wf_stride()) {
+        const int slot = w.list[1][i];
+        if (slot < 0) continue;
+        const float4 SA = w.SA[slot], SB = w.SB[slot];
+        tl.any++;
+        const float4 r = trace_packed<STATS>(a.sc.nodes, a.sc.tris, a.sc.root_link, SA.x, SA.y, SA.z, SB.x, SB.y, SB.z, 1e-4f, SA.w, 1, &tl.ts);
+        w.SC[slot].w = __float_as_int(r.x) >= 0 ? 1.0f : 0.0f;
+    }
+    flush_tally(a, tl);
+}
+
+// Stage B: light-sample contribution given the occlusion result, BSDF sample, throughput update,
+// Russian roulette (prb.py:61-87), and in the adjoint walk the BRDF adjoints + scatter
+// (prb.py:138-187).  The interaction and the texel fetch are recomputed from the hit record (a few
+// hundred instructions) instead of travelling through HBM.  list[1] -> list[0].
+template <bool BWD, bool STATS, bool AGG>
+__global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_MINB) k_wf_shade_b(const __grid_constant__ RenderArgs a) {
+    const WfState& w = a.wf;
+    const SceneView& sc = a.sc;
+    const int n = *(volatile int*)(w.counts + 1);
+    const int n_round = (n + 31) & ~31;
     Tally tl = {};
     Ctx<STATS, AGG> c{a, tl};
     const bool corrected = a.prb_mode == ZDR_PRB_CORRECTED;
@@ -479,153 +634,95 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_MINB) k_wf_shade(cons
         bool survive = false;
         int slot = 0;
         if (i < n) {
-            slot = list[i];
-            const int j = slot / w.P, pix = slot - j * w.P;
-            int x, y;
-            wf_pixel(a, pix, x, y);
-            const int it = w.it_base + j;
-            const float4 A = w.A[slot], B = w.B[slot], C4 = w.C[slot], D4 = w.D[slot], H = w.H[slot];
-            Ray ray = make_ray(f3(A.x, A.y, A.z), f3(B.x, B.y, B.z), 0.0f, 1e30f);
-            float pdf_bsdf = A.w;
-            const unsigned packed = __float_as_uint(B.w);
-            int depth = (int)(packed & 0xffu), phase = (packed & kWfPhaseBit) ? 1 : 0;
-            Sampler sampler = make_sampler(sc, x, y, a.seed, a.spp, it);
-            sampler.dimension = (int)(packed >> 12);
-            float3 beta = f3(C4.x, C4.y, C4.z), L = f3(D4.x, D4.y, D4.z);
-            float3 le_grad = zero;
-            if (BWD) {                                                             // integrator.py:38-40
-                const float4 g = __ldg(a.d_image + ((size_t)x + (size_t)y * a.W));
-                le_grad = f3(g.x / (float)a.spp, g.y / (float)a.spp, g.z / (float)a.spp);
-                if (any_nan(le_grad)) le_grad = zero;
-            }
-            Hit hit;
-            hit.slot = __float_as_int(H.x); hit.u = H.y; hit.v = H.z; hit.t = H.w; hit.inst = -1; hit.prim = -1;
-            if (hit.slot >= 0) {
-                const float4* tp = sc.tris + 3 * (size_t)hit.slot;
-                hit.inst = __float_as_int(__ldg(tp + 1).w);
-                hit.prim = __float_as_int(__ldg(tp + 2).w);
-            }
-            bool end = false;
-            if (hit.inst < 0) {
-                if (ENV && phase == 0 && sc.env_count > 0) {                              // prb.py:26-31
-                    const float3 tex = env_texture(sc, direction_to_uv(ray.d));
-                    const float3 emission = corrected ? tex : beta * tex;
-                    const float mis_weight = balanced_heuristic(pdf_bsdf, env_sampled_light_pdf(sc, ray.d));
-                    L = L + (beta * mis_weight) * emission;
-                }
-                end = true;
+            slot = w.list[1][i];
+            if (slot < 0) {                      // restarted in stage A: straight to the next extend
+                slot &= ~kWfPassThrough;
+                survive = true;
             } else {
+                WfPath p = wf_load(a, slot, true);
+                const Hit hit = wf_hit(a, slot);
+                float3 le_grad = zero;
+                if (BWD && p.phase == 1) {                                         // integrator.py:38-40
+                    const float4 g = __ldg(a.d_image + ((size_t)p.x + (size_t)p.y * a.W));
+                    le_grad = f3(g.x / (float)a.spp, g.y / (float)a.spp, g.z / (float)a.spp);
+                    if (any_nan(le_grad)) le_grad = zero;
+                }
                 const Interaction itx = surface_interact(sc, hit);
-                const float3 emission = inst_emission(sc, hit.inst);
-                if (backfacing(ray.d, itx)) {                                      // prb.py:35-36
-                    end = true;
-                } else if (any_pos(emission)) {                                    // prb.py:39-44 / :117-121
-                    const float mis_weight = balanced_heuristic(pdf_bsdf, sample_light_pdf(sc, ray.o, hit, itx.p));
-                    const float3 contrib = (beta * mis_weight) * emission;
-                    L = (phase == 0) ? L + contrib : L - contrib;
-                    end = true;
-                } else if ((phase == 0 || corrected) && hit.inst > 0) {            // prb.py:45-46
+                const float4 mat = read_bsdf(a.tex, itx.uv);
+                const float3 diffuse = f3(mat.x, mat.y, mat.z);
+                const float roughness = mat.w;
+                const Onb onb = make_onb(itx.ns);
+                const float3 wo_local = to_local(onb, -p.ray.d);
+                const float4 SB = w.SB[slot], SC = w.SC[slot];
+                const float3 light_wi = f3(SB.x, SB.y, SB.z), light_eval = f3(SC.x, SC.y, SC.z);
+                const float light_pdf = SB.w;
+                const bool occluded = SC.w != 0.0f;
+                float4 mat_grad = make_float4(0.f, 0.f, 0.f, 0.f);
+                bool end = false;
+                const float3 wi_light_local = to_local(onb, light_wi);
+                if (!occluded && wi_light_local.z >= 1e-4f) {                                       // prb.py:61-66
+                    const float4 ev = ggx_eval(wo_local, wi_light_local, diffuse, specular, roughness);
+                    const float3 bsdf = f3(ev.x, ev.y, ev.z);
+                    const float mis_weight = balanced_heuristic(light_pdf, ev.w);
+                    const float dn = fmaxf(light_pdf, 1e-4f);
+                    const float3 contrib = (((p.beta * bsdf) * mis_weight) * light_eval) / dn;
+                    if (!BWD || p.phase == 0) {
+                        p.L = p.L + contrib;
+                    } else {
+                        const float3 cot = (((p.beta * mis_weight) * light_eval) / dn) * le_grad;     // prb.py:145
+                        mat_grad = mat_grad + ggx_brdf_grad_nl(wo_local, wi_light_local, specular, roughness, cot);
+                        p.L = p.L - contrib;                                                        // prb.py:147
+                    }
+                }
+                const float3 wi_local = ggx_sample(sc, wo_local, roughness, p.sampler);             // prb.py:69
+                const float4 ev = ggx_eval(wo_local, wi_local, diffuse, specular, roughness);
+                p.pdf_bsdf = ev.w;
+                const float3 wi = to_world(onb, wi_local);
+                if (dot(wi, itx.ng) < 1e-4f || wi_local.z < 1e-4f) {                                // prb.py:73-74
                     end = true;
                 } else {
-                    tl.shaded++;
-                    float4 mat_grad = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 mat = read_bsdf(a.tex, itx.uv);
-                    const float3 diffuse = f3(mat.x, mat.y, mat.z);
-                    const float roughness = mat.w;
-                    const Onb onb = make_onb(itx.ns);
-                    const float3 wo_local = to_local(onb, -ray.d);
-                    const LightSample light = sample_light<ENV>(sc, itx.p, sampler);                     // prb.py:57
-                    const bool occluded = c.occluded(make_ray(itx.p, light.wi, 1e-4f, light.dist));  // prb.py:58-59
-                    const float3 wi_light_local = to_local(onb, light.wi);
-                    if (!occluded && wi_light_local.z >= 1e-4f) {                                   // prb.py:61-66
-                        const float4 ev = ggx_eval(wo_local, wi_light_local, diffuse, specular, roughness);
-                        const float3 bsdf = f3(ev.x, ev.y, ev.z);
-                        pdf_bsdf = ev.w;
-                        const float mis_weight = balanced_heuristic(light.pdf, pdf_bsdf);
-                        const float dn = fmaxf(light.pdf, 1e-4f);
-                        const float3 contrib = (((beta * bsdf) * mis_weight) * light.eval) / dn;
-                        if (!BWD || phase == 0) {
-                            L = L + contrib;
+                    p.ray = make_ray(offset_ray_origin(itx.p, itx.ng), wi, 0.0f, 1e30f);            // prb.py:75
+                    const float3 bsdf = f3(ev.x, ev.y, ev.z);
+                    if (BWD && p.phase == 1) {
+                        float3 cot;
+                        if (corrected)
+                            cot = f3(bsdf.x != 0.0f ? p.L.x / bsdf.x * le_grad.x : 0.0f, bsdf.y != 0.0f ? p.L.y / bsdf.y * le_grad.y : 0.0f,
+                                     bsdf.z != 0.0f ? p.L.z / bsdf.z * le_grad.z : 0.0f);
+                        else
+                            cot = ((p.beta / p.pdf_bsdf) * p.L) * le_grad;                          // prb.py:162
+                        mat_grad = mat_grad + ggx_brdf_grad_nl(wo_local, wi_local, specular, roughness, cot);
+                    }
+                    p.beta = p.beta * (bsdf / p.pdf_bsdf);                                          // prb.py:76
+                    if (p.depth >= a.rr_depth) {                                                    // prb.py:78-87
+                        const float l = luminance(p.beta);
+                        if (l == 0.0f) {
+                            end = true;
                         } else {
-                            const float3 cot = (((beta * mis_weight) * light.eval) / dn) * le_grad;   // prb.py:145
-                            mat_grad = mat_grad + ggx_brdf_grad_nl(wo_local, wi_light_local, specular, roughness, cot);
-                            L = L - contrib;                                                        // prb.py:147
+                            const float q = fmaxf(l, 0.05f);
+                            const float r = sampler_next(sc, p.sampler);
+                            if (r >= q) end = true;
+                            else p.beta = p.beta / q;
                         }
                     }
-                    const float3 wi_local = ggx_sample(sc, wo_local, roughness, sampler);           // prb.py:69
-                    const float4 ev = ggx_eval(wo_local, wi_local, diffuse, specular, roughness);
-                    pdf_bsdf = ev.w;
-                    const float3 wi = to_world(onb, wi_local);
-                    if (dot(wi, itx.ng) < 1e-4f || wi_local.z < 1e-4f) {                            // prb.py:73-74
-                        end = true;
-                    } else {
-                        ray = make_ray(offset_ray_origin(itx.p, itx.ng), wi, 0.0f, 1e30f);          // prb.py:75
-                        const float3 bsdf = f3(ev.x, ev.y, ev.z);
-                        if (BWD && phase == 1) {
-                            float3 cot;
-                            if (corrected)
-                                cot = f3(bsdf.x != 0.0f ? L.x / bsdf.x * le_grad.x : 0.0f, bsdf.y != 0.0f ? L.y / bsdf.y * le_grad.y : 0.0f,
-                                         bsdf.z != 0.0f ? L.z / bsdf.z * le_grad.z : 0.0f);
-                            else
-                                cot = ((beta / pdf_bsdf) * L) * le_grad;                            // prb.py:162
-                            mat_grad = mat_grad + ggx_brdf_grad_nl(wo_local, wi_local, specular, roughness, cot);
-                        }
-                        beta = beta * (bsdf / pdf_bsdf);                                            // prb.py:76
-                        if (depth >= a.rr_depth) {                                                  // prb.py:78-87
-                            const float l = luminance(beta);
-                            if (l == 0.0f) {
-                                end = true;
-                            } else {
-                                const float q = fmaxf(l, 0.05f);
-                                const float r = sampler_next(sc, sampler);
-                                if (r >= q) end = true;
-                                else beta = beta / q;
-                            }
-                        }
-                    }
-                    if (BWD && phase == 1) {                                                        // prb.py:178-187
-                        if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad))
-                            c.scatter(itx.uv, mat_grad);
-                    }
-                    ++depth;
-                    if (depth >= a.max_depth) end = true;                                           // prb.py:23
                 }
-            }
-            if (end) {
-                if (BWD && phase == 0 && !any_nan(L)) {
-                    // prb.py:97-101: Le is known; walk the same path again from the camera with the original sampler state
-                    Sampler cam = make_sampler(sc, x, y, a.seed, a.spp, it);
-                    ray = camera_sample(a, x, y, cam);
-                    sampler.dimension = cam.dimension;
-                    beta = f3(1.f, 1.f, 1.f); pdf_bsdf = 1e30f; depth = 0; phase = 1;
+                if (BWD && p.phase == 1) {                                                          // prb.py:178-187
+                    if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad))
+                        c.scatter(itx.uv, mat_grad);
+                }
+                ++p.depth;
+                if (p.depth >= a.max_depth) end = true;                                             // prb.py:23
+                if (end) {
+                    survive = wf_finish<BWD>(a, p);
+                } else {
                     survive = true;
-                } else if (!BWD) {
-                    if (a.samples_out) {
-                        float* o = a.samples_out + (((size_t)y * a.W + x) * a.spp + it) * 3;
-                        o[0] = L.x; o[1] = L.y; o[2] = L.z;
-                    }
-                    if (!any_nan(L))                                                                // integrator.py:27-28
-                        w.R[slot] = make_float4(clampf(L.x, 0.0f, 100000.0f), clampf(L.y, 0.0f, 100000.0f), clampf(L.z, 0.0f, 100000.0f), 0.f);
+                    w.A[slot] = make_float4(p.ray.o.x, p.ray.o.y, p.ray.o.z, p.pdf_bsdf);
+                    w.B[slot] = make_float4(p.ray.d.x, p.ray.d.y, p.ray.d.z, __uint_as_float(wf_pack(p.depth, p.phase, p.sampler.dimension)));
+                    w.C[slot] = make_float4(p.beta.x, p.beta.y, p.beta.z, 0.f);
+                    w.D[slot] = make_float4(p.L.x, p.L.y, p.L.z, 0.f);
                 }
-            } else {
-                survive = true;
-            }
-            if (survive) {
-                w.A[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, pdf_bsdf);
-                w.B[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(wf_pack(depth, phase, sampler.dimension)));
-                w.C[slot] = make_float4(beta.x, beta.y, beta.z, 0.f);
-                w.D[slot] = make_float4(L.x, L.y, L.z, 0.f);
             }
         }
-        // append the survivors of this warp with one atomic
-        const unsigned alive = __ballot_sync(0xffffffffu, survive);
-        if (alive) {
-            const int lane = threadIdx.x & 31;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(w.counts + (in ^ 1), __popc(alive));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (survive) out_list[base + __popc(alive & ((1u << lane) - 1u))] = slot;
-        }
+        wf_append(w.list[0], w.counts + 0, survive, slot);
     }
     flush_tally(a, tl);
 }
@@ -711,15 +808,16 @@ cudaError_t launch_bwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
 }  // namespace
 
 namespace {
-template <bool BWD, bool STATS, bool AGG>
-void launch_wf_shade3(bool env, int grid, cudaStream_t s, const RenderArgs& a, int in) {
-    if (env) k_wf_shade<BWD, STATS, AGG, true><<<grid, kWfThreads, 0, s>>>(a, in);
-    else k_wf_shade<BWD, STATS, AGG, false><<<grid, kWfThreads, 0, s>>>(a, in);
-}
-void launch_wf_shade(bool bwd, bool stats, bool agg, bool env, int grid, cudaStream_t s, const RenderArgs& a, int in) {
-    if (!bwd) { if (stats) launch_wf_shade3<false, true, false>(env, grid, s, a, in); else launch_wf_shade3<false, false, false>(env, grid, s, a, in); }
-    else if (agg) { if (stats) launch_wf_shade3<true, true, true>(env, grid, s, a, in); else launch_wf_shade3<true, false, true>(env, grid, s, a, in); }
-    else { if (stats) launch_wf_shade3<true, true, false>(env, grid, s, a, in); else launch_wf_shade3<true, false, false>(env, grid, s, a, in); }
+void launch_wf_round(bool bwd, bool stats, bool agg, bool env, int grid, cudaStream_t s, const RenderArgs& a) {
+    if (stats) k_wf_extend<true><<<grid, kWfThreads, 0, s>>>(a);
+    else k_wf_extend<false><<<grid, kWfThreads, 0, s>>>(a);
+    if (bwd) { if (env) k_wf_shade_a<true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_a<true, false><<<grid, kWfThreads, 0, s>>>(a); }
+    else { if (env) k_wf_shade_a<false, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_a<false, false><<<grid, kWfThreads, 0, s>>>(a); }
+    if (stats) k_wf_shadow<true><<<grid, kWfThreads, 0, s>>>(a);
+    else k_wf_shadow<false><<<grid, kWfThreads, 0, s>>>(a);
+    if (!bwd) { if (stats) k_wf_shade_b<false, true, false><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<false, false, false><<<grid, kWfThreads, 0, s>>>(a); }
+    else if (agg) { if (stats) k_wf_shade_b<true, true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<true, false, true><<<grid, kWfThreads, 0, s>>>(a); }
+    else { if (stats) k_wf_shade_b<true, true, false><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<true, false, false><<<grid, kWfThreads, 0, s>>>(a); }
 }
 template <bool BWD, bool STATS, bool AGG>
 void launch_path3(bool env, const RenderArgs& a, cudaStream_t s) {
@@ -755,7 +853,7 @@ cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cud
             return cudaGetLastError();
     }
 }
-size_t wf_bytes_per_slot() { return 6 * sizeof(float4) + 2 * sizeof(int); }
+size_t wf_bytes_per_slot() { return 9 * sizeof(float4) + 2 * sizeof(int); }
 
 // Host side of the wavefront path tracer: batches of S consecutive samples of every pixel of the
 // shard; per batch generate, then max_depth (forward) or 2*max_depth (adjoint: replay + adjoint
@@ -769,7 +867,7 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
     WfState& w = a.wf;
     w.P = a.W * rows;
     const int grid = w.num_sms * ZDR_WF_GRID_MULT;
-    const int rounds = backward ? 2 * a.max_depth : a.max_depth;
+    const int rounds = backward ? 2 * a.max_depth + 1 : a.max_depth;
     const int smax = w.S;      // capacity in samples per batch (buffers hold P * smax slots)
     for (int base = a.it0; base < a.it1; base += smax) {
         w.S = min(smax, a.it1 - base);
@@ -779,12 +877,7 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
         w.last = base + smax >= a.it1;
         if (backward) k_wf_generate<true><<<grid, kWfThreads, 0, s>>>(a);
         else k_wf_generate<false><<<grid, kWfThreads, 0, s>>>(a);
-        for (int r = 0; r < rounds; ++r) {
-            const int in = r & 1;
-            if (stats) k_wf_extend<true><<<grid, kWfThreads, 0, s>>>(a, in);
-            else k_wf_extend<false><<<grid, kWfThreads, 0, s>>>(a, in);
-            launch_wf_shade(backward, stats, backward && a.aggregate_scatter, a.sc.env_count > 0, grid, s, a, in);
-        }
+        for (int r = 0; r < rounds; ++r) launch_wf_round(backward, stats, backward && a.aggregate_scatter, a.sc.env_count > 0, grid, s, a);
         if (!backward && a.image) k_wf_accumulate<<<grid, kWfThreads, 0, s>>>(a);
     }
     return cudaGetLastError();

@@ -15,7 +15,10 @@ struct WfState {
     float4* D;        // L.xyz (radiance accumulated / Le remaining) | -
     float4* H;        // closest hit: slot | u | v | t
     float4* R;        // finished sample: clamped radiance.xyz | -   (forward only)
-    int* list[2];     // ping-pong lists of live slots
+    float4* SA;       // shadow ray origin.xyz (= hit point) | light.dist
+    float4* SB;       // light.wi.xyz | light.pdf
+    float4* SC;       // light.eval.xyz | occluded (written by the shadow stage)
+    int* list[2];     // list[0]: live paths (input of extend); list[1]: paths to shade (output of shade A)
     int* counts;      // counts[0], counts[1]
     int P;            // pixels of this launch (width * rows of the shard)
     int S;            // samples of the current batch
