@@ -442,22 +442,129 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_generate(const __grid_constan
         if (!BWD) w.R[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
         w.list[0][slot] = slot;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { w.counts[0] = a.max_depth > 0 ? w.nslots : 0; w.counts[1] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { w.counts[0] = a.max_depth > 0 ? w.nslots : 0; w.counts[1] = 0; w.counts[2] = 0; w.counts[3] = 0; }
     flush_tally(a, tl);
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_extend(const __grid_constant__ RenderArgs a) {
+// Extend (ANY = false: closest hit of list[0] -> H) and shadow (ANY = true: occlusion of list[1] ->
+// SC.w) stages: persistent traversal with dynamic ray fetch (Aila & Laine 2009).  Rays of one warp
+// need very different numbers of node / triangle steps (secondary rays: 14 of 32 lanes active in
+// the one-ray-per-lane form, profiles/r01h); here a lane that finishes its ray takes the next one
+// from the stage's list, and the lanes still traversing leave the inner loop to let the idle ones
+// refill once fewer than kWfRefill of them are left.
+constexpr int kWfRefill = 20;
+template <bool ANY, bool STATS>
+__global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(const __grid_constant__ RenderArgs a) {
     const WfState& w = a.wf;
-    const int n = *(volatile int*)(w.counts + 0);
-    if (blockIdx.x == 0 && threadIdx.x == 0) w.counts[1] = 0;           // shade A appends to list[1]
+    const int n = *(volatile int*)(w.counts + (ANY ? 1 : 0));
+    int* cursor = w.counts + (ANY ? 3 : 2);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (ANY) { w.counts[0] = 0; w.counts[2] = 0; }       // shade B appends to list[0]; cursor of the next extend
+        else { w.counts[1] = 0; w.counts[3] = 0; }           // shade A appends to list[1]; cursor of the next shadow stage
+    }
+    const int* __restrict__ list = w.list[ANY ? 1 : 0];
+    const float4* __restrict__ nodes = a.sc.nodes;
+    const float4* __restrict__ tris = a.sc.tris;
     Tally tl = {};
-    const int* __restrict__ list = w.list[0];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += wf_stride()) {
-        const int slot = list[i];
-        const float4 A = w.A[slot], B = w.B[slot];
-        tl.closest++;
-        w.H[slot] = trace_packed<STATS>(a.sc.nodes, a.sc.tris, a.sc.root_link, A.x, A.y, A.z, B.x, B.y, B.z, 0.0f, 1e30f, 0, &tl.ts);
+    const int lane = threadIdx.x & 31;
+    // per-lane traversal state
+    bool has_ray = false, exhausted = false;
+    int slot = 0, link = kLinkSentinel, sp = 0, hit_slot = -1, best_gid = 0x7fffffff;
+    float tmin = 0.f, tmax = 0.f, best = 0.f, hit_u = 0.f, hit_v = 0.f, hit_t = 0.f;
+    float3 id = f3(0.f, 0.f, 0.f), oid = id;
+    RayPre rp = {};
+    int stack[kStackSize];
+    for (;;) {
+        // ---- refill idle lanes
+        const unsigned idle = __ballot_sync(0xffffffffu, !has_ray && !exhausted);
+        if (idle) {
+            int base = 0;
+            if (lane == __ffs(idle) - 1) base = atomicAdd(cursor, __popc(idle));
+            base = __shfl_sync(0xffffffffu, base, __ffs(idle) - 1);
+            if (!has_ray && !exhausted) {
+                const int i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i >= n) {
+                    exhausted = true;
+                } else {
+                    slot = list[i];
+                    if (!(ANY && slot < 0)) {          // pass-through entries carry no shadow ray
+                        float3 o, d;
+                        if (ANY) {
+                            const float4 SA = w.SA[slot], SB = w.SB[slot];
+                            o = f3(SA.x, SA.y, SA.z); d = f3(SB.x, SB.y, SB.z); tmin = 1e-4f; tmax = SA.w;
+                            tl.any++;
+                        } else {
+                            const float4 A = w.A[slot], B = w.B[slot];
+                            o = f3(A.x, A.y, A.z); d = f3(B.x, B.y, B.z); tmin = 0.0f; tmax = 1e30f;
+                            tl.closest++;
+                        }
+                        rp = ray_pre(o, d);
+                        id = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        if (!(fabsf(id.x) <= 1e30f)) id.x = copysignf(1e30f, d.x);
+                        if (!(fabsf(id.y) <= 1e30f)) id.y = copysignf(1e30f, d.y);
+                        if (!(fabsf(id.z) <= 1e30f)) id.z = copysignf(1e30f, d.z);
+                        oid = f3(o.x * id.x, o.y * id.y, o.z * id.z);
+                        best = tmax; best_gid = 0x7fffffff; hit_slot = -1; hit_u = hit_v = hit_t = 0.0f;
+                        sp = 0; stack[sp++] = kLinkSentinel; link = a.sc.root_link;
+                        has_ray = true;
+                    }
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, !has_ray)) {
+            if (__all_sync(0xffffffffu, exhausted)) break;
+            continue;                                   // only pass-through entries were fetched
+        }
+        // ---- traverse until done, or until too few lanes are left working
+        while (has_ray) {
+            while (link >= 0) {                          // inner nodes
+                const float4* nd = nodes + 4 * (size_t)link;
+                const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+                if (STATS) tl.ts.nodes++;
+                float t0, t1;
+                const bool h0 = box_test(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, id, oid, tmin, best, t0);
+                const bool h1 = box_test(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, id, oid, tmin, best, t1);
+                const int l0 = __float_as_int(n3.x), l1 = __float_as_int(n3.y);
+                if (h0 && h1) {
+                    const bool swap = t1 < t0;
+                    stack[sp++] = swap ? l0 : l1;
+                    link = swap ? l1 : l0;
+                } else if (h0 || h1) {
+                    link = h0 ? l0 : l1;
+                } else {
+                    link = stack[--sp];
+                }
+            }
+            bool done = link == kLinkSentinel;
+            if (!done) {                                 // leaf
+                const int code = ~link;
+                const int first = code >> 2, count = (code & 3) + 1;
+                for (int k = 0; k < count; ++k) {
+                    const float* tp = reinterpret_cast<const float*>(tris + 3 * (size_t)(first + k));
+                    if (STATS) tl.ts.tris++;
+                    float t, u, v;
+                    if (tri_test(rp, tp, tmin, t, u, v)) {
+                        if (ANY) {
+                            if (t < tmax) { hit_slot = first + k; done = true; break; }
+                            continue;
+                        }
+                        const int gid = __float_as_int(__ldg(tp + 3));
+                        if (t < best || (hit_slot >= 0 && t == best && gid < best_gid)) {
+                            best = t; best_gid = gid;
+                            hit_t = t; hit_u = u; hit_v = v; hit_slot = first + k;
+                        }
+                    }
+                }
+                if (!done) { link = stack[--sp]; done = link == kLinkSentinel; }
+            }
+            if (done && (link == kLinkSentinel || (ANY && hit_slot >= 0))) {
+                if (ANY) w.SC[slot].w = hit_slot >= 0 ? 1.0f : 0.0f;
+                else w.H[slot] = make_float4(__int_as_float(hit_slot), hit_u, hit_v, hit_t);
+                has_ray = false;
+                break;
+            }
+            if (!ANY && __popc(__activemask()) < kWfRefill) break;      // shadow rays are too short for refills to pay (r01i)
+        }
     }
     flush_tally(a, tl);
 }
@@ -502,6 +609,10 @@ ZDR_DEV WfPath wf_load(const RenderArgs& a, int slot, bool with_throughput) {
         p.beta = f3(0.f, 0.f, 0.f); p.L = f3(0.f, 0.f, 0.f);
     }
     return p;
+}
+ZDR_DEV void wf_load_throughput(const RenderArgs& a, WfPath& p) {
+    const float4 C4 = a.wf.C[p.slot], D4 = a.wf.D[p.slot];
+    p.beta = f3(C4.x, C4.y, C4.z); p.L = f3(D4.x, D4.y, D4.z);
 }
 ZDR_DEV Hit wf_hit(const RenderArgs& a, int slot) {
     const float4 H = a.wf.H[slot];
@@ -553,10 +664,11 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_MINB) k_wf_shade_a(co
         bool keep = false;
         int entry = 0;
         if (i < n) {
-            WfPath p = wf_load(a, w.list[0][i], true);
+            WfPath p = wf_load(a, w.list[0][i], false);       // beta / L are only needed when the path ends here
             const Hit hit = wf_hit(a, p.slot);
             bool end = false;
             if (hit.inst < 0) {
+                wf_load_throughput(a, p);
                 if (ENV && p.phase == 0 && sc.env_count > 0) {                     // prb.py:26-31
                     const float3 tex = env_texture(sc, direction_to_uv(p.ray.d));
                     const float3 emission = corrected ? tex : p.beta * tex;
@@ -568,13 +680,16 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_MINB) k_wf_shade_a(co
                 const Interaction itx = surface_interact(sc, hit);
                 const float3 emission = inst_emission(sc, hit.inst);
                 if (backfacing(p.ray.d, itx)) {                                    // prb.py:35-36
+                    wf_load_throughput(a, p);
                     end = true;
                 } else if (any_pos(emission)) {                                    // prb.py:39-44 / :117-121
+                    wf_load_throughput(a, p);
                     const float mis_weight = balanced_heuristic(p.pdf_bsdf, sample_light_pdf(sc, p.ray.o, hit, itx.p));
                     const float3 contrib = (p.beta * mis_weight) * emission;
                     p.L = (p.phase == 0) ? p.L + contrib : p.L - contrib;
                     end = true;
                 } else if ((p.phase == 0 || corrected) && hit.inst > 0) {          // prb.py:45-46
+                    wf_load_throughput(a, p);
                     end = true;
                 } else {
                     tl.shaded++;
@@ -593,24 +708,6 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_MINB) k_wf_shade_a(co
             }
         }
         wf_append(w.list[1], w.counts + 1, keep, entry);
-    }
-    flush_tally(a, tl);
-}
-
-// Shadow stage: any-hit query of every path to shade (prb.py:58-59).  list[1] (read only).
-template <bool STATS>
-__global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_shadow(const __grid_constant__ RenderArgs a) {
-    const WfState& w = a.wf;
-    const int n = *(volatile int*)(w.counts + 1);
-    if (blockIdx.x == 0 && threadIdx.x == 0) w.counts[0] = 0;          // shade B appends the survivors to list[0]
-    Tally tl = {};
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += wf_stride()) {
-        const int slot = w.list[1][i];
-        if (slot < 0) continue;
-        const float4 SA = w.SA[slot], SB = w.SB[slot];
-        tl.any++;
-        const float4 r = trace_packed<STATS>(a.sc.nodes, a.sc.tris, a.sc.root_link, SA.x, SA.y, SA.z, SB.x, SB.y, SB.z, 1e-4f, SA.w, 1, &tl.ts);
-        w.SC[slot].w = __float_as_int(r.x) >= 0 ? 1.0f : 0.0f;
     }
     flush_tally(a, tl);
 }
@@ -809,12 +906,12 @@ cudaError_t launch_bwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
 
 namespace {
 void launch_wf_round(bool bwd, bool stats, bool agg, bool env, int grid, cudaStream_t s, const RenderArgs& a) {
-    if (stats) k_wf_extend<true><<<grid, kWfThreads, 0, s>>>(a);
-    else k_wf_extend<false><<<grid, kWfThreads, 0, s>>>(a);
+    if (stats) k_wf_trace<false, true><<<grid, kWfThreads, 0, s>>>(a);
+    else k_wf_trace<false, false><<<grid, kWfThreads, 0, s>>>(a);
     if (bwd) { if (env) k_wf_shade_a<true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_a<true, false><<<grid, kWfThreads, 0, s>>>(a); }
     else { if (env) k_wf_shade_a<false, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_a<false, false><<<grid, kWfThreads, 0, s>>>(a); }
-    if (stats) k_wf_shadow<true><<<grid, kWfThreads, 0, s>>>(a);
-    else k_wf_shadow<false><<<grid, kWfThreads, 0, s>>>(a);
+    if (stats) k_wf_trace<true, true><<<grid, kWfThreads, 0, s>>>(a);
+    else k_wf_trace<true, false><<<grid, kWfThreads, 0, s>>>(a);
     if (!bwd) { if (stats) k_wf_shade_b<false, true, false><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<false, false, false><<<grid, kWfThreads, 0, s>>>(a); }
     else if (agg) { if (stats) k_wf_shade_b<true, true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<true, false, true><<<grid, kWfThreads, 0, s>>>(a); }
     else { if (stats) k_wf_shade_b<true, true, false><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<true, false, false><<<grid, kWfThreads, 0, s>>>(a); }
