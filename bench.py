@@ -268,12 +268,14 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    launches0 = int(lib.zdr_kernel_launches())
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     barrier()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)                       # L2 flush between timed iterations (outside the events)
         step(evs[k])
     barrier()
+    launches = int(lib.zdr_kernel_launches()) - launches0
     clock_rec = clocks.stop() if rank == 0 else None
     t_fwd = sum(e[0].elapsed_time(e[1]) for e in evs)
     t_bwd = sum(e[1].elapsed_time(e[2]) for e in evs)
@@ -333,8 +335,15 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         rec = json.load(open(tpath))
-        if rec.get("res") == args.res and rec.get("spp") == args.spp and rec.get("integrator") == args.integrator:
-            traffic = rec.get("backward_dram_bytes_per_launch")
+        if rec.get("res") == args.res and rec.get("integrator") == args.integrator and world == 1:
+            # DRAM bytes of one adjoint pass measured with ncu at rec["spp"]; batches of 16 samples are identical, so it scales with spp
+            traffic = int(rec["backward_dram_bytes"] * args.spp / rec["spp"])
+    wavefront = args.integrator == "path" and args.schedule != "megakernel" and (args.schedule == "wavefront" or pixels_local * args.spp >= 1 << 21)
+    if wavefront:
+        kernel_name = ("adjoint pass of the wavefront path tracer: k_wf_generate + (2*depth+1) x [k_wf_trace<closest>, k_wf_shade_a, "
+                       "k_wf_trace<any>, k_wf_shade_b] per 16-sample batch (PRB replay + adjoint walk + gradient scatter)")
+    else:
+        kernel_name = f"adjoint kernel of the {args.integrator} integrator (k_path<BWD> / k_backward: replay + adjoint + gradient scatter)"
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -347,12 +356,14 @@ def run_ours(args):
                    "tris_per_ray": round((c_fwd["tris_tested"] + c_bwd["tris_tested"]) / max(rays_local, 1), 2),
                    "red_v4_per_scatter": round(c_bwd["red_v4"] / max(c_bwd["grad_scatters"], 1), 3)},
         "clocks": clock_rec,
-        "gpu_launches": 2 * args.steps,
-        "roofline": {"bound": "hbm", "kernel": f"k_backward<{args.integrator}> (PRB replay + adjoint + gradient scatter)",
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": kernel_name,
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_bwd),
                      "ms_per_launch": round(ms_bwd, 3),
-                     "note": "working set (BVH < 4 KB, texture 16 MiB, tables 5.5 MiB) is L1/L2 resident: HBM is not the binding bound"},
+                     "note": ("algorithmic bytes = BVH nodes/triangles visited + shading records + texels + scatter footprints (DESIGN.md 6); on "
+                              "the Cornell box these are L1/L2 resident. `traffic` = DRAM bytes ncu measured for the same pass: with the "
+                              "wavefront schedule it is the path state streamed through HBM between stages")},
     }
     if not args.no_e2e:
         out["e2e"] = {"value": round(rays_total / t_e2e / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(mat_np.nbytes),

@@ -154,6 +154,8 @@ int zdr_render_backward_host(zdr_scene* s, int integrator, const zdr_params* p,
 #define ZDR_NUM_COUNTERS 8
 int zdr_get_counters(zdr_scene* s, uint64_t out[ZDR_NUM_COUNTERS]);
 int zdr_reset_counters(zdr_scene* s);
+/* number of CUDA kernels this library has launched so far in this process (render + probe kernels) */
+uint64_t zdr_kernel_launches(void);
 
 /* --- probes (parity tests only; small n). All pointers HOST. ---------------------------- */
 /* closest hit for n rays (o.xyz, d.xyz, tmin, tmax) -> inst, prim, bary u, v, t (inst=-1: miss) */

@@ -96,6 +96,7 @@ SIGNATURES = {
     "zdr_render_backward_host": (C.c_int, [_vp, C.c_int, _pp, _f32p, _f32p, _f32p]),
     "zdr_get_counters": (C.c_int, [_vp, _u64p]),
     "zdr_reset_counters": (C.c_int, [_vp]),
+    "zdr_kernel_launches": (C.c_uint64, []),
     "zdr_probe_trace_closest": (C.c_int, [_vp, _f32p, C.c_int, _i32p, _f32p]),
     "zdr_probe_trace_any": (C.c_int, [_vp, _f32p, C.c_int, _i32p]),
     "zdr_probe_sampler": (C.c_int, [C.c_int, _i32p, C.c_int, C.c_char_p, _f32p]),

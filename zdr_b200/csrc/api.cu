@@ -217,7 +217,9 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
     const long long samples = pixels * (p->it1 - p->it0);
     if (p->flags & ZDR_FLAG_MEGAKERNEL) return ZDR_OK;
     if (!(p->flags & ZDR_FLAG_WAVEFRONT) && samples < (1ll << 21)) return ZDR_OK;
-    const long long target_slots = 1ll << 24;                                   // ~1.7 GB of path state
+    // path-state budget: 2^24 slots (2.5 GB at 152 B per slot) unless ZDR_WF_SLOTS_LOG2 overrides it
+    const char* slots_env = getenv("ZDR_WF_SLOTS_LOG2");
+    const long long target_slots = 1ll << (slots_env ? atoi(slots_env) : 24);
     long long S = target_slots / (pixels > 0 ? pixels : 1);
     if (S < 1) S = 1;
     if (S > p->it1 - p->it0) S = p->it1 - p->it0;
@@ -515,6 +517,8 @@ ZDR_EXPORT int zdr_get_counters(zdr_scene* s, uint64_t out[ZDR_NUM_COUNTERS]) {
     CK(cudaMemcpy(out, s->d_counters, sizeof(uint64_t) * C_NUM, cudaMemcpyDeviceToHost));
     return ZDR_OK;
 }
+ZDR_EXPORT uint64_t zdr_kernel_launches(void) { return kernel_launch_count(); }
+
 ZDR_EXPORT int zdr_reset_counters(zdr_scene* s) {
     if (!s) return fail(ZDR_ERR_ARG, "reset_counters: null");
     int rc = use_device(s->device);

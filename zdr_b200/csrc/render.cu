@@ -1,9 +1,12 @@
 // render.cu — per-pixel render kernels (forward + adjoint) for the collocated, direct and path
 // integrators.  Replaces the LuisaCompute kernels derived at integrator.py:8-53 from
 // collocated.py / direct.py / prb.py and dispatched at render.py:168-171,193-196.
+#include <atomic>
 #include "render.cuh"
 
 namespace zdr {
+
+std::atomic<unsigned long long> g_kernel_launches{0};
 
 namespace {
 
@@ -404,8 +407,14 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
 // stage starts with 32 live paths, each kernel is small, and the state traffic (~190 B per
 // bounce) is what the 7.7 TB/s of HBM3e are for.  Arithmetic per sample is unchanged (same device
 // functions), so images stay bit-identical to the oracle.
-#ifndef ZDR_WF_SHADE_MINB
-#define ZDR_WF_SHADE_MINB 8
+#ifndef ZDR_WF_SHADE_A_MINB
+#define ZDR_WF_SHADE_A_MINB 8
+#endif
+#ifndef ZDR_WF_SHADE_B_MINB
+#define ZDR_WF_SHADE_B_MINB 8
+#endif
+#ifndef ZDR_WF_SHADE_BB_MINB      // adjoint variant of stage B (BRDF adjoints + scatter)
+#define ZDR_WF_SHADE_BB_MINB 6
 #endif
 #ifndef ZDR_WF_EXTEND_MINB
 #define ZDR_WF_EXTEND_MINB 8
@@ -653,7 +662,7 @@ constexpr int kWfPassThrough = (int)0x80000000;     // list[1] entry that skips 
 // Stage A: classify the closest hit (prb.py:26-46); paths that go on get their light sample
 // (prb.py:57) and a shadow-ray record.  list[0] -> list[1].
 template <bool BWD, bool ENV>
-__global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_MINB) k_wf_shade_a(const __grid_constant__ RenderArgs a) {
+__global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_A_MINB) k_wf_shade_a(const __grid_constant__ RenderArgs a) {
     const WfState& w = a.wf;
     const SceneView& sc = a.sc;
     const int n = *(volatile int*)(w.counts + 0);
@@ -717,7 +726,7 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_MINB) k_wf_shade_a(co
 // (prb.py:138-187).  The interaction and the texel fetch are recomputed from the hit record (a few
 // hundred instructions) instead of travelling through HBM.  list[1] -> list[0].
 template <bool BWD, bool STATS, bool AGG>
-__global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_MINB) k_wf_shade_b(const __grid_constant__ RenderArgs a) {
+__global__ void __launch_bounds__(kWfThreads, BWD ? ZDR_WF_SHADE_BB_MINB : ZDR_WF_SHADE_B_MINB) k_wf_shade_b(const __grid_constant__ RenderArgs a) {
     const WfState& w = a.wf;
     const SceneView& sc = a.sc;
     const int n = *(volatile int*)(w.counts + 1);
@@ -886,12 +895,14 @@ dim3 render_grid(const RenderArgs& a) {
 
 template <int I>
 cudaError_t launch_fwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
+    ++g_kernel_launches;
     if (stats) k_forward<I, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
     else k_forward<I, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
     return cudaGetLastError();
 }
 template <int I>
 cudaError_t launch_bwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
+    ++g_kernel_launches;
     if (a.aggregate_scatter) {
         if (stats) k_backward<I, true, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
         else k_backward<I, false, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
@@ -906,6 +917,7 @@ cudaError_t launch_bwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
 
 namespace {
 void launch_wf_round(bool bwd, bool stats, bool agg, bool env, int grid, cudaStream_t s, const RenderArgs& a) {
+    g_kernel_launches += 4;
     if (stats) k_wf_trace<false, true><<<grid, kWfThreads, 0, s>>>(a);
     else k_wf_trace<false, false><<<grid, kWfThreads, 0, s>>>(a);
     if (bwd) { if (env) k_wf_shade_a<true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_a<true, false><<<grid, kWfThreads, 0, s>>>(a); }
@@ -918,6 +930,7 @@ void launch_wf_round(bool bwd, bool stats, bool agg, bool env, int grid, cudaStr
 }
 template <bool BWD, bool STATS, bool AGG>
 void launch_path3(bool env, const RenderArgs& a, cudaStream_t s) {
+    ++g_kernel_launches;
     if (env) k_path<BWD, STATS, AGG, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
     else k_path<BWD, STATS, AGG, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
 }
@@ -950,6 +963,8 @@ cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cud
             return cudaGetLastError();
     }
 }
+unsigned long long kernel_launch_count() { return g_kernel_launches.load(); }
+
 size_t wf_bytes_per_slot() { return 9 * sizeof(float4) + 2 * sizeof(int); }
 
 // Host side of the wavefront path tracer: batches of S consecutive samples of every pixel of the
@@ -972,6 +987,7 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
         w.nslots = w.P * w.S;
         w.first = base == a.it0;
         w.last = base + smax >= a.it1;
+        g_kernel_launches += (!backward && a.image) ? 2 : 1;      // generate (+ accumulate)
         if (backward) k_wf_generate<true><<<grid, kWfThreads, 0, s>>>(a);
         else k_wf_generate<false><<<grid, kWfThreads, 0, s>>>(a);
         for (int r = 0; r < rounds; ++r) launch_wf_round(backward, stats, backward && a.aggregate_scatter, a.sc.env_count > 0, grid, s, a);
@@ -983,17 +999,20 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
 cudaError_t launch_probe_trace(const SceneView& sc, const float* rays, int n, bool any, int* ip, float* uvt, int* occ,
                                cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
+    ++g_kernel_launches;
     k_probe_trace<<<(n + 127) / 128, 128, 0, s>>>(sc, rays, n, any ? 1 : 0, ip, uvt, occ);
     return cudaGetLastError();
 }
 cudaError_t launch_probe_sampler(const SceneView& sc, const int* state, int n, const char* prog, int prog_len, int per,
                                  float* out, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
+    ++g_kernel_launches;
     k_probe_sampler<<<(n + 127) / 128, 128, 0, s>>>(sc, state, n, prog, prog_len, per, out);
     return cudaGetLastError();
 }
 cudaError_t launch_probe_ggx(const float* in, int n, float* out, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
+    ++g_kernel_launches;
     k_probe_ggx<<<(n + 127) / 128, 128, 0, s>>>(in, n, out);
     return cudaGetLastError();
 }

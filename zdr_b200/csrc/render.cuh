@@ -45,6 +45,8 @@ struct RenderArgs {
     WfState wf;
 };
 
+// number of kernels this library has launched (render kernels and probes), for bench.py's gpu_launches
+unsigned long long kernel_launch_count();
 // launchers (render.cu)
 cudaError_t launch_forward(int integrator, const RenderArgs& a, bool stats, cudaStream_t stream);
 cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cudaStream_t stream);
