@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
                     exhausted = true;
                 } else {
                     slot = list[i];
-                    if (!(ANY && slot < 0)) {          // pass-through entries carry no shadow ray
+                    {
                         float3 o, d;
                         if (ANY) {
                             const float4 SA = w.SA[slot], SB = w.SB[slot];
@@ -634,40 +634,31 @@ ZDR_DEV Hit wf_hit(const RenderArgs& a, int slot) {
     }
     return hit;
 }
-// end of a path: forward -> finished sample; adjoint replay (phase 0) -> restart as the adjoint walk
-// (prb.py:97-101); adjoint walk -> dead.  Returns true when the slot stays live.
-template <bool BWD>
-ZDR_DEV bool wf_finish(const RenderArgs& a, WfPath& p) {
+// End of a path.  MODE 0 (forward): finished sample -> R.  MODE 1 (adjoint pass, replay): Le -> D,
+// read back by k_wf_restart (prb.py:97-101).  MODE 2 (adjoint walk): nothing left to do.
+template <int MODE>
+ZDR_DEV void wf_finish(const RenderArgs& a, WfPath& p) {
     const WfState& w = a.wf;
-    if (BWD) {
-        if (p.phase != 0 || any_nan(p.L) || a.max_depth <= 0) return false;
-        Sampler cam = make_sampler(a.sc, p.x, p.y, a.seed, a.spp, p.it);
-        const Ray ray = camera_sample(a, p.x, p.y, cam);
-        w.A[p.slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, 1e30f);
-        w.B[p.slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(wf_pack(0, 1, cam.dimension)));
-        w.C[p.slot] = make_float4(1.f, 1.f, 1.f, 0.f);
-        w.D[p.slot] = make_float4(p.L.x, p.L.y, p.L.z, 0.f);
-        return true;
-    }
+    if (MODE == 1) { w.D[p.slot] = make_float4(p.L.x, p.L.y, p.L.z, 1.0f); return; }
+    if (MODE == 2) return;
     if (a.samples_out) {
         float* o = a.samples_out + (((size_t)p.y * a.W + p.x) * a.spp + p.it) * 3;
         o[0] = p.L.x; o[1] = p.L.y; o[2] = p.L.z;
     }
     if (!any_nan(p.L))                                                             // integrator.py:27-28
         w.R[p.slot] = make_float4(clampf(p.L.x, 0.0f, 100000.0f), clampf(p.L.y, 0.0f, 100000.0f), clampf(p.L.z, 0.0f, 100000.0f), 0.f);
-    return false;
 }
-constexpr int kWfPassThrough = (int)0x80000000;     // list[1] entry that skips shadow + shade B (restarted path)
 
 // Stage A: classify the closest hit (prb.py:26-46); paths that go on get their light sample
 // (prb.py:57) and a shadow-ray record.  list[0] -> list[1].
-template <bool BWD, bool ENV>
+template <int MODE, bool ENV>
 __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_A_MINB) k_wf_shade_a(const __grid_constant__ RenderArgs a) {
     const WfState& w = a.wf;
     const SceneView& sc = a.sc;
     const int n = *(volatile int*)(w.counts + 0);
     const int n_round = (n + 31) & ~31;
     const bool corrected = a.prb_mode == ZDR_PRB_CORRECTED;
+    constexpr int phase = MODE == 2 ? 1 : 0;
     Tally tl = {};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += wf_stride()) {
         bool keep = false;
@@ -678,7 +669,7 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_A_MINB) k_wf_shade_a(
             bool end = false;
             if (hit.inst < 0) {
                 wf_load_throughput(a, p);
-                if (ENV && p.phase == 0 && sc.env_count > 0) {                     // prb.py:26-31
+                if (ENV && phase == 0 && sc.env_count > 0) {                     // prb.py:26-31
                     const float3 tex = env_texture(sc, direction_to_uv(p.ray.d));
                     const float3 emission = corrected ? tex : p.beta * tex;
                     const float mis_weight = balanced_heuristic(p.pdf_bsdf, env_sampled_light_pdf(sc, p.ray.d));
@@ -695,9 +686,9 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_A_MINB) k_wf_shade_a(
                     wf_load_throughput(a, p);
                     const float mis_weight = balanced_heuristic(p.pdf_bsdf, sample_light_pdf(sc, p.ray.o, hit, itx.p));
                     const float3 contrib = (p.beta * mis_weight) * emission;
-                    p.L = (p.phase == 0) ? p.L + contrib : p.L - contrib;
+                    p.L = (phase == 0) ? p.L + contrib : p.L - contrib;
                     end = true;
-                } else if ((p.phase == 0 || corrected) && hit.inst > 0) {          // prb.py:45-46
+                } else if ((phase == 0 || corrected) && hit.inst > 0) {          // prb.py:45-46
                     wf_load_throughput(a, p);
                     end = true;
                 } else {
@@ -706,15 +697,12 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_A_MINB) k_wf_shade_a(
                     w.SA[p.slot] = make_float4(itx.p.x, itx.p.y, itx.p.z, light.dist);
                     w.SB[p.slot] = make_float4(light.wi.x, light.wi.y, light.wi.z, light.pdf);
                     w.SC[p.slot] = make_float4(light.eval.x, light.eval.y, light.eval.z, 0.f);
-                    w.B[p.slot].w = __uint_as_float(wf_pack(p.depth, p.phase, p.sampler.dimension));
+                    w.B[p.slot].w = __uint_as_float(wf_pack(p.depth, phase, p.sampler.dimension));
                     keep = true;
                     entry = p.slot;
                 }
             }
-            if (end) {
-                keep = wf_finish<BWD>(a, p);
-                entry = p.slot | kWfPassThrough;
-            }
+            if (end) wf_finish<MODE>(a, p);
         }
         wf_append(w.list[1], w.counts + 1, keep, entry);
     }
@@ -725,8 +713,8 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_A_MINB) k_wf_shade_a(
 // Russian roulette (prb.py:61-87), and in the adjoint walk the BRDF adjoints + scatter
 // (prb.py:138-187).  The interaction and the texel fetch are recomputed from the hit record (a few
 // hundred instructions) instead of travelling through HBM.  list[1] -> list[0].
-template <bool BWD, bool STATS, bool AGG>
-__global__ void __launch_bounds__(kWfThreads, BWD ? ZDR_WF_SHADE_BB_MINB : ZDR_WF_SHADE_B_MINB) k_wf_shade_b(const __grid_constant__ RenderArgs a) {
+template <int MODE, bool STATS, bool AGG>
+__global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB : ZDR_WF_SHADE_B_MINB) k_wf_shade_b(const __grid_constant__ RenderArgs a) {
     const WfState& w = a.wf;
     const SceneView& sc = a.sc;
     const int n = *(volatile int*)(w.counts + 1);
@@ -736,19 +724,17 @@ __global__ void __launch_bounds__(kWfThreads, BWD ? ZDR_WF_SHADE_BB_MINB : ZDR_W
     const bool corrected = a.prb_mode == ZDR_PRB_CORRECTED;
     const float specular = 0.04f;
     const float3 zero = f3(0.f, 0.f, 0.f);
+    constexpr bool ADJ = MODE == 2;      // adjoint walk: BRDF adjoints + scatter
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += wf_stride()) {
         bool survive = false;
         int slot = 0;
         if (i < n) {
             slot = w.list[1][i];
-            if (slot < 0) {                      // restarted in stage A: straight to the next extend
-                slot &= ~kWfPassThrough;
-                survive = true;
-            } else {
+            {
                 WfPath p = wf_load(a, slot, true);
                 const Hit hit = wf_hit(a, slot);
                 float3 le_grad = zero;
-                if (BWD && p.phase == 1) {                                         // integrator.py:38-40
+                if (ADJ) {                                         // integrator.py:38-40
                     const float4 g = __ldg(a.d_image + ((size_t)p.x + (size_t)p.y * a.W));
                     le_grad = f3(g.x / (float)a.spp, g.y / (float)a.spp, g.z / (float)a.spp);
                     if (any_nan(le_grad)) le_grad = zero;
@@ -772,7 +758,7 @@ __global__ void __launch_bounds__(kWfThreads, BWD ? ZDR_WF_SHADE_BB_MINB : ZDR_W
                     const float mis_weight = balanced_heuristic(light_pdf, ev.w);
                     const float dn = fmaxf(light_pdf, 1e-4f);
                     const float3 contrib = (((p.beta * bsdf) * mis_weight) * light_eval) / dn;
-                    if (!BWD || p.phase == 0) {
+                    if (!ADJ) {
                         p.L = p.L + contrib;
                     } else {
                         const float3 cot = (((p.beta * mis_weight) * light_eval) / dn) * le_grad;     // prb.py:145
@@ -789,7 +775,7 @@ __global__ void __launch_bounds__(kWfThreads, BWD ? ZDR_WF_SHADE_BB_MINB : ZDR_W
                 } else {
                     p.ray = make_ray(offset_ray_origin(itx.p, itx.ng), wi, 0.0f, 1e30f);            // prb.py:75
                     const float3 bsdf = f3(ev.x, ev.y, ev.z);
-                    if (BWD && p.phase == 1) {
+                    if (ADJ) {
                         float3 cot;
                         if (corrected)
                             cot = f3(bsdf.x != 0.0f ? p.L.x / bsdf.x * le_grad.x : 0.0f, bsdf.y != 0.0f ? p.L.y / bsdf.y * le_grad.y : 0.0f,
@@ -811,18 +797,18 @@ __global__ void __launch_bounds__(kWfThreads, BWD ? ZDR_WF_SHADE_BB_MINB : ZDR_W
                         }
                     }
                 }
-                if (BWD && p.phase == 1) {                                                          // prb.py:178-187
+                if (ADJ) {                                                          // prb.py:178-187
                     if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad))
                         c.scatter(itx.uv, mat_grad);
                 }
                 ++p.depth;
                 if (p.depth >= a.max_depth) end = true;                                             // prb.py:23
                 if (end) {
-                    survive = wf_finish<BWD>(a, p);
+                    wf_finish<MODE>(a, p);
                 } else {
                     survive = true;
                     w.A[slot] = make_float4(p.ray.o.x, p.ray.o.y, p.ray.o.z, p.pdf_bsdf);
-                    w.B[slot] = make_float4(p.ray.d.x, p.ray.d.y, p.ray.d.z, __uint_as_float(wf_pack(p.depth, p.phase, p.sampler.dimension)));
+                    w.B[slot] = make_float4(p.ray.d.x, p.ray.d.y, p.ray.d.z, __uint_as_float(wf_pack(p.depth, ADJ ? 1 : 0, p.sampler.dimension)));
                     w.C[slot] = make_float4(p.beta.x, p.beta.y, p.beta.z, 0.f);
                     w.D[slot] = make_float4(p.L.x, p.L.y, p.L.z, 0.f);
                 }
@@ -848,6 +834,33 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_accumulate(const __grid_const
             s = s + f3(r.x, r.y, r.z);
         }
         *px = w.last ? make_float4(s.x / (float)a.spp, s.y / (float)a.spp, s.z / (float)a.spp, 1.0f) : make_float4(s.x, s.y, s.z, 0.f);
+    }
+}
+
+// Between the replay rounds and the adjoint rounds of the adjoint pass (prb.py:97-101): every sample
+// whose replayed radiance Le is not NaN starts again at the camera with the ORIGINAL sampler state,
+// carrying Le as the "radiance still to be explained".
+__global__ void __launch_bounds__(kWfThreads) k_wf_restart(const __grid_constant__ RenderArgs a) {
+    const WfState& w = a.wf;
+    const int n_round = (w.nslots + 31) & ~31;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_round; slot += wf_stride()) {
+        bool keep = false;
+        if (slot < w.nslots && a.max_depth > 0) {
+            const float4 D4 = w.D[slot];
+            const float3 Le = f3(D4.x, D4.y, D4.z);
+            if (!any_nan(Le)) {
+                const int j = slot / w.P, pix = slot - j * w.P;
+                int x, y;
+                wf_pixel(a, pix, x, y);
+                Sampler cam = make_sampler(a.sc, x, y, a.seed, a.spp, w.it_base + j);
+                const Ray ray = camera_sample(a, x, y, cam);
+                w.A[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, 1e30f);
+                w.B[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(wf_pack(0, 1, cam.dimension)));
+                w.C[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+                keep = true;
+            }
+        }
+        wf_append(w.list[0], w.counts + 0, keep, slot);
     }
 }
 
@@ -916,17 +929,22 @@ cudaError_t launch_bwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
 }  // namespace
 
 namespace {
-void launch_wf_round(bool bwd, bool stats, bool agg, bool env, int grid, cudaStream_t s, const RenderArgs& a) {
+template <int MODE>
+void launch_wf_round(bool stats, bool agg, bool env, int grid, cudaStream_t s, const RenderArgs& a) {
     g_kernel_launches += 4;
     if (stats) k_wf_trace<false, true><<<grid, kWfThreads, 0, s>>>(a);
     else k_wf_trace<false, false><<<grid, kWfThreads, 0, s>>>(a);
-    if (bwd) { if (env) k_wf_shade_a<true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_a<true, false><<<grid, kWfThreads, 0, s>>>(a); }
-    else { if (env) k_wf_shade_a<false, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_a<false, false><<<grid, kWfThreads, 0, s>>>(a); }
+    if (env) k_wf_shade_a<MODE, true><<<grid, kWfThreads, 0, s>>>(a);
+    else k_wf_shade_a<MODE, false><<<grid, kWfThreads, 0, s>>>(a);
     if (stats) k_wf_trace<true, true><<<grid, kWfThreads, 0, s>>>(a);
     else k_wf_trace<true, false><<<grid, kWfThreads, 0, s>>>(a);
-    if (!bwd) { if (stats) k_wf_shade_b<false, true, false><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<false, false, false><<<grid, kWfThreads, 0, s>>>(a); }
-    else if (agg) { if (stats) k_wf_shade_b<true, true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<true, false, true><<<grid, kWfThreads, 0, s>>>(a); }
-    else { if (stats) k_wf_shade_b<true, true, false><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<true, false, false><<<grid, kWfThreads, 0, s>>>(a); }
+    if constexpr (MODE == 2) {
+        if (agg) {
+            if (stats) k_wf_shade_b<MODE, true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<MODE, false, true><<<grid, kWfThreads, 0, s>>>(a);
+            return;
+        }
+    }
+    { if (stats) k_wf_shade_b<MODE, true, false><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<MODE, false, false><<<grid, kWfThreads, 0, s>>>(a); }
 }
 template <bool BWD, bool STATS, bool AGG>
 void launch_path3(bool env, const RenderArgs& a, cudaStream_t s) {
@@ -979,7 +997,6 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
     WfState& w = a.wf;
     w.P = a.W * rows;
     const int grid = w.num_sms * ZDR_WF_GRID_MULT;
-    const int rounds = backward ? 2 * a.max_depth + 1 : a.max_depth;
     const int smax = w.S;      // capacity in samples per batch (buffers hold P * smax slots)
     for (int base = a.it0; base < a.it1; base += smax) {
         w.S = min(smax, a.it1 - base);
@@ -990,7 +1007,15 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
         g_kernel_launches += (!backward && a.image) ? 2 : 1;      // generate (+ accumulate)
         if (backward) k_wf_generate<true><<<grid, kWfThreads, 0, s>>>(a);
         else k_wf_generate<false><<<grid, kWfThreads, 0, s>>>(a);
-        for (int r = 0; r < rounds; ++r) launch_wf_round(backward, stats, backward && a.aggregate_scatter, a.sc.env_count > 0, grid, s, a);
+        const bool env = a.sc.env_count > 0;
+        if (!backward) {
+            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<0>(stats, false, env, grid, s, a);
+        } else {
+            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<1>(stats, false, env, grid, s, a);      // replay: Le of every sample
+            ++g_kernel_launches;
+            k_wf_restart<<<grid, kWfThreads, 0, s>>>(a);
+            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<2>(stats, a.aggregate_scatter != 0, env, grid, s, a);   // adjoint walk
+        }
         if (!backward && a.image) k_wf_accumulate<<<grid, kWfThreads, 0, s>>>(a);
     }
     return cudaGetLastError();
