@@ -461,7 +461,10 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_generate(const __grid_constan
 // the one-ray-per-lane form, profiles/r01h); here a lane that finishes its ray takes the next one
 // from the stage's list, and the lanes still traversing leave the inner loop to let the idle ones
 // refill once fewer than kWfRefill of them are left.
-constexpr int kWfRefill = 20;
+#ifndef ZDR_WF_REFILL
+#define ZDR_WF_REFILL 20
+#endif
+constexpr int kWfRefill = ZDR_WF_REFILL;
 template <bool ANY, bool STATS>
 __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(const __grid_constant__ RenderArgs a) {
     const WfState& w = a.wf;
