@@ -340,3 +340,51 @@ def test_envmap_path(oracle):
         dimg = np.ones((48, 64, 4), np.float32)
         assert rel_l2(g.backward(integ, p, mat, dimg), o.render_backward(integ, p, mat, dimg)) <= GRAD_TOL
     g.close()
+
+
+def test_lbvh_large_scene(oracle):
+    """> 16 K triangles takes the GPU LBVH builder (C5 shape: instanced sphere.obj): closest hits, occlusion
+    and a small path render + adjoint must match the oracle's brute-force scan exactly."""
+    models = scenes.sphere_grid_models(20, seed=3, emissive_every=7)          # 19 200 triangles, 2 emissive spheres
+    g, o = GpuScene(models), oracle.OracleScene(models)
+    assert g.lib.zdr_scene_triangle_count(g.h) == 19200
+    rays = _random_rays(3000, 11, (-1, -1, -1), (5, 5, 2))
+    ip_g, uvt_g = g.trace_closest(rays)
+    ip_o, uvt_o = o.trace_closest(rays)
+    assert np.array_equal(ip_g, ip_o)
+    hit = ip_o[:, 0] >= 0
+    assert hit.sum() > 100 and np.array_equal(bits(uvt_g[hit]), bits(uvt_o[hit]))
+    seg = rays.copy()
+    seg[:, 6], seg[:, 7] = 1e-4, 3.0
+    assert np.array_equal(g.trace_any(seg), o.trace_any(seg))
+    cam = scenes.Camera(fov=0.9, origin=scenes.float3(-2.0, 3.0, -4.0), target=scenes.float3(2.0, 0.5, 0.3), up=scenes.float3(0, 1, 0))
+    mat = scenes.random_material((64, 64), 2)
+    for sched in ("megakernel", "wavefront"):
+        p = make_params(cam, (48, 32), mat.shape, 2, 0, max_depth=4, schedule=sched)
+        assert np.array_equal(bits(g.samples(ZDR_PATH, p, mat)), bits(o.render_samples(ZDR_PATH, p, mat)))
+        d = np.ones((32, 48, 4), np.float32)
+        assert rel_l2(g.backward(ZDR_PATH, p, mat, d), o.render_backward(ZDR_PATH, p, mat, d)) <= GRAD_TOL
+    g.close()
+
+
+def test_light_stage_uniform_texture(oracle):
+    """C4 shape: sphere.obj lit by toggled emissive quads, 1x1 and constant textures (every scatter of the
+    launch lands on one texel), collocated / direct / path, both path schedules."""
+    quad = scenes.asset("quad.obj")
+    models = [(scenes.asset("sphere.obj"), None, scenes.float3(0.0)),
+              (quad, scenes.translate_scale(0.0, 3.0, 0.0, 1.5), scenes.float3(12.0)),
+              (quad, scenes.translate_scale(2.5, 2.0, 1.0, 1.0), scenes.float3(0.0))]
+    g, o = GpuScene(models), oracle.OracleScene(models)
+    cam = scenes.Camera(fov=0.7, origin=scenes.float3(0.0, 0.6, 3.2), target=scenes.float3(0.0, 0.0, 0.0), up=scenes.float3(0, 1, 0))
+    for mat in (scenes.constant_material((1, 1)), scenes.constant_material((16, 16), (0.8, 0.4, 0.2, 0.6))):
+        for lights in ([(0, 0, 0), (12, 12, 12), (0, 0, 0)], [(0, 0, 0), (0, 0, 0), (9, 6, 3)]):
+            g.set_emissions(np.asarray(lights, np.float32))
+            o.update_lights(lights)
+            for integ, kw in ((ZDR_COLLOCATED, {}), (ZDR_DIRECT, {}), (ZDR_PATH, {"max_depth": 3, "schedule": "megakernel"}),
+                              (ZDR_PATH, {"max_depth": 3, "schedule": "wavefront"})):
+                p = make_params(cam, (64, 64), mat.shape, 4, 2, **kw)
+                assert np.array_equal(bits(g.forward(integ, p, mat)), bits(o.render_forward(integ, p, mat)))
+                d = np.ones((64, 64, 4), np.float32)
+                gg, go = g.backward(integ, p, mat, d), o.render_backward(integ, p, mat, d)
+                assert rel_l2(gg, go) <= GRAD_TOL, (integ, rel_l2(gg, go))
+    g.close()
