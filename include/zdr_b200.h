@@ -138,6 +138,12 @@ int zdr_render_backward(zdr_scene* s, int integrator, const zdr_params* p,
                         const float* material_dev, const float* d_image_dev,
                         float* d_material_dev, void* stream);
 
+/* Scene.render_duvdxy (render.py:243-257, kernel uvgrad.py:75-98): screen-to-texture Jacobian
+ * (du/dx, dv/dx, du/dy, dv/dy) per pixel, averaged over spp; image_dev: (H,W,4) f32. Not differentiable.
+ * Pixel offsets are drawn with the render kernels' pmj02bn sampler (the reference uses LuisaCompute's
+ * built-in LCG here, which is not reproducible without LuisaCompute). */
+int zdr_render_duvdxy(zdr_scene* s, const zdr_params* p, float* image_dev, void* stream);
+
 /* Same operators with HOST buffers: the call a non-torch embedder (or bench.py's e2e leg)
  * makes; performs H2D of the inputs and D2H of the result inside the call, then syncs. */
 int zdr_render_forward_host(zdr_scene* s, int integrator, const zdr_params* p,

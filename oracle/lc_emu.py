@@ -384,6 +384,12 @@ class Mat:
     def __getitem__(self, c):
         return self.cols[c]
 
+    def __setitem__(self, c, v):
+        self.cols[c] = _vec_type("f", self.n)(v)
+
+    def copy(self):
+        return Mat(self.cols)
+
     def __mul__(self, v):
         if isinstance(v, Vec):
             # sum over columns of column * v[c], plain binary32 operations in column order
@@ -391,19 +397,29 @@ class Mat:
             for c in range(1, self.n):
                 acc = acc + self.cols[c] * v.c[c]
             return acc
+        if isinstance(v, Mat):
+            return Mat([self * v.cols[c] for c in range(v.n)])
         raise NotImplementedError
 
 
-def float4x4(*a):
-    if len(a) == 1:
-        s = float(a[0])
-        return Mat([float4(*[s if r == c else 0.0 for r in range(4)]) for c in range(4)])
-    assert len(a) == 16
-    return Mat([float4(*a[4 * c:4 * c + 4]) for c in range(4)])
+def _square(n, args):
+    """floatNxN(columns...) | floatNxN(matrix of another size: upper-left block, identity elsewhere)."""
+    if len(args) == 1 and isinstance(args[0], Mat):
+        m = args[0]
+        return Mat([_vec_type("f", n)(*[(m.cols[c].c[r] if (c < m.n and r < m.n) else (1.0 if r == c else 0.0)) for r in range(n)]) for c in range(n)])
+    if len(args) == 1:
+        s = float(args[0])
+        return Mat([_vec_type("f", n)(*[s if r == c else 0.0 for r in range(n)]) for c in range(n)])
+    if len(args) == n:
+        return Mat([_vec_type("f", n)(a) for a in args])
+    assert len(args) == n * n
+    return Mat([_vec_type("f", n)(*args[n * c:n * c + n]) for c in range(n)])
 
 
-def make_float3x3(c0, c1, c2):
-    return Mat([float3(c0), float3(c1), float3(c2)])
+def float4x4(*a): return _square(4, a)
+def float3x3(*a): return _square(3, a)
+def float2x2(*a): return _square(2, a)
+def make_float3x3(*a): return _square(3, a)
 
 
 def transpose(m: Mat) -> Mat:
@@ -412,7 +428,11 @@ def transpose(m: Mat) -> Mat:
 
 
 def inverse(m: Mat) -> Mat:
-    """3x3 inverse by cofactors / determinant (binary32 operations)."""
+    """2x2 / 3x3 inverse by cofactors / determinant (binary32 operations)."""
+    if m.n == 2:
+        a, b, c, d = m.cols[0].c[0], m.cols[0].c[1], m.cols[1].c[0], m.cols[1].c[1]      # [[a c],[b d]]
+        inv_det = 1.0 / (a * d - c * b)
+        return Mat([float2(d * inv_det, -b * inv_det), float2(-c * inv_det, a * inv_det)])
     assert m.n == 3
     a = [[m.cols[c].c[r] for c in range(3)] for r in range(3)]     # a[r][c]
     cof = [[None] * 3 for _ in range(3)]
@@ -843,7 +863,7 @@ class Accel:
 # ------------------------------------------------------------------------------------ @luisa.func
 def _copy(x):
     """value semantics of DSL assignment (`twin = sampler` copies, prb.py:96-98)"""
-    return x.copy() if isinstance(x, (Vec, _Struct, Ray)) else x
+    return x.copy() if isinstance(x, (Vec, _Struct, Ray, Mat)) else x
 
 
 class _IfExpToSelect(ast.NodeTransformer):
@@ -910,7 +930,7 @@ _BUILTINS.update(dict(
     make_float2=float2, make_float3=float3, make_float4=float4, make_int2=int2, make_int3=int3, make_int4=int4,
     make_uint2=uint2, make_uint3=uint3, make_uint4=uint4, make_float3x3=make_float3x3, inverse=inverse, transpose=transpose,
     dispatch_id=dispatch_id, dispatch_size=dispatch_size, float2=float2, float3=float3, float4=float4, int2=int2, int3=int3,
-    int4=int4, uint2=uint2, uint3=uint3, uint4=uint4, float4x4=float4x4,
+    int4=int4, uint2=uint2, uint3=uint3, uint4=uint4, float4x4=float4x4, float3x3=float3x3, float2x2=float2x2,
 ))
 
 
@@ -926,7 +946,7 @@ def install(pmj: np.ndarray, bn: np.ndarray, ref_dir: str = "/root/reference", p
     ad = types.ModuleType("luisa.autodiff")
     for k in ("float2", "float3", "float4", "int2", "int3", "int4", "uint2", "uint3", "uint4", "bool2", "bool3", "bool4",
               "make_float2", "make_float3", "make_float4", "make_int2", "make_int3", "make_int4", "make_uint2", "make_uint3",
-              "make_uint4", "float4x4", "make_float3x3"):
+              "make_uint4", "float4x4", "float3x3", "float2x2", "make_float3x3"):
         setattr(mt, k, globals()[k])
         setattr(luisa, k, globals()[k])
     mt.__all__ = [k for k in vars(mt) if not k.startswith("_")]

@@ -50,6 +50,8 @@ def lib():
         L.zo_render_forward.argtypes = [_vp, C.c_int, _pp, _f32p, _f32p]
         L.zo_render_samples.argtypes = [_vp, C.c_int, _pp, _f32p, _f32p]
         L.zo_render_backward.argtypes = [_vp, C.c_int, _pp, _f32p, _f32p, _f32p]
+        L.zo_render_duvdxy.argtypes = [_vp, _pp, _f32p]
+        L.zo_probe_duvdxy.argtypes = [_vp, _f32p, C.c_int, _f32p]
         L.zo_get_ray_counters.argtypes = [_vp, C.POINTER(C.c_uint64)]
         L.zo_reset_ray_counters.argtypes = [_vp]
         L.zo_xxhash32_int4.restype = C.c_uint32
@@ -248,6 +250,18 @@ class OracleScene:
         rc = lib().zo_render_backward(self._h, integrator, C.byref(params), _p(m), _p(g), _p(dm))
         assert rc == 0, rc
         return dm
+
+    def render_duvdxy(self, params: ZdrParams) -> np.ndarray:
+        img = np.zeros((params.height, params.width, 4), dtype=np.float32)
+        rc = lib().zo_render_duvdxy(self._h, C.byref(params), _p(img))
+        assert rc == 0, rc
+        return img
+
+    def duvdxy(self, rays18):
+        r = _f(rays18).reshape(-1, 18)
+        out = np.empty((r.shape[0], 4), np.float32)
+        assert lib().zo_probe_duvdxy(self._h, _p(r), r.shape[0], _p(out)) == 0
+        return out
 
     def ray_counters(self):
         out = (C.c_uint64 * 2)()

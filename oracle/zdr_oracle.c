@@ -1275,6 +1275,92 @@ ZO_API int zo_render_backward(zo_scene* s, int integrator, const zdr_params* p, 
     return ZDR_OK;
 }
 
+/* uvgrad.py:19-49 — screen-to-texture Jacobian (d u / d x, d v / d x, d u / d y, d v / d y) of the first
+ * hit, by ray differentials.  Deviations: triangle corners are taken in WORLD space (the
+ * reference mixes object-space corners with world-space rays, identical for identity transforms), and
+ * the 3x3 products of uvgrad.py:43-46 are evaluated as iaTa * (aT * dp). */
+static f4 trace_duvdxy(zo_scene* s, Ray ray, Ray rdx, Ray rdy) {
+    f4 zero = {0, 0, 0, 0};
+    s->n_closest++;
+    Hit hit = trace_closest(s, ray);
+    if (hit.inst < 0) return zero;
+    Inst* in = &s->inst[hit.inst];
+    int g = in->tri_base + hit.prim;
+    f3 p0 = s->P[3 * g], p1 = s->P[3 * g + 1], p2 = s->P[3 * g + 2];
+    const float* v0 = in->verts + 8 * in->tris[3 * hit.prim + 0];
+    const float* v1 = in->verts + 8 * in->tris[3 * hit.prim + 1];
+    const float* v2 = in->verts + 8 * in->tris[3 * hit.prim + 2];
+    f3 p = interp3(&hit, p0, p1, p2);
+    /* compute_dpduv, uvgrad.py:6-16 */
+    f3 e1 = sub3(p1, p0), e2 = sub3(p2, p0);
+    float a = v1[3] - v0[3], b = v1[4] - v0[4], c = v2[3] - v0[3], d = v2[4] - v0[4];   /* duvde columns (a,b), (c,d) */
+    float det = a * d - c * b;
+    float i00 = d / det, i10 = -b / det, i01 = -c / det, i11 = a / det;                  /* inverse, column-major */
+    f3 dpdu = v3(fmaf(e2.x, i10, e1.x * i00), fmaf(e2.y, i10, e1.y * i00), fmaf(e2.z, i10, e1.z * i00));
+    f3 dpdv = v3(fmaf(e2.x, i11, e1.x * i01), fmaf(e2.y, i11, e1.y * i01), fmaf(e2.z, i11, e1.z * i01));
+    dpdv = neg3(dpdv);                                                                    /* inverted v */
+    f3 ng = normalize3(cross3(e1, e2));
+    float t_dx = dot3(sub3(p, rdx.o), ng) / dot3(rdx.d, ng);
+    float t_dy = dot3(sub3(p, rdy.o), ng) / dot3(rdy.d, ng);
+    f3 dpdx = sub3(v3(fmaf(t_dx, rdx.d.x, rdx.o.x), fmaf(t_dx, rdx.d.y, rdx.o.y), fmaf(t_dx, rdx.d.z, rdx.o.z)), p);
+    f3 dpdy = sub3(v3(fmaf(t_dy, rdy.d.x, rdy.o.x), fmaf(t_dy, rdy.d.y, rdy.o.y), fmaf(t_dy, rdy.d.z, rdy.o.z)), p);
+    float m00 = dot3(dpdu, dpdu), m01 = dot3(dpdu, dpdv), m11 = dot3(dpdv, dpdv);
+    float mdet = m00 * m11 - m01 * m01;
+    float j00 = m11 / mdet, j01 = -m01 / mdet, j11 = m00 / mdet;
+    float bx0 = dot3(dpdu, dpdx), bx1 = dot3(dpdv, dpdx), by0 = dot3(dpdu, dpdy), by1 = dot3(dpdv, dpdy);
+    f4 r = {fmaf(j01, bx1, j00 * bx0), fmaf(j11, bx1, j01 * bx0), fmaf(j01, by1, j00 * by0), fmaf(j11, by1, j01 * by0)};
+    return r;
+}
+static Ray camera_ray_at(const zdr_params* p, int x, int y, f2 off, float ox, float oy) {
+    f2 px;
+    px.x = 2.0f / (float)p->width * ((float)x + off.x + ox) - 1.0f;
+    px.y = 2.0f / (float)p->height * ((float)y + off.y + oy) - 1.0f;
+    px.y *= (float)p->height / (float)p->width;
+    return generate_ray(p, px);
+}
+/* uvgrad.py:75-98; sampler: the render kernels' pmj02bn sampler (integrator.py:17) instead of LuisaCompute's
+ * built-in LCG (unpinned). out: (H,W,4) */
+ZO_API int zo_render_duvdxy(zo_scene* s, const zdr_params* p, float* image) {
+    int rc = check_render_args(s, ZDR_COLLOCATED, p);
+    if (rc) return rc;
+    if (!image) return ZDR_ERR_ARG;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = p->row0; y < p->row1; ++y) {
+        if (!row_in_shard(p, y)) continue;
+        zo_scene local = *s;
+        for (int x = 0; x < p->width; ++x) {
+            f4 acc = {0, 0, 0, 0};
+            for (int it = p->it0; it < p->it1; ++it) {
+                Sampler sm = make_sampler(x, y, p->seed, p->spp, it);
+                f2 off = sampler_next2f(&sm);
+                if (p->use_tent_filter) { off.x = tent_warp1(off.x) + 0.5f; off.y = tent_warp1(off.y) + 0.5f; }
+                Ray ray = camera_ray_at(p, x, y, off, 0.0f, 0.0f);
+                Ray rdx = camera_ray_at(p, x, y, off, 1.0f, 0.0f);
+                Ray rdy = camera_ray_at(p, x, y, off, 0.0f, 1.0f);
+                f4 g = trace_duvdxy(&local, ray, rdx, rdy);
+                if (!(isnan(g.x) || isnan(g.y) || isnan(g.z) || isnan(g.w))) acc = add4(acc, g);
+            }
+            float* o = image + ((size_t)x + (size_t)y * p->width) * 4;
+            o[0] = acc.x / (float)p->spp; o[1] = acc.y / (float)p->spp; o[2] = acc.z / (float)p->spp; o[3] = acc.w / (float)p->spp;
+        }
+    }
+    return ZDR_OK;
+}
+
+/* rays: n x 18 (o,d of the centre ray, of the x-offset ray, of the y-offset ray) -> n x 4 */
+ZO_API int zo_probe_duvdxy(zo_scene* s, const float* rays, int n, float* out) {
+    if (!s || !s->committed) return ZDR_ERR_STATE;
+    for (int i = 0; i < n; ++i) {
+        const float* r = rays + 18 * i;
+        Ray a = {v3(r[0], r[1], r[2]), v3(r[3], r[4], r[5]), 0.0f, 1e30f};
+        Ray bx = {v3(r[6], r[7], r[8]), v3(r[9], r[10], r[11]), 0.0f, 1e30f};
+        Ray by = {v3(r[12], r[13], r[14]), v3(r[15], r[16], r[17]), 0.0f, 1e30f};
+        f4 g = trace_duvdxy(s, a, bx, by);
+        out[4 * i] = g.x; out[4 * i + 1] = g.y; out[4 * i + 2] = g.z; out[4 * i + 3] = g.w;
+    }
+    return ZDR_OK;
+}
+
 ZO_API void zo_get_ray_counters(zo_scene* s, uint64_t* out) { out[0] = s->n_closest; out[1] = s->n_any; }
 ZO_API void zo_reset_ray_counters(zo_scene* s) { s->n_closest = 0; s->n_any = 0; }
 ZO_API int zo_num_threads(void) {

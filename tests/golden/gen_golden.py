@@ -201,6 +201,28 @@ def gen_loadobj():
     print("loadobj.npz")
 
 
+def gen_uvgrad():
+    """uvgrad.py:19-49 `trace_duvdxy` (ray differentials -> screen-to-texture Jacobian) on camera rays of the
+    Cornell box.  The kernel around it (uvgrad.py:75-98) draws its pixel offsets from LuisaCompute's built-in LCG
+    sampler, which is not available to pin, so the rays are supplied directly."""
+    import zdr_ref.uvgrad as R_uv
+    sc = RefScene(scenes.cbox_collocated_models())
+    cam = R_render.Camera(fov=50 / 180 * 3.1415926, origin=E.float3(-0.2, 2.6, 6.0), target=E.float3(-0.2, 2.6, -2.5),
+                          up=E.float3(0.0, 1.0, 0.0))
+    rng = np.random.default_rng(12)
+    rays, outs = [], []
+    res = 32.0
+    for _ in range(150):
+        c = rng.uniform(2, 30, 2)
+        px = [E.float2(*(2.0 / res * (c + np.asarray(o)) - 1.0)) for o in ((0, 0), (1, 0), (0, 1))]
+        rr = [R_camera.generate_ray(cam, q) for q in px]
+        g = R_uv.trace_duvdxy(rr[0], rr[1], rr[2], sc.heap, sc.accel)
+        rays.append(sum([fv(r.get_origin()) + fv(r.get_dir()) for r in rr], []))
+        outs.append(fv(g))
+    np.savez_compressed(os.path.join(OUT, "uvgrad.npz"), rays=np.asarray(rays, np.float32), duvdxy=np.asarray(outs, np.float32))
+    print("uvgrad.npz: mean |duvdxy|", np.abs(np.asarray(outs)).mean(axis=0))
+
+
 # prb.py does not compile as shipped: its call sites disagree with the callee signatures in
 # interaction.py:9, light.py:23,84 and integrator.py:51-52 (SURVEY.md 8a "PRB defects" item 1).  The
 # textual substitutions below are exactly that list — nothing else is changed — and are applied to an
@@ -237,9 +259,11 @@ def load_patched_prb():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path", "loadobj"]
+    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path", "loadobj", "uvgrad"]
     if "loadobj" in which:
         gen_loadobj()
+    if "uvgrad" in which:
+        gen_uvgrad()
     if "sampler" in which:
         gen_sampler()
     if "functions" in which:

@@ -78,3 +78,13 @@ def test_render_kernels_vs_reference_source(oracle, name, models, integ, kw):
     dm = sc.render_backward(integ, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed + 1, **kw), mat, z["d_image"])
     assert np.abs(z["d_material"]).max() > 0
     assert rel_l2(dm, z["d_material"]) <= 1e-3, rel_l2(dm, z["d_material"])
+
+
+def test_duvdxy_vs_reference_source(oracle):
+    """uvgrad.py `trace_duvdxy` executed from the reference source vs the oracle."""
+    z = np.load(os.path.join(G, "uvgrad.npz"))
+    sc = oracle.OracleScene(scenes.cbox_collocated_models())
+    got = sc.duvdxy(z["rays"])
+    assert np.abs(z["duvdxy"]).max() > 0
+    assert rel_l2(got, z["duvdxy"]) <= 1e-4, rel_l2(got, z["duvdxy"])
+    assert np.allclose(got, z["duvdxy"], rtol=5e-3, atol=1e-6)

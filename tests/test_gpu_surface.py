@@ -119,6 +119,18 @@ def test_scatter_modes_agree(oracle):
     assert rel_l2(grads["auto"], grads["plain"]) < 1e-5
 
 
+def test_render_duvdxy_matches_oracle(scene, oracle):
+    """render.py:243-257 / uvgrad.py: screen-to-texture Jacobian; footprint example of example.py:62-64."""
+    mat = torch.from_numpy(scenes.random_material((32, 32), 0)).cuda()
+    out = scene.render_duvdxy(mat, res=(80, 64), spp=4, seed=3)
+    assert out.shape == (64, 80, 4)
+    o = oracle.OracleScene(scenes.cbox_path_models())
+    ref = o.render_duvdxy(make_params(scenes.CBOX_CAMERA, (80, 64), (32, 32), 4, 3))
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    footprints = torch.det(out.reshape(64, 80, 2, 2)).abs() * 1024 * 1024
+    assert float(footprints.mean()) > 1.0
+
+
 def test_errors_are_python_exceptions(scene):
     with pytest.raises(AssertionError):
         scene.render(torch.zeros((4, 4, 3), device="cuda"), res=(8, 8), spp=1)          # render.py:160

@@ -92,6 +92,7 @@ SIGNATURES = {
     "zdr_scene_triangle_count": (C.c_int, [_vp]),
     "zdr_render_forward": (C.c_int, [_vp, C.c_int, _pp, _vp, _vp, _vp]),
     "zdr_render_backward": (C.c_int, [_vp, C.c_int, _pp, _vp, _vp, _vp, _vp]),
+    "zdr_render_duvdxy": (C.c_int, [_vp, _pp, _vp, _vp]),
     "zdr_render_forward_host": (C.c_int, [_vp, C.c_int, _pp, _f32p, _f32p]),
     "zdr_render_backward_host": (C.c_int, [_vp, C.c_int, _pp, _f32p, _f32p, _f32p]),
     "zdr_get_counters": (C.c_int, [_vp, _u64p]),

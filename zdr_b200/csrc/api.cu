@@ -479,6 +479,18 @@ ZDR_EXPORT int zdr_render_backward(zdr_scene* s, int integrator, const zdr_param
     return ZDR_OK;
 }
 
+ZDR_EXPORT int zdr_render_duvdxy(zdr_scene* s, const zdr_params* p, float* image_dev, void* stream) {
+    int rc = check_params(s, ZDR_COLLOCATED, p);
+    if (rc) return rc;
+    if (!image_dev) return fail(ZDR_ERR_ARG, "render_duvdxy: null buffer");
+    if ((rc = use_device(s->device))) return rc;
+    RenderArgs a;
+    if ((rc = make_args(s, p, &a))) return rc;
+    a.image = reinterpret_cast<float4*>(image_dev);
+    CK(launch_duvdxy(a, (cudaStream_t)stream));
+    return ZDR_OK;
+}
+
 ZDR_EXPORT int zdr_render_forward_host(zdr_scene* s, int integrator, const zdr_params* p, const float* material_host,
                                        float* image_host) {
     int rc = check_params(s, integrator, p);

@@ -840,6 +840,69 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_accumulate(const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------------- uvgrad.py
+// Scene.render_duvdxy (render.py:243-257, uvgrad.py:19-98): screen-to-texture Jacobian of the first
+// hit by ray differentials.  Deviations, stated in DESIGN.md: the pixel offsets come from the render
+// kernels' pmj02bn sampler (integrator.py:17; the reference uses LuisaCompute's built-in LCG here),
+// triangle corners are world-space, and the 3x3 products of uvgrad.py:43-46 are evaluated as
+// iaTa * (aT * dp).
+ZDR_DEV Ray camera_ray_at(const RenderArgs& a, int x, int y, float2 off, float ox, float oy) {
+    float px = 2.0f / (float)a.W * ((float)x + off.x + ox) - 1.0f;
+    float py = 2.0f / (float)a.H * ((float)y + off.y + oy) - 1.0f;
+    py *= (float)a.H / (float)a.W;
+    const float sx = px * a.tan_half_fov, sy = py * a.tan_half_fov;
+    const float3 d = f3(sx * a.cam_right.x - sy * a.cam_up.x + a.cam_fwd.x, sx * a.cam_right.y - sy * a.cam_up.y + a.cam_fwd.y,
+                        sx * a.cam_right.z - sy * a.cam_up.z + a.cam_fwd.z);
+    return make_ray(a.cam_o, normalize(d), 0.0f, 1e30f);
+}
+__global__ void __launch_bounds__(kBlockThreads) k_uvgrad(const __grid_constant__ RenderArgs a) {
+    int x, y;
+    pixel_of_thread(a, x, y);
+    Tally tl = {};
+    Ctx<false> c{a, tl};
+    const SceneView& sc = a.sc;
+    if (x < a.W && y < a.row1) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int it = a.it0; it < a.it1; ++it) {
+            Sampler sampler = make_sampler(sc, x, y, a.seed, a.spp, it);
+            float2 off = sampler_next2f(sc, sampler);
+            if (a.use_tent) { off.x = tent_warp1(off.x) + 0.5f; off.y = tent_warp1(off.y) + 0.5f; }
+            const Ray ray = camera_ray_at(a, x, y, off, 0.0f, 0.0f);
+            const Ray rdx = camera_ray_at(a, x, y, off, 1.0f, 0.0f), rdy = camera_ray_at(a, x, y, off, 0.0f, 1.0f);
+            tl.samples++;
+            const Hit hit = c.closest(ray);
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (hit.inst >= 0) {
+                const float4* tp = sc.tris + 3 * (size_t)hit.slot;
+                const float4* sp = sc.shade + 4 * (size_t)hit.slot;
+                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2), s3 = __ldg(sp + 3);
+                const float3 p0 = f3(t0.x, t0.y, t0.z), p1 = f3(t1.x, t1.y, t1.z), p2 = f3(t2.x, t2.y, t2.z);
+                const float w = 1.0f - hit.u - hit.v;
+                const float3 p = lincomb(w, p0, hit.u, p1, hit.v, p2);
+                const float3 e1 = p1 - p0, e2 = p2 - p0;                                   // compute_dpduv, uvgrad.py:6-16
+                const float ua = s1.w - s0.w, ub = s3.y - s3.x, uc = s2.w - s0.w, ud = s3.z - s3.x;
+                const float det = ua * ud - uc * ub;
+                const float i00 = ud / det, i10 = -ub / det, i01 = -uc / det, i11 = ua / det;
+                const float3 dpdu = f3(fmaf(e2.x, i10, e1.x * i00), fmaf(e2.y, i10, e1.y * i00), fmaf(e2.z, i10, e1.z * i00));
+                const float3 dpdv = -f3(fmaf(e2.x, i11, e1.x * i01), fmaf(e2.y, i11, e1.y * i01), fmaf(e2.z, i11, e1.z * i01));
+                const float3 ng = normalize(cross(e1, e2));
+                const float t_dx = dot(p - rdx.o, ng) / dot(rdx.d, ng), t_dy = dot(p - rdy.o, ng) / dot(rdy.d, ng);
+                const float3 dpdx = f3(fmaf(t_dx, rdx.d.x, rdx.o.x), fmaf(t_dx, rdx.d.y, rdx.o.y), fmaf(t_dx, rdx.d.z, rdx.o.z)) - p;
+                const float3 dpdy = f3(fmaf(t_dy, rdy.d.x, rdy.o.x), fmaf(t_dy, rdy.d.y, rdy.o.y), fmaf(t_dy, rdy.d.z, rdy.o.z)) - p;
+                const float m00 = dot(dpdu, dpdu), m01 = dot(dpdu, dpdv), m11 = dot(dpdv, dpdv);
+                const float mdet = m00 * m11 - m01 * m01;
+                const float j00 = m11 / mdet, j01 = -m01 / mdet, j11 = m00 / mdet;
+                const float bx0 = dot(dpdu, dpdx), bx1 = dot(dpdv, dpdx), by0 = dot(dpdu, dpdy), by1 = dot(dpdv, dpdy);
+                g = make_float4(fmaf(j01, bx1, j00 * bx0), fmaf(j11, bx1, j01 * bx0), fmaf(j01, by1, j00 * by0), fmaf(j11, by1, j01 * by0));
+            }
+            if (!any_nan(g)) acc = acc + g;                                                // uvgrad.py:96-97
+        }
+        a.image[(size_t)x + (size_t)y * a.W] = make_float4(acc.x / (float)a.spp, acc.y / (float)a.spp, acc.z / (float)a.spp, acc.w / (float)a.spp);
+    }
+    flush_tally(a, tl);
+}
+
 // Between the replay rounds and the adjoint rounds of the adjoint pass (prb.py:97-101): every sample
 // whose replayed radiance Le is not NaN starts again at the camera with the ORIGINAL sampler state,
 // carrying Le as the "radiance still to be explained".
@@ -984,6 +1047,13 @@ cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cud
             return cudaGetLastError();
     }
 }
+cudaError_t launch_duvdxy(const RenderArgs& a, cudaStream_t s) {
+    if (a.row1 <= a.row0 || a.it1 <= a.it0 || render_grid(a).y == 0) return cudaSuccess;
+    ++g_kernel_launches;
+    k_uvgrad<<<render_grid(a), kBlockThreads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
 unsigned long long kernel_launch_count() { return g_kernel_launches.load(); }
 
 size_t wf_bytes_per_slot() { return 9 * sizeof(float4) + 2 * sizeof(int); }

@@ -53,6 +53,7 @@ cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cud
 // wavefront variant of the path integrator / PRB adjoint; `wf` buffers sized for wf_slot_capacity() slots
 size_t wf_bytes_per_slot();
 cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaStream_t stream);
+cudaError_t launch_duvdxy(const RenderArgs& a, cudaStream_t stream);
 cudaError_t launch_probe_trace(const SceneView& sc, const float* rays_dev, int n, bool any, int* ip_dev,
                                float* uvt_dev, int* occ_dev, cudaStream_t stream);
 cudaError_t launch_probe_sampler(const SceneView& sc, const int* state_dev, int n, const char* prog_dev, int prog_len,

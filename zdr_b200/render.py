@@ -235,6 +235,17 @@ class Scene:
             return self._render_distributed(material, res, spp, seed)
         return Scene.RenderOperator.apply(material, self, res, spp, seed)
 
+    def render_duvdxy(self, material, *, res, spp, seed=0):
+        """Gradient of the texture coordinates w.r.t. screen-space coordinates (``render.py:243-257``):
+        ``(height, width, 4)`` tensor of (dudx, dvdx, dudy, dvdy).  ``material`` only fixes the device, as in
+        the reference.  Not differentiable."""
+        self._check_material(material)
+        image = torch.zeros((res[1], res[0], 4), dtype=torch.float32, device=self.device)
+        p = self._params(material, res, spp, seed)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(self._lib.zdr_render_duvdxy(self._handle, C.byref(p), image.data_ptr(), stream), "zdr_render_duvdxy")
+        return image
+
     # ------------------------------------------------------------------ multi-GPU (distributed.py)
     def distribute(self, group=None):
         """Shard every later :meth:`render` over the ranks of ``group`` (default: WORLD): replicated
