@@ -388,3 +388,72 @@ def test_light_stage_uniform_texture(oracle):
                 gg, go = g.backward(integ, p, mat, d), o.render_backward(integ, p, mat, d)
                 assert rel_l2(gg, go) <= GRAD_TOL, (integ, rel_l2(gg, go))
     g.close()
+
+
+@pytest.mark.parametrize("integ,kw", [(ZDR_DIRECT, {}), (ZDR_PATH, {"max_depth": 4, "schedule": "megakernel"}),
+                                      (ZDR_PATH, {"max_depth": 4, "schedule": "wavefront"})])
+def test_ragged_shapes_and_odd_sample_counts(oracle, integ, kw):
+    """Non-square image (aspect ratio in integrator.py:23), non-square texture (row stride = shape[0],
+    render.py:161 quirk), sample counts that are not powers of two (cycle-walking permutation), a seed that
+    wraps at seed+1 (render.py:196), image sizes that are not multiples of the 16x8 block tile."""
+    models = scenes.cbox_path_models()
+    g, o = GpuScene(models), oracle.OracleScene(models)
+    rng = np.random.default_rng(21)
+    for (W, H), tex, spp, seed in [((37, 19), (24, 40), 3, 5), ((50, 70), (40, 24), 5, 2147483647), ((16, 8), (7, 7), 12, -3), ((1, 1), (1, 1), 1, 0)]:
+        mat = np.clip(rng.random((tex[0], tex[1], 4), dtype=np.float32), 1e-3, 1.0)
+        p = make_params(scenes.CBOX_CAMERA, (W, H), mat.shape, spp, seed, **kw)
+        assert np.array_equal(bits(g.samples(integ, p, mat)), bits(o.render_samples(integ, p, mat))), (W, H, tex, spp)
+        assert np.array_equal(bits(g.forward(integ, p, mat)), bits(o.render_forward(integ, p, mat)))
+        pb = make_params(scenes.CBOX_CAMERA, (W, H), mat.shape, spp, _abi.wrap_i32(seed + 1), **kw)
+        d = rng.normal(size=(H, W, 4)).astype(np.float32)
+        gg, go = g.backward(integ, pb, mat, d), o.render_backward(integ, pb, mat, d)
+        assert rel_l2(gg, go) <= GRAD_TOL or np.abs(go).max() == 0
+    g.close()
+
+
+def test_nan_and_degenerate_inputs(oracle):
+    """NaN hygiene of integrator.py:27,38-40 and prb.py:100-101,179: NaN cotangents are zeroed, NaN texels
+    poison only the samples that read them, degenerate (zero-area) triangles are never hit."""
+    models = scenes.cbox_path_models()
+    g, o = GpuScene(models), oracle.OracleScene(models)
+    mat = scenes.random_material((32, 32), 8)
+    mat[5:9, 5:9, :] = np.nan
+    p = make_params(scenes.CBOX_CAMERA, (48, 48), mat.shape, 4, 0, max_depth=4)
+    img_g, img_o = g.forward(ZDR_PATH, p, mat), o.render_forward(ZDR_PATH, p, mat)
+    assert np.array_equal(bits(img_g), bits(img_o)) and np.isfinite(img_o).all()           # NaN samples are dropped
+    d = np.ones((48, 48, 4), np.float32)
+    d[10:20, 10:20] = np.nan
+    gg, go = g.backward(ZDR_PATH, p, scenes.random_material((32, 32), 8), d), o.render_backward(ZDR_PATH, p, scenes.random_material((32, 32), 8), d)
+    assert np.isfinite(go).all() and rel_l2(gg, go) <= GRAD_TOL
+    g.close()
+    # a mesh with a zero-area triangle and a sliver
+    verts = np.array([[0, 0, 0, 0, 0, 0, 0, 1], [1, 0, 0, 1, 0, 0, 0, 1], [0, 1, 0, 0, 1, 0, 0, 1], [2, 2, 0, 1, 1, 0, 0, 1], [1e-7, 1, 0, 0, 1, 0, 0, 1]], np.float32)
+    tris = np.array([0, 1, 2, 3, 3, 3, 0, 2, 4], np.int32)
+    lib = _abi.load_library()
+    h = C.c_void_p()
+    _abi.check(lib.zdr_scene_create(C.byref(h), 0))
+    _abi.check(lib.zdr_scene_add_mesh(h, np_ptr(verts, C.c_float), 5, np_ptr(tris, C.c_int32), 3, None, None))
+    _abi.check(lib.zdr_scene_commit(h))
+    os_ = oracle.OracleScene([((verts, tris), None, None)])
+    rays = _random_rays(2000, 4, (-0.5, -0.5, 1.0), (1.5, 1.5, 2.0))
+    rays[:, 3:6] = [0, 0, -1]
+    ip, uvt = np.empty((2000, 2), np.int32), np.empty((2000, 3), np.float32)
+    _abi.check(lib.zdr_probe_trace_closest(h, np_ptr(rays, C.c_float), 2000, np_ptr(ip, C.c_int32), np_ptr(uvt, C.c_float)))
+    ip_o, _ = os_.trace_closest(rays)
+    assert np.array_equal(ip, ip_o) and not (ip[:, 1] == 1).any()
+    lib.zdr_scene_destroy(h)
+
+
+def test_error_codes():
+    lib = _abi.load_library()
+    h = C.c_void_p()
+    _abi.check(lib.zdr_scene_create(C.byref(h), 0))
+    assert lib.zdr_scene_commit(h) == -2                                                  # ZDR_ERR_STATE: empty scene
+    p = make_params(scenes.CBOX_CAMERA, (8, 8), (4, 4), 1, 0)
+    assert lib.zdr_render_forward(h, 1, C.byref(p), 1, 1, None) == -2                    # not committed
+    verts = np.zeros((3, 8), np.float32)
+    bad = np.array([0, 1, 7], np.int32)
+    assert lib.zdr_scene_add_mesh(h, np_ptr(verts, C.c_float), 3, np_ptr(bad, C.c_int32), 1, None, None) == -1     # index out of range
+    assert b"out of range" in lib.zdr_last_error()
+    assert lib.zdr_scene_create(C.byref(C.c_void_p()), 999) == -1                         # bad device
+    lib.zdr_scene_destroy(h)
