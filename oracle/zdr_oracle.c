@@ -929,7 +929,6 @@ static void direct_estimator_backward(Ctx* c, Ray ray, Sampler* sampler, f3 le_g
     f4 mat_grad = {0, 0, 0, 0};
     f2 mat_grad_uv = it.uv;
     f4 mat = read_bsdf(&c->tex, it.uv);
-    f3 diffuse = v3(mat.x, mat.y, mat.z);
     float roughness = mat.w;
     const float specular = 0.04f;
     LightSample light = sample_light(s, it.p, sampler);

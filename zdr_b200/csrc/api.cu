@@ -240,14 +240,11 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
     if (e != cudaSuccess) return fail(ZDR_ERR_CUDA, "wavefront state (%zu MiB): %s", bytes >> 20, cudaGetErrorString(e));
     char* base = s->s_wf.p;
     WfState& w = a->wf;
-    w.A = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
-    w.B = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
-    w.C = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
-    w.D = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
+    w.AB = reinterpret_cast<float4*>(base); base += 2 * slots * sizeof(float4);
+    w.CD = reinterpret_cast<float4*>(base); base += 2 * slots * sizeof(float4);
     w.H = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
     w.R = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
-    w.SA = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
-    w.SB = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
+    w.SAB = reinterpret_cast<float4*>(base); base += 2 * slots * sizeof(float4);
     w.SC = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
     w.list[0] = reinterpret_cast<int*>(base); base += slots * sizeof(int);
     w.list[1] = reinterpret_cast<int*>(base); base += slots * sizeof(int);

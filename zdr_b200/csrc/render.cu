@@ -444,10 +444,10 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_generate(const __grid_constan
         Sampler sampler = make_sampler(a.sc, x, y, a.seed, a.spp, w.it_base + j);
         const Ray ray = camera_sample(a, x, y, sampler);
         tl.samples++;
-        w.A[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, 1e30f);                              // prb.py:22
-        w.B[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(wf_pack(0, 0, sampler.dimension)));
-        w.C[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
-        w.D[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w.AB[2 * (size_t)(slot)] = make_float4(ray.o.x, ray.o.y, ray.o.z, 1e30f);                              // prb.py:22
+        w.AB[2 * (size_t)(slot) + 1] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(wf_pack(0, 0, sampler.dimension)));
+        w.CD[2 * (size_t)(slot)] = make_float4(1.f, 1.f, 1.f, 0.f);
+        w.CD[2 * (size_t)(slot) + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!BWD) w.R[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
         w.list[0][slot] = slot;
     }
@@ -502,11 +502,11 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
                     {
                         float3 o, d;
                         if (ANY) {
-                            const float4 SA = w.SA[slot], SB = w.SB[slot];
+                            const float4 SA = w.SAB[2 * (size_t)(slot)], SB = w.SAB[2 * (size_t)(slot) + 1];
                             o = f3(SA.x, SA.y, SA.z); d = f3(SB.x, SB.y, SB.z); tmin = 1e-4f; tmax = SA.w;
                             tl.any++;
                         } else {
-                            const float4 A = w.A[slot], B = w.B[slot];
+                            const float4 A = w.AB[2 * (size_t)(slot)], B = w.AB[2 * (size_t)(slot) + 1];
                             o = f3(A.x, A.y, A.z); d = f3(B.x, B.y, B.z); tmin = 0.0f; tmax = 1e30f;
                             tl.closest++;
                         }
@@ -606,7 +606,7 @@ ZDR_DEV WfPath wf_load(const RenderArgs& a, int slot, bool with_throughput) {
     const int j = slot / w.P, pix = slot - j * w.P;
     wf_pixel(a, pix, p.x, p.y);
     p.it = w.it_base + j;
-    const float4 A = w.A[slot], B = w.B[slot];
+    const float4 A = w.AB[2 * (size_t)(slot)], B = w.AB[2 * (size_t)(slot) + 1];
     p.ray = make_ray(f3(A.x, A.y, A.z), f3(B.x, B.y, B.z), 0.0f, 1e30f);
     p.pdf_bsdf = A.w;
     const unsigned packed = __float_as_uint(B.w);
@@ -615,7 +615,7 @@ ZDR_DEV WfPath wf_load(const RenderArgs& a, int slot, bool with_throughput) {
     p.sampler = make_sampler(a.sc, p.x, p.y, a.seed, a.spp, p.it);
     p.sampler.dimension = (int)(packed >> 12);
     if (with_throughput) {
-        const float4 C4 = w.C[slot], D4 = w.D[slot];
+        const float4 C4 = w.CD[2 * (size_t)(slot)], D4 = w.CD[2 * (size_t)(slot) + 1];
         p.beta = f3(C4.x, C4.y, C4.z); p.L = f3(D4.x, D4.y, D4.z);
     } else {
         p.beta = f3(0.f, 0.f, 0.f); p.L = f3(0.f, 0.f, 0.f);
@@ -623,7 +623,7 @@ ZDR_DEV WfPath wf_load(const RenderArgs& a, int slot, bool with_throughput) {
     return p;
 }
 ZDR_DEV void wf_load_throughput(const RenderArgs& a, WfPath& p) {
-    const float4 C4 = a.wf.C[p.slot], D4 = a.wf.D[p.slot];
+    const float4 C4 = a.wf.CD[2 * (size_t)(p.slot)], D4 = a.wf.CD[2 * (size_t)(p.slot) + 1];
     p.beta = f3(C4.x, C4.y, C4.z); p.L = f3(D4.x, D4.y, D4.z);
 }
 ZDR_DEV Hit wf_hit(const RenderArgs& a, int slot) {
@@ -642,7 +642,7 @@ ZDR_DEV Hit wf_hit(const RenderArgs& a, int slot) {
 template <int MODE>
 ZDR_DEV void wf_finish(const RenderArgs& a, WfPath& p) {
     const WfState& w = a.wf;
-    if (MODE == 1) { w.D[p.slot] = make_float4(p.L.x, p.L.y, p.L.z, 1.0f); return; }
+    if (MODE == 1) { w.CD[2 * (size_t)(p.slot) + 1] = make_float4(p.L.x, p.L.y, p.L.z, 1.0f); return; }
     if (MODE == 2) return;
     if (a.samples_out) {
         float* o = a.samples_out + (((size_t)p.y * a.W + p.x) * a.spp + p.it) * 3;
@@ -697,10 +697,10 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_A_MINB) k_wf_shade_a(
                 } else {
                     tl.shaded++;
                     const LightSample light = sample_light<ENV>(sc, itx.p, p.sampler);                 // prb.py:57
-                    w.SA[p.slot] = make_float4(itx.p.x, itx.p.y, itx.p.z, light.dist);
-                    w.SB[p.slot] = make_float4(light.wi.x, light.wi.y, light.wi.z, light.pdf);
+                    w.SAB[2 * (size_t)(p.slot)] = make_float4(itx.p.x, itx.p.y, itx.p.z, light.dist);
+                    w.SAB[2 * (size_t)(p.slot) + 1] = make_float4(light.wi.x, light.wi.y, light.wi.z, light.pdf);
                     w.SC[p.slot] = make_float4(light.eval.x, light.eval.y, light.eval.z, 0.f);
-                    w.B[p.slot].w = __uint_as_float(wf_pack(p.depth, phase, p.sampler.dimension));
+                    w.AB[2 * (size_t)(p.slot) + 1].w = __uint_as_float(wf_pack(p.depth, phase, p.sampler.dimension));
                     keep = true;
                     entry = p.slot;
                 }
@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
                 const float roughness = mat.w;
                 const Onb onb = make_onb(itx.ns);
                 const float3 wo_local = to_local(onb, -p.ray.d);
-                const float4 SB = w.SB[slot], SC = w.SC[slot];
+                const float4 SB = w.SAB[2 * (size_t)(slot) + 1], SC = w.SC[slot];
                 const float3 light_wi = f3(SB.x, SB.y, SB.z), light_eval = f3(SC.x, SC.y, SC.z);
                 const float light_pdf = SB.w;
                 const bool occluded = SC.w != 0.0f;
@@ -810,10 +810,10 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
                     wf_finish<MODE>(a, p);
                 } else {
                     survive = true;
-                    w.A[slot] = make_float4(p.ray.o.x, p.ray.o.y, p.ray.o.z, p.pdf_bsdf);
-                    w.B[slot] = make_float4(p.ray.d.x, p.ray.d.y, p.ray.d.z, __uint_as_float(wf_pack(p.depth, ADJ ? 1 : 0, p.sampler.dimension)));
-                    w.C[slot] = make_float4(p.beta.x, p.beta.y, p.beta.z, 0.f);
-                    w.D[slot] = make_float4(p.L.x, p.L.y, p.L.z, 0.f);
+                    w.AB[2 * (size_t)(slot)] = make_float4(p.ray.o.x, p.ray.o.y, p.ray.o.z, p.pdf_bsdf);
+                    w.AB[2 * (size_t)(slot) + 1] = make_float4(p.ray.d.x, p.ray.d.y, p.ray.d.z, __uint_as_float(wf_pack(p.depth, ADJ ? 1 : 0, p.sampler.dimension)));
+                    w.CD[2 * (size_t)(slot)] = make_float4(p.beta.x, p.beta.y, p.beta.z, 0.f);
+                    w.CD[2 * (size_t)(slot) + 1] = make_float4(p.L.x, p.L.y, p.L.z, 0.f);
                 }
             }
         }
@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_restart(const __grid_constant
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_round; slot += wf_stride()) {
         bool keep = false;
         if (slot < w.nslots && a.max_depth > 0) {
-            const float4 D4 = w.D[slot];
+            const float4 D4 = w.CD[2 * (size_t)(slot) + 1];
             const float3 Le = f3(D4.x, D4.y, D4.z);
             if (!any_nan(Le)) {
                 const int j = slot / w.P, pix = slot - j * w.P;
@@ -920,9 +920,9 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_restart(const __grid_constant
                 wf_pixel(a, pix, x, y);
                 Sampler cam = make_sampler(a.sc, x, y, a.seed, a.spp, w.it_base + j);
                 const Ray ray = camera_sample(a, x, y, cam);
-                w.A[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, 1e30f);
-                w.B[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(wf_pack(0, 1, cam.dimension)));
-                w.C[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+                w.AB[2 * (size_t)(slot)] = make_float4(ray.o.x, ray.o.y, ray.o.z, 1e30f);
+                w.AB[2 * (size_t)(slot) + 1] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(wf_pack(0, 1, cam.dimension)));
+                w.CD[2 * (size_t)(slot)] = make_float4(1.f, 1.f, 1.f, 0.f);
                 keep = true;
             }
         }

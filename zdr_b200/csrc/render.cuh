@@ -9,14 +9,13 @@ namespace zdr {
 // Global-memory path state of the wavefront path tracer (render.cu, k_wf_*): one slot per
 // (sample-in-batch j, pixel pix), slot = j * P + pix, so a warp works on 32 neighbouring pixels.
 struct WfState {
-    float4* A;        // ray origin.xyz | pdf_bsdf
-    float4* B;        // ray direction.xyz | packed (depth, phase, sampler dimension)
-    float4* C;        // beta.xyz | -
-    float4* D;        // L.xyz (radiance accumulated / Le remaining) | -
+    // pairs of records that are always read together share one 32-byte sector (slots of a compacted list are
+    // not contiguous, so a lone 16-byte record would waste half of every sector fetched):
+    float4* AB;       // [2*slot] ray origin.xyz | pdf_bsdf      [2*slot+1] ray direction.xyz | packed (depth, phase, sampler dimension)
+    float4* CD;       // [2*slot] beta.xyz | -                   [2*slot+1] L.xyz (radiance accumulated / Le remaining) | -
     float4* H;        // closest hit: slot | u | v | t
     float4* R;        // finished sample: clamped radiance.xyz | -   (forward only)
-    float4* SA;       // shadow ray origin.xyz (= hit point) | light.dist
-    float4* SB;       // light.wi.xyz | light.pdf
+    float4* SAB;      // [2*slot] shadow ray origin.xyz (= hit point) | light.dist   [2*slot+1] light.wi.xyz | light.pdf
     float4* SC;       // light.eval.xyz | occluded (written by the shadow stage)
     int* list[2];     // list[0]: live paths (input of extend); list[1]: paths to shade (output of shade A)
     int* counts;      // counts[0], counts[1]
