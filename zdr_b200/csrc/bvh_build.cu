@@ -15,6 +15,7 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 #include <numeric>
 #include <vector>
 #include "bvh_build.h"
@@ -331,7 +332,8 @@ struct SahBuilder {
             }
         }
         const float parent_area = std::max(box.area(), 1e-30f);
-        const float split_cost = 1.0f + best_cost / parent_area;     // node visit + expected children
+        static const float node_cost = getenv("ZDR_SAH_NODE_COST") ? (float)atof(getenv("ZDR_SAH_NODE_COST")) : 1.0f;
+        const float split_cost = node_cost + best_cost / parent_area;     // node visit + expected children
         if (n <= 4 && (n == 1 || (float)n <= split_cost)) return ~((a << 2) | (n - 1));
         std::sort(order.begin() + a, order.begin() + b, [&](int x, int y) {
             const float cx = tb[x].lo[best_axis] + tb[x].hi[best_axis], cy = tb[y].lo[best_axis] + tb[y].hi[best_axis];
