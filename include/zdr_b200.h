@@ -16,7 +16,8 @@
  *    through DLPack at render.py:162-164,179-181).
  *  - *_host pointers are ordinary host memory.
  *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it, no device-wide sync
- *    (the reference does two full barriers per call, render.py:165,172 — we do none).
+ *    (the reference does two full barriers per call, render.py:165,172 — we do none).  A scene
+ *    owns its counters and the wavefront workspace: use it from one stream at a time.
  *  - there is NO CPU fallback: with no usable CUDA device every compute entry fails with
  *    ZDR_ERR_CUDA.
  */

@@ -316,8 +316,8 @@ def test_transformed_instances_and_update_lights(oracle):
         if emis is not None:
             g.set_emissions(np.asarray(emis, np.float32))
             o.update_lights(emis)
-        for integ in (ZDR_DIRECT, ZDR_PATH):
-            p = make_params(cam, (80, 60), mat.shape, 4, 0, max_depth=4)
+        for integ, sched in ((ZDR_DIRECT, "auto"), (ZDR_PATH, "megakernel"), (ZDR_PATH, "wavefront")):
+            p = make_params(cam, (80, 60), mat.shape, 4, 0, max_depth=4, schedule=sched)
             assert np.array_equal(bits(g.samples(integ, p, mat)), bits(o.render_samples(integ, p, mat)))
             dimg = np.ones((60, 80, 4), np.float32)
             assert rel_l2(g.backward(integ, p, mat, dimg), o.render_backward(integ, p, mat, dimg)) <= GRAD_TOL
@@ -333,8 +333,8 @@ def test_envmap_path(oracle):
     o.set_envmap(env)
     mat = scenes.random_material((64, 64), 10)
     cam = scenes.Camera(fov=0.9, origin=scenes.float3(-2.0, 2.5, -4.0), target=scenes.float3(1.0, 0.3, 0.3), up=scenes.float3(0, 1, 0))
-    for integ in (ZDR_DIRECT, ZDR_PATH):
-        p = make_params(cam, (64, 48), mat.shape, 8, 0, max_depth=6)
+    for integ, sched in ((ZDR_DIRECT, "auto"), (ZDR_PATH, "megakernel"), (ZDR_PATH, "wavefront")):
+        p = make_params(cam, (64, 48), mat.shape, 8, 0, max_depth=6, schedule=sched)
         img_g, img_o = g.forward(integ, p, mat), o.render_forward(integ, p, mat)
         assert rel_l2(img_g, img_o) <= IMG_TOL, rel_l2(img_g, img_o)     # acosf/atan2f are libm vs CUDA: tolerance, not bits
         dimg = np.ones((48, 64, 4), np.float32)
