@@ -215,7 +215,7 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
     if (rows <= 0) return ZDR_OK;
     const long long pixels = (long long)p->width * rows;
     const long long samples = pixels * (p->it1 - p->it0);
-    if (p->flags & ZDR_FLAG_MEGAKERNEL) return ZDR_OK;
+    if ((p->flags & ZDR_FLAG_MEGAKERNEL) || p->max_depth > 255) return ZDR_OK;      // path depth is packed into 8 bits of the state
     if (!(p->flags & ZDR_FLAG_WAVEFRONT) && samples < (1ll << 21)) return ZDR_OK;
     // path-state budget: as many samples per batch as fit a quarter of the free HBM, at most 2^28 slots
     // (41 GB at 152 B per slot: all 256 samples of a 1024^2 image in one batch); ZDR_WF_SLOTS_LOG2 overrides.

@@ -392,21 +392,24 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------ wavefront path tracer
-// The same path integrator / PRB adjoint as k_path, cut at the closest-hit query into two small
-// kernels per bounce that run over compacted lists of live paths kept in HBM:
-//   k_wf_generate : camera samples of a batch of S samples x P pixels -> path state, list of all slots
-//   k_wf_extend   : closest-hit traversal of every live path             (ray -> hit record)
-//   k_wf_shade    : everything between two closest-hit queries: emitter / miss / backface tests,
-//                   texture fetch, light sample + shadow ray, BSDF sample, Russian roulette, and in the
-//                   adjoint the BRDF adjoints + gradient scatter; survivors are appended to the
-//                   next list with one warp-aggregated atomic per warp
-//   k_wf_accumulate: per pixel, adds the batch's finished samples IN SAMPLE ORDER (integrator.py:15-28)
-// Why: in the one-kernel form only ~15 of 32 lanes are active (finished lanes idle through
-// shading, traversal trip counts diverge), 128 registers cap occupancy at 16 warps/SM and the
-// code overflows the 32 KB instruction-cache level (profiles/r01d).  Here every warp of the shade
-// stage starts with 32 live paths, each kernel is small, and the state traffic (~190 B per
-// bounce) is what the 7.7 TB/s of HBM3e are for.  Arithmetic per sample is unchanged (same device
-// functions), so images stay bit-identical to the oracle.
+// The same path integrator / PRB adjoint as k_path, cut into small kernels that run over compacted
+// lists of live paths whose state lives in HBM (render.cuh: WfState).  Per batch of S samples x P pixels:
+//   k_wf_generate          camera samples -> path state, list[0] = all slots
+//   per bounce (max_depth rounds):
+//     k_wf_trace<closest>  closest-hit traversal of list[0]                      (ray -> hit record)
+//     k_wf_shade_a         miss / backface / emitter tests, light sample + shadow-ray record; list[0] -> list[1]
+//     k_wf_trace<any>      occlusion query of list[1]
+//     k_wf_shade_b         NEE term, BSDF sample, throughput, Russian roulette, (adjoint walk) BRDF adjoints +
+//                          gradient scatter; list[1] -> list[0] with one warp-aggregated atomic per warp
+//   forward:  k_wf_accumulate adds the batch's finished samples per pixel IN SAMPLE ORDER (integrator.py:15-28)
+//   adjoint:  the rounds run twice — MODE 1 replays every sample to get Le (prb.py:97-99), k_wf_restart puts
+//             the samples back at the camera with the original sampler state, MODE 2 is the adjoint walk.
+// Why: in the one-kernel form only ~15 of 32 lanes are active (finished lanes idle through shading,
+// traversal trip counts diverge), 128 registers cap occupancy at 16 warps/SM and the code overflows the
+// 32 KB instruction-cache level (profiles/r01d).  Here every warp of a shade stage starts with 32 live
+// paths, each kernel is small (64 registers), and the state traffic (~1.5 kB of DRAM per path) is what the
+// 7.7 TB/s of HBM3e are for.  Arithmetic per sample is unchanged (same device functions), so images stay
+// bit-identical to the oracle.
 #ifndef ZDR_WF_SHADE_A_MINB
 #define ZDR_WF_SHADE_A_MINB 8
 #endif
