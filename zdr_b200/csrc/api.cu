@@ -408,8 +408,14 @@ ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
 ZDR_EXPORT int zdr_scene_set_emissions(zdr_scene* s, const float* e3, int n) {   // render.py:130-148
     if (!s || !e3) return fail(ZDR_ERR_ARG, "set_emissions: null");
     if (n != (int)s->meshes.size()) return fail(ZDR_ERR_ARG, "set_emissions: %d emissions for %d instances (render.py:141)", n, (int)s->meshes.size());
-    for (int i = 0; i < n; ++i) memcpy(s->meshes[i].emission, e3 + 3 * i, sizeof(float) * 3);
-    if (!s->committed) return ZDR_OK;
+    bool changed = false;
+    for (int i = 0; i < n; ++i) {
+        changed |= memcmp(s->meshes[i].emission, e3 + 3 * i, sizeof(float) * 3) != 0;
+        memcpy(s->meshes[i].emission, e3 + 3 * i, sizeof(float) * 3);
+    }
+    // RenderOperator.backward re-applies the forward call's emissions on every step (render.py:218): nothing to
+    // upload, and no reason to synchronise the device, when they are what the device already holds
+    if (!s->committed || !changed) return ZDR_OK;
     int rc = use_device(s->device);
     if (rc) return rc;
     return upload_lights(s);
