@@ -22,6 +22,7 @@ ap.add_argument("--res", type=int, nargs=2, default=[960, 540])
 ap.add_argument("--spp", type=int, default=16)
 ap.add_argument("--depth", type=int, default=16)
 ap.add_argument("--check-rays", type=int, default=48)
+ap.add_argument("--stats", action="store_true", help="also count BVH nodes / triangles per ray (slower)")
 args = ap.parse_args()
 
 from zdr_b200.load_obj import load_mesh
@@ -48,6 +49,7 @@ torch.cuda.synchronize()
 t_build = time.perf_counter() - t0
 sc.camera = scenes.sphere_grid_camera(args.inst)
 sc.max_depth = args.depth
+sc.collect_stats = args.stats
 t0 = time.perf_counter()
 sc.add_envmap(scenes.procedural_envmap(2048, 1024, seed=0))
 t_env = time.perf_counter() - t0
@@ -67,6 +69,8 @@ c = sc.counters()
 rays = c["closest_rays"] + c["any_rays"]
 ms_f, ms_b = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
 print(f"instances {len(models)} triangles {sc.triangle_count:,}  scene+BVH build {t_build:.2f} s (host flatten + GPU LBVH)  envmap import {t_env:.2f} s")
+if args.stats:
+    print(f"BVH work per ray: {c['nodes_visited'] / rays:.1f} nodes, {c['tris_tested'] / rays:.1f} triangles; closest {c['closest_rays']:,} any {c['any_rays']:,}")
 print(f"{res[0]}x{res[1]} {args.spp} spp depth {args.depth}: fwd {ms_f:.1f} ms, bwd {ms_b:.1f} ms, {rays / 1e6:.1f} Mrays -> {rays / (ms_f + ms_b) / 1e3:.1f} Mrays/s; "
       f"image mean {float(img.detach()[..., :3].mean()):.4f} finite {bool(torch.isfinite(img).all())}, grad |sum| {float(mat.grad.abs().sum()):.3f} finite {bool(torch.isfinite(mat.grad).all())}")
 if args.check_rays:

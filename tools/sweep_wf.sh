@@ -1,9 +1,10 @@
 #!/bin/bash
-# GPU-box experiment: refill threshold of the persistent traversal kernel.
+# GPU-box experiment: node budget / refill threshold of the traversal kernel on the C5-shaped scene.
 cd "$(dirname "$0")/.."
-run() { python bench.py --spp 64 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e | python -c 'import json,sys; d=json.loads(sys.stdin.read()); print(d["value"], d["config"]["ms_forward"], d["config"]["ms_backward"])'; }
-for r in 0 12 16 20 24 28; do
-  touch zdr_b200/csrc/render.cu
-  make -C zdr_b200/csrc -s -j8 EXTRA="-DZDR_WF_REFILL=$r" > /dev/null 2>&1
-  echo "refill=$r -> $(run)"
+for cfg in "12 20" "6 20" "24 20" "12 26" "6 26" "12 14"; do
+  set -- $cfg
+  sed -i "s/constexpr int kWfNodeBudget = [0-9]*;/constexpr int kWfNodeBudget = $1;/" zdr_b200/csrc/render.cu
+  make -C zdr_b200/csrc -s -j8 EXTRA="-DZDR_WF_REFILL=$2" > /dev/null 2>&1
+  echo "budget=$1 refill=$2 -> $(python tools/run_c5.py --inst 10000 --res 1920 1080 --spp 8 --check-rays 0 2>&1 | tail -1 | cut -c1-110)"
 done
+sed -i "s/constexpr int kWfNodeBudget = [0-9]*;/constexpr int kWfNodeBudget = 12;/" zdr_b200/csrc/render.cu

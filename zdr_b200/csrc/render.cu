@@ -468,6 +468,7 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_generate(const __grid_constan
 #define ZDR_WF_REFILL 20
 #endif
 constexpr int kWfRefill = ZDR_WF_REFILL;
+constexpr int kWfNodeBudget = 12;
 template <bool ANY, bool STATS>
 __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(const __grid_constant__ RenderArgs a) {
     const WfState& w = a.wf;
@@ -482,6 +483,9 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
     const float4* __restrict__ tris = a.sc.tris;
     Tally tl = {};
     const int lane = threadIdx.x & 31;
+    const bool big_scene = a.sc.num_nodes > 1024;      // traversals long enough for refills to pay on every kind of ray
+    const bool refill_any = big_scene;
+    const int node_budget = big_scene ? kWfNodeBudget : 0x3fffffff;
     // per-lane traversal state
     bool has_ray = false, exhausted = false;
     int slot = 0, link = kLinkSentinel, sp = 0, hit_slot = -1, best_gid = 0x7fffffff;
@@ -532,7 +536,10 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
         }
         // ---- traverse until done, or until too few lanes are left working
         while (has_ray) {
-            while (link >= 0) {                          // inner nodes
+            int budget = node_budget;        // bounded, so that the refill test below is reached regularly even when a
+                                             // ray walks hundreds of nodes between two leaves (9.6 M-triangle scene:
+                                             // 9.6 of 32 lanes were active without the bound, profiles/r01p)
+            while (link >= 0 && budget-- > 0) {          // inner nodes
                 const float4* nd = nodes + 4 * (size_t)link;
                 const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
                 if (STATS) tl.ts.nodes++;
@@ -551,7 +558,7 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
                 }
             }
             bool done = link == kLinkSentinel;
-            if (!done) {                                 // leaf
+            if (!done && link < 0) {                     // leaf
                 const int code = ~link;
                 const int first = code >> 2, count = (code & 3) + 1;
                 for (int k = 0; k < count; ++k) {
@@ -578,7 +585,8 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
                 has_ray = false;
                 break;
             }
-            if (!ANY && __popc(__activemask()) < kWfRefill) break;      // shadow rays are too short for refills to pay (r01i)
+            // shadow rays in a small scene are too short for refills to pay (r01i)
+            if ((!ANY || refill_any) && __popc(__activemask()) < kWfRefill) break;
         }
     }
     flush_tally(a, tl);
