@@ -342,9 +342,12 @@ def test_envmap_path(oracle):
     g.close()
 
 
-def test_lbvh_large_scene(oracle):
-    """> 16 K triangles takes the GPU LBVH builder (C5 shape: instanced sphere.obj): closest hits, occlusion
-    and a small path render + adjoint must match the oracle's brute-force scan exactly."""
+@pytest.mark.parametrize("builder", ["csah", "lbvh"])
+def test_lbvh_large_scene(oracle, builder, monkeypatch):
+    """> 16 K triangles takes the GPU builders (C5 shape: instanced sphere.obj) — clustered SAH (default) and the
+    plain LBVH: closest hits, occlusion and a small path render + adjoint must match the oracle's brute-force
+    scan exactly."""
+    monkeypatch.setenv("ZDR_BVH", builder)
     models = scenes.sphere_grid_models(20, seed=3, emissive_every=7)          # 19 200 triangles, 2 emissive spheres
     g, o = GpuScene(models), oracle.OracleScene(models)
     assert g.lib.zdr_scene_triangle_count(g.h) == 19200
@@ -364,6 +367,46 @@ def test_lbvh_large_scene(oracle):
         assert np.array_equal(bits(g.samples(ZDR_PATH, p, mat)), bits(o.render_samples(ZDR_PATH, p, mat)))
         d = np.ones((32, 48, 4), np.float32)
         assert rel_l2(g.backward(ZDR_PATH, p, mat, d), o.render_backward(ZDR_PATH, p, mat, d)) <= GRAD_TOL
+    g.close()
+
+
+def test_clustered_sah_degenerate_geometry(oracle, tmp_path):
+    """Large-scene builder on hostile input: 18 K random triangles of very different sizes, 400 exact copies of one
+    triangle (coincident centroids: the binned split has nothing to separate, the builder falls back to splitting
+    by position), zero-area triangles, one huge triangle over everything.  Hits must equal the brute-force scan,
+    ties going to the lowest scene-order id."""
+    rng = np.random.default_rng(5)
+    n = 18000
+    ctr = rng.uniform(-4, 4, (n, 1, 3))
+    size = np.exp(rng.uniform(np.log(1e-3), np.log(0.8), (n, 1, 1)))
+    tri = ctr + rng.normal(0, 1, (n, 3, 3)) * size
+    dup = np.repeat(np.array([[[0.5, 0.5, 0.0], [1.5, 0.5, 0.2], [0.5, 1.5, 0.1]]]), 400, axis=0)
+    flat = np.repeat(rng.uniform(-4, 4, (200, 1, 3)), 3, axis=1)                     # zero area
+    huge = np.array([[[-50.0, -50.0, -4.5], [50.0, -50.0, -4.5], [0.0, 80.0, -4.5]]])
+    tri = np.concatenate([tri[:9000], dup, flat, tri[9000:], huge]).astype(np.float32)
+    path = tmp_path / "soup.obj"
+    with open(path, "w") as f:
+        for t in tri:
+            for v in t:
+                f.write(f"v {float(v[0])!r} {float(v[1])!r} {float(v[2])!r}\n")
+        for i in range(len(tri)):
+            f.write(f"f {3 * i + 1} {3 * i + 2} {3 * i + 3}\n")
+    models = [(str(path), None, scenes.float3(0.0))]
+    g, o = GpuScene(models), oracle.OracleScene(models)
+    assert g.lib.zdr_scene_triangle_count(g.h) == len(tri)
+    rays = _random_rays(4000, 21, (-4, -4, -4), (4, 4, 4))
+    rays[:500, 0:3] = (0.8, 0.8, 1.0)                                                # straight at the stack of copies
+    rays[:500, 3:6] = rng.normal(0, 0.05, (500, 3)) + (0.0, 0.0, -1.0)
+    ip_g, uvt_g = g.trace_closest(rays)
+    ip_o, uvt_o = o.trace_closest(rays)
+    assert np.array_equal(ip_g, ip_o)
+    hit = ip_o[:, 0] >= 0
+    assert hit.sum() > 1000 and np.array_equal(bits(uvt_g[hit]), bits(uvt_o[hit]))
+    assert not ((ip_o[:500, 1] > 9000) & (ip_o[:500, 1] < 9400)).any()
+    assert (ip_o[:500, 1] == 9000).sum() > 30                                        # the first copy wins every tie
+    seg = rays.copy()
+    seg[:, 6], seg[:, 7] = 1e-4, 2.0
+    assert np.array_equal(g.trace_any(seg), o.trace_any(seg))
     g.close()
 
 

@@ -388,10 +388,11 @@ ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
     if (e == cudaSuccess) e = cudaMemcpy(d_tri, tri.data(), sizeof(float4) * tri.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_shade, shade.data(), sizeof(float4) * shade.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        const char* force = getenv("ZDR_BVH");     // "lbvh" | "sah": builder override for experiments
+        const char* force = getenv("ZDR_BVH");     // "lbvh" | "csah" | "sah": builder override for experiments and tests
         const bool sah = force ? strcmp(force, "sah") == 0 : nt <= (size_t)kSahMaxTris;
+        const bool lbvh = force && strcmp(force, "lbvh") == 0;
         e = sah ? build_bvh_sah_host(tri.data(), shade.data(), (int)nt, lo, hi, s->own_stream, &s->bvh)
-                : build_bvh(d_tri, d_shade, (int)nt, lo, hi, s->own_stream, &s->bvh);
+                : build_bvh(d_tri, d_shade, (int)nt, lo, hi, s->own_stream, &s->bvh, !lbvh);
     }
     cudaFree(d_tri); cudaFree(d_shade);
     if (e != cudaSuccess) return fail(ZDR_ERR_CUDA, "commit/build_bvh: %s", cudaGetErrorString(e));

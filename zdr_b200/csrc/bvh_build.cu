@@ -12,6 +12,12 @@
 //   6. gather of the triangle / shading records into leaf order  (k_gather)
 // Karras leaves cover contiguous ranges of the sorted order, so a collapsed subtree is just
 // (first_slot, count).
+//
+// Default for large scenes (build_bvh_clustered_sah): steps 1-4 as above, then the radix tree is cut
+// into Morton-prefix-aligned clusters of <= kClusterMax triangles; one thread block per cluster builds a
+// binned-SAH subtree in shared memory (k_sah_cluster), a full-sweep SAH tree over the cluster boxes is
+// built on the host meanwhile, and the two are stitched into one flat node array.  The Morton order
+// only decides which triangles share a cluster; every split above and below is a SAH split.
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cfloat>
@@ -179,13 +185,307 @@ __global__ void k_gather(const float4* __restrict__ tri_in, const float4* __rest
     for (int k = 0; k < 4; ++k) shade[4 * (size_t)s + k] = shade_in[4 * (size_t)g + k];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Clustered SAH build
+constexpr int kClusterMax = 2048;      // triangles per cluster (shared-memory resident: 32 B each)
+constexpr int kSahThreads = 256;
+constexpr int kBins = 16;
+
+// Cluster roots of the radix tree: the highest nodes that cover <= kClusterMax triangles.  Written at the
+// first sorted position of the cluster, so that an exclusive scan of the start flags numbers them in order.
+__global__ void k_cluster_mark(const int2* __restrict__ range, const int* __restrict__ parent_inner,
+                               const int* __restrict__ parent_leaf, int n, int* __restrict__ start_flag,
+                               int* __restrict__ count_at, int* __restrict__ box_at) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n - 1) {                                   // inner node i
+        const int2 r = range[i];
+        const int cnt = r.y - r.x + 1;
+        if (cnt <= kClusterMax) {
+            const int p = parent_inner[i];
+            bool top = p < 0;
+            if (!top) { const int2 pr = range[p]; top = pr.y - pr.x + 1 > kClusterMax; }
+            if (top) { start_flag[r.x] = 1; count_at[r.x] = cnt; box_at[r.x] = i; }
+        }
+    }
+    if (i < n) {                                       // sorted triangle i hanging directly off a big node
+        const int2 pr = range[parent_leaf[i]];
+        if (pr.y - pr.x + 1 > kClusterMax) { start_flag[i] = 1; count_at[i] = 1; box_at[i] = n - 1 + i; }
+    }
+}
+
+__global__ void k_cluster_compact(const int* __restrict__ start_flag, const int* __restrict__ cluster_id,
+                                  const int* __restrict__ count_at, const int* __restrict__ box_at,
+                                  const float4* __restrict__ box_lo, const float4* __restrict__ box_hi, int n,
+                                  int* __restrict__ cl_first, int* __restrict__ cl_count, float4* __restrict__ cl_box) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n || !start_flag[s]) return;
+    const int c = cluster_id[s];
+    cl_first[c] = s;
+    cl_count[c] = count_at[s];
+    cl_box[2 * c] = box_lo[box_at[s]];
+    cl_box[2 * c + 1] = box_hi[box_at[s]];
+}
+
+// float <-> int whose signed order is the float order (shared-memory atomicMin/atomicMax on boxes)
+__device__ __forceinline__ int f2o(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float o2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+struct SahShared {
+    float lo[3][kClusterMax], hi[3][kClusterMax];      // triangle boxes by position in the cluster
+    int idx[kClusterMax], idx2[kClusterMax];           // current order / partition scratch
+    int bin_cnt[3][kBins];
+    int bin_lo[3][kBins][3], bin_hi[3][kBins][3];
+    int cb_lo[3], cb_hi[3];                            // centroid bounds of the range
+    float cost[3 * (kBins - 1) + 3];
+    int stack[32][5];                                  // a, b, parent node, side, depth
+    int sp, num_nodes, max_depth, cur_node;
+    int best_axis, best_split, make_leaf;
+    float child_box[2][6];
+    typename cub::BlockScan<int, kSahThreads>::TempStorage scan;
+};
+
+// One block per cluster: top-down binned SAH (16 bins x 3 axes) over the cluster's triangles, entirely
+// in shared memory.  Writes inner nodes to tmp_nodes[first .. first + used) with cluster-local inner
+// links and absolute leaf links, the cluster's root link, the number of nodes used, and the cluster's
+// part of the final triangle order.  The tree depends only on the set of triangles in each range
+// (min / max / count are order-independent; the partition is stable), so builds are reproducible.
+__global__ void __launch_bounds__(kSahThreads) k_sah_cluster(const int* __restrict__ cl_first, const int* __restrict__ cl_count,
+                                                             const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
+                                                             const int* __restrict__ sorted_gid, int n, float eps,
+                                                             float4* __restrict__ tmp_nodes, int* __restrict__ cl_root,
+                                                             int* __restrict__ cl_used, int* __restrict__ final_gid,
+                                                             int* __restrict__ max_depth_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SahShared& sh = *reinterpret_cast<SahShared*>(smem_raw);
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int first = cl_first[c], cnt = cl_count[c];
+    for (int j = tid; j < cnt; j += kSahThreads) {
+        const float4 l = box_lo[n - 1 + first + j], h = box_hi[n - 1 + first + j];
+        sh.lo[0][j] = l.x; sh.lo[1][j] = l.y; sh.lo[2][j] = l.z;
+        sh.hi[0][j] = h.x; sh.hi[1][j] = h.y; sh.hi[2][j] = h.z;
+        sh.idx[j] = j;
+    }
+    if (tid == 0) {
+        sh.sp = 1; sh.num_nodes = 0; sh.max_depth = 0;
+        sh.stack[0][0] = 0; sh.stack[0][1] = cnt; sh.stack[0][2] = -1; sh.stack[0][3] = 0; sh.stack[0][4] = 1;
+    }
+    __syncthreads();
+    for (;;) {
+        const int sp = sh.sp;
+        if (sp == 0) break;
+        int a = sh.stack[sp - 1][0], b = sh.stack[sp - 1][1], parent = sh.stack[sp - 1][2], side = sh.stack[sp - 1][3],
+            depth = sh.stack[sp - 1][4];
+        __syncthreads();
+        if (tid == 0) sh.sp = sp - 1;
+        for (;;) {                                     // this range, then its smaller child, ...
+            const int m = b - a;
+            // ---- centroid bounds of the range
+            if (tid < 3) { sh.cb_lo[tid] = 0x7fffffff; sh.cb_hi[tid] = (int)0x80000000; }
+            for (int k = tid; k < 3 * kBins; k += kSahThreads) {
+                const int ax = k / kBins, bn = k % kBins;
+                sh.bin_cnt[ax][bn] = 0;
+                for (int q = 0; q < 3; ++q) { sh.bin_lo[ax][bn][q] = 0x7fffffff; sh.bin_hi[ax][bn][q] = (int)0x80000000; }
+            }
+            __syncthreads();
+            {
+                float cmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+                for (int j = a + tid; j < b; j += kSahThreads) {
+                    const int e = sh.idx[j];
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) {
+                        const float ctr = sh.lo[ax][e] + sh.hi[ax][e];
+                        cmin[ax] = fminf(cmin[ax], ctr); cmax[ax] = fmaxf(cmax[ax], ctr);
+                    }
+                }
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    for (int o = 16; o > 0; o >>= 1) {
+                        cmin[ax] = fminf(cmin[ax], __shfl_xor_sync(0xffffffffu, cmin[ax], o));
+                        cmax[ax] = fmaxf(cmax[ax], __shfl_xor_sync(0xffffffffu, cmax[ax], o));
+                    }
+                    if (lane == 0 && cmin[ax] <= cmax[ax]) { atomicMin(&sh.cb_lo[ax], f2o(cmin[ax])); atomicMax(&sh.cb_hi[ax], f2o(cmax[ax])); }
+                }
+            }
+            __syncthreads();
+            float cmin[3], scale[3];
+            bool degenerate = true;                    // all centroids coincide: split by position instead
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                cmin[ax] = o2f(sh.cb_lo[ax]);
+                const float ext = o2f(sh.cb_hi[ax]) - cmin[ax];
+                const float sc = (float)kBins / ext;
+                scale[ax] = (ext > 0.0f && sc <= FLT_MAX) ? sc : 0.0f;
+                if (scale[ax] > 0.0f) degenerate = false;
+            }
+            auto bin_of = [&](int j, int e, int ax) -> int {
+                if (degenerate) return ax == 0 ? (int)(((long long)(j - a) * kBins) / m) : 0;
+                if (scale[ax] == 0.0f) return 0;
+                const float ctr = sh.lo[ax][e] + sh.hi[ax][e];
+                return min(kBins - 1, max(0, (int)((ctr - cmin[ax]) * scale[ax])));
+            };
+            // ---- binning
+            for (int j = a + tid; j < b; j += kSahThreads) {
+                const int e = sh.idx[j];
+                int lo_o[3], hi_o[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { lo_o[q] = f2o(sh.lo[q][e]); hi_o[q] = f2o(sh.hi[q][e]); }
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    const int bn = bin_of(j, e, ax);
+                    atomicAdd(&sh.bin_cnt[ax][bn], 1);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { atomicMin(&sh.bin_lo[ax][bn][q], lo_o[q]); atomicMax(&sh.bin_hi[ax][bn][q], hi_o[q]); }
+                }
+            }
+            __syncthreads();
+            // ---- sweep: candidate t = (axis, split after bin s)
+            if (tid < 3 * (kBins - 1)) {
+                const int ax = tid / (kBins - 1), s = tid % (kBins - 1);
+                float bl[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+                float br[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+                int nl = 0, nr = 0;
+                for (int bn = 0; bn < kBins; ++bn) {
+                    const int k = sh.bin_cnt[ax][bn];
+                    if (k == 0) continue;
+                    float* bx = bn <= s ? bl : br;
+                    (bn <= s ? nl : nr) += k;
+                    for (int q = 0; q < 3; ++q) {
+                        bx[q] = fminf(bx[q], o2f(sh.bin_lo[ax][bn][q]));
+                        bx[3 + q] = fmaxf(bx[3 + q], o2f(sh.bin_hi[ax][bn][q]));
+                    }
+                }
+                float cost = FLT_MAX;
+                if (nl > 0 && nr > 0) {
+                    const float lx = bl[3] - bl[0], ly = bl[4] - bl[1], lz = bl[5] - bl[2];
+                    const float rx = br[3] - br[0], ry = br[4] - br[1], rz = br[5] - br[2];
+                    cost = (lx * ly + ly * lz + lz * lx) * (float)nl + (rx * ry + ry * rz + rz * rx) * (float)nr;
+                }
+                sh.cost[tid] = cost;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int best = -1;
+                float best_cost = FLT_MAX;
+                for (int t = 0; t < 3 * (kBins - 1); ++t)
+                    if (sh.cost[t] < best_cost) { best_cost = sh.cost[t]; best = t; }
+                float pb[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+                for (int bn = 0; bn < kBins; ++bn) {
+                    if (sh.bin_cnt[0][bn] == 0) continue;
+                    for (int q = 0; q < 3; ++q) {
+                        pb[q] = fminf(pb[q], o2f(sh.bin_lo[0][bn][q]));
+                        pb[3 + q] = fmaxf(pb[3 + q], o2f(sh.bin_hi[0][bn][q]));
+                    }
+                }
+                const float px = pb[3] - pb[0], py = pb[4] - pb[1], pz = pb[5] - pb[2];
+                const float parent_area = fmaxf(px * py + py * pz + pz * px, 1e-30f);
+                // same leaf rule as the host builder: a node visit costs one triangle test
+                const float split_cost = 1.0f + best_cost / parent_area;
+                const bool leaf = m == 1 || best < 0 || (m <= kLeafMax && (float)m <= split_cost);
+                sh.make_leaf = leaf ? 1 : 0;
+                if (!leaf) {
+                    const int ax = best / (kBins - 1), s = best % (kBins - 1);
+                    sh.best_axis = ax; sh.best_split = s;
+                    for (int ch = 0; ch < 2; ++ch) {
+                        float bx[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+                        for (int bn = ch == 0 ? 0 : s + 1; bn <= (ch == 0 ? s : kBins - 1); ++bn) {
+                            if (sh.bin_cnt[ax][bn] == 0) continue;
+                            for (int q = 0; q < 3; ++q) {
+                                bx[q] = fminf(bx[q], o2f(sh.bin_lo[ax][bn][q]));
+                                bx[3 + q] = fmaxf(bx[3 + q], o2f(sh.bin_hi[ax][bn][q]));
+                            }
+                        }
+                        for (int q = 0; q < 6; ++q) sh.child_box[ch][q] = bx[q];
+                    }
+                    sh.cur_node = sh.num_nodes++;
+                }
+                const int link = leaf ? ~(((first + a) << 2) | (m - 1)) : sh.cur_node;
+                if (parent < 0) cl_root[c] = link;
+                else reinterpret_cast<int*>(tmp_nodes + 4 * (size_t)(first + parent) + 3)[side] = link;
+                sh.max_depth = max(sh.max_depth, depth);
+            }
+            __syncthreads();
+            if (sh.make_leaf) break;
+            // a range of more than kLeafMax coincident-centroid triangles always splits (by position), so m > kLeafMax
+            // cannot reach here with best < 0
+            const int ax = sh.best_axis, split = sh.best_split, node = sh.cur_node;
+            // ---- stable partition of idx[a, b) by bin <= split
+            const int per = (m + kSahThreads - 1) / kSahThreads;
+            const int j0 = min(b, a + tid * per), j1 = min(b, j0 + per);
+            int my_left = 0;
+            for (int j = j0; j < j1; ++j) my_left += bin_of(j, sh.idx[j], ax) <= split ? 1 : 0;
+            int left_before, num_left;
+            cub::BlockScan<int, kSahThreads>(sh.scan).ExclusiveSum(my_left, left_before, num_left);
+            {
+                int lpos = a + left_before, rpos = a + num_left + (j0 - a) - left_before;
+                for (int j = j0; j < j1; ++j) {
+                    const int e = sh.idx[j];
+                    if (bin_of(j, e, ax) <= split) sh.idx2[lpos++] = e; else sh.idx2[rpos++] = e;
+                }
+            }
+            __syncthreads();
+            for (int j = a + tid; j < b; j += kSahThreads) sh.idx[j] = sh.idx2[j];
+            if (tid == 0) {
+                const float* l = sh.child_box[0];
+                const float* r = sh.child_box[1];
+                float4* o = tmp_nodes + 4 * (size_t)(first + node);
+                o[0] = make_float4(l[0] - eps, l[3] + eps, l[1] - eps, l[4] + eps);
+                o[1] = make_float4(r[0] - eps, r[3] + eps, r[1] - eps, r[4] + eps);
+                o[2] = make_float4(l[2] - eps, l[5] + eps, r[2] - eps, r[5] + eps);
+                // o[3] (the links) is written by the children
+            }
+            const int mid = a + num_left;
+            const bool left_small = (mid - a) <= (b - mid);
+            if (tid == 0) {                            // push the larger child: the stack stays <= log2(kClusterMax) deep
+                const int t = sh.sp++;
+                sh.stack[t][0] = left_small ? mid : a; sh.stack[t][1] = left_small ? b : mid;
+                sh.stack[t][2] = node; sh.stack[t][3] = left_small ? 1 : 0; sh.stack[t][4] = depth + 1;
+            }
+            if (left_small) b = mid; else a = mid;
+            parent = node; side = left_small ? 0 : 1; depth += 1;
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+    for (int j = tid; j < cnt; j += kSahThreads) final_gid[first + j] = sorted_gid[first + sh.idx[j]];
+    if (tid == 0) { cl_used[c] = sh.num_nodes; atomicMax(max_depth_out, sh.max_depth); }
+}
+
+// Packs the clusters' nodes behind the top-level nodes and makes their inner links absolute.
+__global__ void k_cluster_pack(const float4* __restrict__ tmp_nodes, const int* __restrict__ start_flag,
+                               const int* __restrict__ cluster_id, const int* __restrict__ cl_first,
+                               const int* __restrict__ cl_used, const int* __restrict__ cl_base, int n, int num_top,
+                               float4* __restrict__ nodes) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int c = cluster_id[p] + start_flag[p] - 1;
+    const int j = p - cl_first[c];
+    if (j >= cl_used[c]) return;
+    const int base = num_top + cl_base[c];
+    const float4* src = tmp_nodes + 4 * (size_t)p;
+    float4* dst = nodes + 4 * (size_t)(base + j);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    float4 l = src[3];
+    int l0 = __float_as_int(l.x), l1 = __float_as_int(l.y);
+    if (l0 >= 0) l0 += base;
+    if (l1 >= 0) l1 += base;
+    dst[3] = make_float4(__int_as_float(l0), __int_as_float(l1), 0.f, 0.f);
+}
+
 #define BVH_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = e_; goto done; } } while (0)
 
 }  // namespace
 
+// full-sweep SAH tree over cluster boxes (defined below, next to the host builder)
+void build_top_level(const std::vector<float4>& cl_box, const std::vector<int>& cl_count, float eps,
+                     std::vector<float4>* nodes, std::vector<int>* leaf_cluster_of_link, int* root_link, int* depth);
+
 cudaError_t build_bvh(const float4* tri_in, const float4* shade_in, int n, float3 lo, float3 hi,
-                      cudaStream_t stream, BvhResult* out) {
+                      cudaStream_t stream, BvhResult* out, bool clustered_sah) {
     cudaError_t err = cudaSuccess;
+    int *start_flag = nullptr, *count_at = nullptr, *box_at = nullptr, *cluster_id = nullptr, *cl_first = nullptr,
+        *cl_count = nullptr, *cl_root = nullptr, *cl_used = nullptr, *cl_base = nullptr, *final_gid = nullptr;
+    float4 *cl_box = nullptr, *tmp_nodes = nullptr;
     uint64_t *keys = nullptr, *keys_alt = nullptr;
     int *vals = nullptr, *vals_alt = nullptr, *parent_inner = nullptr, *parent_leaf = nullptr, *arrive = nullptr,
         *keep = nullptr, *new_index = nullptr, *d_scalars = nullptr;
@@ -222,7 +522,8 @@ cudaError_t build_bvh(const float4* tri_in, const float4* shade_in, int n, float
             if (dv.Current() != vals) { int* t = vals; vals = vals_alt; vals_alt = t; }
             cudaFree(tmp); tmp = nullptr;
         }
-        k_gather<<<gb, T, 0, stream>>>(tri_in, shade_in, vals, n, out->tris, out->shade, out->slot_of_gid);
+        if (n <= kLeafMax || !clustered_sah)
+            k_gather<<<gb, T, 0, stream>>>(tri_in, shade_in, vals, n, out->tris, out->shade, out->slot_of_gid);
         if (n <= kLeafMax) {
             out->root_link = ~((0 << 2) | (n - 1));
             out->num_nodes = 0;
@@ -248,6 +549,79 @@ cudaError_t build_bvh(const float4* tri_in, const float4* shade_in, int n, float
         BVH_CK(cudaMemsetAsync(d_scalars, 0, sizeof(int) * 4, stream));
         k_hierarchy<<<gi, T, 0, stream>>>(keys, n, child, range, parent_inner, parent_leaf);
         k_fit<<<gb, T, 0, stream>>>(tri_in, vals, n, child, parent_inner, parent_leaf, box_lo, box_hi, arrive, d_scalars);
+        if (clustered_sah) {
+            // ---- cut into clusters
+            BVH_CK(cudaMalloc(&start_flag, sizeof(int) * n));
+            BVH_CK(cudaMalloc(&count_at, sizeof(int) * n));
+            BVH_CK(cudaMalloc(&box_at, sizeof(int) * n));
+            BVH_CK(cudaMalloc(&cluster_id, sizeof(int) * n));
+            BVH_CK(cudaMalloc(&final_gid, sizeof(int) * n));
+            BVH_CK(cudaMemsetAsync(start_flag, 0, sizeof(int) * n, stream));
+            k_cluster_mark<<<gb, T, 0, stream>>>(range, parent_inner, parent_leaf, n, start_flag, count_at, box_at);
+            BVH_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, start_flag, cluster_id, n, stream));
+            BVH_CK(cudaMalloc(&tmp, tmp_bytes));
+            BVH_CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, start_flag, cluster_id, n, stream));
+            int h_last_flag = 0, h_last_id = 0;
+            BVH_CK(cudaMemcpyAsync(&h_last_flag, start_flag + n - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            BVH_CK(cudaMemcpyAsync(&h_last_id, cluster_id + n - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            BVH_CK(cudaStreamSynchronize(stream));
+            const int nc = h_last_id + h_last_flag;
+            BVH_CK(cudaMalloc(&cl_first, sizeof(int) * nc));
+            BVH_CK(cudaMalloc(&cl_count, sizeof(int) * nc));
+            BVH_CK(cudaMalloc(&cl_root, sizeof(int) * nc));
+            BVH_CK(cudaMalloc(&cl_used, sizeof(int) * nc));
+            BVH_CK(cudaMalloc(&cl_base, sizeof(int) * nc));
+            BVH_CK(cudaMalloc(&cl_box, sizeof(float4) * 2 * (size_t)nc));
+            BVH_CK(cudaMalloc(&tmp_nodes, sizeof(float4) * 4 * (size_t)n));
+            k_cluster_compact<<<gb, T, 0, stream>>>(start_flag, cluster_id, count_at, box_at, box_lo, box_hi, n, cl_first, cl_count, cl_box);
+            std::vector<float4> h_box(2 * (size_t)nc);
+            std::vector<int> h_count(nc), h_root(nc), h_base(nc);
+            BVH_CK(cudaMemcpyAsync(h_box.data(), cl_box, sizeof(float4) * h_box.size(), cudaMemcpyDeviceToHost, stream));
+            BVH_CK(cudaMemcpyAsync(h_count.data(), cl_count, sizeof(int) * nc, cudaMemcpyDeviceToHost, stream));
+            BVH_CK(cudaStreamSynchronize(stream));
+            // ---- per-cluster SAH subtrees on the GPU, the tree over the clusters on the host meanwhile
+            BVH_CK(cudaFuncSetAttribute(k_sah_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SahShared)));
+            k_sah_cluster<<<nc, kSahThreads, sizeof(SahShared), stream>>>(cl_first, cl_count, box_lo, box_hi, vals, n, eps, tmp_nodes,
+                                                                          cl_root, cl_used, final_gid, d_scalars + 1);
+            BVH_CK(cudaGetLastError());
+            std::vector<float4> top_nodes;
+            std::vector<int> top_leaf;
+            int top_root = 0, top_depth = 0;
+            build_top_level(h_box, h_count, eps, &top_nodes, &top_leaf, &top_root, &top_depth);
+            const int num_top = (int)(top_nodes.size() / 4);
+            cudaFree(tmp); tmp = nullptr;
+            BVH_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cl_used, cl_base, nc, stream));
+            BVH_CK(cudaMalloc(&tmp, tmp_bytes));
+            BVH_CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cl_used, cl_base, nc, stream));
+            int h_last_used = 0, h_last_base = 0, h_cl_depth = 0;
+            BVH_CK(cudaMemcpyAsync(&h_last_used, cl_used + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            BVH_CK(cudaMemcpyAsync(&h_last_base, cl_base + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            BVH_CK(cudaMemcpyAsync(&h_cl_depth, d_scalars + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            BVH_CK(cudaMemcpyAsync(h_root.data(), cl_root, sizeof(int) * nc, cudaMemcpyDeviceToHost, stream));
+            BVH_CK(cudaMemcpyAsync(h_base.data(), cl_base, sizeof(int) * nc, cudaMemcpyDeviceToHost, stream));
+            BVH_CK(cudaStreamSynchronize(stream));
+            const int num_cluster_nodes = h_last_base + h_last_used;
+            // a cluster's root is its local node 0, or a leaf link when the whole cluster is one leaf
+            auto cluster_link = [&](int c) { return h_root[c] >= 0 ? num_top + h_base[c] + h_root[c] : h_root[c]; };
+            for (int k = 0; k < num_top; ++k) {
+                int l[2];
+                memcpy(l, &top_nodes[4 * k + 3], sizeof(l));
+                for (int q = 0; q < 2; ++q)
+                    if (l[q] < 0) l[q] = cluster_link(top_leaf[(~l[q]) >> 2]);
+                memcpy(&top_nodes[4 * k + 3], l, sizeof(l));
+            }
+            out->num_nodes = num_top + num_cluster_nodes;
+            out->max_depth = top_depth + h_cl_depth;
+            out->root_link = num_top > 0 ? top_root : cluster_link(top_leaf[(~top_root) >> 2]);
+            BVH_CK(cudaMalloc(&out->nodes, sizeof(float4) * 4 * (size_t)std::max(out->num_nodes, 1)));
+            if (num_top > 0)
+                BVH_CK(cudaMemcpyAsync(out->nodes, top_nodes.data(), sizeof(float4) * top_nodes.size(), cudaMemcpyHostToDevice, stream));
+            k_cluster_pack<<<gb, T, 0, stream>>>(tmp_nodes, start_flag, cluster_id, cl_first, cl_used, cl_base, n, num_top, out->nodes);
+            k_gather<<<gb, T, 0, stream>>>(tri_in, shade_in, final_gid, n, out->tris, out->shade, out->slot_of_gid);
+            BVH_CK(cudaGetLastError());
+            BVH_CK(cudaStreamSynchronize(stream));
+            goto done;
+        }
         k_mark<<<gi, T, 0, stream>>>(range, n, keep);
         BVH_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, keep, new_index, ni, stream));
         BVH_CK(cudaMalloc(&tmp, tmp_bytes));
@@ -269,6 +643,8 @@ done:
     cudaFree(keys); cudaFree(keys_alt); cudaFree(vals); cudaFree(vals_alt); cudaFree(parent_inner);
     cudaFree(parent_leaf); cudaFree(arrive); cudaFree(keep); cudaFree(new_index); cudaFree(d_scalars);
     cudaFree(child); cudaFree(range); cudaFree(box_lo); cudaFree(box_hi); cudaFree(tmp);
+    cudaFree(start_flag); cudaFree(count_at); cudaFree(box_at); cudaFree(cluster_id); cudaFree(cl_first); cudaFree(cl_count);
+    cudaFree(cl_root); cudaFree(cl_used); cudaFree(cl_base); cudaFree(final_gid); cudaFree(cl_box); cudaFree(tmp_nodes);
     if (err != cudaSuccess) free_bvh(out);
     return err;
 }
@@ -297,6 +673,8 @@ struct SahBuilder {
     std::vector<float> right_area;
     float eps;
     int max_depth = 0;
+    int leaf_max = kLeafMax;          // 1: every leaf is a single element (tree over clusters)
+    const float* weight = nullptr;    // per-element cost in the SAH sum (null: 1)
     SahBuilder(const std::vector<HBox>& b, float e) : tb(b), eps(e) {
         order.resize(b.size());
         std::iota(order.begin(), order.end(), 0);
@@ -321,12 +699,14 @@ struct SahBuilder {
                     return cx < cy || (cx == cy && x < y);
                 });
                 HBox acc; acc.reset();
+                float wtotal = 0.0f, wl = 0.0f;
                 for (int i = b - 1; i > a; --i) { acc.grow(tb[order[i]]); right_area[i] = acc.area(); }
+                for (int i = a; i < b; ++i) wtotal += weight ? weight[order[i]] : 1.0f;
                 acc.reset();
                 for (int i = a; i < b - 1; ++i) {
                     acc.grow(tb[order[i]]);
-                    const int nl = i - a + 1, nr = n - nl;
-                    const float c = acc.area() * (float)nl + right_area[i + 1] * (float)nr;
+                    wl += weight ? weight[order[i]] : 1.0f;
+                    const float c = acc.area() * wl + right_area[i + 1] * (wtotal - wl);
                     if (c < best_cost) { best_cost = c; best_axis = axis; best_split = i + 1; }
                 }
             }
@@ -334,7 +714,7 @@ struct SahBuilder {
         const float parent_area = std::max(box.area(), 1e-30f);
         static const float node_cost = getenv("ZDR_SAH_NODE_COST") ? (float)atof(getenv("ZDR_SAH_NODE_COST")) : 1.0f;
         const float split_cost = node_cost + best_cost / parent_area;     // node visit + expected children
-        if (n <= 4 && (n == 1 || (float)n <= split_cost)) return ~((a << 2) | (n - 1));
+        if (n <= leaf_max && (n == 1 || (float)n <= split_cost)) return ~((a << 2) | (n - 1));
         std::sort(order.begin() + a, order.begin() + b, [&](int x, int y) {
             const float cx = tb[x].lo[best_axis] + tb[x].hi[best_axis], cy = tb[y].lo[best_axis] + tb[y].hi[best_axis];
             return cx < cy || (cx == cy && x < y);
@@ -361,6 +741,29 @@ float inflate_eps(float3 lo, float3 hi) {
 }
 
 }  // namespace
+
+// Tree over the clusters of the large-scene build: elements are cluster boxes, every leaf is one cluster
+// (link ~(position << 2); *leaf_cluster maps position -> cluster), an element's SAH weight is the expected
+// cost of entering its subtree (~ log2 of its triangle count).
+void build_top_level(const std::vector<float4>& cl_box, const std::vector<int>& cl_count, float eps,
+                     std::vector<float4>* nodes, std::vector<int>* leaf_cluster, int* root_link, int* depth) {
+    const int nc = (int)cl_count.size();
+    std::vector<HBox> tb(nc);
+    std::vector<float> w(nc);
+    for (int c = 0; c < nc; ++c) {
+        const float4 l = cl_box[2 * c], h = cl_box[2 * c + 1];
+        tb[c].lo[0] = l.x; tb[c].lo[1] = l.y; tb[c].lo[2] = l.z;
+        tb[c].hi[0] = h.x; tb[c].hi[1] = h.y; tb[c].hi[2] = h.z;
+        w[c] = 1.0f + log2f((float)std::max(cl_count[c], 1));
+    }
+    SahBuilder b(tb, eps);
+    b.leaf_max = 1;
+    b.weight = w.data();
+    *root_link = b.build(0, nc, 1);
+    *nodes = std::move(b.nodes);
+    *leaf_cluster = std::move(b.order);
+    *depth = b.max_depth;
+}
 
 cudaError_t build_bvh_sah_host(const float4* tri, const float4* shade, int n, float3 lo, float3 hi, cudaStream_t stream,
                                BvhResult* out) {

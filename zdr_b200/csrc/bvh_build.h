@@ -1,4 +1,4 @@
-// bvh_build.h — interface of the GPU LBVH builder (bvh_build.cu).
+// bvh_build.h — interface of the BVH builders (bvh_build.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,17 +12,19 @@ struct BvhResult {
     int* slot_of_gid;     // scene-order triangle id -> leaf-order slot
     int root_link;
     int num_nodes;
-    int max_depth;        // of the un-collapsed radix tree (upper bound for the traversal stack)
+    int max_depth;        // upper bound of the tree depth (sizes the traversal stack check)
 };
 
 // tri_in / shade_in: device arrays in scene order (3 resp. 4 float4 per triangle).
 // lo/hi: bounds of all vertices. Synchronises `stream` before returning.
+// clustered_sah: Morton order only groups the triangles into clusters; SAH trees inside the clusters (GPU,
+// one block each) and over them (host).  false: plain LBVH (the radix tree itself).
 cudaError_t build_bvh(const float4* tri_in, const float4* shade_in, int n, float3 lo, float3 hi,
-                      cudaStream_t stream, BvhResult* out);
+                      cudaStream_t stream, BvhResult* out, bool clustered_sah);
 void free_bvh(BvhResult* r);
 
 // Scenes up to this many triangles get a full-sweep SAH tree (built on the host in microseconds to
-// milliseconds, uploaded once); larger ones the GPU LBVH.  tri_host / shade_host: scene order.
+// milliseconds, uploaded once); larger ones the GPU build.  tri_host / shade_host: scene order.
 constexpr int kSahMaxTris = 1 << 14;
 cudaError_t build_bvh_sah_host(const float4* tri_host, const float4* shade_host, int n, float3 lo, float3 hi,
                                cudaStream_t stream, BvhResult* out);
