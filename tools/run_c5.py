@@ -3,6 +3,8 @@ procedural envmap, path integrator with PRB, depth 16.  Reports BVH build time, 
 of closest hits against the oracle's brute-force scan.
 
     python tools/run_c5.py --inst 10000 --res 960 540 --spp 16
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/run_c5.py --res 3840 2160 --spp 64          # the literal C5 shape: tile-sharded, NCCL all-reduce of the gradient
 """
 import argparse
 import os
@@ -27,6 +29,12 @@ args = ap.parse_args()
 
 from zdr_b200.load_obj import load_mesh
 
+world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local_rank)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
 # The reference textures instance 0 only and ends paths on every other instance (direct.py:30, prb.py:45), so a
 # scene of 10 000 separate instances would shade almost nothing.  Here the non-emissive spheres are merged into ONE
 # textured mesh (instance 0, ~9.5 M triangles); every 97th sphere stays a separate emissive instance.
@@ -44,7 +52,7 @@ for i, (obj, xf, em) in enumerate(grid):
     mv.append(v)
 models = [((np.concatenate(mv), np.concatenate(mt)), None, scenes.float3(0.0))] + lights
 t0 = time.perf_counter()
-sc = Scene(models, integrator="path")
+sc = Scene(models, integrator="path", device=local_rank)
 torch.cuda.synchronize()
 t_build = time.perf_counter() - t0
 sc.camera = scenes.sphere_grid_camera(args.inst)
@@ -55,7 +63,12 @@ sc.add_envmap(scenes.procedural_envmap(2048, 1024, seed=0))
 t_env = time.perf_counter() - t0
 mat = torch.from_numpy(scenes.random_material((2048, 2048), 0)).cuda().requires_grad_()
 res = tuple(args.res)
+if world > 1:
+    sc.distribute()                                  # replicated scene, round-robin 8-row tiles, all-reduce of image + gradient
 for rep in range(2):
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     sc.reset_counters()
     mat.grad = None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -68,11 +81,24 @@ for rep in range(2):
 c = sc.counters()
 rays = c["closest_rays"] + c["any_rays"]
 ms_f, ms_b = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+if world > 1:                                        # whole-job rays / max-over-ranks device time
+    t = torch.tensor([ms_f, ms_b], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    r = torch.tensor([float(rays), float(c["nodes_visited"]), float(c["tris_tested"])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(r)
+    ms_f, ms_b, rays = t[0].item(), t[1].item(), int(r[0].item())
+    c["nodes_visited"], c["tris_tested"] = r[1].item(), r[2].item()
+    if rank != 0:
+        dist.destroy_process_group()
+        sys.exit(0)
+    print(f"{world} GPUs (one process each, NCCL all-reduce of image and gradient inside the timed region)")
 print(f"instances {len(models)} triangles {sc.triangle_count:,}  scene+BVH build {t_build:.2f} s (host flatten + GPU build, ZDR_BVH={os.environ.get("ZDR_BVH", "default")})  envmap import {t_env:.2f} s")
 if args.stats:
     print(f"BVH work per ray: {c['nodes_visited'] / rays:.1f} nodes, {c['tris_tested'] / rays:.1f} triangles; closest {c['closest_rays']:,} any {c['any_rays']:,}")
 print(f"{res[0]}x{res[1]} {args.spp} spp depth {args.depth}: fwd {ms_f:.1f} ms, bwd {ms_b:.1f} ms, {rays / 1e6:.1f} Mrays -> {rays / (ms_f + ms_b) / 1e3:.1f} Mrays/s; "
       f"image mean {float(img.detach()[..., :3].mean()):.4f} finite {bool(torch.isfinite(img).all())}, grad |sum| {float(mat.grad.abs().sum()):.3f} finite {bool(torch.isfinite(mat.grad).all())}")
+if world > 1:
+    dist.destroy_process_group()
 if args.check_rays:
     import ctypes as C
     from oracle import oracle as o
