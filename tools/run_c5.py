@@ -92,7 +92,7 @@ if world > 1:                                        # whole-job rays / max-over
         dist.destroy_process_group()
         sys.exit(0)
     print(f"{world} GPUs (one process each, NCCL all-reduce of image and gradient inside the timed region)")
-print(f"instances {len(models)} triangles {sc.triangle_count:,}  scene+BVH build {t_build:.2f} s (host flatten + GPU build, ZDR_BVH={os.environ.get("ZDR_BVH", "default")})  envmap import {t_env:.2f} s")
+print(f"instances {len(models)} triangles {sc.triangle_count:,}  scene+BVH build {t_build:.2f} s (upload + GPU flatten + GPU build, ZDR_BVH={os.environ.get("ZDR_BVH", "default")})  envmap import {t_env:.2f} s")
 if args.stats:
     print(f"BVH work per ray: {c['nodes_visited'] / rays:.1f} nodes, {c['tris_tested'] / rays:.1f} triangles; closest {c['closest_rays']:,} any {c['any_rays']:,}")
 print(f"{res[0]}x{res[1]} {args.spp} spp depth {args.depth}: fwd {ms_f:.1f} ms, bwd {ms_b:.1f} ms, {rays / 1e6:.1f} Mrays -> {rays / (ms_f + ms_b) / 1e3:.1f} Mrays/s; "

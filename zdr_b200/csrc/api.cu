@@ -2,6 +2,7 @@
 // upload (pmj02bn.py:9-16), the forward / adjoint operator launches (render.py:168-171,
 // 193-196) and the parity probes.  Nothing here has a CPU fallback: every compute entry needs a
 // CUDA device and returns ZDR_ERR_CUDA without one.
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -345,30 +346,9 @@ ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
     size_t nt = 0;
     for (Mesh& m : s->meshes) { m.tri_base = (int)nt; nt += m.tris.size() / 3; }
     if (nt >= (1u << 29)) return fail(ZDR_ERR_LIMIT, "too many triangles");
-    // flatten the instances to world space: p = (M * float4(v,1)).xyz as interaction.py:19-21
-    std::vector<float4> tri(3 * nt), shade(4 * nt);
-    float3 lo = f3(INFINITY, INFINITY, INFINITY), hi = f3(-INFINITY, -INFINITY, -INFINITY);
-    for (size_t i = 0; i < s->meshes.size(); ++i) {
-        const Mesh& m = s->meshes[i];
-        const size_t mt = m.tris.size() / 3;
-        for (size_t t = 0; t < mt; ++t) {
-            const size_t g = m.tri_base + t;
-            const float* v[3];
-            float3 p[3];
-            for (int k = 0; k < 3; ++k) {
-                v[k] = m.verts.data() + 8 * (size_t)m.tris[3 * t + k];
-                p[k] = xform_point(m.M, f3(v[k][0], v[k][1], v[k][2]));
-                lo = f3(fminf(lo.x, p[k].x), fminf(lo.y, p[k].y), fminf(lo.z, p[k].z));
-                hi = f3(fmaxf(hi.x, p[k].x), fmaxf(hi.y, p[k].y), fmaxf(hi.z, p[k].z));
-            }
-            tri[3 * g + 0] = make_float4(p[0].x, p[0].y, p[0].z, __builtin_bit_cast(float, (int)g));
-            tri[3 * g + 1] = make_float4(p[1].x, p[1].y, p[1].z, __builtin_bit_cast(float, (int)i));
-            tri[3 * g + 2] = make_float4(p[2].x, p[2].y, p[2].z, __builtin_bit_cast(float, (int)t));
-            for (int k = 0; k < 3; ++k) shade[4 * g + k] = make_float4(v[k][5], v[k][6], v[k][7], v[k][3]);
-            shade[4 * g + 3] = make_float4(v[0][4], v[1][4], v[2][4], 0.0f);
-        }
-    }
-    if (!(lo.x <= hi.x)) return fail(ZDR_ERR_ARG, "commit: non-finite geometry");
+    const char* force = getenv("ZDR_BVH");     // "lbvh" | "csah" | "sah": builder override for experiments and tests
+    const bool sah = force ? strcmp(force, "sah") == 0 : nt <= (size_t)kSahMaxTris;
+    const bool lbvh = force && strcmp(force, "lbvh") == 0;
     {
         const Mesh& m0 = s->meshes[0];
         s->uv_lo[0] = s->uv_lo[1] = INFINITY; s->uv_hi[0] = s->uv_hi[1] = -INFINITY;
@@ -382,19 +362,62 @@ ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
     free_bvh(&s->bvh);
     cudaFree(s->d_inst); cudaFree(s->d_lights);
     s->d_inst = nullptr; s->d_lights = nullptr;
-    float4 *d_tri = nullptr, *d_shade = nullptr;
-    CK(cudaMalloc(&d_tri, sizeof(float4) * tri.size()));
-    cudaError_t e = cudaMalloc(&d_shade, sizeof(float4) * shade.size());
-    if (e == cudaSuccess) e = cudaMemcpy(d_tri, tri.data(), sizeof(float4) * tri.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_shade, shade.data(), sizeof(float4) * shade.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        const char* force = getenv("ZDR_BVH");     // "lbvh" | "csah" | "sah": builder override for experiments and tests
-        const bool sah = force ? strcmp(force, "sah") == 0 : nt <= (size_t)kSahMaxTris;
-        const bool lbvh = force && strcmp(force, "lbvh") == 0;
-        e = sah ? build_bvh_sah_host(tri.data(), shade.data(), (int)nt, lo, hi, s->own_stream, &s->bvh)
-                : build_bvh(d_tri, d_shade, (int)nt, lo, hi, s->own_stream, &s->bvh, !lbvh);
+    s->committed = false;
+    cudaError_t e = cudaSuccess;
+    const bool verbose = getenv("ZDR_VERBOSE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto seconds_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    };
+    if (sah) {
+        // small scene: flatten the instances to world space on the host, p = (M * float4(v,1)).xyz as
+        // interaction.py:19-21, and build the full-sweep SAH tree there
+        std::vector<float4> tri(3 * nt), shade(4 * nt);
+        float3 lo = f3(INFINITY, INFINITY, INFINITY), hi = f3(-INFINITY, -INFINITY, -INFINITY);
+        for (size_t i = 0; i < s->meshes.size(); ++i) {
+            const Mesh& m = s->meshes[i];
+            const size_t mt = m.tris.size() / 3;
+            for (size_t t = 0; t < mt; ++t) {
+                const size_t g = m.tri_base + t;
+                const float* v[3];
+                float3 p[3];
+                for (int k = 0; k < 3; ++k) {
+                    v[k] = m.verts.data() + 8 * (size_t)m.tris[3 * t + k];
+                    p[k] = xform_point(m.M, f3(v[k][0], v[k][1], v[k][2]));
+                    lo = f3(fminf(lo.x, p[k].x), fminf(lo.y, p[k].y), fminf(lo.z, p[k].z));
+                    hi = f3(fmaxf(hi.x, p[k].x), fmaxf(hi.y, p[k].y), fmaxf(hi.z, p[k].z));
+                }
+                tri[3 * g + 0] = make_float4(p[0].x, p[0].y, p[0].z, __builtin_bit_cast(float, (int)g));
+                tri[3 * g + 1] = make_float4(p[1].x, p[1].y, p[1].z, __builtin_bit_cast(float, (int)i));
+                tri[3 * g + 2] = make_float4(p[2].x, p[2].y, p[2].z, __builtin_bit_cast(float, (int)t));
+                for (int k = 0; k < 3; ++k) shade[4 * g + k] = make_float4(v[k][5], v[k][6], v[k][7], v[k][3]);
+                shade[4 * g + 3] = make_float4(v[0][4], v[1][4], v[2][4], 0.0f);
+            }
+        }
+        if (!(lo.x <= hi.x)) return fail(ZDR_ERR_ARG, "commit: non-finite geometry");
+        e = build_bvh_sah_host(tri.data(), shade.data(), (int)nt, lo, hi, s->own_stream, &s->bvh);
+    } else {
+        // large scene: the same records are produced on the GPU (k_flatten), then the GPU build
+        std::vector<FlattenInput> in(s->meshes.size());
+        for (size_t i = 0; i < s->meshes.size(); ++i) {
+            const Mesh& m = s->meshes[i];
+            in[i] = FlattenInput{m.verts.data(), m.tris.data(), (int)(m.verts.size() / 8), (int)(m.tris.size() / 3), m.M};
+        }
+        float4 *d_tri = nullptr, *d_shade = nullptr;
+        float3 lo, hi;
+        bool finite = true;
+        e = flatten_scene_gpu(in.data(), (int)in.size(), s->own_stream, &d_tri, &d_shade, &lo, &hi, &finite);
+        if (e == cudaSuccess && !(finite && lo.x <= hi.x)) {
+            cudaFree(d_tri); cudaFree(d_shade);
+            return fail(ZDR_ERR_ARG, "commit: non-finite geometry");
+        }
+        const double t_flat = seconds_since(t_start);
+        if (e == cudaSuccess) e = build_bvh(d_tri, d_shade, (int)nt, lo, hi, s->own_stream, &s->bvh, !lbvh);
+        cudaFree(d_tri); cudaFree(d_shade);
+        if (verbose)
+            fprintf(stderr, "[zdr] commit: %zu triangles, upload + GPU flatten %.3f s, %s build %.3f s (%d nodes, depth <= %d)\n", nt, t_flat,
+                    lbvh ? "LBVH" : "clustered-SAH", seconds_since(t_start) - t_flat, s->bvh.num_nodes, s->bvh.max_depth);
     }
-    cudaFree(d_tri); cudaFree(d_shade);
     if (e != cudaSuccess) return fail(ZDR_ERR_CUDA, "commit/build_bvh: %s", cudaGetErrorString(e));
     if (s->bvh.max_depth + 2 > kStackSize) return fail(ZDR_ERR_LIMIT, "BVH depth %d exceeds the traversal stack", s->bvh.max_depth);
     s->num_tris = (int)nt;

@@ -476,6 +476,109 @@ __global__ void k_cluster_pack(const float4* __restrict__ tmp_nodes, const int* 
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// Scene flatten on the GPU (large scenes): world-space triangle + shading records of every instance,
+// p = (M * float4(v,1)).xyz as interaction.py:19-21, with the same fmaf chain as the host path
+// (xform_point), so both produce identical bits.  One thread per triangle; its mesh is found by
+// binary search in the (L1-resident) table of first-triangle indices.
+namespace {
+__device__ __forceinline__ float3 dev_xform_point(const float* __restrict__ M, float x, float y, float z) {
+    return make_float3(fmaf(M[8], z, fmaf(M[4], y, fmaf(M[0], x, M[12]))),
+                       fmaf(M[9], z, fmaf(M[5], y, fmaf(M[1], x, M[13]))),
+                       fmaf(M[10], z, fmaf(M[6], y, fmaf(M[2], x, M[14]))));
+}
+
+__global__ void k_flatten(const float* __restrict__ verts, const int* __restrict__ idx, const int* __restrict__ tri_base,
+                          const int* __restrict__ vert_base, const float* __restrict__ xforms, int num_meshes, int nt,
+                          float4* __restrict__ tri, float4* __restrict__ shade, int* __restrict__ bounds) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    bool finite = true;
+    if (g < nt) {
+        int a = 0, b = num_meshes;                    // last mesh with tri_base <= g
+        while (b - a > 1) { const int m = (a + b) >> 1; if (tri_base[m] <= g) a = m; else b = m; }
+        const int t = g - tri_base[a];
+        const float* M = xforms + 16 * a;
+        const float* v[3];
+        float3 p[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[k] = verts + 8 * (size_t)(vert_base[a] + idx[3 * (size_t)g + k]);
+            p[k] = dev_xform_point(M, v[k][0], v[k][1], v[k][2]);
+            lo[0] = fminf(lo[0], p[k].x); lo[1] = fminf(lo[1], p[k].y); lo[2] = fminf(lo[2], p[k].z);
+            hi[0] = fmaxf(hi[0], p[k].x); hi[1] = fmaxf(hi[1], p[k].y); hi[2] = fmaxf(hi[2], p[k].z);
+            finite = finite && isfinite(p[k].x) && isfinite(p[k].y) && isfinite(p[k].z);
+        }
+        tri[3 * (size_t)g + 0] = make_float4(p[0].x, p[0].y, p[0].z, __int_as_float(g));
+        tri[3 * (size_t)g + 1] = make_float4(p[1].x, p[1].y, p[1].z, __int_as_float(a));
+        tri[3 * (size_t)g + 2] = make_float4(p[2].x, p[2].y, p[2].z, __int_as_float(t));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) shade[4 * (size_t)g + k] = make_float4(v[k][5], v[k][6], v[k][7], v[k][3]);
+        shade[4 * (size_t)g + 3] = make_float4(v[0][4], v[1][4], v[2][4], 0.0f);
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[q] = fminf(lo[q], __shfl_xor_sync(0xffffffffu, lo[q], o));
+            hi[q] = fmaxf(hi[q], __shfl_xor_sync(0xffffffffu, hi[q], o));
+        }
+    const bool all_finite = __all_sync(0xffffffffu, finite);
+    if ((threadIdx.x & 31) == 0) {
+        if (lo[0] <= hi[0])
+            for (int q = 0; q < 3; ++q) { atomicMin(&bounds[q], f2o(lo[q])); atomicMax(&bounds[3 + q], f2o(hi[q])); }
+        if (!all_finite) atomicOr(&bounds[6], 1);
+    }
+}
+}  // namespace
+
+cudaError_t flatten_scene_gpu(const FlattenInput* meshes, int num_meshes, cudaStream_t stream, float4** tri_out,
+                              float4** shade_out, float3* lo, float3* hi, bool* finite) {
+    *tri_out = nullptr; *shade_out = nullptr;
+    std::vector<int> tri_base(num_meshes), vert_base(num_meshes);
+    std::vector<float> xf(16 * (size_t)num_meshes);
+    size_t nt = 0, nv = 0;
+    for (int i = 0; i < num_meshes; ++i) {
+        tri_base[i] = (int)nt; vert_base[i] = (int)nv;
+        nt += meshes[i].num_tris; nv += meshes[i].num_verts;
+        memcpy(&xf[16 * (size_t)i], meshes[i].xform, sizeof(float) * 16);
+    }
+    float *d_verts = nullptr, *d_xf = nullptr;
+    int *d_idx = nullptr, *d_tri_base = nullptr, *d_vert_base = nullptr, *d_bounds = nullptr;
+    cudaError_t e = cudaMalloc(&d_verts, sizeof(float) * 8 * nv);
+    if (e == cudaSuccess) e = cudaMalloc(&d_idx, sizeof(int) * 3 * nt);
+    if (e == cudaSuccess) e = cudaMalloc(&d_tri_base, sizeof(int) * num_meshes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_vert_base, sizeof(int) * num_meshes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_xf, sizeof(float) * xf.size());
+    if (e == cudaSuccess) e = cudaMalloc(&d_bounds, sizeof(int) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(tri_out, sizeof(float4) * 3 * nt);
+    if (e == cudaSuccess) e = cudaMalloc(shade_out, sizeof(float4) * 4 * nt);
+    for (int i = 0; i < num_meshes && e == cudaSuccess; ++i) {
+        e = cudaMemcpyAsync(d_verts + 8 * (size_t)vert_base[i], meshes[i].verts, sizeof(float) * 8 * meshes[i].num_verts, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(d_idx + 3 * (size_t)tri_base[i], meshes[i].tris, sizeof(int) * 3 * meshes[i].num_tris, cudaMemcpyHostToDevice, stream);
+    }
+    const int init[8] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000, 0, 0};
+    int h_bounds[8] = {};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tri_base, tri_base.data(), sizeof(int) * num_meshes, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_vert_base, vert_base.data(), sizeof(int) * num_meshes, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_xf, xf.data(), sizeof(float) * xf.size(), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) {
+        k_flatten<<<(unsigned)((nt + 255) / 256), 256, 0, stream>>>(d_verts, d_idx, d_tri_base, d_vert_base, d_xf, num_meshes, (int)nt,
+                                                                    *tri_out, *shade_out, d_bounds);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_bounds, d_bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d_verts); cudaFree(d_idx); cudaFree(d_tri_base); cudaFree(d_vert_base); cudaFree(d_xf); cudaFree(d_bounds);
+    if (e != cudaSuccess) { cudaFree(*tri_out); cudaFree(*shade_out); *tri_out = nullptr; *shade_out = nullptr; return e; }
+    auto dec = [](int i) { const int b = i >= 0 ? i : i ^ 0x7fffffff; float f; memcpy(&f, &b, 4); return f; };
+    *lo = make_float3(dec(h_bounds[0]), dec(h_bounds[1]), dec(h_bounds[2]));
+    *hi = make_float3(dec(h_bounds[3]), dec(h_bounds[4]), dec(h_bounds[5]));
+    *finite = h_bounds[6] == 0;
+    return cudaSuccess;
+}
+
 // full-sweep SAH tree over cluster boxes (defined below, next to the host builder)
 void build_top_level(const std::vector<float4>& cl_box, const std::vector<int>& cl_count, float eps,
                      std::vector<float4>* nodes, std::vector<int>* leaf_cluster_of_link, int* root_link, int* depth);
