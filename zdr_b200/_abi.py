@@ -68,7 +68,8 @@ def make_params(camera, res, tex_shape, spp, seed, *, use_tent_filter=True, max_
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libzdr_b200.so")
+# ZDR_B200_LIB: another build of the same library (kernel-tuning experiments, tools/sweep_*.sh)
+LIB_PATH = os.environ.get("ZDR_B200_LIB") or os.path.join(_HERE, "csrc", "libzdr_b200.so")
 _lib = None
 
 _f32p, _i32p, _u32p, _u16p, _u64p = (C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint32),
