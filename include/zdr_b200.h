@@ -93,6 +93,11 @@ typedef struct zdr_params {
  * machine below that. Both produce bit-identical images. */
 #define ZDR_FLAG_WAVEFRONT 8
 #define ZDR_FLAG_MEGAKERNEL 16
+/* MIS weight of a BSDF-sampled emitter hit in a scene that has BOTH mesh lights and an envmap: the reference's
+ * sample_light_pdf divides by light_count only (light.py:89) while sample_light picks among
+ * env_count + light_count lights (light.py:26), so the two densities disagree by (n_mesh + 1) / n_mesh.
+ * Default: as the reference.  With this bit sample_light_pdf uses the same n as sample_light. */
+#define ZDR_FLAG_LIGHT_PDF_COUNTS_ENV 32
 
 typedef struct zdr_scene zdr_scene;
 

@@ -266,6 +266,7 @@ struct zo_scene {
     int light_count;
     int* lights;        /* render.py:121 */
     int env_count;
+    int pdf_env_count;  /* what sample_light_pdf adds to light_count: 0 (light.py:89) or env_count (ZDR_FLAG_LIGHT_PDF_COUNTS_ENV) */
     /* envmap (envmap.py) */
     int env_w, env_h;
     float* env_tex;     /* rgba, env_h rows (after the row duplication of envmap.py:123-125) */
@@ -788,9 +789,10 @@ static LightSample sample_light(zo_scene* s, f3 origin, Sampler* sampler) {
     t.dist = 0.9999f * sqrtf(sqr_dist);
     return t;
 }
-/* light.py:83-111 — note n EXCLUDES env_count (light.py:89), reproduced */
+/* light.py:83-111 — note n EXCLUDES env_count (light.py:89), reproduced; with ZDR_FLAG_LIGHT_PDF_COUNTS_ENV it
+ * is the n of sample_light (light.py:26) */
 static float sample_light_pdf(zo_scene* s, f3 origin, int inst, int prim, f3 p) {
-    int n = 0 + s->light_count;
+    int n = s->pdf_env_count + s->light_count;
     int trig_count = s->inst[inst].nt;
     f3 p0, p1, p2; inst_triangle(s, inst, prim, &p0, &p1, &p2);
     f3 wi_light = normalize3(sub3(p, origin));
@@ -1204,6 +1206,7 @@ static int render_forward_impl(zo_scene* s, int integrator, const zdr_params* p,
     for (int y = p->row0; y < p->row1; ++y) {
         if (!row_in_shard(p, y)) continue;
         zo_scene local = *s; local.n_closest = 0; local.n_any = 0;
+        local.pdf_env_count = (p->flags & ZDR_FLAG_LIGHT_PDF_COUNTS_ENV) ? s->env_count : 0;
         Ctx c = {&local, {material, NULL, p->tex_res_x, p->tex_res_y, p->bilinear}, p};
         for (int x = 0; x < p->width; ++x) {
             f3 acc = v3(0, 0, 0);
@@ -1251,6 +1254,7 @@ ZO_API int zo_render_backward(zo_scene* s, int integrator, const zdr_params* p, 
     for (int y = p->row0; y < p->row1; ++y) {
         if (!row_in_shard(p, y)) continue;
         zo_scene local = *s; local.n_closest = 0; local.n_any = 0;
+        local.pdf_env_count = (p->flags & ZDR_FLAG_LIGHT_PDF_COUNTS_ENV) ? s->env_count : 0;
         Ctx c = {&local, {material, acc, p->tex_res_x, p->tex_res_y, p->bilinear}, p};
         for (int x = 0; x < p->width; ++x) {
             const float* g = d_image + ((size_t)x + (size_t)y * p->width) * 4;

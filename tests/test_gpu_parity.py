@@ -342,6 +342,30 @@ def test_envmap_path(oracle):
     g.close()
 
 
+def test_envmap_with_mesh_lights_and_consistent_light_pdf(oracle):
+    """Envmap AND emissive meshes in one scene: the reference's sample_light_pdf leaves the envmap out of its light
+    count (light.py:89 vs :26).  Both behaviours — the literal one and ZDR_FLAG_LIGHT_PDF_COUNTS_ENV — must match
+    the oracle, and they must differ from each other (the flag is not a no-op)."""
+    models = scenes.cbox_path_models()                          # Cornell box (open front) + its area light + an envmap
+    env = scenes.procedural_envmap(128, 64, seed=2) * np.float32(0.2)
+    g, o = GpuScene(models), oracle.OracleScene(models)
+    g.set_envmap(env)
+    o.set_envmap(env)
+    mat = scenes.random_material((32, 32), 12)
+    cam = scenes.CBOX_CAMERA
+    dimg = np.ones((48, 64, 4), np.float32)
+    for integ, sched in ((ZDR_DIRECT, "auto"), (ZDR_PATH, "megakernel"), (ZDR_PATH, "wavefront")):
+        imgs = []
+        for flag in (False, True):
+            p = make_params(cam, (64, 48), mat.shape, 8, 3, max_depth=5, schedule=sched, light_pdf_counts_env=flag)
+            img_g, img_o = g.forward(integ, p, mat), o.render_forward(integ, p, mat)
+            assert rel_l2(img_g, img_o) <= IMG_TOL, (integ, flag, rel_l2(img_g, img_o))
+            assert rel_l2(g.backward(integ, p, mat, dimg), o.render_backward(integ, p, mat, dimg)) <= GRAD_TOL
+            imgs.append(img_g)
+        assert rel_l2(imgs[0], imgs[1]) > 1e-3
+    g.close()
+
+
 @pytest.mark.parametrize("builder", ["csah", "lbvh"])
 def test_lbvh_large_scene(oracle, builder, monkeypatch):
     """> 16 K triangles takes the GPU builders (C5 shape: instanced sphere.obj) — clustered SAH (default) and the

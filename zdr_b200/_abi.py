@@ -16,6 +16,7 @@ ZDR_NUM_COUNTERS = 8
 ZDR_FLAG_STATS = 1
 ZDR_FLAG_SCATTER_AGGREGATE, ZDR_FLAG_SCATTER_PLAIN = 2, 4
 ZDR_FLAG_WAVEFRONT, ZDR_FLAG_MEGAKERNEL = 8, 16
+ZDR_FLAG_LIGHT_PDF_COUNTS_ENV = 32
 SCHEDULES = {"auto": 0, "wavefront": ZDR_FLAG_WAVEFRONT, "megakernel": ZDR_FLAG_MEGAKERNEL}
 SCATTER_MODES = {"auto": 0, "aggregate": ZDR_FLAG_SCATTER_AGGREGATE, "plain": ZDR_FLAG_SCATTER_PLAIN}
 COUNTER_NAMES = ("closest_rays", "any_rays", "nodes_visited", "tris_tested",
@@ -48,7 +49,7 @@ def wrap_i32(x: int) -> int:
 
 def make_params(camera, res, tex_shape, spp, seed, *, use_tent_filter=True, max_depth=16, rr_depth=2,
                 use_mis=True, bilinear=True, prb_mode=ZDR_PRB_CORRECTED, rows=None, its=None, shard=None,
-                stats=False, scatter="auto", schedule="auto") -> ZdrParams:
+                stats=False, scatter="auto", schedule="auto", light_pdf_counts_env=False) -> ZdrParams:
     p = ZdrParams()
     p.cam_fov = float(camera.fov)
     p.cam_origin[:] = list(camera.origin)
@@ -63,7 +64,8 @@ def make_params(camera, res, tex_shape, spp, seed, *, use_tent_filter=True, max_
     p.row0, p.row1 = (0, p.height) if rows is None else (int(rows[0]), int(rows[1]))
     p.it0, p.it1 = (0, p.spp) if its is None else (int(its[0]), int(its[1]))
     p.shard_index, p.shard_count = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
-    p.flags = (ZDR_FLAG_STATS if stats else 0) | SCATTER_MODES[scatter] | SCHEDULES[schedule]
+    p.flags = ((ZDR_FLAG_STATS if stats else 0) | SCATTER_MODES[scatter] | SCHEDULES[schedule]
+               | (ZDR_FLAG_LIGHT_PDF_COUNTS_ENV if light_pdf_counts_env else 0))
     return p
 
 

@@ -187,6 +187,7 @@ int make_args(zdr_scene* s, const zdr_params* p, RenderArgs* a) {
     a->W = p->width; a->H = p->height; a->spp = p->spp; a->seed = p->seed;
     a->use_tent = p->use_tent_filter; a->max_depth = p->max_depth; a->rr_depth = p->rr_depth;
     a->use_mis = p->use_mis; a->prb_mode = p->prb_mode;
+    a->sc.pdf_env_count = (p->flags & ZDR_FLAG_LIGHT_PDF_COUNTS_ENV) ? a->sc.env_count : 0;
     a->row0 = p->row0; a->row1 = p->row1; a->it0 = p->it0; a->it1 = p->it1;
     a->shard_count = p->shard_count > 1 ? p->shard_count : 1;
     a->shard_index = p->shard_count > 1 ? p->shard_index : 0;

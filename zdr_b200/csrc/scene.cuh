@@ -35,6 +35,7 @@ struct SceneView {
     int root_link;                       // link of the root (leaf link if the scene is one leaf)
     int num_tris, num_nodes, num_inst;
     int light_count, env_count;
+    int pdf_env_count;                   // added to light_count by sample_light_pdf: 0 (light.py:89) or env_count
     // sampler tables (pmj02bn.py:9-16)
     const float2* __restrict__ pmj;
     const float* __restrict__ bn;

@@ -433,9 +433,9 @@ ZDR_DEV LightSample sample_light(const SceneView& sc, float3 origin, Sampler& sa
     t.dist = 0.9999f * sqrtf(sqr_dist);
     return t;
 }
-// light.py:83-111 — n excludes env_count (light.py:89), reproduced
+// light.py:83-111 — n excludes env_count (light.py:89), reproduced unless ZDR_FLAG_LIGHT_PDF_COUNTS_ENV
 ZDR_DEV float sample_light_pdf(const SceneView& sc, float3 origin, const Hit& h, float3 p) {
-    const int n = 0 + sc.light_count;
+    const int n = sc.pdf_env_count + sc.light_count;
     const int trig_count = sc.inst[h.inst].tri_count;
     const float4* tp = sc.tris + 3 * (size_t)h.slot;
     const float4 a = __ldg(tp), b = __ldg(tp + 1), c4 = __ldg(tp + 2);

@@ -90,6 +90,8 @@ class Scene:
         self.collect_stats = False
         self.schedule = "auto"          # path integrator: 'auto' | 'wavefront' | 'megakernel' (ZDR_FLAG_*)
         self.scatter_mode = "auto"      # 'auto' | 'aggregate' | 'plain' (ZDR_FLAG_SCATTER_*)
+        # light.py:89 leaves the envmap out of sample_light_pdf's light count; True uses sample_light's count (light.py:26)
+        self.light_pdf_counts_env = False
         # data-parallel shard of the dispatch grid; None = whole image
         self.shard_rows = None
         self.shard = None          # (index, count): round-robin 8-row tiles, see zdr_params.shard_index
@@ -157,7 +159,8 @@ class Scene:
         p = make_params(self.camera, res, material.shape[0:2], spp, seed, use_tent_filter=self.use_tent_filter,
                         max_depth=self.max_depth, rr_depth=self.rr_depth, use_mis=self.use_mis, bilinear=self.bilinear,
                         prb_mode=PRB_MODES[self.prb_mode] if isinstance(self.prb_mode, str) else int(self.prb_mode),
-                        rows=rows if rows is not None else self.shard_rows, shard=self.shard, stats=self.collect_stats, scatter=self.scatter_mode, schedule=self.schedule)
+                        rows=rows if rows is not None else self.shard_rows, shard=self.shard, stats=self.collect_stats, scatter=self.scatter_mode, schedule=self.schedule,
+                        light_pdf_counts_env=self.light_pdf_counts_env)
         return p
 
     def _check_material(self, material):
