@@ -469,7 +469,8 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_generate(const __grid_constan
 #endif
 constexpr int kWfRefill = ZDR_WF_REFILL;
 constexpr int kWfNodeBudget = 12;
-template <bool ANY, bool STATS>
+constexpr int kWfBigSceneNodes = 1024;
+template <bool ANY, bool STATS, bool BIG>      // BIG: scene with more than kWfBigSceneNodes nodes (launch_wf_round)
 __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(const __grid_constant__ RenderArgs a) {
     const WfState& w = a.wf;
     const int n = *(volatile int*)(w.counts + (ANY ? 1 : 0));
@@ -483,9 +484,7 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
     const float4* __restrict__ tris = a.sc.tris;
     Tally tl = {};
     const int lane = threadIdx.x & 31;
-    const bool big_scene = a.sc.num_nodes > 1024;      // traversals long enough for refills to pay on every kind of ray
-    const bool refill_any = big_scene;
-    const int node_budget = big_scene ? kWfNodeBudget : 0x3fffffff;
+    constexpr bool refill_any = BIG;                   // traversals long enough for refills to pay on every kind of ray
     // per-lane traversal state
     bool has_ray = false, exhausted = false;
     int slot = 0, link = kLinkSentinel, sp = 0, hit_slot = -1, best_gid = 0x7fffffff;
@@ -536,10 +535,10 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
         }
         // ---- traverse until done, or until too few lanes are left working
         while (has_ray) {
-            int budget = node_budget;        // bounded, so that the refill test below is reached regularly even when a
-                                             // ray walks hundreds of nodes between two leaves (9.6 M-triangle scene:
+            int budget = kWfNodeBudget;      // BIG: bounded, so that the refill test below is reached regularly even when
+                                             // a ray walks hundreds of nodes between two leaves (9.6 M-triangle scene:
                                              // 9.6 of 32 lanes were active without the bound, profiles/r01p)
-            while (link >= 0 && budget-- > 0) {          // inner nodes
+            while (link >= 0 && (!BIG || budget-- > 0)) {    // inner nodes
                 const float4* nd = nodes + 4 * (size_t)link;
                 const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
                 if (STATS) tl.ts.nodes++;
@@ -1009,12 +1008,13 @@ namespace {
 template <int MODE>
 void launch_wf_round(bool stats, bool agg, bool env, int grid, cudaStream_t s, const RenderArgs& a) {
     g_kernel_launches += 4;
-    if (stats) k_wf_trace<false, true><<<grid, kWfThreads, 0, s>>>(a);
-    else k_wf_trace<false, false><<<grid, kWfThreads, 0, s>>>(a);
+    const bool big = a.sc.num_nodes > kWfBigSceneNodes;
+    if (stats) { if (big) k_wf_trace<false, true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_trace<false, true, false><<<grid, kWfThreads, 0, s>>>(a); }
+    else { if (big) k_wf_trace<false, false, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_trace<false, false, false><<<grid, kWfThreads, 0, s>>>(a); }
     if (env) k_wf_shade_a<MODE, true><<<grid, kWfThreads, 0, s>>>(a);
     else k_wf_shade_a<MODE, false><<<grid, kWfThreads, 0, s>>>(a);
-    if (stats) k_wf_trace<true, true><<<grid, kWfThreads, 0, s>>>(a);
-    else k_wf_trace<true, false><<<grid, kWfThreads, 0, s>>>(a);
+    if (stats) { if (big) k_wf_trace<true, true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_trace<true, true, false><<<grid, kWfThreads, 0, s>>>(a); }
+    else { if (big) k_wf_trace<true, false, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_trace<true, false, false><<<grid, kWfThreads, 0, s>>>(a); }
     if constexpr (MODE == 2) {
         if (agg) {
             if (stats) k_wf_shade_b<MODE, true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<MODE, false, true><<<grid, kWfThreads, 0, s>>>(a);
