@@ -338,6 +338,19 @@ def run_ours(args):
         if rec.get("res") == args.res and rec.get("integrator") == args.integrator and world == 1:
             # DRAM bytes of one adjoint pass measured with ncu at rec["spp"]; batches of 16 samples are identical, so it scales with spp
             traffic = int(rec["backward_dram_bytes"] * args.spp / rec["spp"])
+    # the other two denominators SURVEY.md 8(d) asks for, measured by tools/microbench (profiles/r01q_microbench.json)
+    other = None
+    mpath = os.path.join(ROOT, "profiles", "r01q_microbench.json")
+    if os.path.exists(mpath):
+        mb = json.load(open(mpath))
+        l2_64 = next(g["gb_per_s"] for g in mb["gather"] if g["working_set_mib"] == 16 and g["record_bytes"] == 64)
+        red_peak = next(r["gops_per_s"] for r in mb["red"] if r["op"].endswith("v4.f32") and r["addresses"].startswith("random"))
+        red_rate = c_bwd["red_v4"] / (ms_bwd * 1e-3) / 1e9
+        other = {"l2_gather_peak_gbs_64B_records": l2_64, "achieved_over_l2_gather": round(achieved / l2_64, 3),
+                 "red_v4_g_per_s": round(red_rate, 2), "red_v4_peak_g_per_s": red_peak, "red_frac": round(red_rate / red_peak, 4),
+                 "binding": ("none of the three: the BVH (4 KB) is L1-resident, texel gathers are ~2 % of the L2 gather rate and the scatter "
+                             "~2 % of the reduction rate; the stage kernels issue 60-76 % of their cycles (ncu, profiles/r01m) at 19-30 of 32 "
+                             "lanes, i.e. the pass is bound by instruction issue under divergence, with HBM latency on the path state next")}
     wavefront = args.integrator == "path" and args.schedule != "megakernel" and (args.schedule == "wavefront" or pixels_local * args.spp >= 1 << 21)
     if wavefront:
         kernel_name = ("adjoint pass of the wavefront path tracer: k_wf_generate + (2*depth+1) x [k_wf_trace<closest>, k_wf_shade_a, "
@@ -360,7 +373,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": kernel_name,
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_bwd),
-                     "ms_per_launch": round(ms_bwd, 3),
+                     "ms_per_launch": round(ms_bwd, 3), "other_denominators": other,
                      "note": ("algorithmic bytes = BVH nodes/triangles visited + shading records + texels + scatter footprints (DESIGN.md 6); on "
                               "the Cornell box these are L1/L2 resident. `traffic` = DRAM bytes ncu measured for the same pass: with the "
                               "wavefront schedule it is the path state streamed through HBM between stages")},

@@ -25,6 +25,7 @@ ap.add_argument("--spp", type=int, default=16)
 ap.add_argument("--depth", type=int, default=16)
 ap.add_argument("--check-rays", type=int, default=48)
 ap.add_argument("--stats", action="store_true", help="also count BVH nodes / triangles per ray (slower)")
+ap.add_argument("--separate", action="store_true", help="keep every sphere a separate instance (10 000 add_mesh calls; only instance 0 is shaded)")
 args = ap.parse_args()
 
 from zdr_b200.load_obj import load_mesh
@@ -51,6 +52,8 @@ for i, (obj, xf, em) in enumerate(grid):
     mt.append(st + len(mv) * sv.shape[0])
     mv.append(v)
 models = [((np.concatenate(mv), np.concatenate(mt)), None, scenes.float3(0.0))] + lights
+if args.separate:
+    models = grid
 t0 = time.perf_counter()
 sc = Scene(models, integrator="path", device=local_rank)
 torch.cuda.synchronize()
