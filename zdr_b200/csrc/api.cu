@@ -268,6 +268,8 @@ ZDR_EXPORT const char* zdr_last_error(void) { return g_err; }
 ZDR_EXPORT int zdr_set_sampler_tables(int device, const uint32_t* pmj_host, int sets, int n, const uint16_t* bn_host,
                                       int ntex, int res) {
     if (!pmj_host || !bn_host || sets <= 0 || n <= 0 || ntex <= 0 || res <= 0) return fail(ZDR_ERR_ARG, "bad sampler tables");
+    if ((long long)ntex * res * res >= (1ll << 29) || (long long)sets * n >= (1ll << 29))
+        return fail(ZDR_ERR_LIMIT, "sampler tables too large (the kernels index them with 32-bit arithmetic)");
     int rc = use_device(device);
     if (rc) return rc;
     const size_t np = (size_t)sets * n * 2, nb = (size_t)ntex * res * res;

@@ -430,7 +430,7 @@ constexpr unsigned kWfPhaseBit = 1u << 8;
 
 ZDR_DEV unsigned wf_pack(int depth, int phase, int dimension) { return (unsigned)depth | (phase ? kWfPhaseBit : 0u) | ((unsigned)dimension << 12); }
 ZDR_DEV void wf_pixel(const RenderArgs& a, int pix, int& x, int& y) {
-    const int lr = pix / a.W;
+    const int lr = fastdiv(pix, a.wf.div_W);
     x = pix - lr * a.W;
     y = a.row0 + ((lr >> 3) * a.shard_count + a.shard_index) * 8 + (lr & 7);
 }
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_generate(const __grid_constan
     const WfState& w = a.wf;
     Tally tl = {};
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < w.nslots; slot += wf_stride()) {
-        const int j = slot / w.P, pix = slot - j * w.P;
+        const int j = fastdiv(slot, w.div_P), pix = slot - j * w.P;
         int x, y;
         wf_pixel(a, pix, x, y);
         Sampler sampler = make_sampler(a.sc, x, y, a.seed, a.spp, w.it_base + j);
@@ -613,7 +613,7 @@ ZDR_DEV WfPath wf_load(const RenderArgs& a, int slot, bool with_throughput) {
     const WfState& w = a.wf;
     WfPath p;
     p.slot = slot;
-    const int j = slot / w.P, pix = slot - j * w.P;
+    const int j = fastdiv(slot, w.div_P), pix = slot - j * w.P;
     wf_pixel(a, pix, p.x, p.y);
     p.it = w.it_base + j;
     const float4 A = w.AB[2 * (size_t)(slot)], B = w.AB[2 * (size_t)(slot) + 1];
@@ -925,7 +925,7 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_restart(const __grid_constant
             const float4 D4 = w.CD[2 * (size_t)(slot) + 1];
             const float3 Le = f3(D4.x, D4.y, D4.z);
             if (!any_nan(Le)) {
-                const int j = slot / w.P, pix = slot - j * w.P;
+                const int j = fastdiv(slot, w.div_P), pix = slot - j * w.P;
                 int x, y;
                 wf_pixel(a, pix, x, y);
                 Sampler cam = make_sampler(a.sc, x, y, a.seed, a.spp, w.it_base + j);
@@ -1080,6 +1080,8 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
     if (rows <= 0 || a.it1 <= a.it0) return cudaSuccess;
     WfState& w = a.wf;
     w.P = a.W * rows;
+    w.div_P = make_fastdiv(w.P);
+    w.div_W = make_fastdiv(a.W);
     const int grid = w.num_sms * ZDR_WF_GRID_MULT;
     const int smax = w.S;      // capacity in samples per batch (buffers hold P * smax slots)
     for (int base = a.it0; base < a.it1; base += smax) {

@@ -20,6 +20,7 @@ struct WfState {
     int* list[2];     // list[0]: live paths (input of extend); list[1]: paths to shade (output of shade A)
     int* counts;      // counts[0], counts[1]
     int P;            // pixels of this launch (width * rows of the shard)
+    FastDiv div_P, div_W;   // slot -> (sample in batch, pixel), pixel -> (row, column)
     int S;            // samples of the current batch
     int it_base;      // first sample index of the batch
     int nslots;       // P * S

@@ -67,18 +67,33 @@ ZDR_DEV Sampler make_sampler(const SceneView& sc, int px, int py, int seed, int 
     h += (uint32_t)py * P3;
     s.h_xy = P4 * ((h << 17) | (h >> 15));
     const int qx = px ^ seed, qy = py ^ seed;              // pmj02bn.py:108: pixel ^ seed
-    const int cx = qx % sc.bn_res, cy = qy % sc.bn_res;    // truncating %, as the reference's int2 % lowers
+    int cx, cy;                                            // truncating %, as the reference's int2 % lowers
+    if ((sc.bn_res & (sc.bn_res - 1)) == 0) {              // power-of-two table (pbrt's is 128): sign * (|q| & (res - 1))
+        const unsigned m = (unsigned)sc.bn_res - 1u;
+        const unsigned ax = qx < 0 ? 0u - (unsigned)qx : (unsigned)qx, ay = qy < 0 ? 0u - (unsigned)qy : (unsigned)qy;
+        cx = (int)(ax & m); cy = (int)(ay & m);
+        if (qx < 0) cx = -cx;
+        if (qy < 0) cy = -cy;
+    } else {
+        cx = qx % sc.bn_res; cy = qy % sc.bn_res;
+    }
     s.bn_k = (sc.bn_res + cx) * sc.bn_res;
     s.bn_cy = cy;
     return s;
 }
 // pmj02bn.py:19-24 — literal index formula tex*(res+cx)*res+cy; indices past the table wrap
-// modulo its length (upstream: undefined behaviour from dimension 25 on).  The index is below
-// 2*len + res, so the modulo is at most two conditional subtractions.
+// modulo its length (upstream: undefined behaviour from dimension 25 on).  |index| is below
+// 2*len + res, so the modulo is at most two conditional subtractions; zdr_set_sampler_tables keeps len below
+// 2^29, so 32-bit arithmetic is exact.  small_mod: x mod n for an x that is almost always below 2n.
+ZDR_DEV int small_mod(int x, int n) {
+    unsigned t = (unsigned)x;
+    if (t >= (unsigned)n) { t -= (unsigned)n; if (t >= (unsigned)n) t %= (unsigned)n; }
+    return (int)t;
+}
 ZDR_DEV float blue_noise(const float* __restrict__ bn, int ntex, int res, int bn_k, int bn_cy, int tex_id) {
-    const int tex_index = (int)((unsigned)tex_id % (unsigned)ntex);   // tex_id >= 0
-    long long i = (long long)tex_index * bn_k + bn_cy;
-    const long long len = (long long)ntex * res * res;
+    const int tex_index = small_mod(tex_id, ntex);   // tex_id >= 0
+    int i = tex_index * bn_k + bn_cy;
+    const int len = ntex * res * res;
     if (i < 0) i += len;
     if (i >= len) i -= len;
     if (i >= len) i -= len;
@@ -86,10 +101,11 @@ ZDR_DEV float blue_noise(const float* __restrict__ bn, int ntex, int res, int bn
 }
 // pmj02bn.py:26-30
 ZDR_DEV float2 pmj02bn_sample(const float2* __restrict__ pmj, int sets, int n, int set_id, int sample_id) {
-    const int set_index = (int)((unsigned)set_id % (unsigned)sets);
-    long long i = (long long)set_index * n + sample_id;
+    const int set_index = small_mod(set_id, sets);
+    if (sample_id < n) return __ldg(pmj + (set_index * n + sample_id));
+    long long i = (long long)set_index * n + sample_id;     // only for spp > table length
     const long long len = (long long)sets * n;
-    if (i >= len) i %= len;          // only for spp > table length
+    if (i >= len) i %= len;
     return __ldg(pmj + i);
 }
 ZDR_DEV uint32_t hash_dim(uint32_t h_xy, int dimension) {

@@ -112,4 +112,23 @@ void sincos_contract(float phi, float* s_out, float* c_out) {
     *c_out = (float)c;
 }
 
+// Division of 0 <= n < 2^31 by a launch constant d >= 1 as one 32x32 -> 64-bit multiply and a shift:
+// with s = ceil(log2 d) and m = ceil(2^(31+s) / d) < 2^32, floor(n * m / 2^(31+s)) = floor(n / d) exactly
+// (m = 2^(31+s)/d + e, 0 <= e < 1, and n * e * d < 2^(31+s)).  A hardware-less integer division by a runtime
+// value costs ~20 instructions; the wavefront stages do two per path per stage.
+struct FastDiv {
+    unsigned m;
+    int shift, d;
+};
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    int s = 0;
+    while ((1ll << s) < (long long)d) ++s;
+    f.shift = 31 + s;
+    f.m = (unsigned)(((1ull << f.shift) + (unsigned long long)d - 1ull) / (unsigned long long)d);
+    f.d = d;
+    return f;
+}
+ZDR_HD int fastdiv(int n, const FastDiv& f) { return (int)(((unsigned long long)(unsigned)n * f.m) >> f.shift); }
+
 }  // namespace zdr
