@@ -185,6 +185,16 @@ int zdr_probe_render_samples(zdr_scene* s, int integrator, const zdr_params* p,
  * in  n x 13: wo.xyz wi.xyz diffuse.xyz roughness g.xyz ; out n x 7: f.xyz dmat.xyzw */
 int zdr_probe_ggx(int device, const float* in_nx13_host, int n, float* out_nx7_host);
 
+/* --- scene ingest (host only, needs no device) ---------------------------------------------
+ * Wavefront OBJ -> the (verts N x 8, tris T x 3) arrays zdr_scene_add_mesh takes.  Replaces read_obj +
+ * concat_triangles (load_obj.py:1-68) and the recompute_normal call of render.py:101-103, with the same vertex
+ * numbering (first use of each distinct position/uv/normal triple), primitive order (fan triangulation in face
+ * order), defaults (missing vt = (0,0); missing vn = recomputed area-weighted normals).  *verts_out / *tris_out
+ * are malloc'ed; release them with zdr_obj_free.  Errors: ZDR_ERR_ARG, text in zdr_obj_last_error(). */
+int zdr_obj_load(const char* path, float** verts_out, int* num_verts_out, int32_t** tris_out, int* num_tris_out);
+void zdr_obj_free(void* p);
+const char* zdr_obj_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

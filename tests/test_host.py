@@ -84,6 +84,40 @@ def test_load_obj_matches_reference_loader():
     assert (verts[:, 3:5] == 0).all()
 
 
+def test_native_obj_loader_equals_python_loader(tmp_path):
+    """zdr_obj_load (C++) against load_mesh_python, the line-by-line statement of load_obj.py: identical bytes on the
+    shipped assets and on a hostile file (n-gons, a/b/c - a//c - a/b - a corners, negative and zero indices, signed
+    zeros, CRLF, comments, extra components, no normals -> recomputed normals incl. a zero-area triangle)."""
+    from zdr_b200.load_obj import load_mesh_native, load_mesh_python
+    files = [scenes.asset(n) for n in ("cboxuv.obj", "cbox-combined.obj", "cbox-light.obj", "sphere.obj", "quad.obj")]
+    rng = np.random.default_rng(0)
+    lines = ["# hostile", "", "o thing\r"]
+    pts = rng.normal(size=(40, 3)).round(3)
+    pts[3] = (0.0, -0.0, 1.0)
+    pts[4] = (-0.0, 0.0, 1.0)                       # equal to pts[3] as numbers: merges with it
+    for q in pts:
+        lines.append(f"v {float(q[0])!r} {float(q[1])!r} {float(q[2])!r} 1.0")
+    for q in rng.uniform(0, 1, (12, 2)).round(4):
+        lines.append(f"vt {float(q[0])!r} {float(q[1])!r} 0.0\r")
+    lines += ["f 1/1 2/2 3/3 4/4 5/5", "f 4/4 5/4 6/1", "f -1 -2 -3", "f 7 8 9 10 11 12 13", "f 0 1 2",
+              "f 3 4 5", "f 3/2 4/2 5/2", "f 20/3 21/4 22/5\r", "f 30 30 31", "s off", "usemtl x", "f 33/1 34/1 35/1 36/1"]
+    hostile = tmp_path / "hostile.obj"
+    hostile.write_text("\n".join(lines) + "\n")
+    with_normals = tmp_path / "normals.obj"
+    with_normals.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nvn 0 0 1\nvn 0 0 -1\nvt 0.5 0.5\n"
+                            "f 1//1 2//1 3//1\nf 2/1/1 4/1/2 3//1\nf 1//1 2//1 4//2\n")
+    for f in files + [str(hostile), str(with_normals)]:
+        (v0, t0), (v1, t1) = load_mesh_python(f), load_mesh_native(f)
+        assert v0.shape == v1.shape and np.array_equal(v0.view(np.uint32), v1.view(np.uint32)), f
+        assert np.array_equal(t0, t1), f
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nv 1 0 0\nf 1 2 9\n")
+    with pytest.raises(ValueError):
+        load_mesh_native(str(bad))
+    with pytest.raises(ValueError):
+        load_mesh_native(str(tmp_path / "missing.obj"))
+
+
 def test_mathtypes():
     m = float4x4(1.0)
     assert m.flat() == [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]

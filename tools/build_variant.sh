@@ -8,6 +8,6 @@ mkdir -p variants
 make -s -j4 > /dev/null
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off \
      --expt-relaxed-constexpr "$@" -c -o variants/render_$name.o render.cu
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/lib_$name.so api.o variants/render_$name.o bvh_build.o envmap.o -Xcompiler -fPIC
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/lib_$name.so api.o variants/render_$name.o bvh_build.o envmap.o obj_loader.o -Xcompiler -fPIC
 rm -f variants/render_$name.o
 echo variants/lib_$name.so

@@ -106,6 +106,9 @@ SIGNATURES = {
     "zdr_probe_sampler": (C.c_int, [C.c_int, _i32p, C.c_int, C.c_char_p, _f32p]),
     "zdr_probe_render_samples": (C.c_int, [_vp, C.c_int, _pp, _f32p, _f32p]),
     "zdr_probe_ggx": (C.c_int, [C.c_int, _f32p, C.c_int, _f32p]),
+    "zdr_obj_load": (C.c_int, [C.c_char_p, C.POINTER(_f32p), C.POINTER(C.c_int), C.POINTER(_i32p), C.POINTER(C.c_int)]),
+    "zdr_obj_free": (None, [_vp]),
+    "zdr_obj_last_error": (C.c_char_p, []),
 }
 
 

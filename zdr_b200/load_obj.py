@@ -87,10 +87,36 @@ def recompute_normal(verts: np.ndarray, tris: np.ndarray) -> np.ndarray:
     return v
 
 
+def load_mesh_native(file_path: str) -> Tuple[np.ndarray, np.ndarray]:
+    """The same result as :func:`load_mesh_python` from the library's C++ parser (``zdr_obj_load``,
+    ``csrc/obj_loader.cu``): seconds instead of minutes on meshes of millions of triangles."""
+    import ctypes as C
+
+    from . import _abi
+    lib = _abi.load_library()
+    vp, tp = C.POINTER(C.c_float)(), C.POINTER(C.c_int32)()
+    nv, nt = C.c_int(), C.c_int()
+    rc = lib.zdr_obj_load(file_path.encode(), C.byref(vp), C.byref(nv), C.byref(tp), C.byref(nt))
+    if rc != 0:
+        raise ValueError(f"{file_path}: {lib.zdr_obj_last_error().decode()}")
+    try:
+        verts = np.ctypeslib.as_array(vp, shape=(nv.value, 8)).copy()
+        tris = np.ctypeslib.as_array(tp, shape=(nt.value * 3,)).copy()
+    finally:
+        lib.zdr_obj_free(vp)
+        lib.zdr_obj_free(tp)
+    return verts, tris
+
+
 def load_mesh(file_path: str) -> Tuple[np.ndarray, np.ndarray]:
     """OBJ -> (``verts`` float32 (N,8) rows ``px py pz u v nx ny nz`` = the 32-byte ``Vertex`` of
     ``vertex.py:4`` as filled at ``render.py:97``; ``tris`` int32 (T*3,)).  Normals are
-    recomputed when the file has none (``render.py:101-103``)."""
+    recomputed when the file has none (``render.py:101-103``).  Parsed by the library's native loader;
+    :func:`load_mesh_python` is the line-by-line statement of the same algorithm (tests hold them equal)."""
+    return load_mesh_native(file_path)
+
+
+def load_mesh_python(file_path: str) -> Tuple[np.ndarray, np.ndarray]:
     vertices, faces = read_obj(file_path)
     if not vertices or not faces:
         raise ValueError(f"{file_path}: no geometry")
