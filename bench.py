@@ -141,6 +141,7 @@ def run_reference(args):
     from oracle import oracle as o
     from zdr_b200._abi import INTEGRATORS, make_params
     o.build()
+    o.lib().zo_set_num_threads(os.cpu_count() or 1)      # torchrun sets OMP_NUM_THREADS=1 for its workers
     models, cam, material, name = workload(args)
     sc = o.OracleScene(models)
     integ = INTEGRATORS[args.integrator]
@@ -176,6 +177,7 @@ def cpu_baseline(args):
     from oracle import oracle as o
     from zdr_b200._abi import INTEGRATORS, make_params
     o.build()
+    o.lib().zo_set_num_threads(os.cpu_count() or 1)
     models, cam, material, _ = workload(args)
     sc = o.OracleScene(models)
     integ = INTEGRATORS[args.integrator]

@@ -54,6 +54,8 @@ def lib():
         L.zo_probe_duvdxy.argtypes = [_vp, _f32p, C.c_int, _f32p]
         L.zo_get_ray_counters.argtypes = [_vp, C.POINTER(C.c_uint64)]
         L.zo_reset_ray_counters.argtypes = [_vp]
+        L.zo_set_num_threads.argtypes = [C.c_int]
+        L.zo_set_num_threads.restype = None
         L.zo_xxhash32_int4.restype = C.c_uint32
         L.zo_xxhash32_int4.argtypes = [C.c_int] * 4
         L.zo_permutation_element.restype = C.c_int

@@ -1366,6 +1366,14 @@ ZO_API int zo_probe_duvdxy(zo_scene* s, const float* rays, int n, float* out) {
 
 ZO_API void zo_get_ray_counters(zo_scene* s, uint64_t* out) { out[0] = s->n_closest; out[1] = s->n_any; }
 ZO_API void zo_reset_ray_counters(zo_scene* s) { s->n_closest = 0; s->n_any = 0; }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm of bench.py asks for all host threads explicitly */
+ZO_API void zo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 ZO_API int zo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

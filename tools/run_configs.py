@@ -28,6 +28,7 @@ ap.add_argument("--json", default=None)
 ap.add_argument("--only", default=None, help="comma-separated config names")
 args = ap.parse_args()
 o.build()
+o.lib().zo_set_num_threads(os.cpu_count() or 1)
 dev = torch.device("cuda", 0)
 
 
