@@ -384,7 +384,7 @@ def run_ours(args):
         out["e2e"] = {"value": round(rays_total / t_e2e / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(mat_np.nbytes),
                       "d2h_bytes_per_step": int(mat_np.nbytes) + 4, "ms_per_step": round(t_e2e * 1e3, 3),
                       "api": "zdr_b200.Scene.render(...).sum().backward() with pinned-host material in, gradient + loss out"}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # reported at N=1 only (it times the host, not the GPUs)
         out["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(out))
     if world > 1:
