@@ -268,7 +268,7 @@ def run_ours(args):
     barrier()
 
     clocks = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("ZDR_BENCH_NO_CLOCKS"):      # (experiment switch: is the sampler itself a disturbance?)
         clocks.start()
     launches0 = int(lib.zdr_kernel_launches())
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
@@ -366,6 +366,7 @@ def run_ours(args):
         "config": {"workload": name, "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": f"tile-dp{world}",
                    "rays_per_step": int(rays_total), "paths_per_step": 2 * args.res * args.res * args.spp,
                    "ms_forward": round(t_fwd / args.steps, 3), "ms_backward": round(ms_bwd, 3),
+                   "ms_each_step_rank0": [round(e[0].elapsed_time(e[3]), 2) for e in evs],
                    "ms_allreduce": round((t_all - t_fwd - t_bwd) / args.steps, 3),
                    "bvh_nodes_per_ray": round((c_fwd["nodes_visited"] + c_bwd["nodes_visited"]) / max(rays_local, 1), 2),
                    "tris_per_ray": round((c_fwd["tris_tested"] + c_bwd["tris_tested"]) / max(rays_local, 1), 2),

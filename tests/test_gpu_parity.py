@@ -111,14 +111,17 @@ def bits(a):
 
 
 # ----------------------------------------------------------------------------- sampler (bit-exact)
-@pytest.mark.parametrize("spp", [1, 4, 64, 256, 1024])
-def test_sampler_bit_exact(oracle, spp):
+@pytest.mark.parametrize("spp,bounces", [(1, 12), (4, 12), (64, 12), (256, 12), (1024, 12),
+                                         (3, 12), (100, 12),          # not powers of two: cycle walking + signed floor-mod
+                                         (100000, 12),                # more samples than a PMJ set holds: table index wraps
+                                         (64, 40)])                   # dimension ~290: blue-noise texture index wraps > twice
+def test_sampler_bit_exact(oracle, spp, bounces):
     rng = np.random.default_rng(spp)
     n = 4096
     st = np.stack([rng.integers(0, 4096, n), rng.integers(0, 4096, n),
                    rng.choice([0, 1, 12345, 853402567, 19260817, 948377263, 2147483647, -5], n),
                    np.full(n, spp), rng.integers(0, spp, n)], axis=1).astype(np.int32)
-    prog = "2" + "112" + "12" + "1" + ("11212" * 12)     # camera, light, bsdf, rr, ... up to dimension > 64
+    prog = "2" + "112" + "12" + "1" + ("11212" * bounces)     # camera, light, bsdf, rr, ... up to dimension > 64
     ref = oracle.sampler_draws(st, prog)
     out = np.empty_like(ref)
     lib = _abi.load_library()

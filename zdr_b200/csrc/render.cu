@@ -425,6 +425,12 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
 #ifndef ZDR_WF_GRID_MULT
 #define ZDR_WF_GRID_MULT 64
 #endif
+// Blocks per SM of the persistent traversal kernels.  They fetch rays dynamically, so one resident wave (16 blocks of
+// 128 threads at 64 registers) is enough; the 64-per-SM grid of the grid-stride stages only added launch / drain time
+// (sweep r01u: C3 adjoint pass -2 %, one rank's share of an 8-GPU run -4 % forward / -7 % adjoint, C5 -2 %).
+#ifndef ZDR_WF_TRACE_GRID_MULT
+#define ZDR_WF_TRACE_GRID_MULT 16
+#endif
 constexpr int kWfThreads = 128;
 constexpr unsigned kWfPhaseBit = 1u << 8;
 
@@ -1009,12 +1015,13 @@ template <int MODE>
 void launch_wf_round(bool stats, bool agg, bool env, int grid, cudaStream_t s, const RenderArgs& a) {
     g_kernel_launches += 4;
     const bool big = a.sc.num_nodes > kWfBigSceneNodes;
-    if (stats) { if (big) k_wf_trace<false, true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_trace<false, true, false><<<grid, kWfThreads, 0, s>>>(a); }
-    else { if (big) k_wf_trace<false, false, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_trace<false, false, false><<<grid, kWfThreads, 0, s>>>(a); }
+    const int tgrid = a.wf.num_sms * ZDR_WF_TRACE_GRID_MULT;
+    if (stats) { if (big) k_wf_trace<false, true, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<false, true, false><<<tgrid, kWfThreads, 0, s>>>(a); }
+    else { if (big) k_wf_trace<false, false, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<false, false, false><<<tgrid, kWfThreads, 0, s>>>(a); }
     if (env) k_wf_shade_a<MODE, true><<<grid, kWfThreads, 0, s>>>(a);
     else k_wf_shade_a<MODE, false><<<grid, kWfThreads, 0, s>>>(a);
-    if (stats) { if (big) k_wf_trace<true, true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_trace<true, true, false><<<grid, kWfThreads, 0, s>>>(a); }
-    else { if (big) k_wf_trace<true, false, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_trace<true, false, false><<<grid, kWfThreads, 0, s>>>(a); }
+    if (stats) { if (big) k_wf_trace<true, true, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<true, true, false><<<tgrid, kWfThreads, 0, s>>>(a); }
+    else { if (big) k_wf_trace<true, false, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<true, false, false><<<tgrid, kWfThreads, 0, s>>>(a); }
     if constexpr (MODE == 2) {
         if (agg) {
             if (stats) k_wf_shade_b<MODE, true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<MODE, false, true><<<grid, kWfThreads, 0, s>>>(a);
