@@ -163,6 +163,51 @@ def test_inverse_rendering_recovers_texture():
     sc.close()
 
 
+@pytest.mark.parametrize("schedule", ["megakernel", "wavefront"])
+def test_operator_is_cuda_graph_capturable(schedule):
+    """The operator launches on the caller's stream with no synchronisation, allocation or host read-back once its
+    workspace exists, so forward + adjoint capture into a CUDA graph; replays track the material tensor's contents."""
+    import ctypes as C
+    from zdr_b200 import Scene
+    from zdr_b200._abi import ZDR_PATH, check
+    sc = Scene(scenes.cbox_path_models(), integrator="path")
+    lib, h = sc._lib, sc._handle
+    mats = [torch.from_numpy(scenes.random_material((64, 64), k)).cuda() for k in range(3)]
+    material = mats[0].clone()
+    image = torch.zeros((48, 64, 4), device="cuda")
+    d_image = torch.ones_like(image)
+    d_material = torch.zeros_like(material)
+    pf = make_params(scenes.CBOX_CAMERA, (64, 48), (64, 64), 8, 0, max_depth=4, schedule=schedule)
+    pb = make_params(scenes.CBOX_CAMERA, (64, 48), (64, 64), 8, 1, max_depth=4, schedule=schedule)
+
+    def run():
+        st = torch.cuda.current_stream().cuda_stream
+        d_material.zero_()
+        check(lib.zdr_render_forward(h, ZDR_PATH, C.byref(pf), material.data_ptr(), image.data_ptr(), st))
+        check(lib.zdr_render_backward(h, ZDR_PATH, C.byref(pb), material.data_ptr(), d_image.data_ptr(), d_material.data_ptr(), st))
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run()                                        # warm-up: workspace allocation, module loading
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        run()
+    for m in mats[::-1]:
+        material.copy_(m)
+        graph.replay()
+        torch.cuda.synchronize()
+        img_g, grad_g = image.clone(), d_material.clone()
+        run()
+        torch.cuda.synchronize()
+        assert torch.equal(img_g, image)
+        assert rel_l2(grad_g.cpu().numpy(), d_material.cpu().numpy()) < 1e-5
+        assert float(image[..., :3].max()) > 0 and float(d_material.abs().max()) > 0
+    sc.close()
+
+
 def test_errors_are_python_exceptions(scene):
     with pytest.raises(AssertionError):
         scene.render(torch.zeros((4, 4, 3), device="cuda"), res=(8, 8), spp=1)          # render.py:160

@@ -2,6 +2,7 @@
 // upload (pmj02bn.py:9-16), the forward / adjoint operator launches (render.py:168-171,
 // 193-196) and the parity probes.  Nothing here has a CPU fallback: every compute entry needs a
 // CUDA device and returns ZDR_ERR_CUDA without one.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -227,10 +228,15 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
     if (const char* slots_env = getenv("ZDR_WF_SLOTS_LOG2")) {
         target_slots = 1ll << atoi(slots_env);
     } else {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const long long fit = (long long)((free_b + s->s_wf.cap) / 4 / wf_bytes_per_slot());
-            if (fit < target_slots) target_slots = fit;
+        // (no query when the workspace already holds the whole job: the call then makes no CUDA API call besides
+        // kernel launches and can be captured into a CUDA graph)
+        const long long want = std::min(target_slots, samples);
+        if ((size_t)want * wf_bytes_per_slot() + 256 > s->s_wf.cap) {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                const long long fit = (long long)((free_b + s->s_wf.cap) / 4 / wf_bytes_per_slot());
+                if (fit < target_slots) target_slots = fit;
+            }
         }
     }
     long long S = target_slots / (pixels > 0 ? pixels : 1);

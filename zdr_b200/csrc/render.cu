@@ -1,6 +1,7 @@
 // render.cu — per-pixel render kernels (forward + adjoint) for the collocated, direct and path
 // integrators.  Replaces the LuisaCompute kernels derived at integrator.py:8-53 from
 // collocated.py / direct.py / prb.py and dispatched at render.py:168-171,193-196.
+#include <algorithm>
 #include <atomic>
 #include "render.cuh"
 
@@ -1015,7 +1016,7 @@ template <int MODE>
 void launch_wf_round(bool stats, bool agg, bool env, int grid, cudaStream_t s, const RenderArgs& a) {
     g_kernel_launches += 4;
     const bool big = a.sc.num_nodes > kWfBigSceneNodes;
-    const int tgrid = a.wf.num_sms * ZDR_WF_TRACE_GRID_MULT;
+    const int tgrid = min(grid, a.wf.num_sms * ZDR_WF_TRACE_GRID_MULT);
     if (stats) { if (big) k_wf_trace<false, true, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<false, true, false><<<tgrid, kWfThreads, 0, s>>>(a); }
     else { if (big) k_wf_trace<false, false, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<false, false, false><<<tgrid, kWfThreads, 0, s>>>(a); }
     if (env) k_wf_shade_a<MODE, true><<<grid, kWfThreads, 0, s>>>(a);
@@ -1089,8 +1090,12 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
     w.P = a.W * rows;
     w.div_P = make_fastdiv(w.P);
     w.div_W = make_fastdiv(a.W);
-    const int grid = w.num_sms * ZDR_WF_GRID_MULT;
     const int smax = w.S;      // capacity in samples per batch (buffers hold P * smax slots)
+    // persistent grids: ZDR_WF_GRID_MULT blocks per SM, but never more blocks than the batch has work for (a near-empty
+    // kernel of 9 472 blocks costs ~30 us, x ~100 launches per batch: 3 ms on a job of 2^18 paths)
+    const long long max_slots = (long long)w.P * min(smax, a.it1 - a.it0);
+    const int grid = (int)std::min<long long>((long long)w.num_sms * ZDR_WF_GRID_MULT,
+                                               std::max<long long>(w.num_sms, (max_slots + kWfThreads - 1) / kWfThreads));
     for (int base = a.it0; base < a.it1; base += smax) {
         w.S = min(smax, a.it1 - base);
         w.it_base = base;
