@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
 #define ZDR_WF_SHADE_B_MINB 8
 #endif
 #ifndef ZDR_WF_SHADE_BB_MINB      // adjoint variant of stage B (BRDF adjoints + scatter)
-#define ZDR_WF_SHADE_BB_MINB 6
+#define ZDR_WF_SHADE_BB_MINB 8
 #endif
 #ifndef ZDR_WF_EXTEND_MINB
 #define ZDR_WF_EXTEND_MINB 8
