@@ -138,7 +138,10 @@ __global__ void k_fit(const float4* __restrict__ tri_in, const int* __restrict__
     atomicMax(max_depth, depth);
 }
 
-constexpr int kLeafMax = 4;
+#ifndef ZDR_BVH_LEAF_MAX
+#define ZDR_BVH_LEAF_MAX 4
+#endif
+constexpr int kLeafMax = ZDR_BVH_LEAF_MAX;      // triangles per leaf (2 bits of the leaf link hold count - 1)
 
 // an inner node survives iff it covers more than kLeafMax triangles
 __global__ void k_mark(const int2* __restrict__ range, int n, int* __restrict__ keep) {
