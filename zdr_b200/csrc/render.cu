@@ -475,6 +475,9 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_generate(const __grid_constan
 #define ZDR_WF_REFILL 20
 #endif
 constexpr int kWfRefill = ZDR_WF_REFILL;
+#ifndef ZDR_WF_FETCH_CHUNK
+#define ZDR_WF_FETCH_CHUNK 128
+#endif
 constexpr int kWfNodeBudget = 12;
 constexpr int kWfBigSceneNodes = 1024;
 template <bool ANY, bool STATS, bool BIG>      // BIG: scene with more than kWfBigSceneNodes nodes (launch_wf_round)
@@ -499,15 +502,36 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
     float3 id = f3(0.f, 0.f, 0.f), oid = id;
     RayPre rp = {};
     int stack[kStackSize];
+#if ZDR_WF_FETCH_CHUNK
+    // A warp takes list entries from the shared cursor a chunk at a time and hands them to its lanes over several
+    // refills: every refill hitting ONE address with an atomic is what a same-address atomic unit serialises
+    // (tools/microbench: ~1-2 G/s).  The chunk shrinks with the list so that short lists still spread over all warps.
+    const int total_warps = gridDim.x * (kWfThreads / 32);
+    const int chunk = max(32, min(ZDR_WF_FETCH_CHUNK, (n / (4 * total_warps)) & ~31));
+    int chunk_next = 0, chunk_end = 0;                  // warp-uniform
+#endif
     for (;;) {
         // ---- refill idle lanes
         const unsigned idle = __ballot_sync(0xffffffffu, !has_ray && !exhausted);
         if (idle) {
+#if ZDR_WF_FETCH_CHUNK
+            const int need = __popc(idle), have = chunk_end - chunk_next;
+            int base = 0;
+            if (have < need) {
+                if (lane == 0) base = atomicAdd(cursor, chunk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+            }
+            const int rank = __popc(idle & ((1u << lane) - 1u));
+            const int i_next = rank < have ? chunk_next + rank : base + (rank - have);
+            if (have < need) { chunk_next = base + (need - have); chunk_end = base + chunk; } else chunk_next += need;
+#else
             int base = 0;
             if (lane == __ffs(idle) - 1) base = atomicAdd(cursor, __popc(idle));
             base = __shfl_sync(0xffffffffu, base, __ffs(idle) - 1);
+            const int i_next = base + __popc(idle & ((1u << lane) - 1u));
+#endif
             if (!has_ray && !exhausted) {
-                const int i = base + __popc(idle & ((1u << lane) - 1u));
+                const int i = i_next;
                 if (i >= n) {
                     exhausted = true;
                 } else {
