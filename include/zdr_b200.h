@@ -123,8 +123,9 @@ void zdr_scene_destroy(zdr_scene* s);
 int zdr_scene_add_mesh(zdr_scene* s, const float* verts_nx8_host, int nv,
                        const int32_t* tris_host, int nt,
                        const float xform_colmajor[16], const float emission[3]);
-/* accel.update(); heap.update() (render.py:127-128): flattens instances to world space and
- * builds the BVH on the GPU. */
+/* accel.update(); heap.update() (render.py:127-128): flattens the instances to world space and builds the BVH —
+ * up to 16 K triangles on the host (full-sweep SAH), above that on the GPU (flatten kernel, Morton clusters,
+ * per-cluster binned SAH, SAH tree over the clusters).  May be called again after more zdr_scene_add_mesh calls. */
 int zdr_scene_commit(zdr_scene* s);
 /* Scene.update_lights (render.py:130-148): n must equal the instance count. */
 int zdr_scene_set_emissions(zdr_scene* s, const float* emission_nx3_host, int n);
