@@ -527,3 +527,27 @@ def test_error_codes():
     assert b"out of range" in lib.zdr_last_error()
     assert lib.zdr_scene_create(C.byref(C.c_void_p()), 999) == -1                         # bad device
     lib.zdr_scene_destroy(h)
+    # non-finite positions are refused at commit by both ingest paths (host flatten / GPU flatten); a failed commit
+    # leaves the scene unusable but alive, and a later good commit works
+    for n_tris in (4, 20000):
+        h = C.c_void_p()
+        _abi.check(lib.zdr_scene_create(C.byref(h), 0))
+        rng = np.random.default_rng(n_tris)
+        verts = np.zeros((3 * n_tris, 8), np.float32)
+        verts[:, 0:3] = rng.normal(size=(3 * n_tris, 3))
+        verts[:, 5:8] = (0, 0, 1)
+        tris = np.arange(3 * n_tris, dtype=np.int32)
+        poisoned = verts.copy()
+        poisoned[7, 1] = np.inf if n_tris == 4 else np.nan
+        _abi.check(lib.zdr_scene_add_mesh(h, np_ptr(poisoned, C.c_float), len(poisoned), np_ptr(tris, C.c_int32), n_tris, None, None))
+        assert lib.zdr_scene_commit(h) == -1 and b"non-finite" in lib.zdr_last_error()
+        assert lib.zdr_render_forward(h, 1, C.byref(p), 1, 1, None) == -2
+        lib.zdr_scene_destroy(h)
+        h = C.c_void_p()
+        _abi.check(lib.zdr_scene_create(C.byref(h), 0))
+        _abi.check(lib.zdr_scene_add_mesh(h, np_ptr(verts, C.c_float), len(verts), np_ptr(tris, C.c_int32), n_tris, None, None))
+        _abi.check(lib.zdr_scene_commit(h))
+        lib.zdr_scene_destroy(h)
+    # sampler tables whose index range does not fit the kernels' 32-bit arithmetic
+    tiny16, tiny32 = np.zeros(4, np.uint16), np.zeros(4, np.uint32)
+    assert lib.zdr_set_sampler_tables(0, np_ptr(tiny32, C.c_uint32), 5, 65536, np_ptr(tiny16, C.c_uint16), 48, 1 << 14) == -4

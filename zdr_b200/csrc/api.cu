@@ -383,6 +383,7 @@ ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
         // interaction.py:19-21, and build the full-sweep SAH tree there
         std::vector<float4> tri(3 * nt), shade(4 * nt);
         float3 lo = f3(INFINITY, INFINITY, INFINITY), hi = f3(-INFINITY, -INFINITY, -INFINITY);
+        bool finite = true;
         for (size_t i = 0; i < s->meshes.size(); ++i) {
             const Mesh& m = s->meshes[i];
             const size_t mt = m.tris.size() / 3;
@@ -395,6 +396,7 @@ ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
                     p[k] = xform_point(m.M, f3(v[k][0], v[k][1], v[k][2]));
                     lo = f3(fminf(lo.x, p[k].x), fminf(lo.y, p[k].y), fminf(lo.z, p[k].z));
                     hi = f3(fmaxf(hi.x, p[k].x), fmaxf(hi.y, p[k].y), fmaxf(hi.z, p[k].z));
+                    finite = finite && std::isfinite(p[k].x) && std::isfinite(p[k].y) && std::isfinite(p[k].z);
                 }
                 tri[3 * g + 0] = make_float4(p[0].x, p[0].y, p[0].z, __builtin_bit_cast(float, (int)g));
                 tri[3 * g + 1] = make_float4(p[1].x, p[1].y, p[1].z, __builtin_bit_cast(float, (int)i));
@@ -403,7 +405,7 @@ ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
                 shade[4 * g + 3] = make_float4(v[0][4], v[1][4], v[2][4], 0.0f);
             }
         }
-        if (!(lo.x <= hi.x)) return fail(ZDR_ERR_ARG, "commit: non-finite geometry");
+        if (!(finite && lo.x <= hi.x)) return fail(ZDR_ERR_ARG, "commit: non-finite geometry");
         e = build_bvh_sah_host(tri.data(), shade.data(), (int)nt, lo, hi, s->own_stream, &s->bvh);
     } else {
         // large scene: the same records are produced on the GPU (k_flatten), then the GPU build
