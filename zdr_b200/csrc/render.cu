@@ -2,6 +2,7 @@
 // integrators.  Replaces the LuisaCompute kernels derived at integrator.py:8-53 from
 // collocated.py / direct.py / prb.py and dispatched at render.py:168-171,193-196.
 #include <algorithm>
+#include <type_traits>
 #include <atomic>
 #include "render.cuh"
 
@@ -1105,7 +1106,14 @@ size_t wf_bytes_per_slot() { return 9 * sizeof(float4) + 2 * sizeof(int); }
 // shard; per batch generate, then max_depth (forward) or 2*max_depth (adjoint: replay + adjoint
 // walk) rounds of extend + shade, then the ordered accumulation.  No host synchronisation: list
 // lengths stay on the device, the grids are persistent (grid-stride over the live list).
-cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaStream_t s) {
+namespace {
+void wf_shift_set(WfState& w, size_t bytes) {
+    auto sh = [bytes](auto*& p) { p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(reinterpret_cast<char*>(p) + bytes); };
+    sh(w.AB); sh(w.CD); sh(w.H); sh(w.R); sh(w.SAB); sh(w.SC); sh(w.list[0]); sh(w.list[1]); sh(w.counts);
+}
+}  // namespace
+
+cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaStream_t s0, cudaStream_t side, cudaEvent_t* ev) {
     const int tiles = (a.row1 - a.row0 + 7) / 8;
     int rows = 0;
     for (int t = a.shard_index; t < tiles; t += a.shard_count) rows += min(8, a.row1 - (a.row0 + 8 * t));
@@ -1120,25 +1128,49 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
     const long long max_slots = (long long)w.P * min(smax, a.it1 - a.it0);
     const int grid = (int)std::min<long long>((long long)w.num_sms * ZDR_WF_GRID_MULT,
                                                std::max<long long>(w.num_sms, (max_slots + kWfThreads - 1) / kWfThreads));
-    for (int base = a.it0; base < a.it1; base += smax) {
-        w.S = min(smax, a.it1 - base);
-        w.it_base = base;
-        w.nslots = w.P * w.S;
-        w.first = base == a.it0;
-        w.last = base + smax >= a.it1;
+    // Two state sets: batch b runs on stream b & 1 with set b & 1.  Kernels of one batch are ordered by their stream;
+    // the only dependency between batches is the running sum in the image (k_wf_accumulate, sample order).
+    const bool two = w.num_sets == 2 && side && ev && a.it1 - a.it0 > smax;
+    RenderArgs a1 = a;
+    if (two) {
+        wf_shift_set(a1.wf, w.set_bytes);
+        cudaError_t e = cudaEventRecord(ev[0], s0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side, ev[0], 0);
+        if (e != cudaSuccess) return e;
+    }
+    int b = 0;
+    for (int base = a.it0; base < a.it1; base += smax, ++b) {
+        RenderArgs& ab = (two && (b & 1)) ? a1 : a;
+        cudaStream_t s = (two && (b & 1)) ? side : s0;
+        WfState& wb = ab.wf;
+        wb.P = w.P; wb.div_P = w.div_P; wb.div_W = w.div_W;
+        wb.S = min(smax, a.it1 - base);
+        wb.it_base = base;
+        wb.nslots = wb.P * wb.S;
+        wb.first = base == a.it0;
+        wb.last = base + smax >= a.it1;
         g_kernel_launches += (!backward && a.image) ? 2 : 1;      // generate (+ accumulate)
-        if (backward) k_wf_generate<true><<<grid, kWfThreads, 0, s>>>(a);
-        else k_wf_generate<false><<<grid, kWfThreads, 0, s>>>(a);
+        if (backward) k_wf_generate<true><<<grid, kWfThreads, 0, s>>>(ab);
+        else k_wf_generate<false><<<grid, kWfThreads, 0, s>>>(ab);
         const bool env = a.sc.env_count > 0;
         if (!backward) {
-            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<0>(stats, false, env, grid, s, a);
+            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<0>(stats, false, env, grid, s, ab);
         } else {
-            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<1>(stats, false, env, grid, s, a);      // replay: Le of every sample
+            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<1>(stats, false, env, grid, s, ab);      // replay: Le of every sample
             ++g_kernel_launches;
-            k_wf_restart<<<grid, kWfThreads, 0, s>>>(a);
-            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<2>(stats, a.aggregate_scatter != 0, env, grid, s, a);   // adjoint walk
+            k_wf_restart<<<grid, kWfThreads, 0, s>>>(ab);
+            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<2>(stats, a.aggregate_scatter != 0, env, grid, s, ab);   // adjoint walk
         }
-        if (!backward && a.image) k_wf_accumulate<<<grid, kWfThreads, 0, s>>>(a);
+        if (!backward && a.image) {
+            if (two && b > 0) { cudaError_t e = cudaStreamWaitEvent(s, ev[1 + ((b - 1) & 1)], 0); if (e != cudaSuccess) return e; }
+            k_wf_accumulate<<<grid, kWfThreads, 0, s>>>(ab);
+            if (two) { cudaError_t e = cudaEventRecord(ev[1 + (b & 1)], s); if (e != cudaSuccess) return e; }
+        }
+    }
+    if (two) {                                     // join: the caller's stream continues after both
+        cudaError_t e = cudaEventRecord(ev[3], side);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s0, ev[3], 0);
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }
