@@ -102,8 +102,8 @@ struct zdr_scene {
     unsigned long long* d_counters = nullptr;
     float uv_lo[2] = {0.f, 0.f}, uv_hi[2] = {0.f, 0.f};   // uv bounds of instance 0, the textured object (direct.py:30)
     cudaStream_t own_stream = nullptr;       // for the *_host entry points and the probes
-    cudaStream_t side_stream = nullptr;      // second lane of the wavefront schedule (render.cuh launch_path_wavefront)
-    cudaEvent_t wf_events[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t side_streams[kWfMaxSets - 1] = {};      // further lanes of the wavefront schedule (launch_path_wavefront)
+    cudaEvent_t wf_events[kWfMaxSets + 2] = {};
     DevBuf<float> s_mat, s_img, s_dimg, s_dmat, s_misc, s_misc2;
     DevBuf<char> s_wf;                       // wavefront path state (render.cuh WfState)
     int num_sms = 148;
@@ -226,8 +226,8 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
     // (41 GB at 152 B per slot: all 256 samples of a 1024^2 image in one batch); ZDR_WF_SLOTS_LOG2 overrides.
     // Larger batches amortise the ~4*depth launches per batch and the thin tail rounds (measured: 2^24 -> 2^28
     // slots = 4.9 -> 5.5 Grays/s on C3).
-    // Two state sets of half the samples each, worked on from two streams (render.cu launch_path_wavefront), once the
-    // job is large enough for the halves to fill the GPU; ZDR_WF_LANES=1 keeps one.
+    // Several state sets of a fraction of the samples each, worked on from as many streams (render.cu
+    // launch_path_wavefront), once the job is large enough for the parts to fill the GPU; ZDR_WF_LANES=1 keeps one.
     static const int lanes = getenv("ZDR_WF_LANES") ? atoi(getenv("ZDR_WF_LANES")) : 2;
     long long S = 0;
     int sets = 1;
@@ -236,8 +236,9 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
         S = target_slots / (pixels > 0 ? pixels : 1);
         if (S < 1) S = 1;
         if (S > p->it1 - p->it0) S = p->it1 - p->it0;
-        sets = (lanes >= 2 && S >= 2 && pixels * S >= (1ll << 23)) ? 2 : 1;
-        if (sets == 2) S = (S + 1) / 2;
+        sets = 1;                                   // every set keeps at least 2^22 slots
+        while (sets < lanes && sets < kWfMaxSets && S >= 2 * (sets + 1) && pixels * S >= (long long)(sets + 1) << 22) ++sets;
+        S = (S + sets - 1) / sets;
         slots = (size_t)(pixels * S);
         set_bytes = (slots * wf_bytes_per_slot() + 256 + 255) & ~(size_t)255;
         bytes = set_bytes * sets;
@@ -322,8 +323,8 @@ ZDR_EXPORT int zdr_scene_create(zdr_scene** out, int device) {
     cudaError_t e = cudaMalloc(&s->d_counters, sizeof(unsigned long long) * C_NUM);
     if (e == cudaSuccess) e = cudaMemset(s->d_counters, 0, sizeof(unsigned long long) * C_NUM);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking);
-    for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&s->wf_events[k], cudaEventDisableTiming);
+    for (int k = 0; k < kWfMaxSets - 1 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&s->side_streams[k], cudaStreamNonBlocking);
+    for (int k = 0; k < kWfMaxSets + 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&s->wf_events[k], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete s;
         return fail(ZDR_ERR_CUDA, "scene_create: %s", cudaGetErrorString(e));
@@ -341,7 +342,7 @@ ZDR_EXPORT void zdr_scene_destroy(zdr_scene* s) {
     free_envmap(&s->env);
     cudaFree(s->d_inst); cudaFree(s->d_lights); cudaFree(s->d_counters);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
-    if (s->side_stream) cudaStreamDestroy(s->side_stream);
+    for (cudaStream_t st : s->side_streams) if (st) cudaStreamDestroy(st);
     for (cudaEvent_t ev : s->wf_events) if (ev) cudaEventDestroy(ev);
     s->s_mat.release(); s->s_img.release(); s->s_dimg.release(); s->s_dmat.release(); s->s_misc.release();
     s->s_misc2.release(); s->s_int.release(); s->s_int2.release(); s->s_wf.release();
@@ -512,7 +513,7 @@ ZDR_EXPORT int zdr_render_forward(zdr_scene* s, int integrator, const zdr_params
     a.image = reinterpret_cast<float4*>(image_dev);
     bool wavefront;
     if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;
-    if (wavefront) CK(launch_path_wavefront(false, a, want_stats(p), (cudaStream_t)stream, s->side_stream, s->wf_events));
+    if (wavefront) CK(launch_path_wavefront(false, a, want_stats(p), (cudaStream_t)stream, s->side_streams, s->wf_events));
     else CK(launch_forward(integrator, a, want_stats(p), (cudaStream_t)stream));
     return ZDR_OK;
 }
@@ -530,7 +531,7 @@ ZDR_EXPORT int zdr_render_backward(zdr_scene* s, int integrator, const zdr_param
     a.d_image = reinterpret_cast<const float4*>(d_image_dev);
     bool wavefront;
     if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;
-    if (wavefront) CK(launch_path_wavefront(true, a, want_stats(p), (cudaStream_t)stream, s->side_stream, s->wf_events));
+    if (wavefront) CK(launch_path_wavefront(true, a, want_stats(p), (cudaStream_t)stream, s->side_streams, s->wf_events));
     else CK(launch_backward(integrator, a, want_stats(p), (cudaStream_t)stream));
     return ZDR_OK;
 }
@@ -688,7 +689,7 @@ ZDR_EXPORT int zdr_probe_render_samples(zdr_scene* s, int integrator, const zdr_
     a.samples_out = s->s_misc.p;
     bool wavefront;
     if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;
-    if (wavefront) CK(launch_path_wavefront(false, a, want_stats(p), st, s->side_stream, s->wf_events));
+    if (wavefront) CK(launch_path_wavefront(false, a, want_stats(p), st, s->side_streams, s->wf_events));
     else CK(launch_forward(integrator, a, want_stats(p), st));
     CK(cudaMemcpyAsync(out_host, s->s_misc.p, sizeof(float) * nout, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

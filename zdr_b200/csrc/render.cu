@@ -1113,7 +1113,7 @@ void wf_shift_set(WfState& w, size_t bytes) {
 }
 }  // namespace
 
-cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaStream_t s0, cudaStream_t side, cudaEvent_t* ev) {
+cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaStream_t s0, cudaStream_t* side, cudaEvent_t* ev) {
     const int tiles = (a.row1 - a.row0 + 7) / 8;
     int rows = 0;
     for (int t = a.shard_index; t < tiles; t += a.shard_count) rows += min(8, a.row1 - (a.row0 + 8 * t));
@@ -1128,20 +1128,26 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
     const long long max_slots = (long long)w.P * min(smax, a.it1 - a.it0);
     const int grid = (int)std::min<long long>((long long)w.num_sms * ZDR_WF_GRID_MULT,
                                                std::max<long long>(w.num_sms, (max_slots + kWfThreads - 1) / kWfThreads));
-    // Two state sets: batch b runs on stream b & 1 with set b & 1.  Kernels of one batch are ordered by their stream;
-    // the only dependency between batches is the running sum in the image (k_wf_accumulate, sample order).
-    const bool two = w.num_sets == 2 && side && ev && a.it1 - a.it0 > smax;
-    RenderArgs a1 = a;
-    if (two) {
-        wf_shift_set(a1.wf, w.set_bytes);
+    // Several state sets: batch b runs on stream b % K with set b % K.  Kernels of one batch are ordered by their
+    // stream; the only dependency between batches is the running sum in the image (k_wf_accumulate, sample order).
+    const int batches = (a.it1 - a.it0 + smax - 1) / smax;
+    const int K = (side && ev) ? min(min(w.num_sets, kWfMaxSets), batches) : 1;
+    RenderArgs sets[kWfMaxSets];
+    cudaStream_t streams[kWfMaxSets];
+    for (int k = 0; k < K; ++k) {
+        sets[k] = a;
+        if (k) wf_shift_set(sets[k].wf, w.set_bytes * k);
+        streams[k] = k ? side[k - 1] : s0;
+    }
+    if (K > 1) {                                   // fork
         cudaError_t e = cudaEventRecord(ev[0], s0);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(side, ev[0], 0);
+        for (int k = 1; k < K && e == cudaSuccess; ++k) e = cudaStreamWaitEvent(streams[k], ev[0], 0);
         if (e != cudaSuccess) return e;
     }
     int b = 0;
     for (int base = a.it0; base < a.it1; base += smax, ++b) {
-        RenderArgs& ab = (two && (b & 1)) ? a1 : a;
-        cudaStream_t s = (two && (b & 1)) ? side : s0;
+        RenderArgs& ab = sets[b % K];
+        cudaStream_t s = streams[b % K];
         WfState& wb = ab.wf;
         wb.P = w.P; wb.div_P = w.div_P; wb.div_W = w.div_W;
         wb.S = min(smax, a.it1 - base);
@@ -1162,14 +1168,14 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
             for (int r = 0; r < a.max_depth; ++r) launch_wf_round<2>(stats, a.aggregate_scatter != 0, env, grid, s, ab);   // adjoint walk
         }
         if (!backward && a.image) {
-            if (two && b > 0) { cudaError_t e = cudaStreamWaitEvent(s, ev[1 + ((b - 1) & 1)], 0); if (e != cudaSuccess) return e; }
+            if (K > 1 && b > 0) { cudaError_t e = cudaStreamWaitEvent(s, ev[1 + (b - 1) % K], 0); if (e != cudaSuccess) return e; }
             k_wf_accumulate<<<grid, kWfThreads, 0, s>>>(ab);
-            if (two) { cudaError_t e = cudaEventRecord(ev[1 + (b & 1)], s); if (e != cudaSuccess) return e; }
+            if (K > 1) { cudaError_t e = cudaEventRecord(ev[1 + b % K], s); if (e != cudaSuccess) return e; }
         }
     }
-    if (two) {                                     // join: the caller's stream continues after both
-        cudaError_t e = cudaEventRecord(ev[3], side);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s0, ev[3], 0);
+    for (int k = 1; k < K; ++k) {                  // join: the caller's stream continues after all of them
+        cudaError_t e = cudaEventRecord(ev[1 + kWfMaxSets], streams[k]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s0, ev[1 + kWfMaxSets], 0);
         if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();

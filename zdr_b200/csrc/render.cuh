@@ -26,7 +26,7 @@ struct WfState {
     int nslots;       // P * S
     int first, last;  // first / last batch of the launch
     int num_sms;
-    int num_sets;           // 1, or 2: two copies of the state (set 1 = set 0 + set_bytes) worked on from two streams
+    int num_sets;           // 1..kWfMaxSets copies of the state (set k = set 0 + k * set_bytes), one stream each
     size_t set_bytes;
 };
 
@@ -54,9 +54,11 @@ cudaError_t launch_forward(int integrator, const RenderArgs& a, bool stats, cuda
 cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cudaStream_t stream);
 // wavefront variant of the path integrator / PRB adjoint; `wf` buffers sized for wf_slot_capacity() slots
 size_t wf_bytes_per_slot();
-// side / events: the scene's second stream and four timing-less events, used when wf.num_sets == 2 to run consecutive
-// batches from two streams (the tail of every stage kernel overlaps the other stream's work); both may be null otherwise
-cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaStream_t stream, cudaStream_t side,
+// side / events: the scene's kWfMaxSets - 1 extra streams and kWfMaxSets + 2 timing-less events, used when
+// wf.num_sets > 1 to run consecutive batches from several streams (the tail of every stage kernel overlaps the other
+// streams' work); both may be null otherwise
+constexpr int kWfMaxSets = 4;
+cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaStream_t stream, cudaStream_t* side,
                                   cudaEvent_t* events);
 cudaError_t launch_duvdxy(const RenderArgs& a, cudaStream_t stream);
 cudaError_t launch_probe_trace(const SceneView& sc, const float* rays_dev, int n, bool any, int* ip_dev,
