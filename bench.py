@@ -355,8 +355,9 @@ def run_ours(args):
                              "lanes, i.e. the pass is bound by instruction issue under divergence, with HBM latency on the path state next")}
     wavefront = args.integrator == "path" and args.schedule != "megakernel" and (args.schedule == "wavefront" or pixels_local * args.spp >= 1 << 21)
     if wavefront:
-        kernel_name = ("adjoint pass of the wavefront path tracer: k_wf_generate + (2*depth+1) x [k_wf_trace<closest>, k_wf_shade_a, "
-                       "k_wf_trace<any>, k_wf_shade_b] per 16-sample batch (PRB replay + adjoint walk + gradient scatter)")
+        kernel_name = ("adjoint pass of the wavefront path tracer: per batch k_wf_generate + 2*depth x [k_wf_trace<closest>, k_wf_shade_a, "
+                       "k_wf_trace<any>, k_wf_shade_b] + k_wf_restart (PRB replay + adjoint walk + gradient scatter); two half-batches "
+                       "run concurrently on two streams")
     else:
         kernel_name = f"adjoint kernel of the {args.integrator} integrator (k_path<BWD> / k_backward: replay + adjoint + gradient scatter)"
     out = {

@@ -58,12 +58,19 @@ for k in seq:
         passes.append(cur)
     if cur is not None and k["name"].startswith("k_wf_"):
         cur["k"].append(k)
+merged = []                       # the batches of one render call (two lanes: two half-batches) count as one pass
+for p_ in passes:
+    if merged and merged[-1]["kind"] == p_["kind"]:
+        merged[-1]["k"] += p_["k"]
+    else:
+        merged.append({"kind": p_["kind"], "k": list(p_["k"])})
+passes = merged
 plain = [p for p in passes if not any(re.match(r"k_wf_trace<\d, 1", k["name"]) for k in p["k"])]      # not the counting pass
 fw, bw = [p for p in plain if p["kind"] == "fwd"][-1], [p for p in plain if p["kind"] == "bwd"][-1]
 lines = []
 for title, p in (("forward pass", fw), ("adjoint pass", bw)):
     tot, dr = sum(k["t"] for k in p["k"]), sum(k["d"] for k in p["k"])
-    lines.append(f"{title} (1024^2, 16 spp, 1 batch): total {tot:.2f} ms under ncu, DRAM {dr / 1e9:.2f} GB, {len(p['k'])} launches")
+    lines.append(f"{title} (1024^2, 16 spp, {sum(1 for k in p['k'] if k['name'].startswith('k_wf_generate'))} batch(es)): total {tot:.2f} ms under ncu, DRAM {dr / 1e9:.2f} GB, {len(p['k'])} launches")
     agg = defaultdict(lambda: [0, 0.0, 0.0])
     for k in p["k"]:
         a = agg[k["name"]]
