@@ -136,7 +136,10 @@ int zdr_scene_light_count(const zdr_scene* s);
 int zdr_scene_triangle_count(const zdr_scene* s);
 
 /* --- the hot path: replaces the kernel launches at render.py:168-171 / :193-196 -------- */
-/* image_dev: (H,W,4) f32, written for rows [row0,row1). material_dev: (tex_res_x*tex_res_y*4) f32. */
+/* image_dev: (H,W,4) f32, written for rows [row0,row1). material_dev: (tex_res_x*tex_res_y*4) f32.
+ * stream: the caller's cudaStream_t; the call only enqueues (no synchronisation, no allocation once the scene's
+ * workspace holds the job).  Large path-integrator jobs fork onto a stream owned by the scene and join back with
+ * events before returning, so ordering and CUDA-graph capture on `stream` behave as for a single-stream call. */
 int zdr_render_forward(zdr_scene* s, int integrator, const zdr_params* p,
                        const float* material_dev, float* image_dev, void* stream);
 /* d_image_dev: (H,W,4) f32 cotangent; d_material_dev: same shape as material, ACCUMULATED into
