@@ -163,8 +163,9 @@ def test_inverse_rendering_recovers_texture():
     sc.close()
 
 
-@pytest.mark.parametrize("schedule", ["megakernel", "wavefront"])
-def test_operator_is_cuda_graph_capturable(schedule):
+@pytest.mark.parametrize("schedule,res,spp", [("megakernel", (64, 48), 8), ("wavefront", (64, 48), 8),
+                                              ("wavefront", (1024, 1024), 8)])      # 2^23 samples: two streams inside
+def test_operator_is_cuda_graph_capturable(schedule, res, spp):
     """The operator launches on the caller's stream with no synchronisation, allocation or host read-back once its
     workspace exists, so forward + adjoint capture into a CUDA graph; replays track the material tensor's contents."""
     import ctypes as C
@@ -174,11 +175,11 @@ def test_operator_is_cuda_graph_capturable(schedule):
     lib, h = sc._lib, sc._handle
     mats = [torch.from_numpy(scenes.random_material((64, 64), k)).cuda() for k in range(3)]
     material = mats[0].clone()
-    image = torch.zeros((48, 64, 4), device="cuda")
+    image = torch.zeros((res[1], res[0], 4), device="cuda")
     d_image = torch.ones_like(image)
     d_material = torch.zeros_like(material)
-    pf = make_params(scenes.CBOX_CAMERA, (64, 48), (64, 64), 8, 0, max_depth=4, schedule=schedule)
-    pb = make_params(scenes.CBOX_CAMERA, (64, 48), (64, 64), 8, 1, max_depth=4, schedule=schedule)
+    pf = make_params(scenes.CBOX_CAMERA, res, (64, 64), spp, 0, max_depth=4, schedule=schedule)
+    pb = make_params(scenes.CBOX_CAMERA, res, (64, 64), spp, 1, max_depth=4, schedule=schedule)
 
     def run():
         st = torch.cuda.current_stream().cuda_stream
