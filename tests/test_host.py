@@ -142,3 +142,26 @@ def test_sampler_tables_shape_and_provenance():
         pts = pmj[0, :256].astype(np.float64) / 2 ** 32
         cells = (np.floor(pts[:, 0] * 16) * 16 + np.floor(pts[:, 1] * 16)).astype(int)
         assert len(set(cells.tolist())) == 256
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on a tiny workload: one JSON line with the
+    contract's keys, and all host threads even when the launcher exported OMP_NUM_THREADS=1 (torchrun does)."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--res", "32", "--spp", "4",
+                          "--ref-spp", "2", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "prb_fwd_bwd_mrays_per_s" and d["unit"] == "Mrays/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # a non-zero rank under torchrun prints nothing and exits 0
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""

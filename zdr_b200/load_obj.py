@@ -117,6 +117,8 @@ def load_mesh(file_path: str) -> Tuple[np.ndarray, np.ndarray]:
 
 
 def load_mesh_python(file_path: str) -> Tuple[np.ndarray, np.ndarray]:
+    """The line-by-line statement of the ingest (``read_obj`` + ``concat_triangles`` + ``recompute_normal``): what the
+    reference does at ``render.py:93-103``.  ``load_mesh_native`` must return the same bytes."""
     vertices, faces = read_obj(file_path)
     if not vertices or not faces:
         raise ValueError(f"{file_path}: no geometry")
