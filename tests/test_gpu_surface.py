@@ -220,7 +220,8 @@ def test_errors_are_python_exceptions(scene):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpu_nccl_equals_single(tmp_path):
-    """run with gpurun --gpus 2: Scene.distribute over NCCL vs the single-GPU render."""
+    """run with gpurun --gpus 2: Scene.distribute over NCCL (tile axis: bit-identical image; sample axis: equal to
+    float accuracy) vs the single-GPU render."""
     import subprocess
     import sys
     script = tmp_path / "w.py"
@@ -238,6 +239,12 @@ sc.distribute()
 multi = sc.render(mat, res=(96, 80), spp=4, seed=2); multi[..., :3].sum().backward()
 assert torch.equal(single, multi), "image differs"
 err = float((mat.grad - g1).norm() / g1.norm()); assert err < 1e-5, err
+mat.grad = None
+sc.distribute(axis="samples")
+multi = sc.render(mat, res=(96, 80), spp=4, seed=2); multi[..., :3].sum().backward()
+e_img = float((multi - single).norm() / single.norm()); assert e_img < 1e-6, e_img
+assert bool((multi[..., 3] == 1).all())
+err2 = float((mat.grad - g1).norm() / g1.norm()); assert err2 < 1e-5, err2
 dist.destroy_process_group()
 print("rank", rank, "ok", err)
 ''')

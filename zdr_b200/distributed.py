@@ -9,9 +9,15 @@ bit-identical to the single-GPU one.  Two collectives, both plain sums over NVLi
 * backward: ``all_reduce(d_material)`` — every rank scatters the texture gradient of its own rows
   (16 MiB for a 1024^2 texture).
 
+Second axis (``axis="samples"``), for images too small to tile over the ranks (light-stage sized jobs): every rank
+renders ALL pixels but only its contiguous range of sample indices (``zdr_params.it0 / it1``).  Each rank's image is
+then a partial mean (sum of its samples / spp); the all-reduce completes it.  The sum order differs from one GPU's,
+so the image equals the single-GPU one to float accuracy instead of bit for bit.
+
 The host logic is backend-agnostic so that it can be exercised on CPU with gloo (tests/): a backend
-is a pair of callables ``forward(material, res, spp, seed, shard) -> image`` and
-``backward(grad_output, d_material, material, res, spp, seed, shard)``.
+is a pair of callables ``forward(material, res, spp, seed, shard, its=None) -> image`` and
+``backward(grad_output, d_material, material, res, spp, seed, shard, its=None)``; ``shard`` = (index, count) of the
+tile sharding or None, ``its`` = (first, last+1) sample indices or None.
 """
 from __future__ import annotations
 
@@ -38,15 +44,27 @@ def rows_of_shard(height: int, shard: Tuple[int, int], row0: int = 0, tile: int 
     return rows
 
 
+def samples_of_shard(spp: int, shard: Tuple[int, int]) -> Tuple[int, int]:
+    """The contiguous range of sample indices shard (index, count) renders; ranges tile [0, spp) and differ by <= 1."""
+    index, count = shard
+    return spp * index // count, spp * (index + 1) // count
+
+
 class ShardedRenderOperator(torch.autograd.Function):
     """RenderOperator (render.py:201-223) over a process group."""
 
     @staticmethod
-    def forward(ctx, material, fwd: Callable, bwd: Callable, group, res, spp, seed):
+    def forward(ctx, material, fwd: Callable, bwd: Callable, group, res, spp, seed, axis="tiles"):
+        if axis not in ("tiles", "samples"):
+            raise ValueError(f"unknown sharding axis {axis!r}")
         shard = shard_of_rank(group)
         ctx.save_for_backward(material)
         ctx.bwd, ctx.group, ctx.shard, ctx.args = bwd, group, shard, (res, spp, seed)
-        image = fwd(material.detach(), res, spp, seed, shard)
+        ctx.its = samples_of_shard(spp, shard) if (axis == "samples" and shard[1] > 1) else None
+        if ctx.its is not None:
+            image = fwd(material.detach(), res, spp, seed, None, its=ctx.its)
+        else:
+            image = fwd(material.detach(), res, spp, seed, shard)
         if shard[1] > 1:
             dist.all_reduce(image, op=dist.ReduceOp.SUM, group=group)
             image[..., 3] = 1.0          # alpha of the rows other ranks rendered (sum of one 1 and zeros already)
@@ -57,11 +75,15 @@ class ShardedRenderOperator(torch.autograd.Function):
         material, = ctx.saved_tensors
         res, spp, seed = ctx.args
         d_material = torch.zeros_like(material)
-        ctx.bwd(grad_output, d_material, material.detach(), res, spp, seed, ctx.shard)
+        if ctx.its is not None:
+            ctx.bwd(grad_output, d_material, material.detach(), res, spp, seed, None, its=ctx.its)
+        else:
+            ctx.bwd(grad_output, d_material, material.detach(), res, spp, seed, ctx.shard)
         if ctx.shard[1] > 1:
             dist.all_reduce(d_material, op=dist.ReduceOp.SUM, group=ctx.group)
-        return d_material, None, None, None, None, None, None
+        return d_material, None, None, None, None, None, None, None
 
 
-def sharded_render(material, fwd: Callable, bwd: Callable, *, res, spp, seed=0, group: Optional[object] = None):
-    return ShardedRenderOperator.apply(material, fwd, bwd, group, res, spp, seed)
+def sharded_render(material, fwd: Callable, bwd: Callable, *, res, spp, seed=0, group: Optional[object] = None,
+                   axis: str = "tiles"):
+    return ShardedRenderOperator.apply(material, fwd, bwd, group, res, spp, seed, axis)

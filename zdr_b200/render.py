@@ -95,7 +95,9 @@ class Scene:
         # data-parallel shard of the dispatch grid; None = whole image
         self.shard_rows = None
         self.shard = None          # (index, count): round-robin 8-row tiles, see zdr_params.shard_index
+        self.shard_samples = None  # (first, last + 1): sample indices of this launch, see zdr_params.it0 / it1
         self._dist_group = None
+        self._dist_axis = "tiles"
 
     # ------------------------------------------------------------------ scene assembly
     def load_geometry(self, models):
@@ -159,7 +161,7 @@ class Scene:
         p = make_params(self.camera, res, material.shape[0:2], spp, seed, use_tent_filter=self.use_tent_filter,
                         max_depth=self.max_depth, rr_depth=self.rr_depth, use_mis=self.use_mis, bilinear=self.bilinear,
                         prb_mode=PRB_MODES[self.prb_mode] if isinstance(self.prb_mode, str) else int(self.prb_mode),
-                        rows=rows if rows is not None else self.shard_rows, shard=self.shard, stats=self.collect_stats, scatter=self.scatter_mode, schedule=self.schedule,
+                        rows=rows if rows is not None else self.shard_rows, its=self.shard_samples, shard=self.shard, stats=self.collect_stats, scatter=self.scatter_mode, schedule=self.schedule,
                         light_pdf_counts_env=self.light_pdf_counts_env)
         return p
 
@@ -176,7 +178,7 @@ class Scene:
         material = material.detach().contiguous()
         image = torch.empty((res[1], res[0], 4), dtype=torch.float32, device=self.device)
         p = self._params(material, res, spp, seed, rows)
-        if p.row0 > 0 or p.row1 < p.height or p.shard_count > 1:
+        if p.row0 > 0 or p.row1 < p.height or p.shard_count > 1 or p.it1 <= p.it0:
             image.zero_()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         check(self._lib.zdr_render_forward(self._handle, INTEGRATORS[integrator or self.integrator], C.byref(p),
@@ -250,13 +252,18 @@ class Scene:
         return image
 
     # ------------------------------------------------------------------ multi-GPU (distributed.py)
-    def distribute(self, group=None):
+    def distribute(self, group=None, axis: str = "tiles"):
         """Shard every later :meth:`render` over the ranks of ``group`` (default: WORLD): replicated
-        scene, round-robin 8-row tiles, NCCL all-reduce of image and texture gradient."""
+        scene, NCCL all-reduce of image and texture gradient.  ``axis="tiles"``: round-robin 8-row tiles (image
+        bit-identical to one GPU); ``axis="samples"``: every rank renders all pixels for its range of sample indices
+        (for images too small to tile; image equal to float accuracy)."""
         import torch.distributed as dist
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
+        if axis not in ("tiles", "samples"):
+            raise ValueError(f"unknown sharding axis {axis!r}")
         self._dist_group = group if group is not None else dist.group.WORLD
+        self._dist_axis = axis
         return self
 
     def _render_distributed(self, material, res, spp, seed):
@@ -264,24 +271,24 @@ class Scene:
         camera, emissions = self.camera.copy(), list(self.emissions)
         scene_ref = weakref.ref(self)
 
-        def fwd(mat, res_, spp_, seed_, shard):
+        def fwd(mat, res_, spp_, seed_, shard, its=None):
             sc = scene_ref()
-            old, sc.shard = sc.shard, shard
+            old, sc.shard, sc.shard_samples = (sc.shard, sc.shard_samples), shard, its
             try:
                 return sc.render_forward(mat, res_, spp_, seed_)
             finally:
-                sc.shard = old
+                sc.shard, sc.shard_samples = old
 
-        def bwd(grad_output, d_material, mat, res_, spp_, seed_, shard):
+        def bwd(grad_output, d_material, mat, res_, spp_, seed_, shard, its=None):
             sc = scene_ref()
-            old_shard, old_cam = sc.shard, sc.camera
-            sc.shard, sc.camera = shard, camera                    # render.py:216-218: state of the forward call
+            old, old_cam = (sc.shard, sc.shard_samples), sc.camera
+            sc.shard, sc.shard_samples, sc.camera = shard, its, camera       # render.py:216-218: state of the forward call
             sc.update_lights(emissions)
             try:
                 sc.render_backward(grad_output, d_material, mat, res_, spp_, seed_)
             finally:
-                sc.shard, sc.camera = old_shard, old_cam
-        return sharded_render(material, fwd, bwd, res=res, spp=spp, seed=seed, group=self._dist_group)
+                (sc.shard, sc.shard_samples), sc.camera = old, old_cam
+        return sharded_render(material, fwd, bwd, res=res, spp=spp, seed=seed, group=self._dist_group, axis=self._dist_axis)
 
     # ------------------------------------------------------------------ instrumentation
     def counters(self) -> dict:
