@@ -469,6 +469,7 @@ def acos(x): return _map(lambda a: F(_libm.acosf(float(a.v))), x)
 def exp(x): return _map(lambda a: F(_libm.expf(float(a.v))), x)
 def atan2(y, x): return F(_libm.atan2f(float(F._c(y).v), float(F._c(x).v)))
 def floor(x): return _map(lambda a: F(np.floor(a.v)), x)
+def ceil(x): return _map(lambda a: F(np.ceil(a.v)), x)
 def fract(x): return _map(lambda a: a - F(np.floor(a.v)), x)
 def isnan(x):
     if isinstance(x, Vec):
@@ -575,6 +576,10 @@ def _select(cond, a_fn, b_fn):
 _dispatch = {"id": (0, 0, 0), "size": (1, 1, 1)}
 def dispatch_id(): return uint3(*_dispatch["id"])
 def dispatch_size(): return uint3(*_dispatch["size"])
+
+
+# fixture generation only: run a kernel for a subset of its dispatch grid (callable (x, y, z) -> bool)
+DISPATCH_FILTER = None
 
 
 # ------------------------------------------------------------------------------------ autodiff
@@ -700,9 +705,25 @@ def array(xs):
 class Buffer:
     """typed linear buffer over a numpy array (element = scalar, vector or Vertex row)."""
 
-    def __init__(self, dtype=None, size=0, data=None):
+    def __init__(self, *args, dtype=None, size=0, data=None):
+        if len(args) == 1 and isinstance(args[0], (int, np.integer)):     # luisa.Buffer(size, dtype=float)
+            size = int(args[0])
+            if dtype is float and data is None:
+                data = np.zeros(size, dtype=np.float32)
+        elif args:                                                        # Buffer(dtype[, size[, data]])
+            dtype = args[0]
+            size = args[1] if len(args) > 1 else size
+            data = args[2] if len(args) > 2 else data
         self.dtype, self.size = dtype, size
         self.data = data
+
+    def numpy(self):
+        return np.array(self.data, copy=True)
+
+    @staticmethod
+    def from_array(arr):
+        a = np.ascontiguousarray(arr)
+        return Buffer(dtype=float if a.dtype.kind == "f" else int, size=a.shape[0], data=a)
 
     def copy_from_array(self, arr):
         self.data = np.ascontiguousarray(arr)
@@ -735,6 +756,8 @@ class Buffer:
             return int(self.data[i])
         if isinstance(self.dtype, type) and issubclass(self.dtype, Vec):
             return self.dtype(*[x for x in self.data[i]])
+        if isinstance(self.dtype, type) and issubclass(self.dtype, _Struct) and isinstance(self.data, list):
+            return self.data[i].copy()                                           # buffer of struct objects (AliasEntry)
         if isinstance(self.dtype, type) and issubclass(self.dtype, _Struct):     # Vertex rows: 8 floats
             row = self.data[i]
             v = self.dtype()
@@ -755,6 +778,8 @@ class Buffer:
 
 
 def buffer(xs):
+    if len(xs) and isinstance(xs[0], _Struct):
+        return Buffer(dtype=type(xs[0]), size=len(xs), data=[x.copy() for x in xs])
     if len(xs) and isinstance(xs[0], Vec):
         return Buffer(dtype=type(xs[0]), size=len(xs), data=np.asarray([[float(c.v) for c in v.c] for v in xs], dtype=np.float32))
     return Buffer(dtype=int, size=len(xs), data=np.asarray(xs, dtype=np.int64))
@@ -786,7 +811,39 @@ class BindlessArray:
             b.dtype = old
 
     def texture2d_sample(self, slot, uv):
-        raise NotImplementedError("envmap textures are not part of the emulated fixtures")
+        """LuisaCompute's default sampler is not inspectable here (parity unpinned); this is the
+        definition the oracle and the CUDA path share — bilinear, texel centres at +0.5, x wraps, y clamps —
+        so that everything AROUND the texture fetch in envmap.py can be pinned."""
+        img = self.slots[int(slot)].data
+        h, w = img.shape[0], img.shape[1]
+        fx = F(uv.c[0]) * F(w) - F(0.5)
+        fy = F(uv.c[1]) * F(h) - F(0.5)
+        flx, fly = F(np.floor(fx.v)), F(np.floor(fy.v))
+        tx, ty = fx - flx, fy - fly
+        x0, y0 = int(flx.v), int(fly.v)
+        x1, y1 = (x0 + 1) % w, min(max(y0 + 1, 0), h - 1)
+        x0, y0 = x0 % w, min(max(y0, 0), h - 1)
+
+        def fma(a, b, c):                       # binary32 fused multiply-add, as lerpf in the oracle
+            return F(f32(np.float64(a.v) * np.float64(b.v) + np.float64(c.v)))
+
+        def lerpf(a, b, t):
+            return fma(t, b - a, a)
+        out = []
+        for ch in range(4):
+            a, b = F(img[y0, x0, ch]), F(img[y0, x1, ch])
+            c, d = F(img[y1, x0, ch]), F(img[y1, x1, ch])
+            out.append(lerpf(lerpf(a, b, tx), lerpf(c, d, tx), ty))
+        return float4(*out)
+
+
+class Image2D:
+    def __init__(self, arr):
+        self.data = np.ascontiguousarray(arr, dtype=np.float32)      # (H, W, 4)
+
+
+def image2d(arr):
+    return Image2D(arr)
 
 
 class Ray:
@@ -915,6 +972,8 @@ def func(fn):
         for z in range(ds[2]):
             for y in range(ds[1]):
                 for x in range(ds[0]):
+                    if DISPATCH_FILTER is not None and not DISPATCH_FILTER(x, y, z):
+                        continue
                     _dispatch["id"] = (x, y, z)
                     f(*a, **kw)
         return None
@@ -924,7 +983,7 @@ def func(fn):
 
 
 _BUILTINS.update(dict(
-    __lc_select=_select, __lc_copy=_copy, sqrt=sqrt, sin=sin, cos=cos, tan=tan, acos=acos, atan2=atan2, exp=exp, floor=floor, fract=fract,
+    __lc_select=_select, __lc_copy=_copy, sqrt=sqrt, sin=sin, cos=cos, tan=tan, acos=acos, atan2=atan2, exp=exp, floor=floor, ceil=ceil, fract=fract,
     isnan=isnan, abs=lc_abs, max=lc_max, min=lc_min, clamp=clamp, lerp=lerp, dot=dot, cross=cross, length=length,
     length_squared=length_squared, normalize=normalize, reflect=reflect, any=lc_any, all=lc_all,
     make_float2=float2, make_float3=float3, make_float4=float4, make_int2=int2, make_int3=int3, make_int4=int4,
@@ -959,6 +1018,7 @@ def install(pmj: np.ndarray, bn: np.ndarray, ref_dir: str = "/root/reference", p
     luisa.synchronize = lambda: None
     luisa.StructType, luisa.ArrayType, luisa.struct, luisa.array = StructType, ArrayType, struct, array
     luisa.Buffer, luisa.buffer, luisa.BindlessArray, luisa.Accel = Buffer, buffer, BindlessArray, Accel
+    luisa.image2d = image2d
     luisa.make_ray, luisa.offset_ray_origin = make_ray, offset_ray_origin
     luisa.float, luisa.int = float, int
     luisa.__path__ = []                                   # a package: `from luisa.atomic import ...`

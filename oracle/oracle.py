@@ -44,6 +44,11 @@ def lib():
         L.zo_scene_set_emissions.argtypes = [_vp, _f32p, C.c_int]
         L.zo_scene_set_envmap.argtypes = [_vp, _f32p, C.c_int, C.c_int, C.c_int]
         L.zo_scene_get_env_tables.argtypes = [_vp, _f32p, _i32p, _f32p]
+        L.zo_scene_get_env_scale_map.argtypes = [_vp, _f32p]
+        L.zo_probe_sample_envmap.argtypes = [_vp, _f32p, C.c_int, _f32p]
+        L.zo_probe_env_pdf.argtypes = [_vp, _f32p, C.c_int, _f32p]
+        L.zo_probe_env_mapping.argtypes = [_f32p, C.c_int, _f32p]
+        L.zo_probe_env_mapping.restype = None
         L.zo_scene_light_count.argtypes = [_vp]
         L.zo_scene_instance_count.argtypes = [_vp]
         L.zo_set_sampler_tables.argtypes = [C.POINTER(C.c_uint32), C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int, C.c_int]
@@ -170,6 +175,14 @@ def read_bsdf(material, uv, bilinear=True):
     return out
 
 
+def env_mapping(inp):
+    """(n, 5) uv.xy dir.xyz -> (n, 5) uv_to_direction(uv).xyz direction_to_uv(dir).xy (envmap.py:206-219)."""
+    a = _f(inp).reshape(-1, 5)
+    out = np.empty_like(a)
+    lib().zo_probe_env_mapping(_p(a), a.shape[0], _p(out))
+    return out
+
+
 def create_alias_table(values):
     v = np.ascontiguousarray(values, dtype=np.float64)
     n = v.shape[0]
@@ -231,6 +244,26 @@ class OracleScene:
         prob, alias, pdf = np.empty(n, np.float32), np.empty(n, np.int32), np.empty(512 * 256, np.float32)
         assert lib().zo_scene_get_env_tables(self._h, _p(prob), _p(alias, C.c_int32), _p(pdf)) == 0
         return prob, alias, pdf
+
+    def env_scale_map(self):
+        """(256, 512) weight map before MIS compensation (envmap.py:136-160)."""
+        out = np.empty((256, 512), np.float32)
+        assert lib().zo_scene_get_env_scale_map(self._h, _p(out)) == 0
+        return out
+
+    def sample_envmap(self, u):
+        """envmap.py:223-238 on (n, 2) uniform numbers -> (n, 8): wi.xyz pdf eval.xyz dist."""
+        u = _f(u).reshape(-1, 2)
+        out = np.empty((u.shape[0], 8), np.float32)
+        assert lib().zo_probe_sample_envmap(self._h, _p(u), u.shape[0], _p(out)) == 0
+        return out
+
+    def env_pdf(self, dirs):
+        """envmap.py:240-248."""
+        d = _f(dirs).reshape(-1, 3)
+        out = np.empty(d.shape[0], np.float32)
+        assert lib().zo_probe_env_pdf(self._h, _p(d), d.shape[0], _p(out)) == 0
+        return out
 
     def render_forward(self, integrator: int, params: ZdrParams, material) -> np.ndarray:
         m = _f(material)

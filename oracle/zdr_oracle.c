@@ -271,6 +271,7 @@ struct zo_scene {
     int env_w, env_h;
     float* env_tex;     /* rgba, env_h rows (after the row duplication of envmap.py:123-125) */
     float* env_alias_prob; int* env_alias_idx; float* env_pdf;
+    float* env_scale_map;   /* weight map before MIS compensation (envmap.py:136-160), kept for the tests */
     /* counters */
     uint64_t n_closest, n_any;
 };
@@ -281,7 +282,7 @@ ZO_API void zo_scene_destroy(zo_scene* s) {
     if (!s) return;
     for (int i = 0; i < s->ninst; ++i) { free(s->inst[i].verts); free(s->inst[i].tris); }
     free(s->inst); free(s->P); free(s->tri_inst); free(s->lights);
-    free(s->env_tex); free(s->env_alias_prob); free(s->env_alias_idx); free(s->env_pdf);
+    free(s->env_tex); free(s->env_alias_prob); free(s->env_alias_idx); free(s->env_pdf); free(s->env_scale_map);
     free(s);
 }
 
@@ -1449,6 +1450,9 @@ ZO_API int zo_scene_set_envmap(zo_scene* s, const float* rgba, int w, int h, int
                 }
             scale_map[py * W + px] = sum_scale / sum_weight;
         }
+    free(s->env_scale_map);
+    s->env_scale_map = (float*)malloc(sizeof(float) * pixel_count);
+    memcpy(s->env_scale_map, scale_map, sizeof(float) * pixel_count);
     /* envmap.py:167-175 */
     if (compensate_mis) {
         double mean = 0.0;
@@ -1489,6 +1493,37 @@ ZO_API int zo_scene_set_envmap(zo_scene* s, const float* rgba, int w, int h, int
     free(pdfs); free(row); free(row_avg); free(pdf_y); free(scale_map);
     s->env_count = 1;
     return ZDR_OK;
+}
+ZO_API int zo_scene_get_env_scale_map(zo_scene* s, float* out) {
+    if (!s || !s->env_scale_map || !out) return ZDR_ERR_STATE;
+    memcpy(out, s->env_scale_map, sizeof(float) * ENV_MAP_W * ENV_MAP_H);
+    return ZDR_OK;
+}
+/* envmap.py:223-238 on n inputs: out n x 8 = wi.xyz pdf eval.xyz dist */
+ZO_API int zo_probe_sample_envmap(zo_scene* s, const float* u, int n, float* out) {
+    if (!s || !s->env_count) return ZDR_ERR_STATE;
+    for (int i = 0; i < n; ++i) {
+        f2 uu = {u[2 * i], u[2 * i + 1]};
+        LightSample t = sample_envmap(s, uu);
+        float* o = out + 8 * (size_t)i;
+        o[0] = t.wi.x; o[1] = t.wi.y; o[2] = t.wi.z; o[3] = t.pdf; o[4] = t.eval.x; o[5] = t.eval.y; o[6] = t.eval.z; o[7] = t.dist;
+    }
+    return ZDR_OK;
+}
+/* envmap.py:240-248 */
+ZO_API int zo_probe_env_pdf(zo_scene* s, const float* dir, int n, float* out) {
+    if (!s || !s->env_count) return ZDR_ERR_STATE;
+    for (int i = 0; i < n; ++i) out[i] = env_sampled_light_pdf(s, v3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]));
+    return ZDR_OK;
+}
+/* envmap.py:206-219: in n x 5 = uv.xy dir.xyz -> out n x 5 = uv_to_direction(uv).xyz direction_to_uv(dir).xy */
+ZO_API void zo_probe_env_mapping(const float* in, int n, float* out) {
+    for (int i = 0; i < n; ++i) {
+        f2 uv = {in[5 * i], in[5 * i + 1]};
+        f3 d = uv_to_direction(uv);
+        f2 r = direction_to_uv(v3(in[5 * i + 2], in[5 * i + 3], in[5 * i + 4]));
+        out[5 * i] = d.x; out[5 * i + 1] = d.y; out[5 * i + 2] = d.z; out[5 * i + 3] = r.x; out[5 * i + 4] = r.y;
+    }
 }
 /* read back the envmap sampling tables (tests compare them with the GPU build) */
 ZO_API int zo_scene_get_env_tables(zo_scene* s, float* prob, int* alias, float* pdf) {

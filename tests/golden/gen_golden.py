@@ -13,6 +13,8 @@ What is recorded
   sampler.npz     pmj02bn.py draws for a grid of (pixel, seed, spp, sample index, draw program)
   functions.npz   camera.py / onb.py / microfacet.py / light.py device functions on seeded inputs,
                   including the LuisaCompute-autodiff gradient of ggx_brdf (emulated tape AD)
+  envmap.npz      envmap.py: weight-map kernel cells, MIS compensation + alias tables + pdf (host pipeline), sample_envmap,
+                  env_sampled_light_pdf, uv <-> direction, create_alias_table
   render_*.npz    integrator.py kernels built from collocated.py / direct.py on the Cornell box:
                   image, and d_material for a fixed d_image, at fixture sizes
 """
@@ -258,8 +260,84 @@ def load_patched_prb():
     return mod
 
 
+# ------------------------------------------------------------------------------------ envmap.py
+ENV_ROWS = (0, 17, 128, 200, 255)            # conditional tables / pdf rows kept in the fixture
+
+
+def gen_envmap():
+    """envmap.py executed from the reference source: the weight-map kernel on a handful of cells, the host pipeline
+    (MIS compensation, conditional + marginal alias tables, pdf normalisation) on the FULL weight map, the device
+    functions sample_envmap / env_sampled_light_pdf / uv_to_direction / direction_to_uv on the resulting heap, and
+    create_alias_table on small vectors.  The 512 x 256 kernel is 38 M emulated texture fetches, so it runs for 28
+    cells only; the host pipeline then gets the full map from the oracle (whose cells the fixture checks)."""
+    import zdr_ref.envmap as R_env
+    from oracle import oracle as o
+    o.build()
+    img = scenes.procedural_envmap(64, 32, seed=1)
+    osc = o.OracleScene(scenes.cbox_collocated_models())
+    osc.set_envmap(img, True)
+    full = osc.env_scale_map()
+    rng = np.random.default_rng(7)
+    cells = sorted({(int(x), int(y)) for x, y in zip(rng.integers(0, 512, 24), rng.integers(0, 256, 24))}
+                   | {(0, 0), (511, 255), (0, 255), (511, 0)})
+    cellset = set(cells)
+    captured = {}
+    orig_numpy = E.Buffer.numpy
+
+    def numpy_hook(self):                      # envmap.py:160: scale_map = scale_map_buffer.numpy()
+        captured["cells"] = np.asarray([self.data[y * 512 + x] for x, y in cells], np.float32)
+        return full.reshape(-1).copy()
+    E.DISPATCH_FILTER = lambda x, y, z: (x, y) in cellset
+    E.Buffer.numpy = numpy_hook
+    heap = E.BindlessArray()
+    try:
+        R_env.load_envmap(heap, img, compensate_mis=True)
+    finally:
+        E.Buffer.numpy = orig_numpy
+        E.DISPATCH_FILTER = None
+    aliases, pdfs = heap.slots[23330].data, np.asarray(heap.slots[23331].data, np.float32)
+    prob = np.asarray([float(F_(a.prob)) for a in aliases], np.float32)
+    alias = np.asarray([int(a.alias) for a in aliases], np.int32)
+    keep = np.concatenate([np.arange(256)] + [256 + r * 512 + np.arange(512) for r in ENV_ROWS])
+    pdf_keep = np.concatenate([r * 512 + np.arange(512) for r in ENV_ROWS])
+    # device functions on the reference heap
+    u = rng.random((96, 2)).astype(np.float32)
+    smp = []
+    for a, b in u:
+        t = R_env.sample_envmap(heap, E.float2(float(a), float(b)))
+        smp.append(fv(t.wi) + [float(F_(t.pdf))] + fv(t.eval) + [float(F_(t.dist))])
+    d = rng.normal(size=(96, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    pdf_dir = [float(F_(R_env.env_sampled_light_pdf(heap, E.float3(*[float(c) for c in q])))) for q in d]
+    uv = rng.random((64, 2)).astype(np.float32)
+    dd = rng.normal(size=(64, 3))
+    dd = (dd / np.linalg.norm(dd, axis=1, keepdims=True)).astype(np.float32)
+    mapping = [fv(R_env.uv_to_direction(E.float2(float(a), float(b)))) + fv(R_env.direction_to_uv(E.float3(*[float(c) for c in q])))
+               for (a, b), q in zip(uv, dd)]
+    # create_alias_table on plain Python floats (binary64 throughout, as the oracle's)
+    at_in, at_prob, at_alias, at_pdf = [], [], [], []
+    for n in (7, 16, 33):
+        v = rng.random(n)
+        v[rng.integers(0, n, 2)] = 0.0
+        table, pdf = R_env.create_alias_table([float(x) for x in v])
+        at_in.append(v); at_prob.append([float(F_(e.prob)) for e in table]); at_alias.append([int(e.alias) for e in table]); at_pdf.append(pdf)
+    np.savez_compressed(os.path.join(OUT, "envmap.npz"), img=img, cells=np.asarray(cells, np.int32), cell_weights=captured["cells"],
+                        rows=np.asarray(ENV_ROWS), prob=prob[keep], alias=alias[keep], pdf=pdfs[pdf_keep],
+                        pdf_sum=np.float64(pdfs.astype(np.float64).sum()), u=u, samples=np.asarray(smp, np.float32), dirs=d,
+                        pdf_dir=np.asarray(pdf_dir, np.float32), map_uv=uv, map_dir=dd, mapping=np.asarray(mapping, np.float32),
+                        at_in=np.concatenate(at_in), at_prob=np.concatenate(at_prob).astype(np.float32),
+                        at_alias=np.concatenate(at_alias).astype(np.int32), at_pdf=np.concatenate(at_pdf), at_len=np.asarray([7, 16, 33]))
+    print("envmap: cells", len(cells), "tables", prob.shape, "pdf sum", float(pdfs.astype(np.float64).sum()))
+
+
+def F_(x):
+    return x.v if isinstance(x, E.F) else x
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path", "loadobj", "uvgrad"]
+    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path", "loadobj", "uvgrad", "envmap"]
+    if "envmap" in which:
+        gen_envmap()
     if "loadobj" in which:
         gen_loadobj()
     if "uvgrad" in which:

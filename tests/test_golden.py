@@ -88,3 +88,60 @@ def test_duvdxy_vs_reference_source(oracle):
     assert np.abs(z["duvdxy"]).max() > 0
     assert rel_l2(got, z["duvdxy"]) <= 1e-4, rel_l2(got, z["duvdxy"])
     assert np.allclose(got, z["duvdxy"], rtol=5e-3, atol=1e-6)
+
+
+def _alias_masses(prob, alias):
+    """probability mass each index gets from a (prob, alias) table."""
+    n = len(prob)
+    m = prob.astype(np.float64).copy()
+    np.add.at(m, alias, 1.0 - prob.astype(np.float64))
+    return m / n
+
+
+def test_envmap_pipeline_vs_reference_source(oracle):
+    """envmap.py run from the reference source (tests/golden/gen_golden.py::gen_envmap): weight-map cells, MIS
+    compensation + conditional / marginal alias tables + pdf normalisation, sample_envmap, env_sampled_light_pdf,
+    uv <-> direction, create_alias_table.  Tolerances: the reference's host pipeline accumulates in whatever numpy
+    promotes to (float32 under NumPy 2), the oracle in binary64, so table entries agree to ~1e-5 and a sample whose
+    uniform number sits on a table threshold may pick the neighbouring cell."""
+    z = np.load(os.path.join(G, "envmap.npz"))
+    sc = oracle.OracleScene(scenes.cbox_collocated_models())
+    sc.set_envmap(z["img"], True)
+    # the weight-map kernel (envmap.py:136-158) on the cells the reference kernel was run for
+    wm = sc.env_scale_map()
+    got = np.asarray([wm[y, x] for x, y in z["cells"]])
+    assert np.allclose(got, z["cell_weights"], rtol=2e-5, atol=1e-7), np.abs(got - z["cell_weights"]).max()
+    # host pipeline on the full map
+    prob, alias, pdf = sc.env_tables()
+    rows = z["rows"]
+    keep = np.concatenate([np.arange(256)] + [256 + r * 512 + np.arange(512) for r in rows])
+    pdf_keep = np.concatenate([r * 512 + np.arange(512) for r in rows])
+    assert abs(float(pdf.astype(np.float64).sum()) - 512 * 256) < 1.0 and abs(float(z["pdf_sum"]) - 512 * 256) < 1.0
+    assert np.allclose(pdf[pdf_keep], z["pdf"], rtol=2e-4, atol=1e-6), np.abs(pdf[pdf_keep] - z["pdf"]).max()
+    assert ((pdf[pdf_keep] == 0) == (z["pdf"] == 0)).mean() > 0.999           # MIS compensation zeroes the same cells
+    o_prob, o_alias, r_prob, r_alias = prob[keep], alias[keep], z["prob"], z["alias"]
+    off = 0
+    for n in [256] + [512] * len(rows):                                        # every table encodes the same distribution
+        mo = _alias_masses(o_prob[off:off + n], o_alias[off:off + n])
+        mr = _alias_masses(r_prob[off:off + n], r_alias[off:off + n])
+        assert abs(mo.sum() - 1) < 1e-6 and abs(mr.sum() - 1) < 1e-5
+        assert np.allclose(mo, mr, rtol=2e-4, atol=1e-7)
+        off += n
+    # device functions
+    s_o, s_r = sc.sample_envmap(z["u"]), z["samples"]
+    same = np.linalg.norm(s_o[:, :3] - s_r[:, :3], axis=1) < 1e-4
+    assert same.mean() >= 0.95, same.mean()
+    assert np.allclose(s_o[same, 3], s_r[same, 3], rtol=1e-3) and np.allclose(s_o[same, 4:7], s_r[same, 4:7], rtol=1e-4, atol=1e-6)
+    assert (s_o[:, 7] == np.float32(1e30)).all() and np.allclose(np.linalg.norm(s_o[:, :3], axis=1), 1, atol=1e-5)
+    p_o, p_r = sc.env_pdf(z["dirs"]), z["pdf_dir"]
+    close = np.isclose(p_o, p_r, rtol=1e-3, atol=1e-7)
+    assert close.mean() >= 0.97, close.mean()
+    m_in = np.concatenate([z["map_uv"], z["map_dir"]], axis=1)
+    assert np.allclose(oracle.env_mapping(m_in), z["mapping"], atol=2e-6)
+    # create_alias_table (envmap.py:17-57) on binary64 inputs: identical tables
+    off = 0
+    for n in z["at_len"]:
+        pr, al, pd = oracle.create_alias_table(z["at_in"][off:off + n])
+        assert np.array_equal(pr, z["at_prob"][off:off + n]) and np.array_equal(al, z["at_alias"][off:off + n])
+        assert np.allclose(pd, z["at_pdf"][off:off + n], rtol=1e-15)
+        off += n
