@@ -768,6 +768,9 @@ class Buffer:
         raise TypeError(self.dtype)
 
     def write(self, i, val):
+        if isinstance(val, _Struct) and hasattr(val, "_vn"):                      # Vertex row: 8 floats
+            self.data[int(i)] = [float(F._c(x).v) for x in list(val._v) + list(val._vt) + list(val._vn)]
+            return
         self.data[int(i)] = [float(c.v) for c in val.c] if isinstance(val, Vec) else float(F._c(val).v)
 
     def atomic_fetch_add(self, i, val):
@@ -775,6 +778,17 @@ class Buffer:
         old = self.data[int(i)]
         self.data[int(i)] = old + float(F._c(val).v)
         return F(old)
+
+
+def _atomic_access_call(dtype, op, buf, index, nested_level, field, component, value):
+    """luisa.atomic._atomic_access_call as recompute_normal.py:21-29 uses it: float atomic add on component
+    `component` of field number `field` of the Vertex at `index` (binary32, in program order)."""
+    assert dtype is float and op == "ATOMIC_FETCH_ADD" and nested_level == 2
+    col = {0: 0, 1: 3, 2: 5}[int(field)] + int(component)
+    row = buf.data[int(index)]
+    old = f32(row[col])
+    row[col] = f32(old + f32(F._c(value).v))
+    return F(old)
 
 
 def buffer(xs):
@@ -967,6 +981,8 @@ def func(fn):
         f = compiled()
         if dispatch_size is None:
             return f(*a, **kw)
+        if isinstance(dispatch_size, (int, np.integer)):
+            dispatch_size = (int(dispatch_size),)
         ds = tuple(dispatch_size) + (1,) * (3 - len(dispatch_size))
         _dispatch["size"] = ds
         for z in range(ds[2]):
@@ -1023,7 +1039,7 @@ def install(pmj: np.ndarray, bn: np.ndarray, ref_dir: str = "/root/reference", p
     luisa.float, luisa.int = float, int
     luisa.__path__ = []                                   # a package: `from luisa.atomic import ...`
     at = types.ModuleType("luisa.atomic")
-    at._atomic_access_call = lambda *a, **k: None          # recompute_normal.py:2 (load-time helper, not on the hot path)
+    at._atomic_access_call = _atomic_access_call           # recompute_normal.py:2
     ut = types.ModuleType("luisa.util")
     luisa.atomic, luisa.util = at, ut
     sys.modules["luisa.atomic"], sys.modules["luisa.util"] = at, ut

@@ -199,6 +199,17 @@ def gen_loadobj():
         vertices, faces = R_obj.read_obj(scenes.asset(name))
         out[name + ":verts"] = np.array([(*v, *t, *n) for v, t, n in vertices], dtype=np.float32)     # render.py:97
         out[name + ":tris"] = np.array(R_obj.concat_triangles(faces), dtype=np.int32)
+        if np.isnan(out[name + ":verts"][0, 5]):
+            # render.py:95-103: meshes without vn get recompute_normal.py's three kernels (clear, scatter the face normal
+            # to the three corners with float atomics, normalise) — run here in program order
+            import zdr_ref.recompute_normal as R_rn
+            from zdr_ref.vertex import Vertex as V
+            vb = E.Buffer(dtype=V, size=len(vertices))
+            vb.copy_from_array(out[name + ":verts"].copy())
+            tb = E.buffer([int(t) for t in out[name + ":tris"]])
+            with np.errstate(invalid="ignore", divide="ignore"):
+                R_rn.recompute_normal(vb, tb)
+            out[name + ":verts_recomputed"] = np.asarray(vb.data, np.float32)
     np.savez_compressed(os.path.join(OUT, "loadobj.npz"), **out)
     print("loadobj.npz")
 
