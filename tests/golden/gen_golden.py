@@ -165,8 +165,38 @@ class RefScene:
         self.accel.update()
 
 
-def gen_render(name, models, fwd_kernel, bwd_kernel, res, spp, tex, seed, mat_seed, rough_min=0.0):
+def load_envmap_on(heap, img, cells=()):
+    """envmap.py:load_envmap on the emulated heap.  Its weight-map kernel (38 M texture fetches at 512 x 256) runs only
+    for `cells`; the host pipeline (MIS compensation, alias tables, pdf) then gets the full map from the oracle, whose
+    cells gen_envmap() checks against the kernel.  Returns the kernel's values at `cells`."""
+    import zdr_ref.envmap as R_env
+    from oracle import oracle as o
+    o.build()
+    osc = o.OracleScene(scenes.cbox_collocated_models())
+    osc.set_envmap(img, True)
+    full = osc.env_scale_map()
+    cellset, captured = set(cells), {}
+    orig_numpy = E.Buffer.numpy
+
+    def numpy_hook(self):                      # envmap.py:160: scale_map = scale_map_buffer.numpy()
+        captured["cells"] = np.asarray([self.data[y * 512 + x] for x, y in cells], np.float32)
+        return full.reshape(-1).copy()
+    E.DISPATCH_FILTER = lambda x, y, z: (x, y) in cellset
+    E.Buffer.numpy = numpy_hook
+    try:
+        R_env.load_envmap(heap, img, compensate_mis=True)
+    finally:
+        E.Buffer.numpy = orig_numpy
+        E.DISPATCH_FILTER = None
+    return captured["cells"]
+
+
+def gen_render(name, models, fwd_kernel, bwd_kernel, res, spp, tex, seed, mat_seed, rough_min=0.0, envmap=None):
     sc = RefScene(models)
+    env_count = 0
+    if envmap is not None:                     # render.py:150-156
+        load_envmap_on(sc.heap, envmap)
+        env_count = 1
     cam = R_render.Camera(fov=50 / 180 * 3.1415926, origin=E.float3(-0.2, 2.6, 6.0), target=E.float3(-0.2, 2.6, -2.5),
                           up=E.float3(0.0, 1.0, 0.0))
     mat = scenes.random_material((tex, tex), mat_seed)
@@ -178,15 +208,16 @@ def gen_render(name, models, fwd_kernel, bwd_kernel, res, spp, tex, seed, mat_se
     image = E.Buffer(dtype=E.float4, size=W * H, data=np.zeros((W * H, 4), np.float32))
     mbuf = E.Buffer(dtype=float, size=mat.size, data=mat.reshape(-1).copy())
     # render.py:168-171
-    fwd_kernel(image, sc.heap, sc.accel, sc.light_count, 0, mbuf, E.int2(tex, tex), cam, spp, seed, True, dispatch_size=(W, H))
+    fwd_kernel(image, sc.heap, sc.accel, sc.light_count, env_count, mbuf, E.int2(tex, tex), cam, spp, seed, True, dispatch_size=(W, H))
     rng = np.random.default_rng(7)
     d_image = rng.normal(size=(H, W, 4)).astype(np.float32)
     dbuf = E.Buffer(dtype=E.float4, size=W * H, data=d_image.reshape(-1, 4).copy())
     dmat = E.Buffer(dtype=float, size=mat.size, data=np.zeros(mat.size, np.float64))
     # render.py:193-196 (seed+1)
-    bwd_kernel(dbuf, sc.heap, sc.accel, sc.light_count, 0, dmat, mbuf, E.int2(tex, tex), cam, spp, seed + 1, True, dispatch_size=(W, H))
+    bwd_kernel(dbuf, sc.heap, sc.accel, sc.light_count, env_count, dmat, mbuf, E.int2(tex, tex), cam, spp, seed + 1, True, dispatch_size=(W, H))
+    extra = {} if envmap is None else {"envmap": envmap}
     np.savez_compressed(os.path.join(OUT, f"render_{name}.npz"), res=np.asarray(res), spp=spp, tex=tex, seed=seed, mat_seed=mat_seed, rough_min=rough_min,
-                        image=image.data.reshape(H, W, 4).astype(np.float32), d_image=d_image,
+                        image=image.data.reshape(H, W, 4).astype(np.float32), d_image=d_image, **extra,
                         d_material=dmat.data.reshape(tex, tex, 4).astype(np.float32))
     print(f"render_{name}.npz: image mean {image.data[:, :3].mean():.5f}, |d_material| sum {np.abs(dmat.data).sum():.4f}")
 
@@ -282,30 +313,12 @@ def gen_envmap():
     create_alias_table on small vectors.  The 512 x 256 kernel is 38 M emulated texture fetches, so it runs for 28
     cells only; the host pipeline then gets the full map from the oracle (whose cells the fixture checks)."""
     import zdr_ref.envmap as R_env
-    from oracle import oracle as o
-    o.build()
     img = scenes.procedural_envmap(64, 32, seed=1)
-    osc = o.OracleScene(scenes.cbox_collocated_models())
-    osc.set_envmap(img, True)
-    full = osc.env_scale_map()
     rng = np.random.default_rng(7)
     cells = sorted({(int(x), int(y)) for x, y in zip(rng.integers(0, 512, 24), rng.integers(0, 256, 24))}
                    | {(0, 0), (511, 255), (0, 255), (511, 0)})
-    cellset = set(cells)
-    captured = {}
-    orig_numpy = E.Buffer.numpy
-
-    def numpy_hook(self):                      # envmap.py:160: scale_map = scale_map_buffer.numpy()
-        captured["cells"] = np.asarray([self.data[y * 512 + x] for x, y in cells], np.float32)
-        return full.reshape(-1).copy()
-    E.DISPATCH_FILTER = lambda x, y, z: (x, y) in cellset
-    E.Buffer.numpy = numpy_hook
     heap = E.BindlessArray()
-    try:
-        R_env.load_envmap(heap, img, compensate_mis=True)
-    finally:
-        E.Buffer.numpy = orig_numpy
-        E.DISPATCH_FILTER = None
+    captured = {"cells": load_envmap_on(heap, img, cells)}
     aliases, pdfs = heap.slots[23330].data, np.asarray(heap.slots[23331].data, np.float32)
     prob = np.asarray([float(F_(a.prob)) for a in aliases], np.float32)
     alias = np.asarray([int(a.alias) for a in aliases], np.int32)
@@ -346,7 +359,10 @@ def F_(x):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path", "loadobj", "uvgrad", "envmap"]
+    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path", "loadobj", "uvgrad", "envmap", "direct_env"]
+    if "direct_env" in which:                  # direct.py with env_count = 1: Cornell box (open front) + light + envmap
+        gen_render("direct_env", scenes.cbox_path_models(), R_direct.render_direct_kernel, R_direct.render_direct_backward_kernel,
+                   (20, 20), 2, 64, 11, 8, envmap=scenes.procedural_envmap(64, 32, seed=2) * np.float32(0.2))
     if "envmap" in which:
         gen_envmap()
     if "loadobj" in which:

@@ -63,6 +63,8 @@ def test_device_functions_vs_reference_source(oracle):
     # prb.py with ONLY the call-arity substitutions listed in gen_golden.py (it cannot compile as shipped):
     # pins prb_mode=literal, max_depth 16, rr_depth 2 — path_estimator and the PRB adjoint incl. autodiff
     ("path_literal", scenes.cbox_path_models, ZDR_PATH, {"prb_mode": ZDR_PRB_LITERAL, "max_depth": 16, "rr_depth": 2}),
+    # direct.py with env_count = 1: envmap emission on misses, envmap light sampling + MIS (light.py:26-35, envmap.py)
+    ("direct_env", scenes.cbox_path_models, ZDR_DIRECT, {}),
 ])
 def test_render_kernels_vs_reference_source(oracle, name, models, integ, kw):
     """integrator.py kernels derived from collocated.py / direct.py (forward and adjoint with
@@ -73,6 +75,8 @@ def test_render_kernels_vs_reference_source(oracle, name, models, integ, kw):
     rough_min = float(z["rough_min"]) if "rough_min" in z else 0.0          # see gen_golden.gen_render
     mat[..., 3] = np.float32(rough_min) + np.float32(1.0 - rough_min) * mat[..., 3]
     sc = oracle.OracleScene(models())
+    if "envmap" in z:
+        sc.set_envmap(z["envmap"], True)
     img = sc.render_forward(integ, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed, **kw), mat)
     assert rel_l2(img, z["image"]) <= 1e-4, rel_l2(img, z["image"])
     dm = sc.render_backward(integ, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed + 1, **kw), mat, z["d_image"])
