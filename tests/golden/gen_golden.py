@@ -359,11 +359,14 @@ def F_(x):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path", "loadobj", "uvgrad", "envmap", "direct_env", "path_env"]
+    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path", "loadobj", "uvgrad", "envmap", "direct_env", "path_env", "direct_xform"]
     if "path_env" in which:                    # prb.py (arity-patched) with env_count = 1
         prb = load_patched_prb()
         gen_render("path_literal_env", scenes.cbox_path_models(), prb.render_path_kernel, prb.render_path_backward_kernel, (16, 16), 2, 64, 13, 6,
                    rough_min=0.3, envmap=scenes.procedural_envmap(64, 32, seed=2) * np.float32(0.2))
+    if "direct_xform" in which:                # non-rigid instance transforms: p = M v, normals by inverse(transpose(M))
+        gen_render("direct_xform", scenes.cbox_sheared_models(), R_direct.render_direct_kernel, R_direct.render_direct_backward_kernel,
+                   (20, 20), 2, 64, 17, 10)
     if "direct_env" in which:                  # direct.py with env_count = 1: Cornell box (open front) + light + envmap
         gen_render("direct_env", scenes.cbox_path_models(), R_direct.render_direct_kernel, R_direct.render_direct_backward_kernel,
                    (20, 20), 2, 64, 11, 8, envmap=scenes.procedural_envmap(64, 32, seed=2) * np.float32(0.2))

@@ -63,6 +63,23 @@ def rotation_y(angle: float) -> float4x4:
     return float4x4(c, 0, -s, 0, 0, 1, 0, 0, s, 0, c, 0, 0, 0, 0, 1)
 
 
+def cbox_sheared_models():
+    """Cornell box + light under ONE non-rigid transform (rotation about y, non-uniform scale, shift about the box
+    centre): exercises p = M v (interaction.py:19-21) and the normal matrix inverse(transpose(M3x3)) (interaction.py:28)."""
+    c, s_ = math.cos(0.25), math.sin(0.25)
+    sx, sy, sz = 1.1, 0.9, 1.05
+    cx, cy, cz = -0.2, 2.6, -2.5                       # rotate / scale about the box centre
+    rows = [[c * sx, 0.0, s_ * sz, 0.0], [0.0, sy, 0.0, 0.0], [-s_ * sx, 0.0, c * sz, 0.0], [0.0, 0.0, 0.0, 1.0]]
+    lin = np.asarray(rows, np.float64)[:3, :3]
+    t = np.asarray([cx, cy, cz]) - lin @ np.asarray([cx, cy, cz]) + np.asarray([0.1, -0.05, 0.0])
+    for i in range(3):
+        rows[i][3] = float(np.float32(t[i]))
+        for j in range(3):
+            rows[i][j] = float(np.float32(rows[i][j]))
+    m = float4x4.from_rows(rows)
+    return [(asset("cboxuv.obj"), m, float3(0.0)), (asset("cbox-light.obj"), m, float3(17, 12, 4))]
+
+
 def sphere_grid_models(n_inst: int, seed: int = 0, emissive_every: int = 0):
     """C5 shape: instances of sphere.obj on a jittered lattice (uniform scale 0.4, spacing 1.0,
     jitter +-0.25), first n cells of a 22x22x21 grid; instance 0 is the textured object."""

@@ -65,6 +65,8 @@ def test_device_functions_vs_reference_source(oracle):
     ("path_literal", scenes.cbox_path_models, ZDR_PATH, {"prb_mode": ZDR_PRB_LITERAL, "max_depth": 16, "rr_depth": 2}),
     # direct.py with env_count = 1: envmap emission on misses, envmap light sampling + MIS (light.py:26-35, envmap.py)
     ("direct_env", scenes.cbox_path_models, ZDR_DIRECT, {}),
+    # one non-rigid transform on box and light: p = M v and the inverse(transpose(M3x3)) normal matrix (interaction.py:19-28)
+    ("direct_xform", scenes.cbox_sheared_models, ZDR_DIRECT, {}),
     # arity-patched prb.py with env_count = 1: the miss term with the throughput applied twice (prb.py:28-31) and an
     # adjoint walk that knows nothing of the envmap (SURVEY 8a defect 2) — reproduced by prb_mode=literal
     ("path_literal_env", scenes.cbox_path_models, ZDR_PATH, {"prb_mode": ZDR_PRB_LITERAL, "max_depth": 16, "rr_depth": 2}),
