@@ -728,6 +728,10 @@ class Buffer:
     def copy_from_array(self, arr):
         self.data = np.ascontiguousarray(arr)
 
+    def copy_from(self, xs):
+        """host list -> buffer, same element type (render.py:145,148: update_lights rewrites emissions / light list)."""
+        self.data = buffer(list(xs)).data
+
     @staticmethod
     def from_dlpack(t):
         a = t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)

@@ -354,12 +354,52 @@ def gen_envmap():
     print("envmap: cells", len(cells), "tables", prob.shape, "pdf sum", float(pdfs.astype(np.float64).sum()))
 
 
+# ------------------------------------------------------------------------------------ render.py: Scene
+def gen_scene_api():
+    """The reference's own Scene class (render.py:31-241) end to end under the emulator: load_geometry, render through
+    Scene.RenderOperator (torch.autograd), update_lights, and backward() restoring the forward call's camera and lights.
+    There is no GPU here: the two places render.py names the device (torch.empty(..., device='cuda') and
+    torch.cuda.synchronize) are redirected to the CPU for the duration of the run."""
+    import torch
+    models_flat = scenes.cbox_two_light_models()
+    models = [(f, None if m is None else E.float4x4(*m.flat()), E.float3(*[float(c) for c in e])) for f, m, e in models_flat]
+    orig_empty, orig_zeros, orig_sync = torch.empty, torch.zeros, torch.cuda.synchronize
+    torch.empty = lambda *a, **k: orig_empty(*a, **{kk: v for kk, v in k.items() if kk != "device"})
+    torch.zeros = lambda *a, **k: orig_zeros(*a, **{kk: v for kk, v in k.items() if kk != "device"})
+    torch.cuda.synchronize = lambda *a, **k: None
+    try:
+        sc = R_render.Scene(models, integrator="direct")
+        sc.camera = R_render.Camera(fov=50 / 180 * 3.1415926, origin=E.float3(-0.2, 2.6, 6.0), target=E.float3(-0.2, 2.6, -2.5),
+                                    up=E.float3(0.0, 1.0, 0.0))
+        res, spp = (20, 20), 2
+        mat = torch.from_numpy(scenes.random_material((64, 64), 21)).requires_grad_()
+        w = torch.from_numpy(np.random.default_rng(5).uniform(0.5, 1.5, (res[1], res[0], 4)).astype(np.float32))
+        img1 = sc.render(mat, res=res, spp=spp, seed=5)
+        (img1 * w).sum().backward()
+        g1 = mat.grad.clone()
+        mat.grad = None
+        # render.py:130-148: numbers, None and float3 are all accepted
+        sc.update_lights([None, 0, E.float3(9.0, 6.0, 3.0)])
+        lc2 = sc.light_count
+        img2 = sc.render(mat, res=res, spp=spp, seed=6)
+        # the state changes between forward and backward: backward must use the forward call's (render.py:203-218)
+        sc.camera = R_render.Camera(fov=0.5, origin=E.float3(1.0, 1.0, 1.0), target=E.float3(0.0, 0.0, 0.0), up=E.float3(0.0, 1.0, 0.0))
+        sc.update_lights([E.float3(0.0), E.float3(1.0, 1.0, 1.0), E.float3(0.0)])
+        (img2 * w).sum().backward()
+        g2 = mat.grad.clone()
+    finally:
+        torch.empty, torch.zeros, torch.cuda.synchronize = orig_empty, orig_zeros, orig_sync
+    np.savez_compressed(os.path.join(OUT, "scene_api.npz"), res=np.asarray(res), spp=spp, w=w.numpy(), img1=img1.detach().numpy(),
+                        g1=g1.numpy(), img2=img2.detach().numpy(), g2=g2.numpy(), light_count2=lc2, inst_count=sc.inst_count)
+    print("scene_api.npz: means", float(img1[..., :3].mean()), float(img2[..., :3].mean()), "|g|", float(g1.abs().sum()), float(g2.abs().sum()))
+
+
 def F_(x):
     return x.v if isinstance(x, E.F) else x
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path", "loadobj", "uvgrad", "envmap", "direct_env", "path_env", "direct_xform"]
+    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path", "loadobj", "uvgrad", "envmap", "direct_env", "path_env", "direct_xform", "scene_api"]
     if "path_env" in which:                    # prb.py (arity-patched) with env_count = 1
         prb = load_patched_prb()
         gen_render("path_literal_env", scenes.cbox_path_models(), prb.render_path_kernel, prb.render_path_backward_kernel, (16, 16), 2, 64, 13, 6,
@@ -372,6 +412,8 @@ if __name__ == "__main__":
                    (20, 20), 2, 64, 11, 8, envmap=scenes.procedural_envmap(64, 32, seed=2) * np.float32(0.2))
     if "envmap" in which:
         gen_envmap()
+    if "scene_api" in which:
+        gen_scene_api()
     if "loadobj" in which:
         gen_loadobj()
     if "uvgrad" in which:

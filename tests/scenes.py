@@ -80,6 +80,13 @@ def cbox_sheared_models():
     return [(asset("cboxuv.obj"), m, float3(0.0)), (asset("cbox-light.obj"), m, float3(17, 12, 4))]
 
 
+def cbox_two_light_models():
+    """Cornell box, its ceiling light (on) and a second copy of the light moved down and sideways (off): the scene of the
+    update_lights / RenderOperator fixtures."""
+    return [(asset("cboxuv.obj"), None, float3(0.0)), (asset("cbox-light.obj"), None, float3(17, 12, 4)),
+            (asset("cbox-light.obj"), translate_scale(-1.2, -1.5, 0.4, 1.0), float3(0.0))]
+
+
 def sphere_grid_models(n_inst: int, seed: int = 0, emissive_every: int = 0):
     """C5 shape: instances of sphere.obj on a jittered lattice (uniform scale 0.4, spacing 1.0,
     jitter +-0.25), first n cells of a 22x22x21 grid; instance 0 is the textured object."""

@@ -154,3 +154,23 @@ def test_envmap_pipeline_vs_reference_source(oracle):
         assert np.array_equal(pr, z["at_prob"][off:off + n]) and np.array_equal(al, z["at_alias"][off:off + n])
         assert np.allclose(pd, z["at_pdf"][off:off + n], rtol=1e-15)
         off += n
+
+
+def test_scene_class_vs_reference_source(oracle):
+    """render.py's Scene run as shipped under the emulator (gen_golden.py::gen_scene_api): scene assembly order,
+    RenderOperator forward / backward with seed + 1, update_lights (None / number / float3 entries, rebuilt light
+    list) and backward() using the forward call's camera and lights after both were changed."""
+    z = np.load(os.path.join(G, "scene_api.npz"))
+    res, spp = tuple(int(x) for x in z["res"]), int(z["spp"])
+    mat = scenes.random_material((64, 64), 21)
+    sc = oracle.OracleScene(scenes.cbox_two_light_models())
+    assert sc.light_count == 1 and int(z["inst_count"]) == 3
+    img1 = sc.render_forward(ZDR_DIRECT, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, 5), mat)
+    g1 = sc.render_backward(ZDR_DIRECT, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, 6), mat, z["w"])
+    assert rel_l2(img1, z["img1"]) <= 1e-4 and rel_l2(g1, z["g1"]) <= 1e-3, (rel_l2(img1, z["img1"]), rel_l2(g1, z["g1"]))
+    sc.update_lights([None, 0, (9.0, 6.0, 3.0)])
+    assert sc.light_count == int(z["light_count2"]) == 1
+    img2 = sc.render_forward(ZDR_DIRECT, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, 6), mat)
+    g2 = sc.render_backward(ZDR_DIRECT, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, 7), mat, z["w"])
+    assert rel_l2(img2, z["img2"]) <= 1e-4 and rel_l2(g2, z["g2"]) <= 1e-3, (rel_l2(img2, z["img2"]), rel_l2(g2, z["g2"]))
+    assert rel_l2(img2, z["img1"]) > 0.1                                   # the light really moved
