@@ -272,10 +272,13 @@ struct zo_scene {
     float* env_tex;     /* rgba, env_h rows (after the row duplication of envmap.py:123-125) */
     float* env_alias_prob; int* env_alias_idx; float* env_pdf;
     float* env_scale_map;   /* weight map before MIS compensation (envmap.py:136-160), kept for the tests */
+    /* optional acceleration of the brute-force scans for large scenes (same triangle test, same winner) */
+    struct ONode* bvh; int* bvh_order; int bvh_nodes;
     /* counters */
     uint64_t n_closest, n_any;
 };
 typedef struct zo_scene zo_scene;
+struct ONode { float lo[3], hi[3]; int left, right, first, count; };   /* count > 0: leaf over bvh_order[first..] */
 
 ZO_API zo_scene* zo_scene_create(void) { return (zo_scene*)calloc(1, sizeof(zo_scene)); }
 ZO_API void zo_scene_destroy(zo_scene* s) {
@@ -283,6 +286,7 @@ ZO_API void zo_scene_destroy(zo_scene* s) {
     for (int i = 0; i < s->ninst; ++i) { free(s->inst[i].verts); free(s->inst[i].tris); }
     free(s->inst); free(s->P); free(s->tri_inst); free(s->lights);
     free(s->env_tex); free(s->env_alias_prob); free(s->env_alias_idx); free(s->env_pdf); free(s->env_scale_map);
+    free(s->bvh); free(s->bvh_order);
     free(s);
 }
 
@@ -343,6 +347,7 @@ static void rebuild_lights(zo_scene* s) {
     }
 }
 
+static void bvh_build(zo_scene* s);
 ZO_API int zo_scene_commit(zo_scene* s) {
     if (!s || s->ninst == 0) return ZDR_ERR_STATE;
     int nt = 0;
@@ -363,6 +368,7 @@ ZO_API int zo_scene_commit(zo_scene* s) {
         }
     }
     rebuild_lights(s);
+    bvh_build(s);
     s->committed = 1;
     return ZDR_OK;
 }
@@ -430,8 +436,145 @@ static int tri_test(const RayPre* rp, f3 o, f3 p0, f3 p1, f3 p2, float tmin, flo
     return 1;
 }
 
+/* ---- median-split BVH over the world-space triangles (TEST INFRASTRUCTURE for scenes too large to scan) ----
+ * Only a pruning device: every candidate still goes through tri_test, and the winner is the smallest t with ties to
+ * the lowest scene-order triangle — exactly what the in-order scan with a strict '<' keeps — so closest hits,
+ * occlusion answers and ray counts are those of the brute-force scan.  Boxes are inflated and the slab test is
+ * widened, as on the GPU.  Scenes below ZO_BVH_MIN_TRIS keep the scan; ZDR_ORACLE_BVH=0 / 1 forces either. */
+#define ZO_BVH_MIN_TRIS 4096
+#define ZO_BVH_LEAF 4
+static float tri_centroid(const zo_scene* s, int g, int ax) {
+    return comp(s->P[3 * g], ax) + comp(s->P[3 * g + 1], ax) + comp(s->P[3 * g + 2], ax);
+}
+static void bvh_select(const zo_scene* s, int* idx, int lo, int hi, int k, int ax) {   /* quickselect: idx[k] in place */
+    while (hi - lo > 1) {
+        float pivot = tri_centroid(s, idx[lo + (hi - lo) / 2], ax);
+        int i = lo, j = hi - 1;
+        while (i <= j) {
+            while (tri_centroid(s, idx[i], ax) < pivot) ++i;
+            while (tri_centroid(s, idx[j], ax) > pivot) --j;
+            if (i <= j) { int t = idx[i]; idx[i] = idx[j]; idx[j] = t; ++i; --j; }
+        }
+        if (k <= j) hi = j + 1; else if (k >= i) lo = i; else return;
+    }
+}
+static int bvh_build_rec(zo_scene* s, int first, int count, float eps) {
+    int self = s->bvh_nodes++;
+    struct ONode* n = &s->bvh[self];
+    float clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int q = 0; q < 3; ++q) { n->lo[q] = 1e30f; n->hi[q] = -1e30f; }
+    for (int i = first; i < first + count; ++i) {
+        int g = s->bvh_order[i];
+        for (int q = 0; q < 3; ++q) {
+            float c = tri_centroid(s, g, q);
+            clo[q] = fminf(clo[q], c); chi[q] = fmaxf(chi[q], c);
+            for (int k = 0; k < 3; ++k) {
+                float v = comp(s->P[3 * g + k], q);
+                n->lo[q] = fminf(n->lo[q], v); n->hi[q] = fmaxf(n->hi[q], v);
+            }
+        }
+    }
+    for (int q = 0; q < 3; ++q) { n->lo[q] -= eps; n->hi[q] += eps; }
+    n->first = first; n->count = 0; n->left = n->right = -1;
+    if (count <= ZO_BVH_LEAF) { n->count = count; return self; }
+    int ax = 0;
+    if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+    if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+    int mid = first + count / 2;
+    if (chi[ax] > clo[ax]) bvh_select(s, s->bvh_order, first, first + count, mid, ax);   /* else: coincident centroids, split by position */
+    int l = bvh_build_rec(s, first, mid - first, eps);
+    int r = bvh_build_rec(s, mid, first + count - mid, eps);
+    s->bvh[self].left = l; s->bvh[self].right = r;      /* (s->bvh is not reallocated during the build) */
+    return self;
+}
+static void bvh_build(zo_scene* s) {
+    free(s->bvh); free(s->bvh_order);
+    s->bvh = NULL; s->bvh_order = NULL; s->bvh_nodes = 0;
+    const char* force = getenv("ZDR_ORACLE_BVH");
+    int want = force ? atoi(force) != 0 : s->ntri >= ZO_BVH_MIN_TRIS;
+    if (!want || s->ntri == 0) return;
+    float lo = 1e30f, hi = -1e30f;
+    for (int i = 0; i < 3 * s->ntri; ++i) {
+        lo = fminf(lo, fminf(s->P[i].x, fminf(s->P[i].y, s->P[i].z)));
+        hi = fmaxf(hi, fmaxf(s->P[i].x, fmaxf(s->P[i].y, s->P[i].z)));
+    }
+    float eps = 1e-5f * fmaxf(fmaxf(fabsf(lo), fabsf(hi)), 1e-20f);
+    s->bvh = (struct ONode*)malloc(sizeof(struct ONode) * (size_t)(2 * s->ntri));
+    s->bvh_order = (int*)malloc(sizeof(int) * (size_t)s->ntri);
+    for (int g = 0; g < s->ntri; ++g) s->bvh_order[g] = g;
+    bvh_build_rec(s, 0, s->ntri, eps);
+}
+static inline int bvh_box(const struct ONode* n, f3 o, f3 id, float tmin, float tmax, float* tnear) {
+    float x0 = (n->lo[0] - o.x) * id.x, x1 = (n->hi[0] - o.x) * id.x;
+    float y0 = (n->lo[1] - o.y) * id.y, y1 = (n->hi[1] - o.y) * id.y;
+    float z0 = (n->lo[2] - o.z) * id.z, z1 = (n->hi[2] - o.z) * id.z;
+    float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    *tnear = tn;
+    /* NaN (0 * inf on a slab boundary) must not prune */
+    return !(tn * 0.999999f > tf * 1.000001f);
+}
+static inline f3 bvh_inv_dir(f3 d) {
+    f3 id = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    if (!(fabsf(id.x) <= 1e30f)) id.x = copysignf(1e30f, d.x);
+    if (!(fabsf(id.y) <= 1e30f)) id.y = copysignf(1e30f, d.y);
+    if (!(fabsf(id.z) <= 1e30f)) id.z = copysignf(1e30f, d.z);
+    return id;
+}
+static Hit bvh_trace_closest(zo_scene* s, Ray r) {
+    Hit h = {-1, -1, 0, 0, 0};
+    RayPre rp = ray_pre(r.d);
+    f3 id = bvh_inv_dir(r.d);
+    float best = r.tmax;
+    int best_g = 0x7fffffff, have = 0;
+    int stack[128], sp = 0;
+    stack[sp++] = 0;
+    while (sp) {
+        const struct ONode* n = &s->bvh[stack[--sp]];
+        float tn;
+        if (!bvh_box(n, r.o, id, r.tmin, best, &tn)) continue;
+        if (n->count == 0) {                         /* nearer child on top of the stack: best shrinks early */
+            float tl, tr;
+            bvh_box(&s->bvh[n->left], r.o, id, r.tmin, best, &tl);
+            bvh_box(&s->bvh[n->right], r.o, id, r.tmin, best, &tr);
+            if (tl < tr) { stack[sp++] = n->right; stack[sp++] = n->left; }
+            else { stack[sp++] = n->left; stack[sp++] = n->right; }
+            continue;
+        }
+        for (int i = n->first; i < n->first + n->count; ++i) {
+            int g = s->bvh_order[i];
+            float t, u, v;
+            if (!tri_test(&rp, r.o, s->P[3 * g], s->P[3 * g + 1], s->P[3 * g + 2], r.tmin, INFINITY, &t, &u, &v)) continue;
+            if (t < best || (have && t == best && g < best_g)) {
+                best = t; best_g = g; have = 1;
+                h.t = t; h.u = u; h.v = v; h.inst = s->tri_inst[g]; h.prim = g - s->inst[h.inst].tri_base;
+            }
+        }
+    }
+    return h;
+}
+static int bvh_trace_any(zo_scene* s, Ray r) {
+    RayPre rp = ray_pre(r.d);
+    f3 id = bvh_inv_dir(r.d);
+    int stack[128], sp = 0;
+    stack[sp++] = 0;
+    while (sp) {
+        const struct ONode* n = &s->bvh[stack[--sp]];
+        float tn;
+        if (!bvh_box(n, r.o, id, r.tmin, r.tmax, &tn)) continue;
+        if (n->count == 0) { stack[sp++] = n->left; stack[sp++] = n->right; continue; }
+        for (int i = n->first; i < n->first + n->count; ++i) {
+            int g = s->bvh_order[i];
+            float t, u, v;
+            if (tri_test(&rp, r.o, s->P[3 * g], s->P[3 * g + 1], s->P[3 * g + 2], r.tmin, r.tmax, &t, &u, &v)) return 1;
+        }
+    }
+    return 0;
+}
+
 /* accel.trace_closest (collocated.py:16 ...): brute force in scene order; ties keep the first */
 static Hit trace_closest(zo_scene* s, Ray r) {
+    if (s->bvh) return bvh_trace_closest(s, r);
     Hit h = {-1, -1, 0, 0, 0};
     RayPre rp = ray_pre(r.d);
     float best = r.tmax;
@@ -446,6 +589,7 @@ static Hit trace_closest(zo_scene* s, Ray r) {
 }
 /* accel.trace_any (direct.py:44) */
 static int trace_any(zo_scene* s, Ray r) {
+    if (s->bvh) return bvh_trace_any(s, r);
     RayPre rp = ray_pre(r.d);
     for (int g = 0; g < s->ntri; ++g) {
         float t, u, v;

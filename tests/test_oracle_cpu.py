@@ -192,3 +192,40 @@ def test_envmap_tables_and_render_smoke(oracle):
     mat = scenes.random_material((16, 16), 3)
     img = sc.render_forward(ZDR_PATH, make_params(cam, (32, 24), mat.shape, 4, 0, max_depth=4), mat)
     assert np.isfinite(img).all() and img[..., :3].mean() > 0.05
+
+
+def test_oracle_bvh_equals_brute_force_scan(oracle, monkeypatch):
+    """Scenes of >= 4096 triangles are scanned through a median-split BVH inside the oracle (test infrastructure: the
+    same triangle test, smallest t, ties to the lowest scene-order triangle).  It must answer exactly as the in-order
+    brute-force scan does: hits, barycentrics, occlusion, rendered samples, adjoint and ray counts."""
+    rng = np.random.default_rng(2)
+
+    def rays(n, lo, hi):
+        o = rng.uniform(lo, hi, (n, 3))
+        d = rng.normal(size=(n, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        d[: n // 20, rng.integers(0, 3)] = 0.0                      # axis-parallel directions (slab test with 1/0)
+        return np.concatenate([o, d, np.zeros((n, 1)), np.full((n, 1), 1e30)], axis=1).astype(np.float32)
+    models = scenes.sphere_grid_models(12, seed=3, emissive_every=5)          # 11 520 triangles
+    r = rays(1500, (-1, -1, -1), (4, 4, 2))
+    seg = r.copy()
+    seg[:, 6], seg[:, 7] = 1e-4, 2.5
+    cam = scenes.Camera(fov=0.9, origin=scenes.float3(-2.0, 3.0, -4.0), target=scenes.float3(2.0, 0.5, 0.3), up=scenes.float3(0, 1, 0))
+    mat = scenes.random_material((32, 32), 2)
+    p = make_params(cam, (24, 16), mat.shape, 2, 0, max_depth=4)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ZDR_ORACLE_BVH", flag)
+        sc = oracle.OracleScene(models)
+        ip, uvt = sc.trace_closest(r)
+        sc.reset_ray_counters()
+        smp = sc.render_samples(ZDR_PATH, p, mat)
+        grad = sc.render_backward(ZDR_PATH, p, mat, np.ones((16, 24, 4), np.float32))
+        out[flag] = (ip, uvt, sc.trace_any(seg), smp, grad, sc.ray_counters())
+    a, b = out["0"], out["1"]
+    hit = a[0][:, 0] >= 0
+    assert hit.sum() > 50 and np.array_equal(a[0], b[0])
+    assert np.array_equal(a[1][hit].view(np.uint32), b[1][hit].view(np.uint32))
+    assert np.array_equal(a[2], b[2]) and 0 < a[2].sum() < len(a[2])
+    assert np.array_equal(a[3].view(np.uint32), b[3].view(np.uint32)) and a[3].max() > 0
+    assert np.allclose(a[4], b[4], rtol=1e-6, atol=1e-9) and a[5] == b[5]

@@ -25,6 +25,8 @@ ap.add_argument("--spp", type=int, default=16)
 ap.add_argument("--depth", type=int, default=16)
 ap.add_argument("--check-rays", type=int, default=48)
 ap.add_argument("--stats", action="store_true", help="also count BVH nodes / triangles per ray (slower)")
+ap.add_argument("--cpu-baseline", action="store_true",
+                help="also time the CPU oracle (all host threads) on the same scene at 480x270, 2 of --spp samples, fwd + bwd (SURVEY 8d)")
 ap.add_argument("--separate", action="store_true", help="keep every sphere a separate instance (10 000 add_mesh calls; only instance 0 is shaded)")
 args = ap.parse_args()
 
@@ -102,6 +104,27 @@ print(f"{res[0]}x{res[1]} {args.spp} spp depth {args.depth}: fwd {ms_f:.1f} ms, 
       f"image mean {float(img.detach()[..., :3].mean()):.4f} finite {bool(torch.isfinite(img).all())}, grad |sum| {float(mat.grad.abs().sum()):.3f} finite {bool(torch.isfinite(mat.grad).all())}")
 if world > 1:
     dist.destroy_process_group()
+if args.cpu_baseline and rank == 0:
+    from oracle import oracle as o
+    from zdr_b200._abi import ZDR_PATH, make_params
+    o.build()
+    o.lib().zo_set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    osc = o.OracleScene(models)                       # >= 4096 triangles: the oracle prunes its scan with a BVH (same hits)
+    osc.set_envmap(scenes.procedural_envmap(2048, 1024, seed=0))
+    t_scene = time.perf_counter() - t0
+    mat_np = scenes.random_material((2048, 2048), 0)
+    k = min(2, args.spp)
+    pf = make_params(sc.camera, (480, 270), mat_np.shape, args.spp, 0, max_depth=args.depth, its=(0, k))
+    pb = make_params(sc.camera, (480, 270), mat_np.shape, args.spp, 1, max_depth=args.depth, its=(0, k))
+    osc.reset_ray_counters()
+    t0 = time.perf_counter()
+    osc.render_forward(ZDR_PATH, pf, mat_np)
+    osc.render_backward(ZDR_PATH, pb, mat_np, np.ones((270, 480, 4), np.float32))
+    dt = time.perf_counter() - t0
+    cpu_rays = sum(osc.ray_counters())
+    print(f"CPU oracle ({o.lib().zo_num_threads()} threads): scene + BVH + envmap {t_scene:.1f} s; 480x270, samples [0,{k}) of {args.spp}, fwd + bwd: "
+          f"{cpu_rays / 1e6:.2f} Mrays in {dt:.1f} s -> {cpu_rays / dt / 1e6:.3f} Mrays/s; GPU / CPU = {rays / (ms_f + ms_b) / 1e3 / (cpu_rays / dt / 1e6):.0f}x")
 if args.check_rays:
     import ctypes as C
     from oracle import oracle as o
