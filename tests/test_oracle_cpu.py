@@ -229,3 +229,43 @@ def test_oracle_bvh_equals_brute_force_scan(oracle, monkeypatch):
     assert np.array_equal(a[2], b[2]) and 0 < a[2].sum() < len(a[2])
     assert np.array_equal(a[3].view(np.uint32), b[3].view(np.uint32)) and a[3].max() > 0
     assert np.allclose(a[4], b[4], rtol=1e-6, atol=1e-9) and a[5] == b[5]
+
+
+def test_oracle_bvh_equals_scan_on_degenerate_geometry(oracle, monkeypatch, tmp_path):
+    """The same equivalence on hostile input: 6 000 triangles of very different sizes, 300 exact copies of one triangle
+    (every tie must go to the first copy), zero-area triangles, one huge triangle under everything."""
+    rng = np.random.default_rng(5)
+    n = 6000
+    ctr = rng.uniform(-4, 4, (n, 1, 3))
+    size = np.exp(rng.uniform(np.log(1e-3), np.log(0.8), (n, 1, 1)))
+    tri = ctr + rng.normal(0, 1, (n, 3, 3)) * size
+    dup = np.repeat(np.array([[[0.5, 0.5, 0.0], [1.5, 0.5, 0.2], [0.5, 1.5, 0.1]]]), 300, axis=0)
+    flat = np.repeat(rng.uniform(-4, 4, (100, 1, 3)), 3, axis=1)
+    huge = np.array([[[-50.0, -50.0, -4.5], [50.0, -50.0, -4.5], [0.0, 80.0, -4.5]]])
+    tri = np.concatenate([tri[:3000], dup, flat, tri[3000:], huge]).astype(np.float32)
+    path = tmp_path / "soup.obj"
+    with open(path, "w") as f:
+        for t in tri:
+            for v in t:
+                f.write(f"v {float(v[0])!r} {float(v[1])!r} {float(v[2])!r}\n")
+        for i in range(len(tri)):
+            f.write(f"f {3 * i + 1} {3 * i + 2} {3 * i + 3}\n")
+    o = rng.uniform(-4, 4, (3000, 3))
+    d = rng.normal(size=(3000, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d, np.zeros((3000, 1)), np.full((3000, 1), 1e30)], axis=1).astype(np.float32)
+    rays[:400, 0:3] = (0.8, 0.8, 1.0)                                                # straight at the stack of copies
+    rays[:400, 3:6] = rng.normal(0, 0.05, (400, 3)) + (0.0, 0.0, -1.0)
+    seg = rays.copy()
+    seg[:, 6], seg[:, 7] = 1e-4, 2.0
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ZDR_ORACLE_BVH", flag)
+        sc = oracle.OracleScene([(str(path), None, scenes.float3(0.0))])
+        out[flag] = sc.trace_closest(rays) + (sc.trace_any(seg),)
+    a, b = out["0"], out["1"]
+    hit = a[0][:, 0] >= 0
+    assert hit.sum() > 500 and np.array_equal(a[0], b[0]) and np.array_equal(a[1][hit].view(np.uint32), b[1][hit].view(np.uint32))
+    assert np.array_equal(a[2], b[2])
+    copies = (a[0][:400, 1] >= 3000) & (a[0][:400, 1] < 3300)
+    assert copies.sum() > 20 and (a[0][:400, 1][copies] == 3000).all()
