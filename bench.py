@@ -1,26 +1,34 @@
 #!/usr/bin/env python
-"""bench.py — PRB fwd+bwd Mrays/s on the Cornell box (BASELINE.json metric).
+"""bench.py — PRB fwd+bwd Mrays/s (BASELINE.json metric) on any of the BASELINE configs.
 
-A step = one forward render + one adjoint (PRB) render of the workload, `d_image = 1`
-(benchmark.py:37-39: `I.sum().backward()`).  Default workload = BASELINE.json configs[2] (C3):
-cboxuv.obj + cbox-light.obj (17,12,4), path integrator, max depth 8, rr depth 2, 1024x1024,
-256 spp, 1024^2 random texture, seed 0 (fwd) / 1 (bwd).
+A step = one forward render + one adjoint render of the workload, `d_image = 1` (benchmark.py:37-39:
+`I.sum().backward()`); light-stage configs (c4, c4d) loop that over their 8 lights with `update_lights`
+between the renders (test_lightstage.py:46-54).  Default workload = BASELINE.json configs[2] (c3, the config the
+metric is quoted on): cboxuv.obj + cbox-light.obj (17,12,4), path integrator + PRB, max depth 8, rr depth 2,
+1024x1024, 256 spp, 1024^2 random texture, seed 0 (fwd) / 1 (bwd).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]          # our CUDA path
+    python bench.py [--config c1|c2|c3|c4|c4d|c5] [--gpus N] [--steps K] [--warmup W]     # our CUDA path
     python bench.py --impl reference ...                          # CPU restatement (oracle), all host threads
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One JSON line on rank 0.  `value` = rays (closest + any queries of forward pass, adjoint replay
-pass and adjoint walk, device counters) of ALL ranks / max-over-ranks device time; inputs
-resident in HBM.  `e2e` = same metric through the torch surface (`Scene.render` +
-`.backward()`) with the material coming from pinned host memory and the gradient + loss going
-back to the host every step.  N > 1: strong scaling — the image's 8-row tiles are dealt
-round-robin to the ranks, texture gradients are summed with one NCCL all-reduce inside the step.
+One JSON line on rank 0.  `value` = rays (closest + any queries of forward pass, adjoint replay pass and adjoint
+walk, device counters) of ALL ranks / max-over-ranks device time; inputs resident in HBM.  `e2e` = same metric
+through the torch surface (`Scene.render` + `.backward()`) with the material coming from pinned host memory and the
+gradient + loss going back to the host every step.  N > 1: strong scaling — the image's 8-row tiles are dealt
+round-robin to the ranks, texture gradients are summed with one NCCL all-reduce inside the step; after the timed
+region the all-reduced image and gradient are compared with a one-rank render of the same job
+(`multi_gpu_check`; the run FAILS above 1e-3).
+
+`roofline` names the bound ncu shows for this path — warp-instruction issue, not HBM: achieved = warp instructions
+per second (instruction count of one step from the committed ncu launch list `profiles/<round>_issue_<config>.json`,
+scaled by the live ray count, over the live CUDA-event time) against 148 SMs x 4 schedulers x SM clock; `traffic` and
+`hbm` give the measured DRAM bytes of the step and the HBM fraction they amount to.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import glob
 import json
 import os
 import subprocess
@@ -36,16 +44,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "prb_fwd_bwd_mrays_per_s"
 UNIT = "Mrays/s"
-
-# algorithmic bytes per unit of work (DESIGN.md "Algorithmic bytes")
-B_NODE = 64            # one BVH2 node record (both child boxes + links)
-B_TRI = 48             # one triangle record (3 x float4)
-B_SHADE = 48 + 64 + 64 + 36      # hit triangle + shading record + 4 texels + instance normal matrix
-B_LIGHT = 4 + 48                 # slot_of_gid + light triangle (mesh-light NEE sample)
-B_SAMPLER_VERTEX = 4 * 4 + 2 * 16  # 4 one-dimensional + 2 two-dimensional draws per path vertex
-B_SCATTER = 128        # 4 texels x 16 B, read-modify-write
-B_CAMERA = 16          # the camera sample's 2-D draw
-B_PIXEL = 16           # image write (fwd) / d_image read (bwd)
+GRAD_TOL = 1e-3          # multi_gpu_check: relative L2 of the all-reduced gradient vs one rank (north star: <= 1e-3)
 
 
 def parse_args():
@@ -54,27 +53,32 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--res", type=int, default=1024)
-    ap.add_argument("--spp", type=int, default=256)
-    ap.add_argument("--depth", type=int, default=8)
-    ap.add_argument("--tex", type=int, default=1024)
-    ap.add_argument("--integrator", default="path", choices=["path", "direct", "collocated"])
-    ap.add_argument("--ref-spp", type=int, default=2, help="samples per pixel (of --spp) one reference step renders")
-    ap.add_argument("--cpu-spp", type=int, default=32, help="samples per pixel of the cpu_baseline sample")
-    ap.add_argument("--schedule", default="auto", choices=["auto", "wavefront", "megakernel"])
+    ap.add_argument("--config", default="c3", help="BASELINE.json config: c1 | c2 | c3 (default, the metric's) | c4 | c4d | c5")
+    ap.add_argument("--res", type=int, nargs="+", default=None, help="override the config's image size: N (square) or W H")
+    ap.add_argument("--spp", type=int, default=None)
+    ap.add_argument("--depth", type=int, default=None)
+    ap.add_argument("--tex", type=int, default=None)
+    ap.add_argument("--integrator", default=None, choices=["path", "direct", "collocated"])
+    ap.add_argument("--ref-spp", type=int, default=None, help="samples per pixel (of --spp) one reference step renders")
+    ap.add_argument("--cpu-spp", type=int, default=None, help="samples per pixel of the cpu_baseline sample")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "persistent", "wavefront", "megakernel"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-multi-gpu-check", action="store_true")
     return ap.parse_args()
 
 
-def workload(args):
-    from tests import scenes
-    models = {"path": scenes.cbox_path_models, "direct": scenes.cbox_direct_models,
-              "collocated": scenes.cbox_collocated_models}[args.integrator]()
-    material = scenes.random_material((args.tex, args.tex), 0)
-    name = (f"cornell-box {args.integrator} (cboxuv.obj + cbox-light.obj) max_depth {args.depth} rr_depth 2, "
-            f"{args.res}x{args.res}, {args.spp} spp, texture {args.tex}^2 random, fwd seed 0 / bwd seed 1, d_image=1")
-    return models, scenes.CBOX_CAMERA, material, name
+def get_workload(args):
+    from bench import scenes
+    res = None
+    if args.res:
+        res = (args.res[0], args.res[0]) if len(args.res) == 1 else (args.res[0], args.res[1])
+    w = scenes.workload(args.config, res=res, spp=args.spp, depth=args.depth, tex=args.tex, integrator=args.integrator)
+    if args.ref_spp:
+        w.ref_its = (0, min(args.ref_spp, w.spp))
+    if args.cpu_spp:
+        w.cpu_its = (0, min(args.cpu_spp, w.spp))
+    return w
 
 
 # ------------------------------------------------------------------------------------------------
@@ -124,37 +128,72 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def algorithmic_bytes(c: dict, pixels: int) -> int:
-    """Σ bytes the hot path has to touch for the counted work."""
-    return (c["nodes_visited"] * B_NODE + c["tris_tested"] * B_TRI + c["shaded_vertices"] * (B_SHADE + B_LIGHT + B_SAMPLER_VERTEX)
-            + c["grad_scatters"] * B_SCATTER + c["camera_samples"] * B_CAMERA + pixels * B_PIXEL)
-
-
 # ------------------------------------------------------------------------------------------------
+def oracle_scene(w):
+    from oracle import oracle as o
+    o.build()
+    o.lib().zo_set_num_threads(os.cpu_count() or 1)      # torchrun sets OMP_NUM_THREADS=1 for its workers
+    sc = o.OracleScene(w.models())
+    env = w.envmap()
+    if env is not None:
+        sc.set_envmap(env)
+    return o, sc
+
+
+def oracle_step(w, sc, material, res, its, lights):
+    """One bounded CPU step: forward + adjoint over samples `its` of every pixel of a `res` image, for `lights`
+    renders of a light-stage loop (1 otherwise)."""
+    from bench import scenes
+    from zdr_b200._abi import INTEGRATORS, make_params
+    integ = INTEGRATORS[w.integrator]
+    d_img = np.ones((res[1], res[0], 4), np.float32)
+    for k in range(max(1, lights)):
+        if w.lights:
+            sc.update_lights(scenes.light_stage_emissions(k, w.lights))
+        pf = make_params(w.camera, res, material.shape, w.spp, 0, max_depth=w.depth, its=its)
+        pb = make_params(w.camera, res, material.shape, w.spp, 1, max_depth=w.depth, its=its)
+        sc.render_forward(integ, pf, material)
+        sc.render_backward(integ, pb, material, d_img)
+
+
+def cpu_sample_text(w, res, its, lights, rays, dt=None):
+    s = f"{res[0]}x{res[1]}, samples [{its[0]},{its[1]}) of {w.spp} spp per pixel"
+    if w.lights:
+        s += f", {lights} of {w.lights} lights"
+    s += f", fwd+bwd, {rays} rays" + (f" in {dt:.2f} s" if dt is not None else "/step")
+    return s
+
+
 def run_reference(args):
-    """The reference's CPU implementation of the path: the plain-C restatement in oracle/
-    (the reference itself is LuisaCompute-JIT Python and cannot be installed here),
-    all host threads, each step = samples [0, ref_spp) of every pixel of the same workload."""
+    """The reference's CPU implementation of the path: the plain-C restatement in oracle/ (the reference itself is
+    LuisaCompute-JIT Python and cannot be installed here; bench/ref_luisa.py runs it where it can), all host
+    threads, each step = a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as o
-    from zdr_b200._abi import INTEGRATORS, make_params
-    o.build()
-    o.lib().zo_set_num_threads(os.cpu_count() or 1)      # torchrun sets OMP_NUM_THREADS=1 for its workers
-    models, cam, material, name = workload(args)
-    sc = o.OracleScene(models)
-    integ = INTEGRATORS[args.integrator]
-    k = min(args.ref_spp, args.spp)
-    pf = make_params(cam, (args.res, args.res), material.shape, args.spp, 0, max_depth=args.depth, its=(0, k))
-    pb = make_params(cam, (args.res, args.res), material.shape, args.spp, 1, max_depth=args.depth, its=(0, k))
-    d_img = np.ones((args.res, args.res, 4), np.float32)
+    try:                                   # the true reference, where luisa-python and the pbrt tables exist (bench/ref_luisa.py)
+        import luisa  # noqa: F401
+        if args.config in ("c1", "c2", "c3"):
+            cmd = [sys.executable, os.path.join(ROOT, "bench", "ref_luisa.py"), "--config", args.config, "--steps", str(args.steps),
+                   "--warmup", str(args.warmup), "--gpus", str(args.gpus)] + (["--res", str(args.res[0])] if args.res else [])
+            out = subprocess.run(cmd, capture_output=True, text=True).stdout
+            lines = [l for l in out.splitlines() if l.startswith("{") and "unavailable" not in l]
+            if lines:
+                print(lines[-1])
+                return
+    except ImportError:
+        pass
+    w = get_workload(args)
+    o, sc = oracle_scene(w)
+    material = w.material()
+    its = w.ref_its or (0, w.spp)
+    res = w.cpu_res
+    lights = min(w.lights, 1) if w.lights else 0
     times, rays = [], 0
     for i in range(args.warmup + args.steps):
         sc.reset_ray_counters()
         t0 = time.perf_counter()
-        sc.render_forward(integ, pf, material)
-        sc.render_backward(integ, pb, material, d_img)
+        oracle_step(w, sc, material, res, its, lights)
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
@@ -162,43 +201,50 @@ def run_reference(args):
     ms = 1e3 * sum(times) / len(times)
     value = rays / (ms * 1e-3) / 1e6
     cores = o.lib().zo_num_threads()
-    sample = f"{args.res}x{args.res}, samples [0,{k}) of {args.spp} spp per pixel, fwd+bwd, {rays} rays/step"
+    sample = cpu_sample_text(w, res, its, lights, rays)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": name, "sample_per_step": sample},
+        "dtype": "f32", "data": "synthetic", "config": {"workload": w.name(), "sample_per_step": sample},
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def cpu_baseline(args):
-    from oracle import oracle as o
-    from zdr_b200._abi import INTEGRATORS, make_params
-    o.build()
-    o.lib().zo_set_num_threads(os.cpu_count() or 1)
-    models, cam, material, _ = workload(args)
-    sc = o.OracleScene(models)
-    integ = INTEGRATORS[args.integrator]
-    k = min(args.cpu_spp, args.spp)
-    pf = make_params(cam, (args.res, args.res), material.shape, args.spp, 0, max_depth=args.depth, its=(0, k))
-    pb = make_params(cam, (args.res, args.res), material.shape, args.spp, 1, max_depth=args.depth, its=(0, k))
-    d_img = np.ones((args.res, args.res, 4), np.float32)
+def cpu_baseline(w):
+    o, sc = oracle_scene(w)
+    material = w.material()
+    its = w.cpu_its or (0, w.spp)
+    lights = min(w.lights, 2) if w.lights else 0
     sc.reset_ray_counters()
     t0 = time.perf_counter()
-    sc.render_forward(integ, pf, material)
-    sc.render_backward(integ, pb, material, d_img)
+    oracle_step(w, sc, material, w.cpu_res, its, lights)
     dt = time.perf_counter() - t0
     rays = sum(sc.ray_counters())
     return {"value": round(rays / dt / 1e6, 3), "unit": UNIT, "cores": o.lib().zo_num_threads(), "kind": "port",
-            "sample": f"{args.res}x{args.res}, samples [0,{k}) of {args.spp} spp per pixel, fwd+bwd, {rays} rays in {dt:.2f} s"}
+            "sample": cpu_sample_text(w, w.cpu_res, its, lights, rays, dt)}
 
 
 # ------------------------------------------------------------------------------------------------
+def issue_profile(key: str, schedule: str):
+    """Latest committed ncu launch-list summary of this config and schedule (tools/issue_summary.py): warp / thread
+    instruction counts and DRAM bytes of one step, with the ray count they belong to."""
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_issue_*.json"))):
+        try:
+            rec = json.load(open(path))
+        except (OSError, ValueError):
+            continue
+        if rec.get("config") == key and rec.get("schedule", "auto") == schedule:
+            best = (path, rec)
+    return best
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    from bench import scenes
     from zdr_b200 import Scene
     from zdr_b200._abi import INTEGRATORS, check, make_params
 
@@ -211,35 +257,52 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    models, cam, mat_np, name = workload(args)
-    scene = Scene(models, integrator=args.integrator, device=local_rank)
-    scene.camera = cam.copy()
-    scene.max_depth = args.depth
+    w = get_workload(args)
+    t0 = time.perf_counter()
+    scene = Scene(w.models(), integrator=w.integrator, device=local_rank)
+    env = w.envmap()
+    if env is not None:
+        scene.add_envmap(env)
+    torch.cuda.synchronize(dev)
+    t_scene = time.perf_counter() - t0
+    scene.camera = w.camera.copy()
+    scene.max_depth = w.depth
     scene.schedule = args.schedule
-    if world > 1:
-        scene.shard = (rank, world)
     lib, h = scene._lib, scene._handle
-    integ = INTEGRATORS[args.integrator]
-    res = (args.res, args.res)
+    integ = INTEGRATORS[w.integrator]
+    res = w.res
+    mat_np = w.material()
+    loops = max(1, w.lights)
     shard = (rank, world) if world > 1 else None
-    pf = make_params(cam, res, mat_np.shape, args.spp, 0, max_depth=args.depth, shard=shard, schedule=args.schedule)
-    pb = make_params(cam, res, mat_np.shape, args.spp, 1, max_depth=args.depth, shard=shard, schedule=args.schedule)
+
+    def params(seed, shard_=shard, stats=False):
+        return make_params(w.camera, res, mat_np.shape, w.spp, seed, max_depth=w.depth, shard=shard_, stats=stats, schedule=args.schedule)
+    pf, pb = params(0), params(1)
     material = torch.from_numpy(mat_np).to(dev)
-    image = torch.zeros((args.res, args.res, 4), dtype=torch.float32, device=dev)
+    image = torch.zeros((res[1], res[0], 4), dtype=torch.float32, device=dev)
     d_image = torch.ones_like(image)
     d_material = torch.zeros_like(material)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
 
+    def render_pair(pf_, pb_, img, dmat):
+        for k in range(loops):
+            if w.lights:
+                scene.update_lights(scenes.light_stage_emissions(k, w.lights))      # test_lightstage.py:46-54
+            check(lib.zdr_render_forward(h, integ, C.byref(pf_), material.data_ptr(), img.data_ptr(), stream.cuda_stream))
+            if k == loops - 1 and render_pair.ev:
+                render_pair.ev[1].record(stream)
+            check(lib.zdr_render_backward(h, integ, C.byref(pb_), material.data_ptr(), d_image.data_ptr(), dmat.data_ptr(),
+                                          stream.cuda_stream))
+    render_pair.ev = None
+
     def step(ev=None):
         d_material.zero_()
         if ev:
             ev[0].record(stream)
-        check(lib.zdr_render_forward(h, integ, C.byref(pf), material.data_ptr(), image.data_ptr(), stream.cuda_stream))
-        if ev:
-            ev[1].record(stream)
-        check(lib.zdr_render_backward(h, integ, C.byref(pb), material.data_ptr(), d_image.data_ptr(), d_material.data_ptr(),
-                                      stream.cuda_stream))
+        render_pair.ev = ev
+        render_pair(pf, pb, image, d_material)
+        render_pair.ev = None
         if ev:
             ev[2].record(stream)
         if world > 1:
@@ -252,17 +315,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # one instrumented pass (untimed): rays per step and the algorithmic bytes of each kernel
+    # one instrumented pass (untimed): rays per step
     scene.reset_counters()
-    pfs = make_params(cam, res, mat_np.shape, args.spp, 0, max_depth=args.depth, shard=shard, stats=True, schedule=args.schedule)
-    pbs = make_params(cam, res, mat_np.shape, args.spp, 1, max_depth=args.depth, shard=shard, stats=True, schedule=args.schedule)
-    check(lib.zdr_render_forward(h, integ, C.byref(pfs), material.data_ptr(), image.data_ptr(), stream.cuda_stream))
-    c_fwd = scene.counters()
-    scene.reset_counters()
-    check(lib.zdr_render_backward(h, integ, C.byref(pbs), material.data_ptr(), d_image.data_ptr(), d_material.data_ptr(),
-                                  stream.cuda_stream))
-    c_bwd = scene.counters()
-    rays_local = c_fwd["closest_rays"] + c_fwd["any_rays"] + c_bwd["closest_rays"] + c_bwd["any_rays"]
+    pfs, pbs = params(0, stats=True), params(1, stats=True)
+    render_pair(pfs, pbs, image, d_material)
+    c_all = scene.counters()
+    rays_local = c_all["closest_rays"] + c_all["any_rays"]
     for _ in range(max(0, args.warmup - 1)):
         step()
     barrier()
@@ -279,118 +337,140 @@ def run_ours(args):
     barrier()
     launches = int(lib.zdr_kernel_launches()) - launches0
     clock_rec = clocks.stop() if rank == 0 else None
-    t_fwd = sum(e[0].elapsed_time(e[1]) for e in evs)
-    t_bwd = sum(e[1].elapsed_time(e[2]) for e in evs)
     t_all = sum(e[0].elapsed_time(e[3]) for e in evs)
+    t_render = sum(e[0].elapsed_time(e[2]) for e in evs)
+    # forward / adjoint split of the LAST render of the step (the only one of a non-light-stage config)
+    t_bwd_last = sum(e[1].elapsed_time(e[2]) for e in evs)
+
+    # ---- multi-GPU correctness (outside the timed region): all-reduced image + gradient vs a one-rank render
+    mg_check = None
+    if world > 1 and not args.no_multi_gpu_check:
+        image.zero_()
+        step()                                       # sharded image (own rows) + all-reduced gradient of every rank
+        dist.all_reduce(image)
+        if rank == 0:
+            img1 = torch.zeros_like(image)
+            g1 = torch.zeros_like(material)
+            render_pair(params(0, None), params(1, None), img1, g1)
+            torch.cuda.synchronize(dev)
+            bits = bool(torch.equal(image.view(torch.int32), img1.view(torch.int32)))
+            i_rel = float((image - img1).norm() / img1.norm().clamp_min(1e-30))
+            g_rel = float((d_material - g1).norm() / g1.norm().clamp_min(1e-30))
+            mg_check = {"image_bits_equal": bits, "image_rel_l2": i_rel, "grad_rel_l2": g_rel, "grad_tol": GRAD_TOL,
+                        "ok": bool(bits and g_rel <= GRAD_TOL),
+                        "what": f"{world}-rank tile-sharded render, all_reduce(image) and all_reduce(d_material), against rank 0 rendering the whole job alone"}
+        barrier()
 
     # ---- e2e: torch surface, host buffers in the timed region
-    e2e = None
+    t_e2e = 0.0
     if not args.no_e2e:
         host_mat = torch.from_numpy(mat_np).pin_memory()
         host_grad = torch.empty_like(host_mat).pin_memory()
+        if world > 1:
+            scene.shard = (rank, world)
 
         def e2e_step():
             m = host_mat.to(dev, non_blocking=True).requires_grad_()
-            img = scene.render(m, res=res, spp=args.spp, seed=0)
-            loss = img.sum()
-            loss.backward()
+            loss_v = 0.0
+            for k in range(loops):
+                if w.lights:
+                    scene.update_lights(scenes.light_stage_emissions(k, w.lights))
+                img = scene.render(m, res=res, spp=w.spp, seed=0)
+                loss = img.sum()
+                loss.backward()
+                loss_v += float(loss.item())
             g = m.grad
             if world > 1:
                 dist.all_reduce(g)
             host_grad.copy_(g, non_blocking=True)
-            return float(loss.item())
-        for _ in range(1):
+            torch.cuda.current_stream(dev).synchronize()
+            return loss_v
+        for _ in range(2):
             e2e_step()
         barrier()
+        n_e2e = max(1, args.steps)
         t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 2))
         for _ in range(n_e2e):
             e2e_step()
         barrier()
         t_e2e = (time.perf_counter() - t0) / n_e2e
+        scene.shard = None
     # ---- reductions over ranks
-    stats = torch.tensor([t_all, t_fwd, t_bwd, float(rays_local), t_e2e if not args.no_e2e else 0.0], dtype=torch.float64, device=dev)
+    stats = torch.tensor([t_all, t_render, t_bwd_last, float(rays_local), t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        t_all, t_fwd, t_bwd, t_e2e = mx[0].item(), mx[1].item(), mx[2].item(), mx[4].item()
+        t_all, t_render, t_bwd_last, t_e2e = mx[0].item(), mx[1].item(), mx[2].item(), mx[4].item()
         rays_total = sm[3].item()
     else:
         rays_total = float(rays_local)
-        t_e2e = stats[4].item()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     ms_per_step = t_all / args.steps
+    ms_render = t_render / args.steps
     value = rays_total / (ms_per_step * 1e-3) / 1e6
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    sm_max = 1965.0
     if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        pk = json.load(open(peaks_path))
+        hbm_peak, peak_src = float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        sm_max = float(pk.get("sm_max_mhz", sm_max))
     else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    pixels_local = (args.res * args.res + world - 1) // world
-    bytes_bwd = algorithmic_bytes(c_bwd, pixels_local)
-    ms_bwd = t_bwd / args.steps
-    achieved = bytes_bwd / (ms_bwd * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        rec = json.load(open(tpath))
-        if rec.get("res") == args.res and rec.get("integrator") == args.integrator and world == 1:
-            # DRAM bytes of one adjoint pass measured with ncu at rec["spp"]; batches of 16 samples are identical, so it scales with spp
-            traffic = int(rec["backward_dram_bytes"] * args.spp / rec["spp"])
-    # the other two denominators SURVEY.md 8(d) asks for, measured by tools/microbench (profiles/r01q_microbench.json)
-    other = None
-    mpath = os.path.join(ROOT, "profiles", "r01q_microbench.json")
-    if os.path.exists(mpath):
-        mb = json.load(open(mpath))
-        l2_64 = next(g["gb_per_s"] for g in mb["gather"] if g["working_set_mib"] == 16 and g["record_bytes"] == 64)
-        red_peak = next(r["gops_per_s"] for r in mb["red"] if r["op"].endswith("v4.f32") and r["addresses"].startswith("random"))
-        red_rate = c_bwd["red_v4"] / (ms_bwd * 1e-3) / 1e9
-        other = {"l2_gather_peak_gbs_64B_records": l2_64, "achieved_over_l2_gather": round(achieved / l2_64, 3),
-                 "red_v4_g_per_s": round(red_rate, 2), "red_v4_peak_g_per_s": red_peak, "red_frac": round(red_rate / red_peak, 4),
-                 "binding": ("none of the three: the BVH (4 KB) is L1-resident, texel gathers are ~2 % of the L2 gather rate and the scatter "
-                             "~2 % of the reduction rate; the stage kernels issue 60-76 % of their cycles (ncu, profiles/r01m) at 19-30 of 32 "
-                             "lanes, i.e. the pass is bound by instruction issue under divergence, with HBM latency on the path state next")}
-    wavefront = args.integrator == "path" and args.schedule != "megakernel" and (args.schedule == "wavefront" or pixels_local * args.spp >= 1 << 21)
-    if wavefront:
-        kernel_name = ("adjoint pass of the wavefront path tracer: per batch k_wf_generate + 2*depth x [k_wf_trace<closest>, k_wf_shade_a, "
-                       "k_wf_trace<any>, k_wf_shade_b] + k_wf_restart (PRB replay + adjoint walk + gradient scatter); two half-batches "
-                       "run concurrently on two streams")
-    else:
-        kernel_name = f"adjoint kernel of the {args.integrator} integrator (k_path<BWD> / k_backward: replay + adjoint + gradient scatter)"
+        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    num_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    issue_peak = num_sms * 4 * sm_max * 1e6 / 1e9            # G warp-instructions / s: one per scheduler per clock
+    roof = {"bound": "issue", "kernel": "all kernels of one step (forward + adjoint pass)", "achieved": None, "peak": round(issue_peak, 1),
+            "unit": "Gwarp-inst/s", "frac": None, "traffic": None,
+            "peak_source": f"{num_sms} SMs x 4 warp schedulers x {sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz)",
+            "note": ("nothing here is a dense contraction and the Cornell-box working set (tree 4 KB, texture 16 MiB, tables 5.5 MiB) is "
+                     "cache-resident: ncu shows the step bound by warp-instruction issue under divergence, not by HBM. `achieved` = warp "
+                     "instructions of one step (ncu smsp__inst_executed.sum over the step's launches, committed profile, scaled by the live "
+                     "ray count) / live CUDA-event time; `hbm` = measured DRAM bytes of the step against the HBM copy bandwidth")}
+    prof = issue_profile(w.key, args.schedule)
+    if prof is not None and world == 1:
+        path, rec = prof
+        scale = rays_total / max(rec["rays_per_step"], 1)
+        inst = rec["warp_inst_per_step"] * scale
+        dram = rec["dram_bytes_per_step"] * scale
+        ach = inst / (ms_render * 1e-3) / 1e9
+        roof.update({"achieved": round(ach, 1), "frac": round(ach / issue_peak, 4), "traffic": int(dram),
+                     "lanes_per_warp_inst": rec.get("lanes_per_warp_inst"),
+                     "warp_inst_per_ray": round(rec["warp_inst_per_step"] / max(rec["rays_per_step"], 1), 2),
+                     "hbm": {"achieved": round(dram / (ms_render * 1e-3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
+                             "frac": round(dram / (ms_render * 1e-3) / 1e9 / hbm_peak, 4), "peak_source": peak_src},
+                     "source": os.path.relpath(path, ROOT), "scaled_by_rays": round(scale, 4)})
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": f"tile-dp{world}",
-                   "rays_per_step": int(rays_total), "paths_per_step": 2 * args.res * args.res * args.spp,
-                   "ms_forward": round(t_fwd / args.steps, 3), "ms_backward": round(ms_bwd, 3),
+        "config": {"workload": w.name(), "config": w.key, "schedule": args.schedule,
+                   "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": f"tile-dp{world}",
+                   "sampler_tables": scene.sampler_tables_provenance, "prb_mode": scene.prb_mode,
+                   "rays_per_step": int(rays_total), "camera_samples_per_step": 2 * res[0] * res[1] * w.spp * loops,
+                   "ms_render": round(ms_render, 3), "ms_backward_last_render": round(t_bwd_last / args.steps, 3),
                    "ms_each_step_rank0": [round(e[0].elapsed_time(e[3]), 2) for e in evs],
-                   "ms_allreduce": round((t_all - t_fwd - t_bwd) / args.steps, 3),
-                   "bvh_nodes_per_ray": round((c_fwd["nodes_visited"] + c_bwd["nodes_visited"]) / max(rays_local, 1), 2),
-                   "tris_per_ray": round((c_fwd["tris_tested"] + c_bwd["tris_tested"]) / max(rays_local, 1), 2),
-                   "red_v4_per_scatter": round(c_bwd["red_v4"] / max(c_bwd["grad_scatters"], 1), 3)},
+                   "ms_allreduce": round((t_all - t_render) / args.steps, 3),
+                   "red_v4_per_scatter": round(c_all["red_v4"] / max(c_all["grad_scatters"], 1), 4),
+                   "scene_build_s": round(t_scene, 3), "triangles": scene.triangle_count},
         "clocks": clock_rec,
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": kernel_name,
-                     "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_bwd),
-                     "ms_per_launch": round(ms_bwd, 3), "other_denominators": other,
-                     "note": ("algorithmic bytes = BVH nodes/triangles visited + shading records + texels + scatter footprints (DESIGN.md 6); on "
-                              "the Cornell box these are L1/L2 resident. `traffic` = DRAM bytes ncu measured for the same pass: with the "
-                              "wavefront schedule it is the path state streamed through HBM between stages")},
+        "roofline": roof,
     }
+    if mg_check is not None:
+        out["multi_gpu_check"] = mg_check
     if not args.no_e2e:
         out["e2e"] = {"value": round(rays_total / t_e2e / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(mat_np.nbytes),
-                      "d2h_bytes_per_step": int(mat_np.nbytes) + 4, "ms_per_step": round(t_e2e * 1e3, 3),
+                      "d2h_bytes_per_step": int(mat_np.nbytes) + 4 * loops, "ms_per_step": round(t_e2e * 1e3, 3),
                       "api": "zdr_b200.Scene.render(...).sum().backward() with pinned-host material in, gradient + loss out"}
     if not args.no_cpu_baseline and world == 1:          # reported at N=1 only (it times the host, not the GPUs)
-        out["cpu_baseline"] = cpu_baseline(args)
-    print(json.dumps(out))
+        out["cpu_baseline"] = cpu_baseline(w)
+    print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if mg_check is not None and not mg_check["ok"]:
+        sys.exit(f"bench.py: multi_gpu_check failed: {mg_check}")
 
 
 def main():

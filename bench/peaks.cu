@@ -1,4 +1,4 @@
-// microbench.cu — the two denominators SURVEY.md §8(d) asks for besides the HBM copy bandwidth of
+// peaks.cu (was tools/microbench.cu) — the two denominators SURVEY.md §8(d) asks for besides the HBM copy bandwidth of
 // MEASURED_PEAKS.json: random-sector gather bandwidth (the access pattern of BVH nodes, triangle records,
 // texels and sampler tables) and float reduction (red.global.add) throughput (the gradient scatter).
 //

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from oracle import oracle as o
-from tests import scenes
+from bench import scenes
 from zdr_b200 import Scene
 from zdr_b200._abi import INTEGRATORS, check, make_params
 

@@ -127,6 +127,9 @@ int zdr_scene_add_mesh(zdr_scene* s, const float* verts_nx8_host, int nv,
  * up to 16 K triangles on the host (full-sweep SAH), above that on the GPU (flatten kernel, Morton clusters,
  * per-cluster binned SAH, SAH tree over the clusters).  May be called again after more zdr_scene_add_mesh calls. */
 int zdr_scene_commit(zdr_scene* s);
+/* Back to the state after zdr_scene_create: Scene.load_geometry builds a fresh luisa.Accel() and BindlessArray()
+ * on every call (render.py:74-76), so a second load_geometry replaces the instances instead of appending. */
+int zdr_scene_clear(zdr_scene* s);
 /* Scene.update_lights (render.py:130-148): n must equal the instance count. */
 int zdr_scene_set_emissions(zdr_scene* s, const float* emission_nx3_host, int n);
 /* Scene.add_envmap -> load_envmap (render.py:150-156, envmap.py:116-202). rgba float, h rows. */

@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 from zdr_b200._abi import ZdrParams
-from zdr_b200.load_obj import load_mesh
+from zdr_b200.load_obj import load_mesh_python as load_mesh   # the line-by-line Python statement, not the product library
 from zdr_b200.mathtypes import float3, float4x4
 from zdr_b200.tables import get_tables
 

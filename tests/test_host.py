@@ -172,3 +172,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_ref_luisa_hook_reports_unavailable_without_luisa():
+    """bench/ref_luisa.py: upstream zdr on LuisaCompute's CPU backend where `luisa-python` and the pbrt tables
+    exist; in this container it must say why it cannot run, as one JSON line, and exit 0."""
+    import json
+    import subprocess
+    import sys
+    try:
+        import luisa  # noqa: F401
+        pytest.skip("luisa-python is installed here")
+    except ImportError:
+        pass
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench", "ref_luisa.py")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and "luisa" in d["unavailable"]

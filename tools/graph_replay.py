@@ -9,7 +9,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from tests import scenes
+from bench import scenes
 from zdr_b200 import Scene
 from zdr_b200._abi import INTEGRATORS, check, make_params
 

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from tests import scenes
+from bench import scenes
 from zdr_b200 import Scene
 
 ap = argparse.ArgumentParser()

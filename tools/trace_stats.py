@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from tests import scenes
+from bench import scenes
 from zdr_b200 import Scene
 
 for integ, models in (("path", scenes.cbox_path_models()), ("direct", scenes.cbox_direct_models())):

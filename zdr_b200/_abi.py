@@ -17,7 +17,8 @@ ZDR_FLAG_STATS = 1
 ZDR_FLAG_SCATTER_AGGREGATE, ZDR_FLAG_SCATTER_PLAIN = 2, 4
 ZDR_FLAG_WAVEFRONT, ZDR_FLAG_MEGAKERNEL = 8, 16
 ZDR_FLAG_LIGHT_PDF_COUNTS_ENV = 32
-SCHEDULES = {"auto": 0, "wavefront": ZDR_FLAG_WAVEFRONT, "megakernel": ZDR_FLAG_MEGAKERNEL}
+ZDR_FLAG_PERSISTENT = 64
+SCHEDULES = {"auto": 0, "wavefront": ZDR_FLAG_WAVEFRONT, "megakernel": ZDR_FLAG_MEGAKERNEL, "persistent": ZDR_FLAG_PERSISTENT}
 SCATTER_MODES = {"auto": 0, "aggregate": ZDR_FLAG_SCATTER_AGGREGATE, "plain": ZDR_FLAG_SCATTER_PLAIN}
 COUNTER_NAMES = ("closest_rays", "any_rays", "nodes_visited", "tris_tested",
                  "grad_scatters", "red_v4", "shaded_vertices", "camera_samples")
@@ -88,6 +89,7 @@ SIGNATURES = {
     "zdr_scene_destroy": (None, [_vp]),
     "zdr_scene_add_mesh": (C.c_int, [_vp, _f32p, C.c_int, _i32p, C.c_int, _f32p, _f32p]),
     "zdr_scene_commit": (C.c_int, [_vp]),
+    "zdr_scene_clear": (C.c_int, [_vp]),
     "zdr_scene_set_emissions": (C.c_int, [_vp, _f32p, C.c_int]),
     "zdr_scene_set_envmap": (C.c_int, [_vp, _f32p, C.c_int, C.c_int, C.c_int]),
     "zdr_scene_instance_count": (C.c_int, [_vp]),

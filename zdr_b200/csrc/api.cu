@@ -112,13 +112,25 @@ struct zdr_scene {
 
 namespace {
 
-int use_device(int device) {
+// Every entry point makes the scene's device current for its own duration only and puts the caller's
+// device back on return: torch reads its current device with cudaGetDevice, so a Scene on cuda:1 must not
+// silently move a caller that works on cuda:0.
+struct DevGuard {
+    int prev = -1;
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+int use_device(int device, DevGuard& g) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
         return fail(ZDR_ERR_CUDA, "no CUDA device (%s); zdr_b200 has no CPU fallback", cudaGetErrorString(e));
     if (device < 0 || device >= count || device >= kMaxDevices) return fail(ZDR_ERR_ARG, "bad device %d", device);
-    CK(cudaSetDevice(device));
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
+    if (cur != device) {
+        CK(cudaSetDevice(device));
+        if (g.prev < 0) g.prev = cur;
+    }
     return ZDR_OK;
 }
 
@@ -291,7 +303,8 @@ ZDR_EXPORT int zdr_set_sampler_tables(int device, const uint32_t* pmj_host, int 
     if (!pmj_host || !bn_host || sets <= 0 || n <= 0 || ntex <= 0 || res <= 0) return fail(ZDR_ERR_ARG, "bad sampler tables");
     if ((long long)ntex * res * res >= (1ll << 29) || (long long)sets * n >= (1ll << 29))
         return fail(ZDR_ERR_LIMIT, "sampler tables too large (the kernels index them with 32-bit arithmetic)");
-    int rc = use_device(device);
+    DevGuard dev_guard;
+    int rc = use_device(device, dev_guard);
     if (rc) return rc;
     const size_t np = (size_t)sets * n * 2, nb = (size_t)ntex * res * res;
     std::vector<float> pf(np), bf(nb);
@@ -315,7 +328,8 @@ ZDR_EXPORT int zdr_set_sampler_tables(int device, const uint32_t* pmj_host, int 
 ZDR_EXPORT int zdr_scene_create(zdr_scene** out, int device) {
     if (!out) return fail(ZDR_ERR_ARG, "null out");
     *out = nullptr;
-    int rc = use_device(device);
+    DevGuard dev_guard;
+    int rc = use_device(device, dev_guard);
     if (rc) return rc;
     zdr_scene* s = new (std::nothrow) zdr_scene();
     if (!s) return fail(ZDR_ERR_ARG, "out of host memory");
@@ -336,7 +350,8 @@ ZDR_EXPORT int zdr_scene_create(zdr_scene** out, int device) {
 
 ZDR_EXPORT void zdr_scene_destroy(zdr_scene* s) {
     if (!s) return;
-    cudaSetDevice(s->device);
+    DevGuard dev_guard;
+    if (use_device(s->device, dev_guard) != ZDR_OK) return;
     cudaDeviceSynchronize();
     free_bvh(&s->bvh);
     free_envmap(&s->env);
@@ -367,9 +382,28 @@ ZDR_EXPORT int zdr_scene_add_mesh(zdr_scene* s, const float* verts, int nv, cons
     return ZDR_OK;
 }
 
+// Scene.load_geometry starts from a fresh luisa.Accel() / BindlessArray() on every call (render.py:74-76): the
+// instances, the tree and the envmap of an earlier call are dropped.
+ZDR_EXPORT int zdr_scene_clear(zdr_scene* s) {
+    if (!s) return fail(ZDR_ERR_ARG, "scene_clear: null");
+    DevGuard dev_guard;
+    int rc = use_device(s->device, dev_guard);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    s->meshes.clear();
+    free_bvh(&s->bvh);
+    free_envmap(&s->env);
+    cudaFree(s->d_inst); cudaFree(s->d_lights);
+    s->d_inst = nullptr; s->d_lights = nullptr;
+    s->light_count = 0; s->num_tris = 0;
+    s->committed = false;
+    return ZDR_OK;
+}
+
 ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
     if (!s || s->meshes.empty()) return fail(ZDR_ERR_STATE, "commit: empty scene");
-    int rc = use_device(s->device);
+    DevGuard dev_guard;
+    int rc = use_device(s->device, dev_guard);
     if (rc) return rc;
     size_t nt = 0;
     for (Mesh& m : s->meshes) { m.tri_base = (int)nt; nt += m.tris.size() / 3; }
@@ -470,7 +504,8 @@ ZDR_EXPORT int zdr_scene_set_emissions(zdr_scene* s, const float* e3, int n) {  
     // RenderOperator.backward re-applies the forward call's emissions on every step (render.py:218): nothing to
     // upload, and no reason to synchronise the device, when they are what the device already holds
     if (!s->committed || !changed) return ZDR_OK;
-    int rc = use_device(s->device);
+    DevGuard dev_guard;
+    int rc = use_device(s->device, dev_guard);
     if (rc) return rc;
     return upload_lights(s);
 }
@@ -478,7 +513,8 @@ ZDR_EXPORT int zdr_scene_set_emissions(zdr_scene* s, const float* e3, int n) {  
 ZDR_EXPORT int zdr_scene_set_envmap(zdr_scene* s, const float* rgba, int w, int h, int compensate_mis) {
     if (!s || !rgba || w <= 0 || h <= 0) return fail(ZDR_ERR_ARG, "set_envmap: bad arguments");
     if (h != w && w != 2 * h) return fail(ZDR_ERR_ARG, "set_envmap: image must be 1:1 or 2:1 (envmap.py:122-128)");
-    int rc = use_device(s->device);
+    DevGuard dev_guard;
+    int rc = use_device(s->device, dev_guard);
     if (rc) return rc;
     CK(cudaDeviceSynchronize());
     cudaError_t e = build_envmap(rgba, w, h, compensate_mis != 0, s->own_stream, &s->env);
@@ -506,7 +542,8 @@ ZDR_EXPORT int zdr_render_forward(zdr_scene* s, int integrator, const zdr_params
     int rc = check_params(s, integrator, p);
     if (rc) return rc;
     if (!material_dev || !image_dev) return fail(ZDR_ERR_ARG, "render_forward: null buffer");
-    if ((rc = use_device(s->device))) return rc;
+    DevGuard dev_guard;
+    if ((rc = use_device(s->device, dev_guard))) return rc;
     RenderArgs a;
     if ((rc = make_args(s, p, &a))) return rc;
     a.tex.mat = reinterpret_cast<const float4*>(material_dev);
@@ -523,7 +560,8 @@ ZDR_EXPORT int zdr_render_backward(zdr_scene* s, int integrator, const zdr_param
     int rc = check_params(s, integrator, p);
     if (rc) return rc;
     if (!material_dev || !d_image_dev || !d_material_dev) return fail(ZDR_ERR_ARG, "render_backward: null buffer");
-    if ((rc = use_device(s->device))) return rc;
+    DevGuard dev_guard;
+    if ((rc = use_device(s->device, dev_guard))) return rc;
     RenderArgs a;
     if ((rc = make_args(s, p, &a))) return rc;
     a.tex.mat = reinterpret_cast<const float4*>(material_dev);
@@ -540,7 +578,8 @@ ZDR_EXPORT int zdr_render_duvdxy(zdr_scene* s, const zdr_params* p, float* image
     int rc = check_params(s, ZDR_COLLOCATED, p);
     if (rc) return rc;
     if (!image_dev) return fail(ZDR_ERR_ARG, "render_duvdxy: null buffer");
-    if ((rc = use_device(s->device))) return rc;
+    DevGuard dev_guard;
+    if ((rc = use_device(s->device, dev_guard))) return rc;
     RenderArgs a;
     if ((rc = make_args(s, p, &a))) return rc;
     a.image = reinterpret_cast<float4*>(image_dev);
@@ -553,13 +592,15 @@ ZDR_EXPORT int zdr_render_forward_host(zdr_scene* s, int integrator, const zdr_p
     int rc = check_params(s, integrator, p);
     if (rc) return rc;
     if (!material_host || !image_host) return fail(ZDR_ERR_ARG, "render_forward_host: null buffer");
-    if ((rc = use_device(s->device))) return rc;
+    DevGuard dev_guard;
+    if ((rc = use_device(s->device, dev_guard))) return rc;
     const size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4, nimg = (size_t)p->width * p->height * 4;
     CK(s->s_mat.reserve(nmat));
     CK(s->s_img.reserve(nimg));
     cudaStream_t st = s->own_stream;
     CK(cudaMemcpyAsync(s->s_mat.p, material_host, sizeof(float) * nmat, cudaMemcpyHostToDevice, st));
-    if (p->shard_count > 1) CK(cudaMemsetAsync(s->s_img.p, 0, sizeof(float) * nimg, st));      // rows of the other shards
+    // rows of the other shards, and every row when the launch has no samples to render (it0 == it1)
+    if (p->shard_count > 1 || p->it1 <= p->it0) CK(cudaMemsetAsync(s->s_img.p, 0, sizeof(float) * nimg, st));
     if ((rc = zdr_render_forward(s, integrator, p, s->s_mat.p, s->s_img.p, st))) return rc;
     const size_t off = (size_t)p->row0 * p->width * 4, cnt = (size_t)(p->row1 - p->row0) * p->width * 4;
     CK(cudaMemcpyAsync(image_host + off, s->s_img.p + off, sizeof(float) * cnt, cudaMemcpyDeviceToHost, st));
@@ -572,7 +613,8 @@ ZDR_EXPORT int zdr_render_backward_host(zdr_scene* s, int integrator, const zdr_
     int rc = check_params(s, integrator, p);
     if (rc) return rc;
     if (!material_host || !d_image_host || !d_material_host) return fail(ZDR_ERR_ARG, "render_backward_host: null buffer");
-    if ((rc = use_device(s->device))) return rc;
+    DevGuard dev_guard;
+    if ((rc = use_device(s->device, dev_guard))) return rc;
     const size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4, nimg = (size_t)p->width * p->height * 4;
     CK(s->s_mat.reserve(nmat));
     CK(s->s_dmat.reserve(nmat));
@@ -590,7 +632,8 @@ ZDR_EXPORT int zdr_render_backward_host(zdr_scene* s, int integrator, const zdr_
 // ---- instrumentation ------------------------------------------------------------------------
 ZDR_EXPORT int zdr_get_counters(zdr_scene* s, uint64_t out[ZDR_NUM_COUNTERS]) {
     if (!s || !out) return fail(ZDR_ERR_ARG, "get_counters: null");
-    int rc = use_device(s->device);
+    DevGuard dev_guard;
+    int rc = use_device(s->device, dev_guard);
     if (rc) return rc;
     static_assert(C_NUM == ZDR_NUM_COUNTERS, "counter count");
     CK(cudaDeviceSynchronize());
@@ -601,7 +644,8 @@ ZDR_EXPORT uint64_t zdr_kernel_launches(void) { return kernel_launch_count(); }
 
 ZDR_EXPORT int zdr_reset_counters(zdr_scene* s) {
     if (!s) return fail(ZDR_ERR_ARG, "reset_counters: null");
-    int rc = use_device(s->device);
+    DevGuard dev_guard;
+    int rc = use_device(s->device, dev_guard);
     if (rc) return rc;
     CK(cudaDeviceSynchronize());
     CK(cudaMemset(s->d_counters, 0, sizeof(uint64_t) * C_NUM));
@@ -611,7 +655,8 @@ ZDR_EXPORT int zdr_reset_counters(zdr_scene* s) {
 // ---- probes ---------------------------------------------------------------------------------
 ZDR_EXPORT int zdr_probe_trace_closest(zdr_scene* s, const float* rays, int n, int32_t* inst_prim, float* uvt) {
     if (!s || !rays || !inst_prim || !uvt || n < 0) return fail(ZDR_ERR_ARG, "probe_trace_closest: bad arguments");
-    int rc = use_device(s->device);
+    DevGuard dev_guard;
+    int rc = use_device(s->device, dev_guard);
     if (rc) return rc;
     SceneView sc;
     if ((rc = scene_view(s, &sc))) return rc;
@@ -630,7 +675,8 @@ ZDR_EXPORT int zdr_probe_trace_closest(zdr_scene* s, const float* rays, int n, i
 
 ZDR_EXPORT int zdr_probe_trace_any(zdr_scene* s, const float* rays, int n, int32_t* occluded) {
     if (!s || !rays || !occluded || n < 0) return fail(ZDR_ERR_ARG, "probe_trace_any: bad arguments");
-    int rc = use_device(s->device);
+    DevGuard dev_guard;
+    int rc = use_device(s->device, dev_guard);
     if (rc) return rc;
     SceneView sc;
     if ((rc = scene_view(s, &sc))) return rc;
@@ -647,7 +693,8 @@ ZDR_EXPORT int zdr_probe_trace_any(zdr_scene* s, const float* rays, int n, int32
 
 ZDR_EXPORT int zdr_probe_sampler(int device, const int32_t* state, int n, const char* prog, float* out) {
     if (!state || !prog || !out || n < 0) return fail(ZDR_ERR_ARG, "probe_sampler: bad arguments");
-    int rc = use_device(device);
+    DevGuard dev_guard;
+    int rc = use_device(device, dev_guard);
     if (rc) return rc;
     const Tables& t = g_tables[device];
     if (!t.pmj || !t.bn) return fail(ZDR_ERR_STATE, "sampler tables not set for device %d", device);
@@ -676,7 +723,8 @@ ZDR_EXPORT int zdr_probe_render_samples(zdr_scene* s, int integrator, const zdr_
     int rc = check_params(s, integrator, p);
     if (rc) return rc;
     if (!material_host || !out_host) return fail(ZDR_ERR_ARG, "probe_render_samples: null buffer");
-    if ((rc = use_device(s->device))) return rc;
+    DevGuard dev_guard;
+    if ((rc = use_device(s->device, dev_guard))) return rc;
     const size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4, nout = (size_t)p->width * p->height * p->spp * 3;
     CK(s->s_mat.reserve(nmat));
     CK(s->s_misc.reserve(nout));
@@ -698,7 +746,8 @@ ZDR_EXPORT int zdr_probe_render_samples(zdr_scene* s, int integrator, const zdr_
 
 ZDR_EXPORT int zdr_probe_ggx(int device, const float* in, int n, float* out) {
     if (!in || !out || n < 0) return fail(ZDR_ERR_ARG, "probe_ggx: bad arguments");
-    int rc = use_device(device);
+    DevGuard dev_guard;
+    int rc = use_device(device, dev_guard);
     if (rc) return rc;
     if (n == 0) return ZDR_OK;
     float *d_in = nullptr, *d_out = nullptr;

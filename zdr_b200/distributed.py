@@ -74,7 +74,7 @@ class ShardedRenderOperator(torch.autograd.Function):
     def backward(ctx, grad_output):
         material, = ctx.saved_tensors
         res, spp, seed = ctx.args
-        d_material = torch.zeros_like(material)
+        d_material = torch.zeros(material.shape, dtype=material.dtype, device=material.device)
         if ctx.its is not None:
             ctx.bwd(grad_output, d_material, material.detach(), res, spp, seed, None, its=ctx.its)
         else:

@@ -28,15 +28,24 @@ from .tables import get_tables
 _tables_on_device = set()
 
 
-def _ensure_tables(device_index: int):
-    """Uploads the pmj02bn tables once per device (the module-level uploads of pmj02bn.py:9-16)."""
+def _ensure_tables(device_index: int) -> str:
+    """Uploads the pmj02bn tables once per device (the module-level uploads of pmj02bn.py:9-16).
+    Returns their provenance: ``'user:<dir>'`` (real pbrt-v4 tables) or ``'surrogate'`` (tables.py)."""
+    pmj, bn, provenance = get_tables()
     if device_index in _tables_on_device:
-        return
-    pmj, bn, _ = get_tables()
+        return provenance
     lib = load_library()
     check(lib.zdr_set_sampler_tables(device_index, np_ptr(pmj, C.c_uint32), pmj.shape[0], pmj.shape[1],
                                      np_ptr(bn, C.c_uint16), bn.shape[0], bn.shape[1]), "zdr_set_sampler_tables")
     _tables_on_device.add(device_index)
+    return provenance
+
+
+def _aligned16(t: torch.Tensor) -> torch.Tensor:
+    """The kernels read texels / cotangents as 16-byte vectors and scatter with red.global.add.v4.f32: a
+    contiguous view whose storage offset is not a multiple of 4 floats (a slice of a flat parameter vector) would
+    fault.  Such a view is copied once; torch allocations themselves are 512-byte aligned."""
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
 
 
 def _emission3(e) -> float3:
@@ -73,7 +82,8 @@ class Scene:
         self._lib = load_library()
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
-        _ensure_tables(self.device_index)
+        #: 'user:<dir>' when ZDR_TABLES_DIR supplied pbrt-v4's tables, 'surrogate' otherwise (tables.py warns once)
+        self.sampler_tables_provenance = _ensure_tables(self.device_index)
         self._handle = C.c_void_p()
         check(self._lib.zdr_scene_create(C.byref(self._handle), self.device_index), "zdr_scene_create")
         self.loaded_obj = {}
@@ -101,8 +111,11 @@ class Scene:
 
     # ------------------------------------------------------------------ scene assembly
     def load_geometry(self, models):
-        """render.py:73-128."""
+        """render.py:73-128.  As upstream, every call starts from an empty accel / heap (render.py:74-76):
+        a second call REPLACES the instances."""
         lib = self._lib
+        check(lib.zdr_scene_clear(self._handle), "zdr_scene_clear")
+        self.loaded_obj = {}                                                           # render.py:76
         emissions = []
         for obj_file, transform, emission in models:
             if transform is None:
@@ -175,7 +188,7 @@ class Scene:
     def render_forward(self, material, res, spp, seed, integrator: Optional[str] = None, rows=None):
         """``render.py:159-173``: -> ``(H, W, 4)`` float32 cuda tensor, alpha = 1."""
         self._check_material(material)
-        material = material.detach().contiguous()
+        material = _aligned16(material.detach().contiguous())
         image = torch.empty((res[1], res[0], 4), dtype=torch.float32, device=self.device)
         p = self._params(material, res, spp, seed, rows)
         if p.row0 > 0 or p.row1 < p.height or p.shard_count > 1 or p.it1 <= p.it0:
@@ -190,11 +203,15 @@ class Scene:
         """``render.py:176-199``: accumulates into ``d_material``; the adjoint is estimated with
         ``seed+1`` (``render.py:196``)."""
         self._check_material(material)
-        material = material.detach().contiguous()
+        material = _aligned16(material.detach().contiguous())
         d_image = grad_output.reshape((res[0] * res[1], 4)).contiguous()              # render.py:181
         if d_image.dtype != torch.float32:
             d_image = d_image.float()
+        d_image = _aligned16(d_image)
         assert d_material.is_contiguous() and d_material.shape == material.shape
+        if d_material.data_ptr() % 16 != 0:
+            raise ValueError("d_material must be 16-byte aligned (gradients are accumulated with 16-byte vector reductions); "
+                             "pass a tensor of its own, not a view at an odd offset")
         p = self._params(material, res, spp, wrap_i32(int(seed) + 1), rows)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         check(self._lib.zdr_render_backward(self._handle, INTEGRATORS[integrator or self.integrator], C.byref(p),

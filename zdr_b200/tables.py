@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import importlib.util
 import os
+import warnings
 from functools import lru_cache
 from typing import Tuple
 
@@ -116,5 +117,12 @@ def get_tables() -> Tuple[np.ndarray, np.ndarray, str]:
         if got is None:
             raise FileNotFoundError(f"ZDR_TABLES_DIR={d}: no pmj02bn_tables.npz or pmj02tables.py+bluenoise.py")
         return np.ascontiguousarray(got[0]), np.ascontiguousarray(got[1]), f"user:{d}"
+    if os.environ.get("ZDR_TABLES_STRICT", "") not in ("", "0"):
+        raise FileNotFoundError("ZDR_TABLES_STRICT is set and ZDR_TABLES_DIR is not: refusing the surrogate sampler tables")
+    warnings.warn(
+        "zdr_b200: pbrt-v4's PMJ02bn / blue-noise tables are not available (the reference's pmj02tables.py and bluenoise.py are "
+        "missing blobs); using deterministic SURROGATE tables of the same shape.  Sample positions and noise spectrum differ from "
+        "upstream zdr.  Point ZDR_TABLES_DIR at pmj02tables.py + bluenoise.py (or pmj02bn_tables.npz) for the real ones; "
+        "ZDR_TABLES_STRICT=1 turns this warning into an error.", RuntimeWarning, stacklevel=2)
     pmj, bn = make_surrogate_tables()
     return np.ascontiguousarray(pmj), np.ascontiguousarray(bn), "surrogate"
