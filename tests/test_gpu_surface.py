@@ -253,3 +253,58 @@ print("rank", rank, "ok", err)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29671", str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_load_geometry_twice_replaces_the_scene(oracle):
+    """Upstream load_geometry builds a fresh Accel / heap on every call (render.py:74-76): a second call must replace the
+    instances (not append), keep Python's and the library's instance counts equal, and render the NEW scene."""
+    from zdr_b200 import Scene
+    sc = Scene(scenes.cbox_two_light_models(), integrator="direct")
+    assert sc.inst_count == 3 and sc._lib.zdr_scene_instance_count(sc._handle) == 3
+    sc.load_geometry(scenes.cbox_path_models())
+    assert sc.inst_count == 2 and sc._lib.zdr_scene_instance_count(sc._handle) == 2 and sc.light_count == 1
+    sc.update_lights([None, scenes.float3(17, 12, 4)])                                 # render.py:141: len == inst_count
+    sc.camera = scenes.CBOX_CAMERA.copy()
+    mat_np = scenes.random_material((32, 32), 1)
+    img = sc.render(torch.from_numpy(mat_np).cuda(), res=(32, 32), spp=2, seed=3)
+    ref = oracle.OracleScene(scenes.cbox_path_models()).render_forward(INTEGRATORS["direct"], make_params(scenes.CBOX_CAMERA, (32, 32), mat_np.shape, 2, 3), mat_np)
+    assert np.array_equal(img.cpu().numpy(), ref)
+    sc.close()
+
+
+def test_material_view_at_an_odd_offset(scene):
+    """The kernels read 16-byte texels; a contiguous view whose storage offset is not a multiple of 4 floats (a slice of a
+    flat parameter vector) is copied instead of faulting, and its gradient flows back to the flat vector."""
+    base = scenes.random_material((32, 32), 2)
+    flat = torch.zeros(1 + base.size, device="cuda")
+    flat[1:] = torch.from_numpy(base.ravel()).cuda()
+    flat.requires_grad_()
+    view = flat[1:].view(32, 32, 4)
+    assert view.data_ptr() % 16 != 0 and view.is_contiguous()
+    img = scene.render(view, res=(32, 32), spp=2, seed=1)
+    img[..., :3].sum().backward()
+    m = torch.from_numpy(base).cuda().requires_grad_()
+    img2 = scene.render(m, res=(32, 32), spp=2, seed=1)
+    img2[..., :3].sum().backward()
+    assert torch.equal(img, img2)
+    assert rel_l2(flat.grad[1:].cpu().numpy(), m.grad.ravel().cpu().numpy()) < 1e-5 and float(flat.grad[0]) == 0.0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_scene_on_another_device_leaves_the_current_device_alone():
+    """Every C entry point restores the caller's current device (torch reads it with cudaGetDevice)."""
+    from zdr_b200 import Scene
+    torch.cuda.set_device(0)
+    sc = Scene(scenes.cbox_path_models(), integrator="direct", device=1)
+    assert torch.cuda.current_device() == 0
+    sc.camera = scenes.CBOX_CAMERA.copy()
+    mat = torch.from_numpy(scenes.random_material((32, 32), 2)).to("cuda:1").requires_grad_()
+    with torch.cuda.device(1):
+        pass
+    img = sc.render(mat, res=(32, 32), spp=2)
+    assert torch.cuda.current_device() == 0
+    img[..., :3].sum().backward()
+    assert torch.cuda.current_device() == 0 and torch.zeros(1, device="cuda").device.index == 0
+    assert img.device.index == 1 and float(mat.grad.abs().sum()) > 0
+    sc.close()
+    assert torch.cuda.current_device() == 0
