@@ -272,9 +272,12 @@ def test_load_geometry_twice_replaces_the_scene(oracle):
     sc.close()
 
 
-def test_material_view_at_an_odd_offset(scene):
+def test_material_view_at_an_odd_offset():
     """The kernels read 16-byte texels; a contiguous view whose storage offset is not a multiple of 4 floats (a slice of a
     flat parameter vector) is copied instead of faulting, and its gradient flows back to the flat vector."""
+    from zdr_b200 import Scene
+    scene = Scene(scenes.cbox_path_models(), integrator="direct")
+    scene.camera = scenes.CBOX_CAMERA.copy()
     base = scenes.random_material((32, 32), 2)
     flat = torch.zeros(1 + base.size, device="cuda")
     flat[1:] = torch.from_numpy(base.ravel()).cuda()

@@ -5,6 +5,7 @@
 #include <type_traits>
 #include <atomic>
 #include "render.cuh"
+#include "render_common.cuh"
 
 namespace zdr {
 
@@ -29,8 +30,6 @@ struct Ctx {
         tl.red += AGG ? write_bsdf_grad_aggregated(a.tex, uv, g) : write_bsdf_grad(a.tex, uv, g);
     }
 };
-
-ZDR_DEV Ray make_ray(float3 o, float3 d, float tmin, float tmax) { Ray r; r.o = o; r.d = d; r.tmin = tmin; r.tmax = tmax; return r; }
 
 // ------------------------------------------------------------------------------ collocated.py
 template <class CTX>
@@ -61,10 +60,6 @@ ZDR_DEV void collocated_estimator_backward(CTX& c, const Ray& ray, float3 le_gra
     const float inv = 1.0f / hit.t;
     const float li = 1.0f * (inv * inv);
     c.scatter(it.uv, ggx_brdf_grad(wo_local, wo_local, 0.04f, mat.w, le_grad * li));
-}
-
-ZDR_DEV float3 env_emission(const SceneView& sc, float3 dir) {                     // direct.py:24
-    return sc.env_count > 0 ? env_texture(sc, direction_to_uv(dir)) : f3(0.f, 0.f, 0.f);
 }
 
 // ---------------------------------------------------------------------------------- direct.py
@@ -143,27 +138,6 @@ ZDR_DEV float3 direct_walk(CTX& c, const Ray& ray, Sampler& sampler, float3 le_g
     return radiance;
 }
 
-// --------------------------------------------------------------------- camera.py, integrator.py
-ZDR_DEV float tent_warp1(float u) {                                                // camera.py:20-31
-    return u < 0.5f ? 1.0f * (sqrtf(2.0f * u) - 1.0f) : 1.0f * (1.0f - sqrtf(2.0f - 2.0f * u));
-}
-ZDR_DEV Ray camera_sample(const RenderArgs& a, int x, int y, Sampler& sampler) {    // integrator.py:17-25, camera.py:5-17
-    float2 off = sampler_next2f(a.sc, sampler);
-    if (a.use_tent) { off.x = tent_warp1(off.x) + 0.5f; off.y = tent_warp1(off.y) + 0.5f; }
-    float px = 2.0f / (float)a.W * ((float)x + off.x) - 1.0f;
-    float py = 2.0f / (float)a.H * ((float)y + off.y) - 1.0f;
-    py *= (float)a.H / (float)a.W;
-    const float sx = px * a.tan_half_fov, sy = py * a.tan_half_fov;
-    const float3 d = f3(sx * a.cam_right.x - sy * a.cam_up.x + a.cam_fwd.x, sx * a.cam_right.y - sy * a.cam_up.y + a.cam_fwd.y,
-                        sx * a.cam_right.z - sy * a.cam_up.z + a.cam_fwd.z);
-    return make_ray(a.cam_o, normalize(d), 0.0f, 1e30f);
-}
-
-ZDR_DEV unsigned warp_sum(unsigned v) {
-#pragma unroll 1
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 ZDR_DEV void flush_tally(const RenderArgs& a, const Tally& t) {
     const unsigned v[C_NUM] = {t.closest, t.any, t.ts.nodes, t.ts.tris, t.scatter, t.red, t.shaded, t.samples};
 #pragma unroll 1
@@ -434,14 +408,6 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
 #define ZDR_WF_TRACE_GRID_MULT 16
 #endif
 constexpr int kWfThreads = 128;
-constexpr unsigned kWfPhaseBit = 1u << 8;
-
-ZDR_DEV unsigned wf_pack(int depth, int phase, int dimension) { return (unsigned)depth | (phase ? kWfPhaseBit : 0u) | ((unsigned)dimension << 12); }
-ZDR_DEV void wf_pixel(const RenderArgs& a, int pix, int& x, int& y) {
-    const int lr = fastdiv(pix, a.wf.div_W);
-    x = pix - lr * a.W;
-    y = a.row0 + ((lr >> 3) * a.shard_count + a.shard_index) * 8 + (lr & 7);
-}
 ZDR_DEV int wf_stride() { return gridDim.x * blockDim.x; }
 
 template <bool BWD>

@@ -30,6 +30,22 @@ struct WfState {
     size_t set_bytes;
 };
 
+// Persistent per-SM wavefront (persistent.cu, k_pw): one resident CTA per SM keeps a pool of paths in SHARED memory and
+// runs the stages of the wavefront as barrier-separated phases over shared-memory queues.  Nothing but finished samples
+// (forward) leaves the SM.
+struct PwState {
+    float4* R;            // forward: finished samples of the batch, [sample-in-batch * P + pixel] (clamped radiance.xyz | -)
+    unsigned* next;       // work counter of the launch: camera samples handed out so far (zeroed by the launcher)
+    unsigned total;       // P * S camera samples of the batch
+    int P;                // pixels of this launch (width * rows of the shard)
+    FastDiv div_P, div_W; // sample id -> (sample in batch, pixel), pixel -> (row, column)
+    int S, it_base;       // samples per pixel of the batch, first sample index
+    int first, last;      // first / last batch of the launch
+    int pool;             // path slots per CTA
+    int stack_depth;      // SMALL scenes: entries of the per-thread traversal stack in shared memory
+    int bulk_copy;        // SMALL scenes: stage the scene with cp.async.bulk + mbarrier (else a cooperative copy loop)
+};
+
 struct RenderArgs {
     SceneView sc;
     TexView tex;
@@ -45,6 +61,7 @@ struct RenderArgs {
     float* samples_out;       // probe: (H,W,spp,3) un-clamped per-sample radiance, or null
     unsigned long long* counters;
     WfState wf;
+    PwState pw;
 };
 
 // number of kernels this library has launched (render kernels and probes), for bench.py's gpu_launches
@@ -60,6 +77,15 @@ size_t wf_bytes_per_slot();
 constexpr int kWfMaxSets = 4;
 cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaStream_t stream, cudaStream_t* side,
                                   cudaEvent_t* events);
+// persistent shared-memory schedule of the path integrator / PRB adjoint (persistent.cu).  `a.pw.R` (forward) holds
+// pw_forward_slots() float4 records; `counter_dev`: one unsigned per batch, zeroed by the call.
+struct PwPlan {
+    int pool, threads, stack_depth, small, grid;
+    size_t smem_bytes;
+};
+cudaError_t pw_plan(const SceneView& sc, int bvh_depth, int num_sms, PwPlan* out);
+cudaError_t launch_path_persistent(bool backward, RenderArgs a, bool stats, const PwPlan& plan, size_t r_capacity_slots,
+                                   unsigned* counters_dev, int max_batches, cudaStream_t stream);
 cudaError_t launch_duvdxy(const RenderArgs& a, cudaStream_t stream);
 cudaError_t launch_probe_trace(const SceneView& sc, const float* rays_dev, int n, bool any, int* ip_dev,
                                float* uvt_dev, int* occ_dev, cudaStream_t stream);

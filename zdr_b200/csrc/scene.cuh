@@ -47,6 +47,17 @@ struct SceneView {
     int env_w, env_h;
 };
 
+// Loads of scene records (nodes / tris / shade).  Default: read-only global loads.  A translation unit that may stage a small
+// scene in shared memory (persistent.cu) defines ZDR_SCENE_GENERIC_LOADS before including the headers: the same
+// device functions then work on either address space (ld.global.nc on a shared-memory address would fault).
+#ifdef ZDR_SCENE_GENERIC_LOADS
+ZDR_DEV float4 ld_scene(const float4* p) { return *p; }
+ZDR_DEV float ld_scene(const float* p) { return *p; }
+#else
+ZDR_DEV float4 ld_scene(const float4* p) { return __ldg(p); }
+ZDR_DEV float ld_scene(const float* p) { return __ldg(p); }
+#endif
+
 struct Ray { float3 o, d; float tmin, tmax; };
 struct Hit { int inst, prim, slot; float u, v, t; };   // inst < 0: miss; (u,v) weights of v1, v2
 

@@ -32,8 +32,8 @@ struct Interaction { float3 p; float2 uv; float3 ns, ng; };       // interaction
 ZDR_DEV Interaction surface_interact(const SceneView& sc, const Hit& h) {
     const float4* tp = sc.tris + 3 * (size_t)h.slot;
     const float4* sp = sc.shade + 4 * (size_t)h.slot;
-    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-    const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2), s3 = __ldg(sp + 3);
+    const float4 a = ld_scene(tp), b = ld_scene(tp + 1), c = ld_scene(tp + 2);
+    const float4 s0 = ld_scene(sp), s1 = ld_scene(sp + 1), s2 = ld_scene(sp + 2), s3 = ld_scene(sp + 3);
     const float3 p0 = f3(a.x, a.y, a.z), p1 = f3(b.x, b.y, b.z), p2 = f3(c.x, c.y, c.z);
     const float w = 1.0f - h.u - h.v;
     Interaction it;
@@ -388,7 +388,7 @@ ZDR_DEV float3 sample_uniform_triangle(float2 u) {                        // lig
 ZDR_DEV void inst_triangle(const SceneView& sc, int inst, int prim, float3& p0, float3& p1, float3& p2) {
     const int slot = __ldg(sc.slot_of_gid + sc.inst[inst].tri_base + prim);
     const float4* tp = sc.tris + 3 * (size_t)slot;
-    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+    const float4 a = ld_scene(tp), b = ld_scene(tp + 1), c = ld_scene(tp + 2);
     p0 = f3(a.x, a.y, a.z); p1 = f3(b.x, b.y, b.z); p2 = f3(c.x, c.y, c.z);
 }
 ZDR_DEV float3 inst_emission(const SceneView& sc, int inst) {
@@ -438,7 +438,7 @@ ZDR_DEV float sample_light_pdf(const SceneView& sc, float3 origin, const Hit& h,
     const int n = sc.pdf_env_count + sc.light_count;
     const int trig_count = sc.inst[h.inst].tri_count;
     const float4* tp = sc.tris + 3 * (size_t)h.slot;
-    const float4 a = __ldg(tp), b = __ldg(tp + 1), c4 = __ldg(tp + 2);
+    const float4 a = ld_scene(tp), b = ld_scene(tp + 1), c4 = ld_scene(tp + 2);
     const float3 p0 = f3(a.x, a.y, a.z), p1 = f3(b.x, b.y, b.z), p2 = f3(c4.x, c4.y, c4.z);
     const float3 dd = p - origin;
     const float3 wi_light = normalize(dd);

@@ -58,9 +58,9 @@ ZDR_DEV RayPre ray_pre(float3 o, float3 d) {
 // each); the permuted components are fetched with per-lane offsets instead of being selected
 // out of vector registers (two FSEL per component cost more issue slots than the loads).
 ZDR_DEV bool tri_test(const RayPre& rp, const float* __restrict__ tp, float tmin, float& t_out, float& u_out, float& v_out) {
-    const float Akx = __ldg(tp + rp.kx) - rp.okx, Aky = __ldg(tp + rp.ky) - rp.oky, Akz = __ldg(tp + rp.kz) - rp.okz;
-    const float Bkx = __ldg(tp + 4 + rp.kx) - rp.okx, Bky = __ldg(tp + 4 + rp.ky) - rp.oky, Bkz = __ldg(tp + 4 + rp.kz) - rp.okz;
-    const float Ckx = __ldg(tp + 8 + rp.kx) - rp.okx, Cky = __ldg(tp + 8 + rp.ky) - rp.oky, Ckz = __ldg(tp + 8 + rp.kz) - rp.okz;
+    const float Akx = ld_scene(tp + rp.kx) - rp.okx, Aky = ld_scene(tp + rp.ky) - rp.oky, Akz = ld_scene(tp + rp.kz) - rp.okz;
+    const float Bkx = ld_scene(tp + 4 + rp.kx) - rp.okx, Bky = ld_scene(tp + 4 + rp.ky) - rp.oky, Bkz = ld_scene(tp + 4 + rp.kz) - rp.okz;
+    const float Ckx = ld_scene(tp + 8 + rp.kx) - rp.okx, Cky = ld_scene(tp + 8 + rp.ky) - rp.oky, Ckz = ld_scene(tp + 8 + rp.kz) - rp.okz;
     const float Ax = fmaf(-rp.Sx, Akz, Akx), Ay = fmaf(-rp.Sy, Akz, Aky);
     const float Bx = fmaf(-rp.Sx, Bkz, Bkx), By = fmaf(-rp.Sy, Bkz, Bky);
     const float Cx = fmaf(-rp.Sx, Ckz, Ckx), Cy = fmaf(-rp.Sy, Ckz, Cky);
@@ -128,7 +128,7 @@ static __device__ __noinline__ float4 trace_packed(const float4* __restrict__ no
     for (;;) {
         while (link >= 0) {                      // inner nodes
             const float4* n = nodes + 4 * (size_t)link;
-            const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
+            const float4 n0 = ld_scene(n), n1 = ld_scene(n + 1), n2 = ld_scene(n + 2), n3 = ld_scene(n + 3);
             if (STATS) st->nodes++;
             float t0, t1;
             // ties on t must stay reachable: cull with <= best
@@ -158,7 +158,7 @@ static __device__ __noinline__ float4 trace_packed(const float4* __restrict__ no
                         if (t < tmax) return make_float4(__int_as_float(first + k), u, v, t);
                         continue;
                     }
-                    const int gid = __float_as_int(__ldg(tp + 3));
+                    const int gid = __float_as_int(ld_scene(tp + 3));
                     // smallest t wins; equal t goes to the lowest scene-order triangle id, which is
                     // what the oracle's in-order scan with a strict '<' keeps
                     if (t < best || (hit_slot >= 0 && t == best && gid < best_gid)) {
@@ -182,8 +182,8 @@ ZDR_DEV Hit trace(const SceneView& sc, const Ray& ray, TraceStats& st) {
     hit.inst = -1; hit.prim = -1;
     if (!ANY && hit.slot >= 0) {
         const float4* tp = sc.tris + 3 * (size_t)hit.slot;
-        hit.inst = __float_as_int(__ldg(tp + 1).w);
-        hit.prim = __float_as_int(__ldg(tp + 2).w);
+        hit.inst = __float_as_int(ld_scene(tp + 1).w);
+        hit.prim = __float_as_int(ld_scene(tp + 2).w);
     } else if (ANY && hit.slot >= 0) {
         hit.inst = 0;
     }
