@@ -93,6 +93,9 @@ typedef struct zdr_params {
  * machine below that. Both produce bit-identical images. */
 #define ZDR_FLAG_WAVEFRONT 8
 #define ZDR_FLAG_MEGAKERNEL 16
+/* persistent schedule: one resident CTA per SM, path state and ray queues in SHARED memory, the stages as phases of one
+ * kernel per pass (persistent.cu); default from 2^17 camera samples per launch on.  Bit-identical images again. */
+#define ZDR_FLAG_PERSISTENT 64
 /* MIS weight of a BSDF-sampled emitter hit in a scene that has BOTH mesh lights and an envmap: the reference's
  * sample_light_pdf divides by light_count only (light.py:89) while sample_light picks among
  * env_count + light_count lights (light.py:26), so the two densities disagree by (n_mesh + 1) / n_mesh.
@@ -175,6 +178,10 @@ int zdr_get_counters(zdr_scene* s, uint64_t out[ZDR_NUM_COUNTERS]);
 int zdr_reset_counters(zdr_scene* s);
 /* number of CUDA kernels this library has launched so far in this process (render + probe kernels) */
 uint64_t zdr_kernel_launches(void);
+/* profile of the scene's last persistent-schedule launch (only filled when the environment has ZDR_PW_PROFILE=1): SM cycles
+ * summed over the CTAs for [0] claim + regenerate [1] extend [2] shade A [3] shadow [4] shade B, [5] rounds, [6] live
+ * paths summed over rounds, [7] total cycles.  Blocks until the launch finished. */
+int zdr_debug_phase_cycles(zdr_scene* s, uint64_t out[8]);
 
 /* --- probes (parity tests only; small n). All pointers HOST. ---------------------------- */
 /* closest hit for n rays (o.xyz, d.xyz, tmin, tmax) -> inst, prim, bary u, v, t (inst=-1: miss) */

@@ -48,6 +48,11 @@ def test_c3_full_size_partitions_and_schedules(c3):
     # the one-kernel schedule on a band of rows equals the wavefront schedule's rows
     band = g.forward(ZDR_PATH, make_params(scenes.CBOX_CAMERA, (1024, 1024), mat.shape, 256, 0, rows=(300, 332), schedule="megakernel", **kw), mat)
     assert np.array_equal(bits(band[300:332]), bits(full[300:332]))
+    # every schedule renders the same full-size image: HBM wavefront, persistent shared-memory pools
+    for sched in ("wavefront", "persistent"):
+        kw2 = dict(kw, schedule=sched)
+        img = g.forward(ZDR_PATH, make_params(scenes.CBOX_CAMERA, (1024, 1024), mat.shape, 256, 0, **kw2), mat)
+        assert np.array_equal(bits(img), bits(full)), sched
 
 
 def test_c3_full_size_gradient_rows_vs_oracle_and_linearity(c3):
@@ -74,6 +79,16 @@ def test_c3_full_size_gradient_rows_vs_oracle_and_linearity(c3):
     assert np.isfinite(whole).all() and rel_l2(halves, whole) < 1e-5
     c = g.counters()
     assert c["closest_rays"] > 0
+    # the schedules are the same sum in a different order: HBM wavefront (the default at this size) vs persistent pools;
+    # and they trace the same rays
+    counts = {}
+    for sched in ("wavefront", "persistent"):
+        g.reset_counters()
+        p_s = make_params(scenes.CBOX_CAMERA, (1024, 1024), mat.shape, 256, 1, schedule=sched, **kw)
+        assert rel_l2(g.backward(ZDR_PATH, p_s, mat, ones), whole) < 1e-5, sched
+        c2 = g.counters()
+        counts[sched] = (c2["closest_rays"], c2["any_rays"], c2["camera_samples"], c2["shaded_vertices"], c2["grad_scatters"])
+    assert counts["wavefront"] == counts["persistent"] and counts["persistent"][0] > 0, counts
 
 
 def test_c2_full_size_vs_oracle(oracle):

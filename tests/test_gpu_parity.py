@@ -228,6 +228,13 @@ CASES = {
     "c3_path_small_wavefront": (scenes.cbox_path_models, ZDR_PATH, (96, 96), 8, lambda: scenes.random_material((1024, 1024), 0), {"max_depth": 8, "schedule": "wavefront"}),
     "path_literal_wavefront": (scenes.cbox_path_models, ZDR_PATH, (64, 64), 4, lambda: scenes.random_material((128, 128), 4), {"max_depth": 5, "prb_mode": _abi.ZDR_PRB_LITERAL, "schedule": "wavefront"}),
     "path_depth1_wavefront": (scenes.cbox_path_models, ZDR_PATH, (40, 24), 3, lambda: scenes.random_material((64, 64), 6), {"max_depth": 1, "schedule": "wavefront"}),
+    # the persistent schedule (path state and ray queues in shared memory; persistent.cu)
+    "c3_path_small_persistent": (scenes.cbox_path_models, ZDR_PATH, (96, 96), 8, lambda: scenes.random_material((1024, 1024), 0), {"max_depth": 8, "schedule": "persistent"}),
+    "path_literal_persistent": (scenes.cbox_path_models, ZDR_PATH, (64, 64), 4, lambda: scenes.random_material((128, 128), 4), {"max_depth": 5, "prb_mode": _abi.ZDR_PRB_LITERAL, "schedule": "persistent"}),
+    "path_depth1_persistent": (scenes.cbox_path_models, ZDR_PATH, (40, 24), 3, lambda: scenes.random_material((64, 64), 6), {"max_depth": 1, "schedule": "persistent"}),
+    "path_depth16_persistent": (scenes.cbox_path_models, ZDR_PATH, (48, 48), 4, lambda: scenes.random_material((128, 128), 5), {"max_depth": 16, "schedule": "persistent"}),
+    # enough samples that every CTA's pool turns over many times (148 pools x 1536 slots = 227 K paths in flight)
+    "path_persistent_many": (scenes.cbox_path_models, ZDR_PATH, (256, 192), 16, lambda: scenes.random_material((256, 256), 7), {"max_depth": 6, "schedule": "persistent"}),
 }
 
 
@@ -278,7 +285,7 @@ def test_backward_parity(oracle, case_cache, name):
     assert (cg["closest_rays"], cg["any_rays"]) == (oc, oa)
 
 
-@pytest.mark.parametrize("case", ["c3_path_small", "c3_path_small_wavefront"])
+@pytest.mark.parametrize("case", ["c3_path_small", "c3_path_small_wavefront", "c3_path_small_persistent"])
 def test_shard_rows_and_samples(oracle, case_cache, case):
     """Row tiles are bit-identical to the full render; sample-range shards sum to it (§8e)."""
     c = _run_case(oracle, case, case_cache)
@@ -319,7 +326,7 @@ def test_transformed_instances_and_update_lights(oracle):
         if emis is not None:
             g.set_emissions(np.asarray(emis, np.float32))
             o.update_lights(emis)
-        for integ, sched in ((ZDR_DIRECT, "auto"), (ZDR_PATH, "megakernel"), (ZDR_PATH, "wavefront")):
+        for integ, sched in ((ZDR_DIRECT, "auto"), (ZDR_PATH, "megakernel"), (ZDR_PATH, "wavefront"), (ZDR_PATH, "persistent")):
             p = make_params(cam, (80, 60), mat.shape, 4, 0, max_depth=4, schedule=sched)
             assert np.array_equal(bits(g.samples(integ, p, mat)), bits(o.render_samples(integ, p, mat)))
             dimg = np.ones((60, 80, 4), np.float32)
@@ -336,7 +343,7 @@ def test_envmap_path(oracle):
     o.set_envmap(env)
     mat = scenes.random_material((64, 64), 10)
     cam = scenes.Camera(fov=0.9, origin=scenes.float3(-2.0, 2.5, -4.0), target=scenes.float3(1.0, 0.3, 0.3), up=scenes.float3(0, 1, 0))
-    for integ, sched in ((ZDR_DIRECT, "auto"), (ZDR_PATH, "megakernel"), (ZDR_PATH, "wavefront")):
+    for integ, sched in ((ZDR_DIRECT, "auto"), (ZDR_PATH, "megakernel"), (ZDR_PATH, "wavefront"), (ZDR_PATH, "persistent")):
         p = make_params(cam, (64, 48), mat.shape, 8, 0, max_depth=6, schedule=sched)
         img_g, img_o = g.forward(integ, p, mat), o.render_forward(integ, p, mat)
         assert rel_l2(img_g, img_o) <= IMG_TOL, rel_l2(img_g, img_o)     # acosf/atan2f are libm vs CUDA: tolerance, not bits
@@ -357,7 +364,7 @@ def test_envmap_with_mesh_lights_and_consistent_light_pdf(oracle):
     mat = scenes.random_material((32, 32), 12)
     cam = scenes.CBOX_CAMERA
     dimg = np.ones((48, 64, 4), np.float32)
-    for integ, sched in ((ZDR_DIRECT, "auto"), (ZDR_PATH, "megakernel"), (ZDR_PATH, "wavefront")):
+    for integ, sched in ((ZDR_DIRECT, "auto"), (ZDR_PATH, "megakernel"), (ZDR_PATH, "wavefront"), (ZDR_PATH, "persistent")):
         imgs = []
         for flag in (False, True):
             p = make_params(cam, (64, 48), mat.shape, 8, 3, max_depth=5, schedule=sched, light_pdf_counts_env=flag)
@@ -389,7 +396,7 @@ def test_lbvh_large_scene(oracle, builder, monkeypatch):
     assert np.array_equal(g.trace_any(seg), o.trace_any(seg))
     cam = scenes.Camera(fov=0.9, origin=scenes.float3(-2.0, 3.0, -4.0), target=scenes.float3(2.0, 0.5, 0.3), up=scenes.float3(0, 1, 0))
     mat = scenes.random_material((64, 64), 2)
-    for sched in ("megakernel", "wavefront"):
+    for sched in ("megakernel", "wavefront", "persistent"):
         p = make_params(cam, (48, 32), mat.shape, 2, 0, max_depth=4, schedule=sched)
         assert np.array_equal(bits(g.samples(ZDR_PATH, p, mat)), bits(o.render_samples(ZDR_PATH, p, mat)))
         d = np.ones((32, 48, 4), np.float32)
@@ -451,7 +458,7 @@ def test_light_stage_uniform_texture(oracle):
             g.set_emissions(np.asarray(lights, np.float32))
             o.update_lights(lights)
             for integ, kw in ((ZDR_COLLOCATED, {}), (ZDR_DIRECT, {}), (ZDR_PATH, {"max_depth": 3, "schedule": "megakernel"}),
-                              (ZDR_PATH, {"max_depth": 3, "schedule": "wavefront"})):
+                              (ZDR_PATH, {"max_depth": 3, "schedule": "wavefront"}), (ZDR_PATH, {"max_depth": 3, "schedule": "persistent"})):
                 p = make_params(cam, (64, 64), mat.shape, 4, 2, **kw)
                 assert np.array_equal(bits(g.forward(integ, p, mat)), bits(o.render_forward(integ, p, mat)))
                 d = np.ones((64, 64, 4), np.float32)
@@ -461,7 +468,7 @@ def test_light_stage_uniform_texture(oracle):
 
 
 @pytest.mark.parametrize("integ,kw", [(ZDR_DIRECT, {}), (ZDR_PATH, {"max_depth": 4, "schedule": "megakernel"}),
-                                      (ZDR_PATH, {"max_depth": 4, "schedule": "wavefront"})])
+                                      (ZDR_PATH, {"max_depth": 4, "schedule": "wavefront"}), (ZDR_PATH, {"max_depth": 4, "schedule": "persistent"})])
 def test_ragged_shapes_and_odd_sample_counts(oracle, integ, kw):
     """Non-square image (aspect ratio in integrator.py:23), non-square texture (row stride = shape[0],
     render.py:161 quirk), sample counts that are not powers of two (cycle-walking permutation), a seed that

@@ -164,7 +164,8 @@ def test_inverse_rendering_recovers_texture():
 
 
 @pytest.mark.parametrize("schedule,res,spp", [("megakernel", (64, 48), 8), ("wavefront", (64, 48), 8),
-                                              ("wavefront", (1024, 1024), 8)])      # 2^23 samples: two streams inside
+                                              ("wavefront", (1024, 1024), 8),       # 2^23 samples: two streams inside
+                                              ("persistent", (64, 48), 8), ("persistent", (512, 512), 8)])
 def test_operator_is_cuda_graph_capturable(schedule, res, spp):
     """The operator launches on the caller's stream with no synchronisation, allocation or host read-back once its
     workspace exists, so forward + adjoint capture into a CUDA graph; replays track the material tensor's contents."""

@@ -10,7 +10,7 @@ make -s -j4 > /dev/null
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off \
      --expt-relaxed-constexpr "$@" -c -o variants/${FILE:=render}_$name.o $FILE.cu
 objs=""
-for o in api render bvh_build envmap obj_loader; do
+for o in api render persistent bvh_build envmap obj_loader; do
   if [ "$o" == "$FILE" ]; then objs="$objs variants/${FILE}_$name.o"; else objs="$objs $o.o"; fi
 done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/lib_$name.so $objs -Xcompiler -fPIC

@@ -103,6 +103,7 @@ SIGNATURES = {
     "zdr_get_counters": (C.c_int, [_vp, _u64p]),
     "zdr_reset_counters": (C.c_int, [_vp]),
     "zdr_kernel_launches": (C.c_uint64, []),
+    "zdr_debug_phase_cycles": (C.c_int, [_vp, _u64p]),
     "zdr_probe_trace_closest": (C.c_int, [_vp, _f32p, C.c_int, _i32p, _f32p]),
     "zdr_probe_trace_any": (C.c_int, [_vp, _f32p, C.c_int, _i32p]),
     "zdr_probe_sampler": (C.c_int, [C.c_int, _i32p, C.c_int, C.c_char_p, _f32p]),

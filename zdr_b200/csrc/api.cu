@@ -290,6 +290,41 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
     return ZDR_OK;
 }
 
+// Persistent shared-memory schedule (persistent.cu).  Workspace: 64 batch counters + (forward only) one float4 per camera
+// sample of a batch; the batch shrinks to fit `ZDR_PW_R_BYTES` (default 2 GiB) — the adjoint pass needs no buffer at all.
+constexpr int kPwMaxBatches = 64;
+constexpr size_t kPwHeaderBytes = 512;      // 64 batch counters + 8 profile accumulators, then the sample buffer
+int setup_persistent(zdr_scene* s, int integrator, const zdr_params* p, const RenderArgs* a, bool backward, bool* use, PwPlan* plan,
+                     size_t* r_slots, unsigned** counters) {
+    *use = false;
+    if (integrator != ZDR_PATH || p->max_depth < 1 || p->max_depth > 255) return ZDR_OK;
+    if (p->flags & (ZDR_FLAG_WAVEFRONT | ZDR_FLAG_MEGAKERNEL)) return ZDR_OK;
+    long long rows = 0;
+    for (int t = a->shard_index, tiles = (p->row1 - p->row0 + 7) / 8; t < tiles; t += a->shard_count)
+        rows += (p->row1 - (p->row0 + 8 * t)) < 8 ? (p->row1 - (p->row0 + 8 * t)) : 8;
+    if (rows <= 0 || p->it1 <= p->it0) return ZDR_OK;
+    const long long pixels = (long long)p->width * rows, its = p->it1 - p->it0;
+    static const int auto_log2 = getenv("ZDR_PW_AUTO_LOG2") ? atoi(getenv("ZDR_PW_AUTO_LOG2")) : -1;
+    if (!(p->flags & ZDR_FLAG_PERSISTENT) && (auto_log2 < 0 || pixels * its < (1ll << auto_log2))) return ZDR_OK;
+    cudaError_t e = pw_plan(a->sc, s->bvh.max_depth, s->num_sms, plan);
+    if (e != cudaSuccess) return fail(ZDR_ERR_CUDA, "persistent schedule: %s", cudaGetErrorString(e));
+    static const long long r_cap = getenv("ZDR_PW_R_BYTES") ? atoll(getenv("ZDR_PW_R_BYTES")) : (2ll << 30);
+    size_t slots = 0;
+    if (!backward) {
+        long long smax = r_cap / 16 / pixels;
+        if (smax < 1) smax = 1;
+        if (smax > its) smax = its;
+        while ((its + smax - 1) / smax > kPwMaxBatches) ++smax;
+        slots = (size_t)(pixels * smax);
+    }
+    const size_t bytes = kPwHeaderBytes + slots * sizeof(float4);
+    if ((e = s->s_wf.reserve(bytes)) != cudaSuccess) return fail(ZDR_ERR_CUDA, "persistent workspace (%zu MiB): %s", bytes >> 20, cudaGetErrorString(e));
+    *counters = reinterpret_cast<unsigned*>(s->s_wf.p);
+    *r_slots = slots;
+    *use = true;
+    return ZDR_OK;
+}
+
 inline bool want_stats(const zdr_params* p) { return (p->flags & ZDR_FLAG_STATS) != 0; }
 
 }  // namespace
@@ -548,7 +583,16 @@ ZDR_EXPORT int zdr_render_forward(zdr_scene* s, int integrator, const zdr_params
     if ((rc = make_args(s, p, &a))) return rc;
     a.tex.mat = reinterpret_cast<const float4*>(material_dev);
     a.image = reinterpret_cast<float4*>(image_dev);
-    bool wavefront;
+    bool persistent, wavefront;
+    PwPlan plan;
+    size_t r_slots = 0;
+    unsigned* pw_counters = nullptr;
+    if ((rc = setup_persistent(s, integrator, p, &a, false, &persistent, &plan, &r_slots, &pw_counters))) return rc;
+    if (persistent) {
+        a.pw.R = reinterpret_cast<float4*>(s->s_wf.p + kPwHeaderBytes);
+        CK(launch_path_persistent(false, a, want_stats(p), plan, r_slots, pw_counters, kPwMaxBatches, (cudaStream_t)stream));
+        return ZDR_OK;
+    }
     if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;
     if (wavefront) CK(launch_path_wavefront(false, a, want_stats(p), (cudaStream_t)stream, s->side_streams, s->wf_events));
     else CK(launch_forward(integrator, a, want_stats(p), (cudaStream_t)stream));
@@ -567,7 +611,15 @@ ZDR_EXPORT int zdr_render_backward(zdr_scene* s, int integrator, const zdr_param
     a.tex.mat = reinterpret_cast<const float4*>(material_dev);
     a.tex.dmat = reinterpret_cast<float4*>(d_material_dev);
     a.d_image = reinterpret_cast<const float4*>(d_image_dev);
-    bool wavefront;
+    bool persistent, wavefront;
+    PwPlan plan;
+    size_t r_slots = 0;
+    unsigned* pw_counters = nullptr;
+    if ((rc = setup_persistent(s, integrator, p, &a, true, &persistent, &plan, &r_slots, &pw_counters))) return rc;
+    if (persistent) {
+        CK(launch_path_persistent(true, a, want_stats(p), plan, 0, pw_counters, kPwMaxBatches, (cudaStream_t)stream));
+        return ZDR_OK;
+    }
     if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;
     if (wavefront) CK(launch_path_wavefront(true, a, want_stats(p), (cudaStream_t)stream, s->side_streams, s->wf_events));
     else CK(launch_backward(integrator, a, want_stats(p), (cudaStream_t)stream));
@@ -641,6 +693,19 @@ ZDR_EXPORT int zdr_get_counters(zdr_scene* s, uint64_t out[ZDR_NUM_COUNTERS]) {
     return ZDR_OK;
 }
 ZDR_EXPORT uint64_t zdr_kernel_launches(void) { return kernel_launch_count(); }
+
+// Phase profile of the scene's last persistent launch (environment ZDR_PW_PROFILE=1): SM cycles summed over the CTAs for
+// claim + regenerate, extend, shade A, shadow, shade B; rounds; live paths summed over rounds; total cycles.
+ZDR_EXPORT int zdr_debug_phase_cycles(zdr_scene* s, uint64_t out[8]) {
+    if (!s || !out) return fail(ZDR_ERR_ARG, "debug_phase_cycles: null");
+    DevGuard dev_guard;
+    int rc = use_device(s->device, dev_guard);
+    if (rc) return rc;
+    if (s->s_wf.cap < kPwHeaderBytes) return fail(ZDR_ERR_STATE, "debug_phase_cycles: no persistent launch yet");
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, s->s_wf.p + 256, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost));
+    return ZDR_OK;
+}
 
 ZDR_EXPORT int zdr_reset_counters(zdr_scene* s) {
     if (!s) return fail(ZDR_ERR_ARG, "reset_counters: null");
@@ -735,10 +800,19 @@ ZDR_EXPORT int zdr_probe_render_samples(zdr_scene* s, int integrator, const zdr_
     CK(cudaMemsetAsync(s->s_misc.p, 0, sizeof(float) * nout, st));
     a.tex.mat = reinterpret_cast<const float4*>(s->s_mat.p);
     a.samples_out = s->s_misc.p;
-    bool wavefront;
-    if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;
-    if (wavefront) CK(launch_path_wavefront(false, a, want_stats(p), st, s->side_streams, s->wf_events));
-    else CK(launch_forward(integrator, a, want_stats(p), st));
+    bool persistent, wavefront;
+    PwPlan plan;
+    size_t r_slots = 0;
+    unsigned* pw_counters = nullptr;
+    if ((rc = setup_persistent(s, integrator, p, &a, false, &persistent, &plan, &r_slots, &pw_counters))) return rc;
+    if (persistent) {
+        a.pw.R = reinterpret_cast<float4*>(s->s_wf.p + kPwHeaderBytes);
+        CK(launch_path_persistent(false, a, want_stats(p), plan, r_slots, pw_counters, kPwMaxBatches, st));
+    } else {
+        if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;
+        if (wavefront) CK(launch_path_wavefront(false, a, want_stats(p), st, s->side_streams, s->wf_events));
+        else CK(launch_forward(integrator, a, want_stats(p), st));
+    }
     CK(cudaMemcpyAsync(out_host, s->s_misc.p, sizeof(float) * nout, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return ZDR_OK;

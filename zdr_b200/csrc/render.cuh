@@ -44,6 +44,8 @@ struct PwState {
     int pool;             // path slots per CTA
     int stack_depth;      // SMALL scenes: entries of the per-thread traversal stack in shared memory
     int bulk_copy;        // SMALL scenes: stage the scene with cp.async.bulk + mbarrier (else a cooperative copy loop)
+    int refill_closest, refill_any;   // a warp of the traversal phases refills its idle lanes once fewer than this many are busy
+    unsigned long long* phase_cycles; // profile (ZDR_PW_PROFILE): 8 accumulators, or null
 };
 
 struct RenderArgs {
