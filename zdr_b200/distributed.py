@@ -5,7 +5,8 @@ sharded: the image's 8-row tiles are dealt round-robin to the ranks (``zdr_param
 shard_count``), so every pixel keeps its whole sample loop on one GPU and the forward image is
 bit-identical to the single-GPU one.  Two collectives, both plain sums over NVLink (NCCL):
 
-* forward:  ``all_reduce(image)``      — ranks hold disjoint rows, the rest is zero, so the sum is exact;
+* forward:  ``all_gather`` of the rows each rank owns (tile axis: 1/N of the image per rank instead of an all-reduce over
+  the whole image — ranks hold disjoint rows, nothing has to be summed);
 * backward: ``all_reduce(d_material)`` — every rank scatters the texture gradient of its own rows
   (16 MiB for a 1024^2 texture).
 
@@ -50,6 +51,37 @@ def samples_of_shard(spp: int, shard: Tuple[int, int]) -> Tuple[int, int]:
     return spp * index // count, spp * (index + 1) // count
 
 
+_row_index_cache = {}
+
+
+def _row_indices(height: int, count: int, device):
+    """Per rank: the image rows it owns, padded to the longest list (index tensors, cached)."""
+    key = (height, count, str(device))
+    if key not in _row_index_cache:
+        rows = [rows_of_shard(height, (r, count)) for r in range(count)]
+        n_max = max(len(r) for r in rows)
+        own = [torch.tensor(r + [r[-1] if r else 0] * (n_max - len(r)), dtype=torch.long, device=device) for r in rows]
+        dst = torch.tensor([y for r in rows for y in r], dtype=torch.long, device=device)
+        src = torch.tensor([k * n_max + i for k, r in enumerate(rows) for i in range(len(r))], dtype=torch.long, device=device)
+        _row_index_cache[key] = (own, dst, src, n_max)
+    return _row_index_cache[key]
+
+
+def gather_tiles(image: torch.Tensor, shard: Tuple[int, int], group=None) -> torch.Tensor:
+    """Completes a tile-sharded image: every rank contributes only the rows it rendered (1/N of the image) and receives
+    the others' — an all-gather of disjoint rows, where the first version all-reduced the whole image (rows of the
+    other ranks as zeros).  Bit-identical to the single-GPU image: nothing is added."""
+    index, count = shard
+    H = image.shape[0]
+    own, dst, src, n_max = _row_indices(H, count, image.device)
+    mine = image.index_select(0, own[index]).contiguous()
+    parts = [torch.empty_like(mine) for _ in range(count)]
+    dist.all_gather(parts, mine, group=group)
+    full = torch.empty_like(image)
+    full.index_copy_(0, dst, torch.cat(parts, 0).index_select(0, src))
+    return full
+
+
 class ShardedRenderOperator(torch.autograd.Function):
     """RenderOperator (render.py:201-223) over a process group."""
 
@@ -66,8 +98,11 @@ class ShardedRenderOperator(torch.autograd.Function):
         else:
             image = fwd(material.detach(), res, spp, seed, shard)
         if shard[1] > 1:
-            dist.all_reduce(image, op=dist.ReduceOp.SUM, group=group)
-            image[..., 3] = 1.0          # alpha of the rows other ranks rendered (sum of one 1 and zeros already)
+            if ctx.its is None:
+                image = gather_tiles(image, shard, group)            # disjoint rows: gather, nothing to sum
+            else:
+                dist.all_reduce(image, op=dist.ReduceOp.SUM, group=group)      # partial means over sample ranges
+                image[..., 3] = 1.0
         return image
 
     @staticmethod
