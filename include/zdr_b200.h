@@ -88,6 +88,12 @@ typedef struct zdr_params {
  * textured object covers fewer than 64 texels in u or v (uniform / uv-less meshes), plain otherwise. */
 #define ZDR_FLAG_SCATTER_AGGREGATE 2
 #define ZDR_FLAG_SCATTER_PLAIN 4
+/* on top of the warp aggregation: every CTA adds into a duplicate of the gradient buffer in its SHARED memory (an
+ * open-addressing table of 256 texels) and folds it into d_material once, when it ends — the "per-SM duplicated gradient
+ * buffers" of the README's to-do (README.md:21); with the persistent schedule the table lives for the whole pass.  Cuts the
+ * global reductions per scatter to ~1e-4 (C2) but is NOT the default: after warp aggregation the L2 reductions are off the
+ * critical path, and the shared-memory atomics cost more than they save (profiles/r02e). */
+#define ZDR_FLAG_SCATTER_BLOCK 128
 /* schedule of the path integrator / PRB adjoint. Default (neither bit): wavefront kernels (path state
  * in HBM, compacted live lists) from 2^21 camera samples per launch on, the one-kernel bounce state
  * machine below that. Both produce bit-identical images. */

@@ -104,19 +104,28 @@ def test_uniform_texture_contention_case(oracle):
 
 
 def test_scatter_modes_agree(oracle):
-    """plain and warp-aggregated scatter are two schedules of the same sum."""
+    """plain, warp-aggregated and block-level (shared-memory duplicate buffer) scatter are schedules of the same sum, on every
+    schedule of the path integrator and for the direct integrator on a uv-less mesh (every scatter on one texel)."""
     from zdr_b200 import Scene
-    sc = Scene(scenes.cbox_path_models(), integrator="path")
-    sc.camera = scenes.CBOX_CAMERA.copy()
-    sc.max_depth = 5
-    grads = {}
-    for mode in ("plain", "aggregate", "auto"):
-        sc.scatter_mode = mode
-        mat = torch.from_numpy(scenes.random_material((64, 64), 7)).cuda().requires_grad_()
-        sc.render(mat, res=(64, 64), spp=4, seed=3)[..., :3].sum().backward()
-        grads[mode] = mat.grad.cpu().numpy()
-    assert rel_l2(grads["aggregate"], grads["plain"]) < 1e-5
-    assert rel_l2(grads["auto"], grads["plain"]) < 1e-5
+    for models, integrator, schedules in ((scenes.cbox_path_models, "path", ("megakernel", "wavefront", "persistent")),
+                                          (scenes.cbox_direct_models, "direct", ("auto",))):
+        sc = Scene(models(), integrator=integrator)
+        sc.camera = scenes.CBOX_CAMERA.copy()
+        sc.max_depth = 5
+        for schedule in schedules:
+            sc.schedule = schedule
+            grads, reds = {}, {}
+            for mode in ("plain", "aggregate", "block", "auto"):
+                sc.scatter_mode = mode
+                sc.reset_counters()
+                mat = torch.from_numpy(scenes.random_material((64, 64), 7)).cuda().requires_grad_()
+                sc.render(mat, res=(64, 64), spp=4, seed=3)[..., :3].sum().backward()
+                grads[mode] = mat.grad.cpu().numpy()
+                reds[mode] = sc.counters()["red_v4"]
+            for mode in ("aggregate", "block", "auto"):
+                assert rel_l2(grads[mode], grads["plain"]) < 1e-5, (integrator, schedule, mode)
+            assert reds["block"] <= reds["aggregate"] <= reds["plain"], (integrator, schedule, reds)
+        sc.close()
 
 
 def test_render_duvdxy_matches_oracle(scene, oracle):

@@ -19,7 +19,9 @@ ZDR_FLAG_WAVEFRONT, ZDR_FLAG_MEGAKERNEL = 8, 16
 ZDR_FLAG_LIGHT_PDF_COUNTS_ENV = 32
 ZDR_FLAG_PERSISTENT = 64
 SCHEDULES = {"auto": 0, "wavefront": ZDR_FLAG_WAVEFRONT, "megakernel": ZDR_FLAG_MEGAKERNEL, "persistent": ZDR_FLAG_PERSISTENT}
-SCATTER_MODES = {"auto": 0, "aggregate": ZDR_FLAG_SCATTER_AGGREGATE, "plain": ZDR_FLAG_SCATTER_PLAIN}
+ZDR_FLAG_SCATTER_BLOCK = 128
+SCATTER_MODES = {"auto": 0, "aggregate": ZDR_FLAG_SCATTER_AGGREGATE, "plain": ZDR_FLAG_SCATTER_PLAIN,
+                 "block": ZDR_FLAG_SCATTER_AGGREGATE | ZDR_FLAG_SCATTER_BLOCK}
 COUNTER_NAMES = ("closest_rays", "any_rays", "nodes_visited", "tris_tested",
                  "grad_scatters", "red_v4", "shaded_vertices", "camera_samples")
 

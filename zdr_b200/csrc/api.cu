@@ -210,7 +210,8 @@ int make_args(zdr_scene* s, const zdr_params* p, RenderArgs* a) {
     a->counters = s->d_counters;
     // gradient scatter strategy: warp aggregation pays when many lanes of a warp share a footprint,
     // i.e. when the textured object's uv range covers only a few texels (uniform / uv-less meshes)
-    if (p->flags & ZDR_FLAG_SCATTER_AGGREGATE) a->aggregate_scatter = 1;
+    a->block_scatter = (p->flags & ZDR_FLAG_SCATTER_BLOCK) ? 1 : 0;
+    if (p->flags & (ZDR_FLAG_SCATTER_AGGREGATE | ZDR_FLAG_SCATTER_BLOCK)) a->aggregate_scatter = 1;
     else if (p->flags & ZDR_FLAG_SCATTER_PLAIN) a->aggregate_scatter = 0;
     else {
         const float span_x = (s->uv_hi[0] - s->uv_lo[0]) * (float)(p->tex_res_x - 1);
@@ -294,7 +295,7 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
 // sample of a batch; the batch shrinks to fit `ZDR_PW_R_BYTES` (default 2 GiB) — the adjoint pass needs no buffer at all.
 constexpr int kPwMaxBatches = 64;
 constexpr size_t kPwHeaderBytes = 512;      // 64 batch counters + 8 profile accumulators, then the sample buffer
-int setup_persistent(zdr_scene* s, int integrator, const zdr_params* p, const RenderArgs* a, bool backward, bool* use, PwPlan* plan,
+int setup_persistent(zdr_scene* s, int integrator, const zdr_params* p, RenderArgs* a, bool backward, bool* use, PwPlan* plan,
                      size_t* r_slots, unsigned** counters) {
     *use = false;
     if (integrator != ZDR_PATH || p->max_depth < 1 || p->max_depth > 255) return ZDR_OK;
@@ -317,9 +318,11 @@ int setup_persistent(zdr_scene* s, int integrator, const zdr_params* p, const Re
         while ((its + smax - 1) / smax > kPwMaxBatches) ++smax;
         slots = (size_t)(pixels * smax);
     }
-    const size_t bytes = kPwHeaderBytes + slots * sizeof(float4);
+    const size_t bytes = kPwHeaderBytes + plan->gstate_bytes + slots * sizeof(float4);
     if ((e = s->s_wf.reserve(bytes)) != cudaSuccess) return fail(ZDR_ERR_CUDA, "persistent workspace (%zu MiB): %s", bytes >> 20, cudaGetErrorString(e));
     *counters = reinterpret_cast<unsigned*>(s->s_wf.p);
+    a->pw.gstate = reinterpret_cast<float4*>(s->s_wf.p + kPwHeaderBytes);
+    a->pw.R = reinterpret_cast<float4*>(s->s_wf.p + kPwHeaderBytes + plan->gstate_bytes);
     *r_slots = slots;
     *use = true;
     return ZDR_OK;
@@ -589,7 +592,6 @@ ZDR_EXPORT int zdr_render_forward(zdr_scene* s, int integrator, const zdr_params
     unsigned* pw_counters = nullptr;
     if ((rc = setup_persistent(s, integrator, p, &a, false, &persistent, &plan, &r_slots, &pw_counters))) return rc;
     if (persistent) {
-        a.pw.R = reinterpret_cast<float4*>(s->s_wf.p + kPwHeaderBytes);
         CK(launch_path_persistent(false, a, want_stats(p), plan, r_slots, pw_counters, kPwMaxBatches, (cudaStream_t)stream));
         return ZDR_OK;
     }
@@ -806,7 +808,6 @@ ZDR_EXPORT int zdr_probe_render_samples(zdr_scene* s, int integrator, const zdr_
     unsigned* pw_counters = nullptr;
     if ((rc = setup_persistent(s, integrator, p, &a, false, &persistent, &plan, &r_slots, &pw_counters))) return rc;
     if (persistent) {
-        a.pw.R = reinterpret_cast<float4*>(s->s_wf.p + kPwHeaderBytes);
         CK(launch_path_persistent(false, a, want_stats(p), plan, r_slots, pw_counters, kPwMaxBatches, st));
     } else {
         if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;

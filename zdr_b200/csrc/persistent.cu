@@ -47,8 +47,13 @@ namespace {
 #endif
 constexpr int kPwThreads = ZDR_PW_THREADS;
 constexpr int kPwBlocks = ZDR_PW_BLOCKS;
-constexpr int kPwBytesPerSlot = 7 * 16 + 4 * 2;       // 7 float4 records + 4 queue entries
-constexpr int kPwHeader = 256;
+#ifndef ZDR_PW_GSTATE          // 1: the path state records live in global memory (a per-CTA slice of the workspace, L2-resident:
+#define ZDR_PW_GSTATE 0        //    148 pools x 4096 slots x 112 B = 68 MB of the 126 MB L2), only the queues in shared memory
+#endif
+constexpr bool kPwGlobalState = ZDR_PW_GSTATE != 0;
+constexpr int kPwStateBytes = 7 * 16;                  // 7 float4 records per slot
+constexpr int kPwBytesPerSlot = (kPwGlobalState ? 0 : kPwStateBytes) + 4 * 2;       // shared memory per slot: (state +) 4 queue entries
+constexpr int kPwHeader = 256 + kGradCacheSlots * 20;      // counters + mbarrier, then the CTA's gradient duplicate (shading.cuh GradCache)
 constexpr int kPwNodeBudget = 12;
 
 // counters in shared memory (ints)
@@ -271,9 +276,16 @@ __global__ void __launch_bounds__(kPwThreads, kPwBlocks) k_pw(const __grid_const
     const int N = w.pool, tid = threadIdx.x;
     int* ctr = reinterpret_cast<int*>(smem);
     Pool pool;
-    pool.ro = reinterpret_cast<float4*>(smem + kPwHeader);
+    GradCache gcache = grad_cache_null();
+    if (MODE && a.aggregate_scatter && a.block_scatter) {      // per-SM duplicate of the gradient buffer, alive for the whole pass, folded once at the end
+        gcache.key = reinterpret_cast<int*>(smem + 256);
+        gcache.acc = reinterpret_cast<float*>(smem + 256 + kGradCacheSlots * 4);
+        grad_cache_init(gcache);
+    }
+    if constexpr (kPwGlobalState) pool.ro = w.gstate + (size_t)blockIdx.x * 7 * (size_t)N;
+    else pool.ro = reinterpret_cast<float4*>(smem + kPwHeader);
     pool.rd = pool.ro + N; pool.bi = pool.rd + N; pool.Ls = pool.bi + N; pool.hit = pool.Ls + N; pool.lw = pool.hit + N; pool.le = pool.lw + N;
-    unsigned short* l0a = reinterpret_cast<unsigned short*>(pool.le + N);
+    unsigned short* l0a = kPwGlobalState ? reinterpret_cast<unsigned short*>(smem + kPwHeader) : reinterpret_cast<unsigned short*>(pool.le + N);
     unsigned short* l0b = l0a + N;
     unsigned short* l1 = l0b + N;          // stage-B queue: replay paths from index 0 up, adjoint-walk paths from N-1 down
     unsigned short* fr = l1 + N;           // free slots from index 0 up, restart entries from N-1 down
@@ -566,7 +578,7 @@ __global__ void __launch_bounds__(kPwThreads, kPwBlocks) k_pw(const __grid_const
                     if (ADJ) {                                                          // prb.py:178-187
                         if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad)) {
                             scatters++;
-                            reds += a.aggregate_scatter ? write_bsdf_grad_aggregated(a.tex, itx.uv, mat_grad) : write_bsdf_grad(a.tex, itx.uv, mat_grad);
+                            reds += a.aggregate_scatter ? write_bsdf_grad_aggregated(a.tex, itx.uv, mat_grad, gcache) : write_bsdf_grad(a.tex, itx.uv, mat_grad);
                         }
                     }
                     ++depth;
@@ -597,6 +609,10 @@ __global__ void __launch_bounds__(kPwThreads, kPwBlocks) k_pw(const __grid_const
         atomicAdd(w.phase_cycles + 5, (unsigned long long)n_rounds);
         atomicAdd(w.phase_cycles + 6, (unsigned long long)n_paths);
         atomicAdd(w.phase_cycles + 7, (unsigned long long)(clock64() - t_start));
+    }
+    if (MODE && a.aggregate_scatter && a.block_scatter) {
+        pw_tally(ctr, C_RED, grad_cache_flush(gcache, a.tex.dmat));
+        __syncthreads();
     }
     if (tid < C_NUM) {
         const unsigned v = reinterpret_cast<unsigned*>(ctr)[PW_TALLY0 + tid];
@@ -654,12 +670,13 @@ cudaError_t pw_plan(const SceneView& sc, int bvh_depth, int num_sms, PwPlan* out
     p.stack_depth = p.small ? bvh_depth + 2 : 0;
     const size_t fixed = kPwHeader + (p.small ? (size_t)p.stack_depth * kPwThreads * sizeof(int) + scene_bytes : 0);
     static const int pool_env = getenv("ZDR_PW_POOL") ? atoi(getenv("ZDR_PW_POOL")) : 0;
-    int pool = pool_env > 0 ? pool_env : (p.small ? 1536 : 1024);
+    int pool = pool_env > 0 ? pool_env : (kPwGlobalState ? 4096 : (p.small ? 1536 : 1024));
     const int fit = (int)(((size_t)max_smem - fixed) / kPwBytesPerSlot);
     pool = std::min(pool, fit) & ~31;
     if (pool < 64 || pool > 65535) return cudaErrorInvalidConfiguration;
     p.pool = pool;
     p.smem_bytes = fixed + (size_t)pool * kPwBytesPerSlot;
+    p.gstate_bytes = kPwGlobalState ? (size_t)p.grid * pool * kPwStateBytes : 0;
     *out = p;
     return cudaSuccess;
 }

@@ -23,11 +23,12 @@ template <bool STATS, bool AGG = false>
 struct Ctx {
     const RenderArgs& a;
     Tally& tl;
+    GradCache gc = grad_cache_null();      // AGG kernels: the CTA's shared-memory duplicate of the gradient buffer (shading.cuh)
     ZDR_DEV Hit closest(const Ray& r) { tl.closest++; return trace<false, STATS>(a.sc, r, tl.ts); }
     ZDR_DEV bool occluded(const Ray& r) { tl.any++; return trace<true, STATS>(a.sc, r, tl.ts).inst >= 0; }
     ZDR_DEV void scatter(float2 uv, float4 g) {
         tl.scatter++;
-        tl.red += AGG ? write_bsdf_grad_aggregated(a.tex, uv, g) : write_bsdf_grad(a.tex, uv, g);
+        tl.red += AGG ? write_bsdf_grad_aggregated(a.tex, uv, g, gc) : write_bsdf_grad(a.tex, uv, g);
     }
 };
 
@@ -138,6 +139,14 @@ ZDR_DEV float3 direct_walk(CTX& c, const Ray& ray, Sampler& sampler, float3 le_g
     return radiance;
 }
 
+// AGG kernels: declare, clear and (at the end, by every thread of the CTA) fold the shared-memory gradient duplicate
+#define ZDR_GRAD_CACHE_BEGIN(c)                                               \
+    __shared__ int gc_key_[AGG ? kGradCacheSlots : 1];                       \
+    __shared__ float gc_acc_[AGG ? 4 * kGradCacheSlots : 1];                 \
+    if (AGG && a.block_scatter) { (c).gc.key = gc_key_; (c).gc.acc = gc_acc_; grad_cache_init((c).gc); }
+#define ZDR_GRAD_CACHE_END(c, a, tl) \
+    if (AGG && (a).block_scatter) (tl).red += grad_cache_flush((c).gc, (a).tex.dmat);
+
 ZDR_DEV void flush_tally(const RenderArgs& a, const Tally& t) {
     const unsigned v[C_NUM] = {t.closest, t.any, t.ts.nodes, t.ts.tris, t.scatter, t.red, t.shaded, t.samples};
 #pragma unroll 1
@@ -189,6 +198,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_backward(const __grid_constan
     pixel_of_thread(a, x, y);
     Tally tl = {};
     Ctx<STATS, AGG> c{a, tl};
+    ZDR_GRAD_CACHE_BEGIN(c)
     if (x < a.W && y < a.row1) {
         const float4 g = __ldg(a.d_image + ((size_t)x + (size_t)y * a.W));          // integrator.py:38-40
         float3 le_grad = f3(g.x / (float)a.spp, g.y / (float)a.spp, g.z / (float)a.spp);
@@ -201,6 +211,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_backward(const __grid_constan
             else direct_walk<true>(c, ray, sampler, le_grad);
         }
     }
+    ZDR_GRAD_CACHE_END(c, a, tl)
     flush_tally(a, tl);
 }
 
@@ -223,6 +234,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
     const SceneView& sc = a.sc;
     Tally tl = {};
     Ctx<STATS, AGG> c{a, tl};
+    if constexpr (BWD) { ZDR_GRAD_CACHE_BEGIN(c) }
     const bool corrected = a.prb_mode == ZDR_PRB_CORRECTED;
     const float specular = 0.04f;
     const float3 zero = f3(0.f, 0.f, 0.f);
@@ -364,6 +376,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
         if (!BWD && a.image)
             a.image[(size_t)x + (size_t)y * a.W] = make_float4(acc.x / (float)a.spp, acc.y / (float)a.spp, acc.z / (float)a.spp, 1.0f);
     }
+    if constexpr (BWD) { ZDR_GRAD_CACHE_END(c, a, tl) }
     flush_tally(a, tl);
 }
 
@@ -732,6 +745,7 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
     const int n_round = (n + 31) & ~31;
     Tally tl = {};
     Ctx<STATS, AGG> c{a, tl};
+    if constexpr (MODE == 2) { ZDR_GRAD_CACHE_BEGIN(c) }
     const bool corrected = a.prb_mode == ZDR_PRB_CORRECTED;
     const float specular = 0.04f;
     const float3 zero = f3(0.f, 0.f, 0.f);
@@ -827,6 +841,7 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
         }
         wf_append(w.list[0], w.counts + 0, survive, slot);
     }
+    if constexpr (MODE == 2) { ZDR_GRAD_CACHE_END(c, a, tl) }
     flush_tally(a, tl);
 }
 

@@ -35,6 +35,7 @@ struct WfState {
 // (forward) leaves the SM.
 struct PwState {
     float4* R;            // forward: finished samples of the batch, [sample-in-batch * P + pixel] (clamped radiance.xyz | -)
+    float4* gstate;       // build variant ZDR_PW_GSTATE: the pools' state records in global memory (7 * pool float4 per CTA)
     unsigned* next;       // work counter of the launch: camera samples handed out so far (zeroed by the launcher)
     unsigned total;       // P * S camera samples of the batch
     int P;                // pixels of this launch (width * rows of the shard)
@@ -57,6 +58,7 @@ struct RenderArgs {
     int W, H, spp, seed, use_tent, max_depth, rr_depth, use_mis, prb_mode;
     int row0, row1, it0, it1;
     int shard_index, shard_count;
+    int block_scatter;        // with aggregate_scatter: also the CTA-level shared-memory duplicate (shading.cuh GradCache)
     int aggregate_scatter;    // warp-aggregated gradient scatter (shading.cuh) instead of plain red.v4   // 8-row CTA tiles of [row0,row1) are dealt round-robin to shard_count shards
     float4* image;            // forward: (H,W) float4
     const float4* d_image;    // backward: (H,W) float4 cotangent
@@ -84,6 +86,7 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
 struct PwPlan {
     int pool, threads, stack_depth, small, grid;
     size_t smem_bytes;
+    size_t gstate_bytes;      // global-memory path state (build variant ZDR_PW_GSTATE), else 0
 };
 cudaError_t pw_plan(const SceneView& sc, int bvh_depth, int num_sms, PwPlan* out);
 cudaError_t launch_path_persistent(bool backward, RenderArgs a, bool stats, const PwPlan& plan, size_t r_capacity_slots,

@@ -104,10 +104,70 @@ ZDR_DEV int texel_index(const TexView& t, int cx, int cy) {                // in
     return clampi(cx, 0, t.rx - 1) + t.rx * clampi(cy, 0, t.ry - 1);
 }
 ZDR_DEV float4 scale4(float k, float4 d) { return make_float4(k * d.x, k * d.y, k * d.z, k * d.w); }
+// Block-level stage of the contended scatter (north star item 6: "per-SM duplicated gradient buffers"; the README's
+// "Need to add duplicate buffer for that", README.md:21).  Warp aggregation stops at 32 lanes: on a uniform / uv-less
+// texture every warp of every CTA still sends its sum to the SAME texel, and same-address reductions serialise in the L2
+// atomic unit (0.65 G red.v4/s, profiles/r01q_microbench.json).  Each CTA therefore owns a small duplicate of the gradient
+// buffer in SHARED memory — an open-addressing table of kGradCacheSlots (texel, float4) entries — that the group leaders add
+// into with shared-memory atomics; it is folded into the global buffer ONCE, when the CTA ends (one red.v4 per distinct
+// texel the CTA touched).  The persistent kernel keeps one CTA per SM alive for the whole pass, so there the table is
+// literally a per-SM duplicate buffer.  A full table (more than ~kGradCacheSlots distinct texels in one CTA) falls back to
+// the direct reduction.
+constexpr int kGradCacheSlots = 256;
+struct GradCache {
+    int* key;        // texel index, -1 = empty
+    float* acc;      // 4 floats per slot
+};
+ZDR_DEV GradCache grad_cache_null() { GradCache c; c.key = nullptr; c.acc = nullptr; return c; }
+// all threads of the CTA; ends with a barrier
+ZDR_DEV void grad_cache_init(GradCache c) {
+    for (int i = threadIdx.x; i < kGradCacheSlots; i += blockDim.x) {
+        c.key[i] = -1;
+        c.acc[4 * i] = 0.f; c.acc[4 * i + 1] = 0.f; c.acc[4 * i + 2] = 0.f; c.acc[4 * i + 3] = 0.f;
+    }
+    __syncthreads();
+}
+ZDR_DEV bool grad_cache_add(GradCache c, int texel, float4 v) {
+    const unsigned h = ((unsigned)texel * 2654435761u) >> 24;
+#pragma unroll 1
+    for (int p = 0; p < 4; ++p) {
+        const int s = (int)((h + (unsigned)p) & (unsigned)(kGradCacheSlots - 1));
+        const int old = atomicCAS(c.key + s, -1, texel);
+        if (old == -1 || old == texel) {
+            float* a = c.acc + 4 * s;
+            if (v.x != 0.0f) atomicAdd(a, v.x);
+            if (v.y != 0.0f) atomicAdd(a + 1, v.y);
+            if (v.z != 0.0f) atomicAdd(a + 2, v.z);
+            if (v.w != 0.0f) atomicAdd(a + 3, v.w);
+            return true;
+        }
+    }
+    return false;
+}
+// all threads of the CTA, after its last scatter; returns the number of red.v4 this thread issued
+ZDR_DEV unsigned grad_cache_flush(GradCache c, float4* dmat) {
+    __syncthreads();
+    unsigned issued = 0;
+    for (int i = threadIdx.x; i < kGradCacheSlots; i += blockDim.x) {
+        const int texel = c.key[i];
+        if (texel >= 0) {
+            const float4 v = make_float4(c.acc[4 * i], c.acc[4 * i + 1], c.acc[4 * i + 2], c.acc[4 * i + 3]);
+            if (!is_zero4(v)) { red_add_f4(dmat + texel, v); ++issued; }
+        }
+    }
+    return issued;
+}
+ZDR_DEV unsigned scatter_one(const GradCache& c, float4* dmat, int texel, float4 v) {
+    if (c.key && grad_cache_add(c, texel, v)) return 0u;
+    red_add_f4(dmat + texel, v);
+    return 1u;
+}
 static __device__ __noinline__ unsigned write_bsdf_grad_agg_nl(float4* __restrict__ dmat, int rx, int ry, int bilinear, float uvx, float uvy,
-                                                            float dx, float dy, float dz, float dw) {  // interaction.py:62-89
+                                                            float dx, float dy, float dz, float dw, int* cache_key, float* cache_acc) {  // interaction.py:62-89
     TexView t;
     t.mat = nullptr; t.dmat = dmat; t.rx = rx; t.ry = ry; t.bilinear = bilinear;
+    GradCache cache;
+    cache.key = cache_key; cache.acc = cache_acc;
     const float2 uv = make_float2(uvx, uvy);
     const float4 d = make_float4(dx, dy, dz, dw);
     const float px = uv.x * (float)(t.rx - 1), py = (1.0f - uv.y) * (float)(t.ry - 1);
@@ -135,7 +195,7 @@ static __device__ __noinline__ unsigned write_bsdf_grad_agg_nl(float4* __restric
     if (peers == (1u << lane)) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (k < n && !is_zero4(v[k])) { red_add_f4(t.dmat + idx[k], v[k]); ++issued; }
+            if (k < n && !is_zero4(v[k])) issued += scatter_one(cache, t.dmat, idx[k], v[k]);
         return issued;
     }
     const bool full = peers == 0xffffffffu;
@@ -144,14 +204,14 @@ static __device__ __noinline__ unsigned write_bsdf_grad_agg_nl(float4* __restric
     for (int k = 0; k < 4; ++k) {
         if (k < n) {
             const float4 sum = group_sum4(peers, full, v[k]);
-            if (leader && !is_zero4(sum)) { red_add_f4(t.dmat + idx[k], sum); ++issued; }
+            if (leader && !is_zero4(sum)) issued += scatter_one(cache, t.dmat, idx[k], sum);
         }
     }
     return issued;
 }
 
-ZDR_DEV unsigned write_bsdf_grad_aggregated(const TexView& t, float2 uv, float4 d) {
-    return write_bsdf_grad_agg_nl(t.dmat, t.rx, t.ry, t.bilinear, uv.x, uv.y, d.x, d.y, d.z, d.w);
+ZDR_DEV unsigned write_bsdf_grad_aggregated(const TexView& t, float2 uv, float4 d, GradCache cache = grad_cache_null()) {
+    return write_bsdf_grad_agg_nl(t.dmat, t.rx, t.ry, t.bilinear, uv.x, uv.y, d.x, d.y, d.z, d.w, cache.key, cache.acc);
 }
 // Plain scatter: one red.v4 per texel of the footprint (the reference issues four scalar atomics per
 // texel, interaction.py:67-70).  Used when the footprints of a warp are spread over the texture
