@@ -94,13 +94,13 @@ typedef struct zdr_params {
  * global reductions per scatter to ~1e-4 (C2) but is NOT the default: after warp aggregation the L2 reductions are off the
  * critical path, and the shared-memory atomics cost more than they save (profiles/r02e). */
 #define ZDR_FLAG_SCATTER_BLOCK 128
-/* schedule of the path integrator / PRB adjoint. Default (neither bit): wavefront kernels (path state
- * in HBM, compacted live lists) from 2^21 camera samples per launch on, the one-kernel bounce state
- * machine below that. Both produce bit-identical images. */
+/* schedule of the path integrator / PRB adjoint. Default (no bit), by camera samples per launch: below 2^14 the
+ * one-kernel bounce state machine; up to 3 * 2^20 the persistent shared-memory schedule (ZDR_FLAG_PERSISTENT); above
+ * that the wavefront kernels (path state in HBM, compacted live lists). All produce bit-identical images. */
 #define ZDR_FLAG_WAVEFRONT 8
 #define ZDR_FLAG_MEGAKERNEL 16
 /* persistent schedule: one resident CTA per SM, path state and ray queues in SHARED memory, the stages as phases of one
- * kernel per pass (persistent.cu); default from 2^17 camera samples per launch on.  Bit-identical images again. */
+ * kernel per pass (persistent.cu). */
 #define ZDR_FLAG_PERSISTENT 64
 /* MIS weight of a BSDF-sampled emitter hit in a scene that has BOTH mesh lights and an envmap: the reference's
  * sample_light_pdf divides by light_count only (light.py:89) while sample_light picks among

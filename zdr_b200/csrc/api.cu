@@ -234,7 +234,7 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
     const long long pixels = (long long)p->width * rows;
     const long long samples = pixels * (p->it1 - p->it0);
     if ((p->flags & ZDR_FLAG_MEGAKERNEL) || p->max_depth > 255) return ZDR_OK;      // path depth is packed into 8 bits of the state
-    if (!(p->flags & ZDR_FLAG_WAVEFRONT) && samples < (1ll << 21)) return ZDR_OK;
+    if (!(p->flags & ZDR_FLAG_WAVEFRONT) && samples < (3ll << 20)) return ZDR_OK;      // (smaller jobs: persistent schedule, setup_persistent)
     // path-state budget: as many samples per batch as fit a quarter of the free HBM, at most 2^28 slots
     // (41 GB at 152 B per slot: all 256 samples of a 1024^2 image in one batch); ZDR_WF_SLOTS_LOG2 overrides.
     // Larger batches amortise the ~4*depth launches per batch and the thin tail rounds (measured: 2^24 -> 2^28
@@ -305,8 +305,13 @@ int setup_persistent(zdr_scene* s, int integrator, const zdr_params* p, RenderAr
         rows += (p->row1 - (p->row0 + 8 * t)) < 8 ? (p->row1 - (p->row0 + 8 * t)) : 8;
     if (rows <= 0 || p->it1 <= p->it0) return ZDR_OK;
     const long long pixels = (long long)p->width * rows, its = p->it1 - p->it0;
-    static const int auto_log2 = getenv("ZDR_PW_AUTO_LOG2") ? atoi(getenv("ZDR_PW_AUTO_LOG2")) : -1;
-    if (!(p->flags & ZDR_FLAG_PERSISTENT) && (auto_log2 < 0 || pixels * its < (1ll << auto_log2))) return ZDR_OK;
+    // Default schedule by job size (tools/schedule_sweep.py, profiles/r02g_schedule_sweep.json: C3 scene, forward + adjoint):
+    //   < 2^14 camera samples: one-kernel state machine (everything is launch-bound there);
+    //   2^14 .. 3 * 2^20:      this persistent shared-memory schedule (2 launches per pass: 1.3-3x the others);
+    //   above:                 HBM wavefront (its ~100 launches per pass amortise; 7.0 vs 5.1 Grays/s at 2^26+).
+    static const long long auto_lo = 1ll << (getenv("ZDR_PW_AUTO_LOG2") ? atoi(getenv("ZDR_PW_AUTO_LOG2")) : 14);
+    static const long long auto_hi = getenv("ZDR_PW_AUTO_MAX") ? atoll(getenv("ZDR_PW_AUTO_MAX")) : 3ll << 20;
+    if (!(p->flags & ZDR_FLAG_PERSISTENT) && (pixels * its < auto_lo || pixels * its >= auto_hi)) return ZDR_OK;
     cudaError_t e = pw_plan(a->sc, s->bvh.max_depth, s->num_sms, plan);
     if (e != cudaSuccess) return fail(ZDR_ERR_CUDA, "persistent schedule: %s", cudaGetErrorString(e));
     static const long long r_cap = getenv("ZDR_PW_R_BYTES") ? atoll(getenv("ZDR_PW_R_BYTES")) : (2ll << 30);

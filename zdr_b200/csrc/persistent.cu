@@ -185,7 +185,8 @@ ZDR_DEV void pw_trace(const SceneView& sc, const Pool& pool, const unsigned shor
             int budget = kPwNodeBudget;
             while (link >= 0 && (!BIG || budget-- > 0)) {        // inner nodes
                 const float4* nd = nodes + 4 * (size_t)link;
-                const float4 n0 = ld_scene(nd), n1 = ld_scene(nd + 1), n2 = ld_scene(nd + 2), n3 = ld_scene(nd + 3);
+                float4 n0, n1, n2, n3;
+                ld_node(nd, n0, n1, n2, n3);
                 if (STATS) ts.nodes++;
                 float t0, t1;
                 const bool h0 = box_test(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, id, oid, tmin, best, t0);

@@ -458,6 +458,12 @@ constexpr int kWfRefill = ZDR_WF_REFILL;
 #ifndef ZDR_WF_FETCH_CHUNK
 #define ZDR_WF_FETCH_CHUNK 128
 #endif
+#ifndef ZDR_WF_TRACE_PREFETCH      // measured r02h: 6917 (on) vs 6936 (off) Mrays/s on C3 at 64 spp — no gain, off
+#define ZDR_WF_TRACE_PREFETCH 0
+#endif
+#ifndef ZDR_WF_REFILL_ANY_SMALL      // shadow rays of small scenes also refill idle lanes (cheap once the records are prefetched)
+#define ZDR_WF_REFILL_ANY_SMALL 0
+#endif
 constexpr int kWfNodeBudget = 12;
 constexpr int kWfBigSceneNodes = 1024;
 template <bool ANY, bool STATS, bool BIG>      // BIG: scene with more than kWfBigSceneNodes nodes (launch_wf_round)
@@ -474,7 +480,7 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
     const float4* __restrict__ tris = a.sc.tris;
     Tally tl = {};
     const int lane = threadIdx.x & 31;
-    constexpr bool refill_any = BIG;                   // traversals long enough for refills to pay on every kind of ray
+    constexpr bool refill_any = BIG || ZDR_WF_REFILL_ANY_SMALL;      // traversals long enough for refills to pay on every kind of ray
     // per-lane traversal state
     bool has_ray = false, exhausted = false;
     int slot = 0, link = kLinkSentinel, sp = 0, hit_slot = -1, best_gid = 0x7fffffff;
@@ -503,7 +509,22 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
             }
             const int rank = __popc(idle & ((1u << lane) - 1u));
             const int i_next = rank < have ? chunk_next + rank : base + (rank - have);
-            if (have < need) { chunk_next = base + (need - have); chunk_end = base + chunk; } else chunk_next += need;
+            if (have < need) {
+#if ZDR_WF_TRACE_PREFETCH
+                // The chunk's ray records are 128 random 32-byte sectors of HBM that the lanes will ask for one refill at a
+                // time over the next thousands of cycles: ask L2 for all of them now (profiles/r01w: long_scoreboard 12
+                // warps per issue in this kernel = the two dependent HBM round trips of every refill).
+                for (int k = lane; k < chunk; k += 32) {
+                    const int j = base + k;
+                    if (j < n) {
+                        const int sl = list[j];
+                        const float4* rec = ANY ? w.SAB + 2 * (size_t)sl : w.AB + 2 * (size_t)sl;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec));
+                    }
+                }
+#endif
+                chunk_next = base + (need - have); chunk_end = base + chunk;
+            } else chunk_next += need;
 #else
             int base = 0;
             if (lane == __ffs(idle) - 1) base = atomicAdd(cursor, __popc(idle));
@@ -551,7 +572,8 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
                                              // 9.6 of 32 lanes were active without the bound, profiles/r01p)
             while (link >= 0 && (!BIG || budget-- > 0)) {    // inner nodes
                 const float4* nd = nodes + 4 * (size_t)link;
-                const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+                float4 n0, n1, n2, n3;
+                ld_node(nd, n0, n1, n2, n3);
                 if (STATS) tl.ts.nodes++;
                 float t0, t1;
                 const bool h0 = box_test(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, id, oid, tmin, best, t0);

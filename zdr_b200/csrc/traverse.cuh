@@ -22,6 +22,9 @@ namespace zdr {
 // node record: n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y), n1 = same for child 1,
 //              n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z), n3 = (link0, link1, -, -) as int bits.
 // link >= 0: inner node index; link < 0: leaf, ~link = (first_slot << 2) | (count - 1).
+#ifndef ZDR_TRI_VECTOR_LOADS        // measured r02i: three 16-byte loads + 18 selects instead of nine scalar loads: C3 -5 % (wavefront) / -10 %
+#define ZDR_TRI_VECTOR_LOADS 0      // (persistent): the traversal is bound by issue slots, not by load wavefronts
+#endif
 constexpr int kStackSize = 64;
 constexpr int kLinkSentinel = (int)0x80000000;   // a "leaf" link no leaf can have (first_slot < 2^29)
 
@@ -57,34 +60,71 @@ ZDR_DEV RayPre ray_pre(float3 o, float3 d) {
 // upper bound); watertight on shared edges.  `tp` points at the 48-byte record v0|v1|v2 (float4
 // each); the permuted components are fetched with per-lane offsets instead of being selected
 // out of vector registers (two FSEL per component cost more issue slots than the loads).
+// Every product and sum below is written with an explicit round-to-nearest intrinsic (or fmaf): the expression is part of
+// the numeric contract (it decides primitive ids), so it must not change when the rest of the library is built with
+// floating-point contraction (the "fma" performance build, Makefile).
 ZDR_DEV bool tri_test(const RayPre& rp, const float* __restrict__ tp, float tmin, float& t_out, float& u_out, float& v_out) {
-    const float Akx = ld_scene(tp + rp.kx) - rp.okx, Aky = ld_scene(tp + rp.ky) - rp.oky, Akz = ld_scene(tp + rp.kz) - rp.okz;
-    const float Bkx = ld_scene(tp + 4 + rp.kx) - rp.okx, Bky = ld_scene(tp + 4 + rp.ky) - rp.oky, Bkz = ld_scene(tp + 4 + rp.kz) - rp.okz;
-    const float Ckx = ld_scene(tp + 8 + rp.kx) - rp.okx, Cky = ld_scene(tp + 8 + rp.ky) - rp.oky, Ckz = ld_scene(tp + 8 + rp.kz) - rp.okz;
+#if ZDR_TRI_VECTOR_LOADS
+    // three 16-byte loads + selects: a third of the L1 / shared-memory wavefronts of nine scalar loads at lane-dependent
+    // offsets (the traversal stages are bound by load wavefronts, not by issue slots: DESIGN.md)
+    const float4 va = ld_scene(reinterpret_cast<const float4*>(tp)), vb = ld_scene(reinterpret_cast<const float4*>(tp) + 1),
+                 vc = ld_scene(reinterpret_cast<const float4*>(tp) + 2);
+    const float Akx = __fsub_rn(comp(f3(va.x, va.y, va.z), rp.kx), rp.okx), Aky = __fsub_rn(comp(f3(va.x, va.y, va.z), rp.ky), rp.oky),
+                Akz = __fsub_rn(comp(f3(va.x, va.y, va.z), rp.kz), rp.okz);
+    const float Bkx = __fsub_rn(comp(f3(vb.x, vb.y, vb.z), rp.kx), rp.okx), Bky = __fsub_rn(comp(f3(vb.x, vb.y, vb.z), rp.ky), rp.oky),
+                Bkz = __fsub_rn(comp(f3(vb.x, vb.y, vb.z), rp.kz), rp.okz);
+    const float Ckx = __fsub_rn(comp(f3(vc.x, vc.y, vc.z), rp.kx), rp.okx), Cky = __fsub_rn(comp(f3(vc.x, vc.y, vc.z), rp.ky), rp.oky),
+                Ckz = __fsub_rn(comp(f3(vc.x, vc.y, vc.z), rp.kz), rp.okz);
+#else
+    const float Akx = __fsub_rn(ld_scene(tp + rp.kx), rp.okx), Aky = __fsub_rn(ld_scene(tp + rp.ky), rp.oky), Akz = __fsub_rn(ld_scene(tp + rp.kz), rp.okz);
+    const float Bkx = __fsub_rn(ld_scene(tp + 4 + rp.kx), rp.okx), Bky = __fsub_rn(ld_scene(tp + 4 + rp.ky), rp.oky), Bkz = __fsub_rn(ld_scene(tp + 4 + rp.kz), rp.okz);
+    const float Ckx = __fsub_rn(ld_scene(tp + 8 + rp.kx), rp.okx), Cky = __fsub_rn(ld_scene(tp + 8 + rp.ky), rp.oky), Ckz = __fsub_rn(ld_scene(tp + 8 + rp.kz), rp.okz);
+#endif
     const float Ax = fmaf(-rp.Sx, Akz, Akx), Ay = fmaf(-rp.Sy, Akz, Aky);
     const float Bx = fmaf(-rp.Sx, Bkz, Bkx), By = fmaf(-rp.Sy, Bkz, Bky);
     const float Cx = fmaf(-rp.Sx, Ckz, Ckx), Cy = fmaf(-rp.Sy, Ckz, Cky);
-    float U = Cx * By - Cy * Bx;
-    float V = Ax * Cy - Ay * Cx;
-    float W = Bx * Ay - By * Ax;
+    float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+    float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+    float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
     if (U == 0.0f || V == 0.0f || W == 0.0f) {
-        const double CxBy = (double)Cx * (double)By, CyBx = (double)Cy * (double)Bx;
-        U = (float)(CxBy - CyBx);
-        const double AxCy = (double)Ax * (double)Cy, AyCx = (double)Ay * (double)Cx;
-        V = (float)(AxCy - AyCx);
-        const double BxAy = (double)Bx * (double)Ay, ByAx = (double)By * (double)Ax;
-        W = (float)(BxAy - ByAx);
+        const double CxBy = __dmul_rn((double)Cx, (double)By), CyBx = __dmul_rn((double)Cy, (double)Bx);
+        U = (float)__dsub_rn(CxBy, CyBx);
+        const double AxCy = __dmul_rn((double)Ax, (double)Cy), AyCx = __dmul_rn((double)Ay, (double)Cx);
+        V = (float)__dsub_rn(AxCy, AyCx);
+        const double BxAy = __dmul_rn((double)Bx, (double)Ay), ByAx = __dmul_rn((double)By, (double)Ax);
+        W = (float)__dsub_rn(BxAy, ByAx);
     }
     if (fminf(fminf(U, V), W) < 0.0f && fmaxf(fmaxf(U, V), W) > 0.0f) return false;
-    const float det = U + V + W;
+    const float det = __fadd_rn(__fadd_rn(U, V), W);
     if (det == 0.0f) return false;
-    const float Az = rp.Sz * Akz, Bz = rp.Sz * Bkz, Cz = rp.Sz * Ckz;
-    const float T = fmaf(W, Cz, fmaf(V, Bz, U * Az));
-    const float rcp = 1.0f / det;
-    const float t = T * rcp;
+    const float Az = __fmul_rn(rp.Sz, Akz), Bz = __fmul_rn(rp.Sz, Bkz), Cz = __fmul_rn(rp.Sz, Ckz);
+    const float T = fmaf(W, Cz, fmaf(V, Bz, __fmul_rn(U, Az)));
+    const float rcp = __fdiv_rn(1.0f, det);
+    const float t = __fmul_rn(T, rcp);
     if (!(t > tmin)) return false;
-    t_out = t; u_out = V * rcp; v_out = W * rcp;
+    t_out = t; u_out = __fmul_rn(V, rcp); v_out = __fmul_rn(W, rcp);
     return true;
+}
+
+// One 64-byte node record.  sm_100 has 256-bit global loads (LDG.E.256): two instead of four load instructions per node step,
+// i.e. half the L1 wavefronts when the lanes of a warp sit on different nodes.
+#ifndef ZDR_NODE_LOAD_256           // measured r02i: C3 +0.4 %, C5-shaped scene +2.8 % (1531 -> 1573 Mrays/s)
+#define ZDR_NODE_LOAD_256 1
+#endif
+ZDR_DEV void ld_node(const float4* nd, float4& n0, float4& n1, float4& n2, float4& n3) {
+#if ZDR_NODE_LOAD_256 && !defined(ZDR_SCENE_GENERIC_LOADS)
+    float a0, a1, a2, a3, a4, a5, a6, a7, b0, b1, b2, b3, b4, b5, b6, b7;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3), "=f"(a4), "=f"(a5), "=f"(a6), "=f"(a7)
+                 : "l"(nd));
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3), "=f"(b4), "=f"(b5), "=f"(b6), "=f"(b7)
+                 : "l"(nd + 2));
+    n0 = make_float4(a0, a1, a2, a3); n1 = make_float4(a4, a5, a6, a7);
+    n2 = make_float4(b0, b1, b2, b3); n3 = make_float4(b4, b5, b6, b7);
+#else
+    n0 = ld_scene(nd); n1 = ld_scene(nd + 1); n2 = ld_scene(nd + 2); n3 = ld_scene(nd + 3);
+#endif
 }
 
 // Conservative slab test (entry distance in tn).  Not part of the numeric contract: the boxes are
