@@ -87,6 +87,16 @@ def cbox_two_light_models():
             (asset("cbox-light.obj"), translate_scale(-1.2, -1.5, 0.4, 1.0), float3(0.0))]
 
 
+def cbox_material_sets_models():
+    """Scene of the material-set ("polymorphic materials") fixtures: Cornell box (texture set 0), its light, sphere.obj inside
+    the box (texture set 1) and a second, switched-off copy of the light quad (no texture set: a terminal surface).
+    Returns (models, set of every instance)."""
+    models = [(asset("cboxuv.obj"), None, float3(0.0)), (asset("cbox-light.obj"), None, float3(17, 12, 4)),
+              (asset("sphere.obj"), translate_scale(-0.2, 1.4, -2.4, 1.1), float3(0.0)),
+              (asset("cbox-light.obj"), translate_scale(-1.2, -2.5, 0.4, 1.0), float3(0.0))]
+    return models, [0, -1, 1, -1]
+
+
 def sphere_grid_models(n_inst: int, seed: int = 0, emissive_every: int = 0):
     """C5 shape: instances of sphere.obj on a jittered lattice (uniform scale 0.4, spacing 1.0,
     jitter +-0.25), first n cells of a 22x22x21 grid; instance 0 is the textured object."""

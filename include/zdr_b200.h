@@ -80,7 +80,9 @@ typedef struct zdr_params {
      * one GPU, so the image is bit-identical to the unsharded one). 0 or 1 = no interleave. */
     int32_t shard_index, shard_count;
     int32_t flags;            /* ZDR_FLAG_* */
-    int32_t reserved[1];
+    /* texture sets in the material buffer (0 or 1: one, the reference's layout).  K > 1: material / d_material are
+     * (K, tex_res_x, tex_res_y, 4), and zdr_scene_set_material_sets says which set shades which instance. */
+    int32_t num_material_sets;
 } zdr_params;
 #define ZDR_FLAG_STATS 1      /* also count BVH nodes visited / triangles tested (slower) */
 /* texture-gradient scatter (replaces the atomic_fetch_add of interaction.py:67-70). Default (neither
@@ -143,6 +145,11 @@ int zdr_scene_clear(zdr_scene* s);
 int zdr_scene_set_emissions(zdr_scene* s, const float* emission_nx3_host, int n);
 /* Scene.add_envmap -> load_envmap (render.py:150-156, envmap.py:116-202). rgba float, h rows. */
 int zdr_scene_set_envmap(zdr_scene* s, const float* rgba_host, int w, int h, int compensate_mis);
+/* "Polymorphic" materials — several texture sets, the item the reference lists as not implemented (README.md:5: "currently
+ * only one set of material").  set_of_instance[i] >= 0: instance i is shaded with that texture set of the material buffer;
+ * -1: the instance is a light / terminal surface.  The default (instance 0 -> 0, all others -1) is the reference's rule
+ * "treat everything as light other than the first object" (direct.py:30, prb.py:45). n must equal the instance count. */
+int zdr_scene_set_material_sets(zdr_scene* s, const int32_t* set_of_instance_host, int n);
 int zdr_scene_instance_count(const zdr_scene* s);
 int zdr_scene_light_count(const zdr_scene* s);
 int zdr_scene_triangle_count(const zdr_scene* s);

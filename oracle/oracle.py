@@ -42,6 +42,7 @@ def lib():
         L.zo_scene_add_mesh.argtypes = [_vp, _f32p, C.c_int, _i32p, C.c_int, _f32p, _f32p]
         L.zo_scene_commit.argtypes = [_vp]
         L.zo_scene_set_emissions.argtypes = [_vp, _f32p, C.c_int]
+        L.zo_scene_set_material_sets.argtypes = [_vp, _i32p, C.c_int]
         L.zo_scene_set_envmap.argtypes = [_vp, _f32p, C.c_int, C.c_int, C.c_int]
         L.zo_scene_get_env_tables.argtypes = [_vp, _f32p, _i32p, _f32p]
         L.zo_scene_get_env_scale_map.argtypes = [_vp, _f32p]
@@ -233,6 +234,10 @@ class OracleScene:
     def update_lights(self, emissions):
         e = _f([_emission3(x) for x in emissions])
         assert lib().zo_scene_set_emissions(self._h, _p(e), e.shape[0]) == 0
+
+    def set_material_sets(self, sets):
+        a = np.ascontiguousarray(sets, dtype=np.int32)
+        assert lib().zo_scene_set_material_sets(self._h, a.ctypes.data_as(_i32p), a.shape[0]) == 0
 
     def set_envmap(self, rgba, compensate_mis=True):
         img = _f(rgba)

@@ -254,6 +254,8 @@ typedef struct {
     float N[9];         /* inverse(transpose(M3x3)), column-major (interaction.py:28) */
     f3 emission;
     int tri_base;       /* first global triangle id */
+    int material_set;   /* texture set that shades the instance, -1 = light / terminal surface; default: instance 0 -> 0, others -1
+                           ("treat everything as light other than the first object", direct.py:30, prb.py:45) */
 } Inst;
 
 struct zo_scene {
@@ -333,7 +335,16 @@ ZO_API int zo_scene_add_mesh(zo_scene* s, const float* verts, int nv, const int3
     memcpy(in->M, xform ? xform : I16, sizeof(float) * 16);
     normal_matrix(in->M, in->N);
     in->emission = emission ? v3(emission[0], emission[1], emission[2]) : v3(0, 0, 0);
+    in->material_set = (s->ninst == 1) ? 0 : -1;      /* direct.py:30: only the first object is textured */
     s->committed = 0;
+    return ZDR_OK;
+}
+
+/* material sets ("polymorphic materials", README.md:5 — not implemented upstream): texture set per instance, -1 = light / terminal */
+ZO_API int zo_scene_set_material_sets(zo_scene* s, const int32_t* set_of_instance, int n) {
+    if (!s || !set_of_instance || n != s->ninst) return ZDR_ERR_ARG;
+    for (int i = 0; i < n; ++i) if (set_of_instance[i] < -1) return ZDR_ERR_ARG;
+    for (int i = 0; i < n; ++i) s->inst[i].material_set = set_of_instance[i];
     return ZDR_OK;
 }
 
@@ -655,6 +666,14 @@ static Interaction surface_interact(zo_scene* s, const Hit* h) {
 }
 
 typedef struct { const float* mat; double* dmat; int rx, ry; int bilinear; } Tex;
+/* material sets ("polymorphic materials", README.md:5): set k of the material buffer starts k * rx * ry texels in */
+static inline Tex tex_set(const Tex* t, int set) {
+    Tex r = *t;
+    const size_t off = (size_t)(set < 0 ? 0 : set) * (size_t)t->rx * (size_t)t->ry * 4;
+    r.mat = t->mat + off;
+    if (t->dmat) r.dmat = t->dmat + off;
+    return r;
+}
 
 /* interaction.py:35-44 */
 static inline f4 read_single_bsdf(const Tex* t, int cx, int cy) {
@@ -974,7 +993,8 @@ static f3 collocated_estimator(Ctx* c, Ray ray, Sampler* sampler) {
     if (hit.inst < 0) return v3(0, 0, 0);
     Interaction it = surface_interact(c->s, &hit);
     if (backfacing(ray.d, &it)) return v3(0, 0, 0);
-    f4 mat = read_bsdf(&c->tex, it.uv);
+    const Tex tex = tex_set(&c->tex, c->s->inst[hit.inst].material_set);      /* collocated.py:22 shades any instance */
+    f4 mat = read_bsdf(&tex, it.uv);
     Onb onb = make_onb(it.ns);
     f3 wo_local = to_local(&onb, neg3(ray.d));
     f3 beta = ggx_brdf(wo_local, wo_local, v3(mat.x, mat.y, mat.z), 0.04f, mat.w);
@@ -990,13 +1010,14 @@ static void collocated_estimator_backward(Ctx* c, Ray ray, Sampler* sampler, f3 
     if (hit.inst < 0) return;
     Interaction it = surface_interact(c->s, &hit);
     if (backfacing(ray.d, &it)) return;
-    f4 mat = read_bsdf(&c->tex, it.uv);
+    const Tex tex = tex_set(&c->tex, c->s->inst[hit.inst].material_set);
+    f4 mat = read_bsdf(&tex, it.uv);
     Onb onb = make_onb(it.ns);
     f3 wo_local = to_local(&onb, neg3(ray.d));
     float inv = 1.0f / hit.t;
     float li = 1.0f * (inv * inv);
     f4 mat_grad = ggx_brdf_grad(wo_local, wo_local, 0.04f, mat.w, scale3(le_grad, li));
-    write_bsdf_grad(&c->tex, it.uv, mat_grad);
+    write_bsdf_grad(&tex, it.uv, mat_grad);
 }
 
 static f3 env_emission(Ctx* c, f3 dir) {   /* direct.py:24 */
@@ -1012,8 +1033,9 @@ static f3 direct_estimator(Ctx* c, Ray ray, Sampler* sampler) {
     Interaction it = surface_interact(s, &hit);
     if (backfacing(ray.d, &it)) return v3(0, 0, 0);
     f3 emission = s->inst[hit.inst].emission;
-    if (hit.inst > 0) return emission;
-    f4 mat = read_bsdf(&c->tex, it.uv);
+    if (s->inst[hit.inst].material_set < 0) return emission;        /* direct.py:30: `hit.inst > 0` with one material set */
+    const Tex tex = tex_set(&c->tex, s->inst[hit.inst].material_set);
+    f4 mat = read_bsdf(&tex, it.uv);
     f3 diffuse = v3(mat.x, mat.y, mat.z);
     float roughness = mat.w;
     const float specular = 0.04f;
@@ -1072,10 +1094,11 @@ static void direct_estimator_backward(Ctx* c, Ray ray, Sampler* sampler, f3 le_g
     Interaction it = surface_interact(s, &hit);
     if (backfacing(ray.d, &it)) return;
     f3 emission;
-    if (hit.inst > 0) return;
+    if (s->inst[hit.inst].material_set < 0) return;                   /* direct.py:98 */
+    const Tex tex = tex_set(&c->tex, s->inst[hit.inst].material_set);  /* the gradient belongs to the PRIMARY hit's texture set */
     f4 mat_grad = {0, 0, 0, 0};
     f2 mat_grad_uv = it.uv;
-    f4 mat = read_bsdf(&c->tex, it.uv);
+    f4 mat = read_bsdf(&tex, it.uv);
     float roughness = mat.w;
     const float specular = 0.04f;
     LightSample light = sample_light(s, it.p, sampler);
@@ -1100,7 +1123,7 @@ static void direct_estimator_backward(Ctx* c, Ray ray, Sampler* sampler, f3 le_g
         f3 wi_local = ggx_sample(wo_local, roughness, sampler);
         f3 wi = to_world(&onb, wi_local);
         if (dot3(wi, it.ng) < 1e-4f || wi_local.z < 1e-4f) {
-            write_bsdf_grad(&c->tex, it.uv, mat_grad);                    /* direct.py:138 */
+            write_bsdf_grad(&tex, it.uv, mat_grad);                       /* direct.py:138 */
             return;
         }
         Ray r2 = {offset_ray_origin(it.p, it.ng), wi, 0.0f, 1e30f};
@@ -1116,7 +1139,7 @@ static void direct_estimator_backward(Ctx* c, Ray ray, Sampler* sampler, f3 le_g
             if (backfacing(r2.d, &it2)) {
                 /* direct.py:152 scatters at `it.uv` AFTER `it` was reassigned to the second
                  * hit (direct.py:149): reproduced literally. */
-                write_bsdf_grad(&c->tex, it2.uv, mat_grad);
+                write_bsdf_grad(&tex, it2.uv, mat_grad);
                 return;
             }
             emission = s->inst[hit2.inst].emission;
@@ -1130,7 +1153,7 @@ static void direct_estimator_backward(Ctx* c, Ray ray, Sampler* sampler, f3 le_g
             mat_grad = add4(mat_grad, ggx_brdf_grad(wo_local, wi_local, specular, roughness, cot));
         }
     }
-    write_bsdf_grad(&c->tex, mat_grad_uv, mat_grad);                      /* direct.py:167 */
+    write_bsdf_grad(&tex, mat_grad_uv, mat_grad);                         /* direct.py:167 */
 }
 
 static inline float luminance(f3 b) { return dot3(v3(0.212671f, 0.715160f, 0.072169f), b); } /* prb.py:80 */
@@ -1164,8 +1187,9 @@ static f3 path_estimator(Ctx* c, Ray ray, Sampler* sampler) {
             radiance = add3(radiance, mul3(scale3(beta, mis_weight), emission));
             break;
         }
-        if (hit.inst > 0) break;
-        f4 mat = read_bsdf(&c->tex, it.uv);
+        if (s->inst[hit.inst].material_set < 0) break;              /* prb.py:45 */
+        const Tex tex = tex_set(&c->tex, s->inst[hit.inst].material_set);
+        f4 mat = read_bsdf(&tex, it.uv);
         f3 diffuse = v3(mat.x, mat.y, mat.z);
         float roughness = mat.w;
         Onb onb = make_onb(it.ns);
@@ -1224,9 +1248,10 @@ static void path_estimator_backward(Ctx* c, Ray ray, Sampler* sampler, f3 le_gra
             Le = sub3(Le, mul3(scale3(beta, mis_weight), emission));
             break;
         }
-        if (corrected && hit.inst > 0) break;             /* missing upstream (defect 2) */
+        if (corrected && s->inst[hit.inst].material_set < 0) break;             /* missing upstream (defect 2) */
+        const Tex tex = tex_set(&c->tex, s->inst[hit.inst].material_set);      /* literal mode shades any instance: set 0 for -1 */
         f4 mat_grad = {0, 0, 0, 0};
-        f4 mat = read_bsdf(&c->tex, it.uv);
+        f4 mat = read_bsdf(&tex, it.uv);
         f3 diffuse = v3(mat.x, mat.y, mat.z);
         float roughness = mat.w;
         Onb onb = make_onb(it.ns);
@@ -1280,7 +1305,7 @@ static void path_estimator_backward(Ctx* c, Ray ray, Sampler* sampler, f3 le_gra
         /* prb.py:178-187: per-vertex flush (in-loop or after-loop, same `it`), NaNs dropped */
         if (mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) {
             if (!(isnan(mat_grad.x) || isnan(mat_grad.y) || isnan(mat_grad.z) || isnan(mat_grad.w)))
-                write_bsdf_grad(&c->tex, it.uv, mat_grad);
+                write_bsdf_grad(&tex, it.uv, mat_grad);
         }
         if (done) break;
     }
@@ -1392,7 +1417,7 @@ ZO_API int zo_render_backward(zo_scene* s, int integrator, const zdr_params* p, 
     int rc = check_render_args(s, integrator, p);
     if (rc) return rc;
     if (!material || !d_image || !d_material) return ZDR_ERR_ARG;
-    size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4;
+    size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4 * (size_t)(p->num_material_sets > 1 ? p->num_material_sets : 1);
     double* acc = (double*)calloc(nmat, sizeof(double));
     uint64_t nc = 0, na = 0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : nc, na)

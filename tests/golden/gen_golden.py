@@ -302,6 +302,87 @@ def load_patched_prb():
     return mod
 
 
+# ------------------------------------------------------------------------------------ material sets
+# "Polymorphic materials" (several texture sets) are listed as NOT implemented upstream (README.md:5), so the reference cannot
+# pin them as shipped.  The fixture below runs the reference's own direct.py / interaction.py with the smallest textual change
+# that adds a set index — nothing else is touched:
+#   interaction.py: read_single_bsdf / read_bsdf / write_single_bsdf_grad / write_bsdf_grad take `mat_set` and offset the texel
+#                   index by mat_set * texture_res.x * texture_res.y;
+#   direct.py:      `mat_set = heap.buffer_read(int, 23336, hit.inst)` next to the emission read, `if hit.inst > 0` becomes
+#                   `if mat_set < 0` (direct.py:30,98: "treat everything as light other than the first object" generalised to
+#                   "... other than the textured objects"), and every read_bsdf / write_bsdf_grad passes mat_set (the set of
+#                   the PRIMARY hit, as mat_grad_uv is the primary hit's uv).
+MS_INTERACTION_PATCHES = [
+    ("def read_single_bsdf(coord: int2, material_buffer, texture_res):", "def read_single_bsdf(coord: int2, material_buffer, texture_res, mat_set):"),
+    ("    idx = coord.x + texture_res.x * coord.y\n    return float4(", "    idx = coord.x + texture_res.x * coord.y + mat_set * texture_res.x * texture_res.y\n    return float4("),
+    ("def read_bsdf(uv: float2, material_buffer, texture_res):", "def read_bsdf(uv: float2, material_buffer, texture_res, mat_set):"),
+    ("return read_single_bsdf(nearest, material_buffer, texture_res)", "return read_single_bsdf(nearest, material_buffer, texture_res, mat_set)"),
+    ("read_single_bsdf(ip + int2(0,0), material_buffer, texture_res)", "read_single_bsdf(ip + int2(0,0), material_buffer, texture_res, mat_set)"),
+    ("read_single_bsdf(ip + int2(0,1), material_buffer, texture_res)", "read_single_bsdf(ip + int2(0,1), material_buffer, texture_res, mat_set)"),
+    ("read_single_bsdf(ip + int2(1,0), material_buffer, texture_res)", "read_single_bsdf(ip + int2(1,0), material_buffer, texture_res, mat_set)"),
+    ("read_single_bsdf(ip + int2(1,1), material_buffer, texture_res)", "read_single_bsdf(ip + int2(1,1), material_buffer, texture_res, mat_set)"),
+    ("def write_single_bsdf_grad(coord: int2, dmat, d_material_buffer, texture_res):", "def write_single_bsdf_grad(coord: int2, dmat, d_material_buffer, texture_res, mat_set):"),
+    ("    idx = coord.x + texture_res.x * coord.y\n    _ = d_material_buffer", "    idx = coord.x + texture_res.x * coord.y + mat_set * texture_res.x * texture_res.y\n    _ = d_material_buffer"),
+    ("def write_bsdf_grad(uv: float2, dmat, d_material_buffer, texture_res):", "def write_bsdf_grad(uv: float2, dmat, d_material_buffer, texture_res, mat_set):"),
+    ("write_single_bsdf_grad(nearest, dmat, d_material_buffer, texture_res)", "write_single_bsdf_grad(nearest, dmat, d_material_buffer, texture_res, mat_set)"),
+    ("k00 * dmat, d_material_buffer, texture_res)", "k00 * dmat, d_material_buffer, texture_res, mat_set)"),
+    ("k01 * dmat, d_material_buffer, texture_res)", "k01 * dmat, d_material_buffer, texture_res, mat_set)"),
+    ("k10 * dmat, d_material_buffer, texture_res)", "k10 * dmat, d_material_buffer, texture_res, mat_set)"),
+    ("k11 * dmat, d_material_buffer, texture_res)", "k11 * dmat, d_material_buffer, texture_res, mat_set)"),
+]
+MS_DIRECT_PATCHES = [      # (old, new, occurrences)
+    ("from .interaction import read_bsdf, write_bsdf_grad, surface_interact", "from .interaction_ms import read_bsdf, write_bsdf_grad\nfrom .interaction import surface_interact", 1),
+    ("    emission = heap.buffer_read(float3, 23333, hit.inst)\n    if hit.inst > 0: # treat everything as light other than the first object",
+     "    emission = heap.buffer_read(float3, 23333, hit.inst)\n    mat_set = heap.buffer_read(int, 23336, hit.inst)\n    if mat_set < 0: # treat everything as light other than the textured objects", 2),
+    ("read_bsdf(it.uv, material_buffer, texture_res)", "read_bsdf(it.uv, material_buffer, texture_res, mat_set)", 2),
+    ("write_bsdf_grad(it.uv, mat_grad, d_material_buffer, texture_res)", "write_bsdf_grad(it.uv, mat_grad, d_material_buffer, texture_res, mat_set)", 2),
+    ("write_bsdf_grad(mat_grad_uv, mat_grad, d_material_buffer, texture_res)", "write_bsdf_grad(mat_grad_uv, mat_grad, d_material_buffer, texture_res, mat_set)", 1),
+]
+
+
+def _load_patched(module, patches, new_name):
+    import importlib.util
+    import tempfile
+    src = open(f"/root/reference/{module}.py").read()
+    for pt in patches:
+        a, b, n = pt if len(pt) == 3 else (pt[0], pt[1], 1)
+        assert src.count(a) == n, (module, a, src.count(a))
+        src = src.replace(a, b)
+    path = os.path.join(tempfile.mkdtemp(), new_name + ".py")
+    open(path, "w").write(src)
+    spec = importlib.util.spec_from_file_location("zdr_ref." + new_name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["zdr_ref." + new_name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def gen_material_sets():
+    """Cornell box (set 0) + light + a textured sphere inside the box (set 1) + a second, untextured quad (set -1): direct.py
+    with the material-set patch above, forward and adjoint."""
+    _load_patched("interaction", MS_INTERACTION_PATCHES, "interaction_ms")
+    dms = _load_patched("direct", MS_DIRECT_PATCHES, "direct_ms")
+    models, sets = scenes.cbox_material_sets_models()
+    sc = RefScene(models)
+    sc.heap.emplace(23336, E.buffer([int(x) for x in sets]))
+    cam = R_render.Camera(fov=50 / 180 * 3.1415926, origin=E.float3(-0.2, 2.6, 6.0), target=E.float3(-0.2, 2.6, -2.5),
+                          up=E.float3(0.0, 1.0, 0.0))
+    res, spp, tex, seed = (24, 24), 2, 32, 21
+    W, H = res
+    mat = np.stack([scenes.random_material((tex, tex), 12), scenes.random_material((tex, tex), 13)])
+    image = E.Buffer(dtype=E.float4, size=W * H, data=np.zeros((W * H, 4), np.float32))
+    mbuf = E.Buffer(dtype=float, size=mat.size, data=mat.reshape(-1).copy())
+    dms.render_direct_kernel(image, sc.heap, sc.accel, sc.light_count, 0, mbuf, E.int2(tex, tex), cam, spp, seed, True, dispatch_size=(W, H))
+    d_image = np.random.default_rng(7).normal(size=(H, W, 4)).astype(np.float32)
+    dbuf = E.Buffer(dtype=E.float4, size=W * H, data=d_image.reshape(-1, 4).copy())
+    dmat = E.Buffer(dtype=float, size=mat.size, data=np.zeros(mat.size, np.float64))
+    dms.render_direct_backward_kernel(dbuf, sc.heap, sc.accel, sc.light_count, 0, dmat, mbuf, E.int2(tex, tex), cam, spp, seed + 1, True, dispatch_size=(W, H))
+    dm = dmat.data.reshape(2, tex, tex, 4).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "render_direct_material_sets.npz"), res=np.asarray(res), spp=spp, tex=tex, seed=seed, sets=np.asarray(sets, np.int32),
+                        material=mat, image=image.data.reshape(H, W, 4).astype(np.float32), d_image=d_image, d_material=dm)
+    print(f"render_direct_material_sets.npz: image mean {image.data[:, :3].mean():.5f}, |d_material| per set {np.abs(dm).sum(axis=(1, 2, 3))}")
+
+
 # ------------------------------------------------------------------------------------ envmap.py
 ENV_ROWS = (0, 17, 128, 200, 255)            # conditional tables / pdf rows kept in the fixture
 
@@ -399,7 +480,7 @@ def F_(x):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path", "loadobj", "uvgrad", "envmap", "direct_env", "path_env", "direct_xform", "scene_api"]
+    which = sys.argv[1:] or ["sampler", "functions", "collocated", "direct", "path", "loadobj", "uvgrad", "envmap", "direct_env", "path_env", "direct_xform", "scene_api", "material_sets"]
     if "path_env" in which:                    # prb.py (arity-patched) with env_count = 1
         prb = load_patched_prb()
         gen_render("path_literal_env", scenes.cbox_path_models(), prb.render_path_kernel, prb.render_path_backward_kernel, (16, 16), 2, 64, 13, 6,
@@ -428,6 +509,8 @@ if __name__ == "__main__":
     if "direct" in which:
         gen_render("direct", scenes.cbox_path_models(), R_direct.render_direct_kernel, R_direct.render_direct_backward_kernel,
                    (20, 20), 2, 64, 5, 4)
+    if "material_sets" in which:
+        gen_material_sets()
     if "path" in which:
         prb = load_patched_prb()
         assert prb.max_depth == 16 and prb.rr_depth == 2

@@ -89,6 +89,26 @@ def test_render_kernels_vs_reference_source(oracle, name, models, integ, kw):
     assert rel_l2(dm, z["d_material"]) <= 1e-3, rel_l2(dm, z["d_material"])
 
 
+def test_material_sets_vs_patched_reference_source(oracle):
+    """Several texture sets ("polymorphic materials") are listed as not implemented upstream (README.md:5).  The fixture runs
+    the reference's own direct.py / interaction.py with the smallest textual change that adds a set index (gen_golden.py
+    MS_*_PATCHES: texel index offset, `hit.inst > 0` -> `mat_set < 0`) under the emulator; the oracle's material sets must
+    reproduce image and the gradient of BOTH sets."""
+    z = np.load(os.path.join(G, "render_direct_material_sets.npz"))
+    res, spp, seed = tuple(int(x) for x in z["res"]), int(z["spp"]), int(z["seed"])
+    models, sets = scenes.cbox_material_sets_models()
+    assert sets == [int(x) for x in z["sets"]]
+    mat = z["material"]
+    sc = oracle.OracleScene(models)
+    sc.set_material_sets(sets)
+    img = sc.render_forward(ZDR_DIRECT, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed), mat)
+    assert rel_l2(img, z["image"]) <= 1e-4, rel_l2(img, z["image"])
+    dm = sc.render_backward(ZDR_DIRECT, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed + 1), mat, z["d_image"])
+    assert dm.shape == mat.shape and np.abs(z["d_material"][0]).max() > 0 and np.abs(z["d_material"][1]).max() > 0
+    for k in range(2):
+        assert rel_l2(dm[k], z["d_material"][k]) <= 1e-3, (k, rel_l2(dm[k], z["d_material"][k]))
+
+
 def test_duvdxy_vs_reference_source(oracle):
     """uvgrad.py `trace_duvdxy` executed from the reference source vs the oracle."""
     z = np.load(os.path.join(G, "uvgrad.npz"))

@@ -57,6 +57,10 @@ class GpuScene:
         e = np.ascontiguousarray(e, np.float32)
         _abi.check(self.lib.zdr_scene_set_emissions(self.h, np_ptr(e, C.c_float), e.shape[0]))
 
+    def set_material_sets(self, sets):
+        a = np.ascontiguousarray(sets, np.int32)
+        _abi.check(self.lib.zdr_scene_set_material_sets(self.h, np_ptr(a, C.c_int32), a.shape[0]))
+
     def set_envmap(self, img, compensate=True):
         img = np.ascontiguousarray(img, np.float32)
         _abi.check(self.lib.zdr_scene_set_envmap(self.h, np_ptr(img, C.c_float), img.shape[1], img.shape[0], int(compensate)))
@@ -558,3 +562,40 @@ def test_error_codes():
     # sampler tables whose index range does not fit the kernels' 32-bit arithmetic
     tiny16, tiny32 = np.zeros(4, np.uint16), np.zeros(4, np.uint32)
     assert lib.zdr_set_sampler_tables(0, np_ptr(tiny32, C.c_uint32), 5, 65536, np_ptr(tiny16, C.c_uint16), 48, 1 << 14) == -4
+
+
+@pytest.mark.parametrize("integ,kw", [(ZDR_COLLOCATED, {}), (ZDR_DIRECT, {}), (ZDR_DIRECT, {"scatter": "aggregate"}),
+                                      (ZDR_PATH, {"max_depth": 5, "schedule": "megakernel"}), (ZDR_PATH, {"max_depth": 5, "schedule": "wavefront"}),
+                                      (ZDR_PATH, {"max_depth": 5, "schedule": "persistent"}),
+                                      (ZDR_PATH, {"max_depth": 5, "schedule": "persistent", "prb_mode": _abi.ZDR_PRB_LITERAL})])
+def test_material_sets_match_oracle(oracle, integ, kw):
+    """Several texture sets ("polymorphic materials", README.md:5; pinned against the patched reference source in
+    tests/test_golden.py): Cornell box on set 0, a sphere inside it on set 1, a quad without a set.  Every integrator and
+    schedule: image bit-identical to the oracle's, gradients of both sets within the tolerance; the committed fixture too."""
+    models, sets = scenes.cbox_material_sets_models()
+    g, o = GpuScene(models), oracle.OracleScene(models)
+    g.set_material_sets(sets)
+    o.set_material_sets(sets)
+    mat = np.stack([scenes.random_material((48, 48), 12), scenes.random_material((48, 48), 13)])
+    res, spp = (72, 56), 4
+    pf = make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, 4, **kw)
+    pb = make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, 5, **kw)
+    assert pf.num_material_sets == 2 and (pf.tex_res_x, pf.tex_res_y) == (48, 48)
+    assert np.array_equal(bits(g.forward(integ, pf, mat)), bits(o.render_forward(integ, pf, mat)))
+    dimg = np.random.default_rng(3).uniform(0.5, 1.5, (res[1], res[0], 4)).astype(np.float32)
+    dg, do = g.backward(integ, pb, mat, dimg), o.render_backward(integ, pb, mat, dimg)
+    assert dg.shape == mat.shape and np.abs(do[0]).max() > 0 and np.abs(do[1]).max() > 0
+    for k in range(2):
+        assert rel_l2(dg[k], do[k]) <= GRAD_TOL, (k, rel_l2(dg[k], do[k]))
+    # a set index beyond the buffer is an error, not an out-of-bounds read
+    one = make_params(scenes.CBOX_CAMERA, res, mat[0].shape, spp, 4, **kw)
+    with pytest.raises(_abi.ZdrError):
+        g.forward(integ, one, mat[0])
+    if integ == ZDR_DIRECT and not kw:
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render_direct_material_sets.npz"))
+        r2 = tuple(int(x) for x in z["res"])
+        img = g.forward(ZDR_DIRECT, make_params(scenes.CBOX_CAMERA, r2, z["material"].shape, int(z["spp"]), int(z["seed"])), z["material"])
+        assert rel_l2(img, z["image"]) <= 1e-4
+        dm = g.backward(ZDR_DIRECT, make_params(scenes.CBOX_CAMERA, r2, z["material"].shape, int(z["spp"]), int(z["seed"]) + 1), z["material"], z["d_image"])
+        assert rel_l2(dm, z["d_material"]) <= 1e-3
+    g.close()

@@ -321,3 +321,25 @@ def test_scene_on_another_device_leaves_the_current_device_alone():
     assert img.device.index == 1 and float(mat.grad.abs().sum()) > 0
     sc.close()
     assert torch.cuda.current_device() == 0
+
+
+def test_material_sets_through_the_torch_surface():
+    """Scene.set_material_sets + a (K, Ht, Wt, 4) material tensor: image and a gradient of the same shape through autograd;
+    too few sets in the tensor is a Python exception."""
+    from zdr_b200 import Scene
+    models, sets = scenes.cbox_material_sets_models()
+    sc = Scene(models, integrator="path")
+    sc.camera = scenes.CBOX_CAMERA.copy()
+    sc.max_depth = 4
+    assert sc.material_sets == [0, -1, -1, -1]
+    one = torch.from_numpy(scenes.random_material((32, 32), 1)).cuda().requires_grad_()
+    base = sc.render(one, res=(48, 40), spp=4, seed=2)
+    sc.set_material_sets(sets)
+    with pytest.raises(ValueError):
+        sc.render(one, res=(48, 40), spp=4, seed=2)
+    two = torch.stack([one.detach(), torch.from_numpy(scenes.random_material((32, 32), 2)).cuda()]).requires_grad_()
+    img = sc.render(two, res=(48, 40), spp=4, seed=2)
+    assert img.shape == base.shape and not torch.equal(img, base)
+    img[..., :3].sum().backward()
+    assert two.grad.shape == two.shape and float(two.grad[0].abs().sum()) > 0 and float(two.grad[1].abs().sum()) > 0
+    sc.close()

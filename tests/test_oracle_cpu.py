@@ -269,3 +269,35 @@ def test_oracle_bvh_equals_scan_on_degenerate_geometry(oracle, monkeypatch, tmp_
     assert np.array_equal(a[2], b[2])
     copies = (a[0][:400, 1] >= 3000) & (a[0][:400, 1] < 3300)
     assert copies.sum() > 20 and (a[0][:400, 1][copies] == 3000).all()
+
+
+@pytest.mark.parametrize("integ,kw", [(ZDR_COLLOCATED, {}), (ZDR_DIRECT, {}), (ZDR_PATH, {"max_depth": 4}),
+                                      (ZDR_PATH, {"max_depth": 4, "prb_mode": ZDR_PRB_LITERAL})])
+def test_material_sets_properties(oracle, integ, kw):
+    """Material sets ("polymorphic materials", README.md:5): (1) the default assignment is the reference's single-set rule;
+    (2) two sets holding the SAME texels render the same image as one set shared by both instances, and the shared set's
+    gradient is the sum of the two sets' gradients; (3) a perturbation of set 1 moves only pixels that see instance 2."""
+    models, sets = scenes.cbox_material_sets_models()
+    res, spp = (24, 24), 2
+    tex = scenes.random_material((16, 16), 3)
+    two = np.stack([tex, tex])
+    d_img = np.random.default_rng(5).uniform(0.5, 1.5, (res[1], res[0], 4)).astype(np.float32)
+    sc = oracle.OracleScene(models)
+    base = sc.render_forward(integ, make_params(scenes.CBOX_CAMERA, res, tex.shape, spp, 2, **kw), tex)      # default: [0, -1, -1, -1]
+    sc.set_material_sets([0, -1, -1, -1])
+    assert np.array_equal(base, sc.render_forward(integ, make_params(scenes.CBOX_CAMERA, res, tex.shape, spp, 2, **kw), tex))
+    sc.set_material_sets([0, -1, 0, -1])                                  # both textured instances share set 0
+    shared = sc.render_forward(integ, make_params(scenes.CBOX_CAMERA, res, tex.shape, spp, 2, **kw), tex)
+    g_shared = sc.render_backward(integ, make_params(scenes.CBOX_CAMERA, res, tex.shape, spp, 3, **kw), tex, d_img)
+    sc.set_material_sets(sets)                                            # [0, -1, 1, -1]
+    split = sc.render_forward(integ, make_params(scenes.CBOX_CAMERA, res, two.shape, spp, 2, **kw), two)
+    g_split = sc.render_backward(integ, make_params(scenes.CBOX_CAMERA, res, two.shape, spp, 3, **kw), two, d_img)
+    assert np.array_equal(shared, split)
+    assert g_split.shape == two.shape and np.abs(g_split[1]).max() > 0
+    assert np.allclose(g_split[0] + g_split[1], g_shared, rtol=1e-5, atol=1e-7)
+    if integ != ZDR_COLLOCATED:
+        assert not np.array_equal(base, split)                            # the sphere is shaded now, it was a black terminal before
+    other = two.copy()
+    other[1] = scenes.random_material((16, 16), 9)
+    moved = sc.render_forward(integ, make_params(scenes.CBOX_CAMERA, res, two.shape, spp, 2, **kw), other)
+    assert not np.array_equal(moved, split)

@@ -41,7 +41,7 @@ class ZdrParams(C.Structure):
         ("use_mis", C.c_int32), ("bilinear", C.c_int32), ("prb_mode", C.c_int32),
         ("row0", C.c_int32), ("row1", C.c_int32), ("it0", C.c_int32), ("it1", C.c_int32),
         ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("flags", C.c_int32),
-        ("reserved", C.c_int32 * 1),
+        ("num_material_sets", C.c_int32),
     ]
 
 
@@ -52,13 +52,16 @@ def wrap_i32(x: int) -> int:
 
 def make_params(camera, res, tex_shape, spp, seed, *, use_tent_filter=True, max_depth=16, rr_depth=2,
                 use_mis=True, bilinear=True, prb_mode=ZDR_PRB_CORRECTED, rows=None, its=None, shard=None,
-                stats=False, scatter="auto", schedule="auto", light_pdf_counts_env=False) -> ZdrParams:
+                stats=False, scatter="auto", schedule="auto", light_pdf_counts_env=False, num_material_sets=1) -> ZdrParams:
     p = ZdrParams()
     p.cam_fov = float(camera.fov)
     p.cam_origin[:] = list(camera.origin)
     p.cam_target[:] = list(camera.target)
     p.cam_up[:] = list(camera.up)
     p.width, p.height = int(res[0]), int(res[1])                  # res = (W, H), render.py:232
+    if len(tex_shape) == 4:                                       # (K, Ht, Wt, 4): K texture sets
+        num_material_sets, tex_shape = int(tex_shape[0]), tex_shape[1:]
+    p.num_material_sets = int(num_material_sets)
     p.tex_res_x, p.tex_res_y = int(tex_shape[0]), int(tex_shape[1])  # int2(*material.shape[0:2]), render.py:161,170
     p.spp, p.seed = int(spp), wrap_i32(seed)
     p.use_tent_filter = 1 if use_tent_filter else 0
@@ -94,6 +97,7 @@ SIGNATURES = {
     "zdr_scene_clear": (C.c_int, [_vp]),
     "zdr_scene_set_emissions": (C.c_int, [_vp, _f32p, C.c_int]),
     "zdr_scene_set_envmap": (C.c_int, [_vp, _f32p, C.c_int, C.c_int, C.c_int]),
+    "zdr_scene_set_material_sets": (C.c_int, [_vp, _i32p, C.c_int]),
     "zdr_scene_instance_count": (C.c_int, [_vp]),
     "zdr_scene_light_count": (C.c_int, [_vp]),
     "zdr_scene_triangle_count": (C.c_int, [_vp]),

@@ -55,6 +55,7 @@ struct Mesh {
     float N[9];
     float emission[3];
     int tri_base = 0;
+    int material_set = -2;        // -2: default (instance 0 -> set 0, others -1 = upstream); else zdr_scene_set_material_sets
 };
 
 // inverse(transpose(M3x3)), interaction.py:28 — cofactor expansion, plain binary32 operations
@@ -134,6 +135,21 @@ int use_device(int device, DevGuard& g) {
     return ZDR_OK;
 }
 
+// uv bounds of the textured instances (instance 0 upstream, direct.py:30): decides the default scatter strategy
+void update_uv_bounds(zdr_scene* s) {
+    s->uv_lo[0] = s->uv_lo[1] = INFINITY; s->uv_hi[0] = s->uv_hi[1] = -INFINITY;
+    for (size_t i = 0; i < s->meshes.size(); ++i) {
+        const Mesh& m = s->meshes[i];
+        const int ms = m.material_set == -2 ? (i == 0 ? 0 : -1) : m.material_set;
+        if (ms < 0 && i != 0) continue;
+        for (size_t v = 0; v < m.verts.size() / 8; ++v)
+            for (int k = 0; k < 2; ++k) {
+                s->uv_lo[k] = fminf(s->uv_lo[k], m.verts[8 * v + 3 + k]);
+                s->uv_hi[k] = fmaxf(s->uv_hi[k], m.verts[8 * v + 3 + k]);
+            }
+    }
+}
+
 int upload_lights(zdr_scene* s) {   // render.py:116-126, :141-148
     const int n = (int)s->meshes.size();
     std::vector<InstData> inst(n);
@@ -145,6 +161,7 @@ int upload_lights(zdr_scene* s) {   // render.py:116-126, :141-148
         memcpy(inst[i].emission, m.emission, sizeof(m.emission));
         inst[i].tri_base = m.tri_base;
         inst[i].tri_count = (int)(m.tris.size() / 3);
+        inst[i].material_set = m.material_set == -2 ? (i == 0 ? 0 : -1) : m.material_set;
         if (m.emission[0] > 0.f || m.emission[1] > 0.f || m.emission[2] > 0.f) lights.push_back(i);   // render.py:89-90
     }
     s->light_count = (int)lights.size();
@@ -207,6 +224,15 @@ int make_args(zdr_scene* s, const zdr_params* p, RenderArgs* a) {
     a->shard_count = p->shard_count > 1 ? p->shard_count : 1;
     a->shard_index = p->shard_count > 1 ? p->shard_index : 0;
     a->tex.rx = p->tex_res_x; a->tex.ry = p->tex_res_y; a->tex.bilinear = p->bilinear;
+    a->tex.set_texels = p->tex_res_x * p->tex_res_y;
+    {
+        const int num_sets = p->num_material_sets > 1 ? p->num_material_sets : 1;
+        for (size_t i = 0; i < s->meshes.size(); ++i) {
+            const int ms = s->meshes[i].material_set;
+            if (ms >= num_sets) return fail(ZDR_ERR_ARG, "instance %zu uses material set %d but the material buffer holds %d set(s)", i, ms, num_sets);
+        }
+        if ((long long)num_sets * a->tex.set_texels >= (1ll << 31)) return fail(ZDR_ERR_LIMIT, "material sets too large");
+    }
     a->counters = s->d_counters;
     // gradient scatter strategy: warp aggregation pays when many lanes of a warp share a footprint,
     // i.e. when the textured object's uv range covers only a few texels (uniform / uv-less meshes)
@@ -454,15 +480,7 @@ ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
     const char* force = getenv("ZDR_BVH");     // "lbvh" | "csah" | "sah": builder override for experiments and tests
     const bool sah = force ? strcmp(force, "sah") == 0 : nt <= (size_t)kSahMaxTris;
     const bool lbvh = force && strcmp(force, "lbvh") == 0;
-    {
-        const Mesh& m0 = s->meshes[0];
-        s->uv_lo[0] = s->uv_lo[1] = INFINITY; s->uv_hi[0] = s->uv_hi[1] = -INFINITY;
-        for (size_t v = 0; v < m0.verts.size() / 8; ++v)
-            for (int k = 0; k < 2; ++k) {
-                s->uv_lo[k] = fminf(s->uv_lo[k], m0.verts[8 * v + 3 + k]);
-                s->uv_hi[k] = fmaxf(s->uv_hi[k], m0.verts[8 * v + 3 + k]);
-            }
-    }
+    update_uv_bounds(s);
     CK(cudaDeviceSynchronize());
     free_bvh(&s->bvh);
     cudaFree(s->d_inst); cudaFree(s->d_lights);
@@ -547,6 +565,23 @@ ZDR_EXPORT int zdr_scene_set_emissions(zdr_scene* s, const float* e3, int n) {  
     // RenderOperator.backward re-applies the forward call's emissions on every step (render.py:218): nothing to
     // upload, and no reason to synchronise the device, when they are what the device already holds
     if (!s->committed || !changed) return ZDR_OK;
+    DevGuard dev_guard;
+    int rc = use_device(s->device, dev_guard);
+    if (rc) return rc;
+    return upload_lights(s);
+}
+
+// Material sets ("polymorphic materials", README.md:5): set_of_instance[i] = the texture set that shades instance i, or -1 for
+// a light / terminal surface.  The default — instance 0 -> set 0, every other instance -1 — is the reference's rule "treat
+// everything as light other than the first object" (direct.py:30, prb.py:45).
+ZDR_EXPORT int zdr_scene_set_material_sets(zdr_scene* s, const int32_t* set_of_instance, int n) {
+    if (!s || !set_of_instance) return fail(ZDR_ERR_ARG, "set_material_sets: null");
+    if (n != (int)s->meshes.size()) return fail(ZDR_ERR_ARG, "set_material_sets: %d entries for %d instances", n, (int)s->meshes.size());
+    for (int i = 0; i < n; ++i)
+        if (set_of_instance[i] < -1) return fail(ZDR_ERR_ARG, "set_material_sets: entry %d is %d (>= -1 expected)", i, set_of_instance[i]);
+    for (int i = 0; i < n; ++i) s->meshes[i].material_set = set_of_instance[i];
+    update_uv_bounds(s);
+    if (!s->committed) return ZDR_OK;
     DevGuard dev_guard;
     int rc = use_device(s->device, dev_guard);
     if (rc) return rc;
@@ -653,7 +688,7 @@ ZDR_EXPORT int zdr_render_forward_host(zdr_scene* s, int integrator, const zdr_p
     if (!material_host || !image_host) return fail(ZDR_ERR_ARG, "render_forward_host: null buffer");
     DevGuard dev_guard;
     if ((rc = use_device(s->device, dev_guard))) return rc;
-    const size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4, nimg = (size_t)p->width * p->height * 4;
+    const size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4 * (p->num_material_sets > 1 ? p->num_material_sets : 1), nimg = (size_t)p->width * p->height * 4;
     CK(s->s_mat.reserve(nmat));
     CK(s->s_img.reserve(nimg));
     cudaStream_t st = s->own_stream;
@@ -674,7 +709,7 @@ ZDR_EXPORT int zdr_render_backward_host(zdr_scene* s, int integrator, const zdr_
     if (!material_host || !d_image_host || !d_material_host) return fail(ZDR_ERR_ARG, "render_backward_host: null buffer");
     DevGuard dev_guard;
     if ((rc = use_device(s->device, dev_guard))) return rc;
-    const size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4, nimg = (size_t)p->width * p->height * 4;
+    const size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4 * (p->num_material_sets > 1 ? p->num_material_sets : 1), nimg = (size_t)p->width * p->height * 4;
     CK(s->s_mat.reserve(nmat));
     CK(s->s_dmat.reserve(nmat));
     CK(s->s_dimg.reserve(nimg));
@@ -797,7 +832,7 @@ ZDR_EXPORT int zdr_probe_render_samples(zdr_scene* s, int integrator, const zdr_
     if (!material_host || !out_host) return fail(ZDR_ERR_ARG, "probe_render_samples: null buffer");
     DevGuard dev_guard;
     if ((rc = use_device(s->device, dev_guard))) return rc;
-    const size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4, nout = (size_t)p->width * p->height * p->spp * 3;
+    const size_t nmat = (size_t)p->tex_res_x * p->tex_res_y * 4 * (p->num_material_sets > 1 ? p->num_material_sets : 1), nout = (size_t)p->width * p->height * p->spp * 3;
     CK(s->s_mat.reserve(nmat));
     CK(s->s_misc.reserve(nout));
     RenderArgs a;

@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kPwThreads, kPwBlocks) k_pw(const __grid_const
                         const float3 emission = inst_emission(sc, hit.inst);
                         const bool back = backfacing(ray.d, itx);                  // prb.py:35-36
                         const bool emit = !back && any_pos(emission);              // prb.py:39-44 / :117-121
-                        if (back || emit || ((phase == 0 || corrected) && hit.inst > 0)) {      // prb.py:45-46
+                        if (back || emit || ((phase == 0 || corrected) && inst_material_set(sc, hit.inst) < 0)) {      // prb.py:45-46
                             const float4 B4 = pool.bi[slot], L4 = pool.Ls[slot];
                             beta = f3(B4.x, B4.y, B4.z); L = f3(L4.x, L4.y, L4.z);
                             if (emit) {
@@ -517,7 +517,8 @@ __global__ void __launch_bounds__(kPwThreads, kPwBlocks) k_pw(const __grid_const
                         if (any_nan(le_grad)) le_grad = zero;
                     }
                     const Interaction itx = surface_interact(sc, hit);
-                    const float4 mat = read_bsdf(a.tex, itx.uv);
+                    const int mset = inst_texture_set(sc, hit.inst);
+                    const float4 mat = read_bsdf(a.tex, itx.uv, mset);
                     const float3 diffuse = f3(mat.x, mat.y, mat.z);
                     const float roughness = mat.w;
                     const Onb onb = make_onb(itx.ns);
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(kPwThreads, kPwBlocks) k_pw(const __grid_const
                     if (ADJ) {                                                          // prb.py:178-187
                         if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad)) {
                             scatters++;
-                            reds += a.aggregate_scatter ? write_bsdf_grad_aggregated(a.tex, itx.uv, mat_grad, gcache) : write_bsdf_grad(a.tex, itx.uv, mat_grad);
+                            reds += a.aggregate_scatter ? write_bsdf_grad_aggregated(a.tex, itx.uv, mat_grad, gcache, mset) : write_bsdf_grad(a.tex, itx.uv, mat_grad, mset);
                         }
                     }
                     ++depth;

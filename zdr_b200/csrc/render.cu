@@ -26,9 +26,9 @@ struct Ctx {
     GradCache gc = grad_cache_null();      // AGG kernels: the CTA's shared-memory duplicate of the gradient buffer (shading.cuh)
     ZDR_DEV Hit closest(const Ray& r) { tl.closest++; return trace<false, STATS>(a.sc, r, tl.ts); }
     ZDR_DEV bool occluded(const Ray& r) { tl.any++; return trace<true, STATS>(a.sc, r, tl.ts).inst >= 0; }
-    ZDR_DEV void scatter(float2 uv, float4 g) {
+    ZDR_DEV void scatter(float2 uv, float4 g, int set) {
         tl.scatter++;
-        tl.red += AGG ? write_bsdf_grad_aggregated(a.tex, uv, g, gc) : write_bsdf_grad(a.tex, uv, g);
+        tl.red += AGG ? write_bsdf_grad_aggregated(a.tex, uv, g, gc, set) : write_bsdf_grad(a.tex, uv, g, set);
     }
 };
 
@@ -40,7 +40,7 @@ ZDR_DEV float3 collocated_estimator(CTX& c, const Ray& ray) {               // c
     const Interaction it = surface_interact(c.a.sc, hit);
     if (backfacing(ray.d, it)) return f3(0.f, 0.f, 0.f);
     c.tl.shaded++;
-    const float4 mat = read_bsdf(c.a.tex, it.uv);
+    const float4 mat = read_bsdf(c.a.tex, it.uv, inst_texture_set(c.a.sc, hit.inst));
     const Onb onb = make_onb(it.ns);
     const float3 wo_local = to_local(onb, -ray.d);
     const float3 beta = ggx_brdf(wo_local, wo_local, f3(mat.x, mat.y, mat.z), 0.04f, mat.w);
@@ -55,12 +55,13 @@ ZDR_DEV void collocated_estimator_backward(CTX& c, const Ray& ray, float3 le_gra
     const Interaction it = surface_interact(c.a.sc, hit);
     if (backfacing(ray.d, it)) return;
     c.tl.shaded++;
-    const float4 mat = read_bsdf(c.a.tex, it.uv);
+    const int mset = inst_texture_set(c.a.sc, hit.inst);
+    const float4 mat = read_bsdf(c.a.tex, it.uv, mset);
     const Onb onb = make_onb(it.ns);
     const float3 wo_local = to_local(onb, -ray.d);
     const float inv = 1.0f / hit.t;
     const float li = 1.0f * (inv * inv);
-    c.scatter(it.uv, ggx_brdf_grad(wo_local, wo_local, 0.04f, mat.w, le_grad * li));
+    c.scatter(it.uv, ggx_brdf_grad(wo_local, wo_local, 0.04f, mat.w, le_grad * li), mset);
 }
 
 // ---------------------------------------------------------------------------------- direct.py
@@ -75,9 +76,10 @@ ZDR_DEV float3 direct_walk(CTX& c, const Ray& ray, Sampler& sampler, float3 le_g
     const Interaction it = surface_interact(sc, hit);
     if (backfacing(ray.d, it)) return zero;
     float3 emission = inst_emission(sc, hit.inst);
-    if (hit.inst > 0) return BWD ? zero : emission;                                // direct.py:30-32
+    const int mset = inst_material_set(sc, hit.inst);
+    if (mset < 0) return BWD ? zero : emission;                                    // direct.py:30-32 (`hit.inst > 0` upstream)
     c.tl.shaded++;
-    const float4 mat = read_bsdf(c.a.tex, it.uv);
+    const float4 mat = read_bsdf(c.a.tex, it.uv, mset);
     const float3 diffuse = f3(mat.x, mat.y, mat.z);
     const float roughness = mat.w;
     const float specular = 0.04f;
@@ -104,7 +106,7 @@ ZDR_DEV float3 direct_walk(CTX& c, const Ray& ray, Sampler& sampler, float3 le_g
         const float3 wi_local = ggx_sample(sc, wo_local, roughness, sampler);
         const float3 wi = to_world(onb, wi_local);
         if (dot(wi, it.ng) < 1e-4f || wi_local.z < 1e-4f) {
-            if (BWD) c.scatter(it.uv, mat_grad);                                   // direct.py:138
+            if (BWD) c.scatter(it.uv, mat_grad, mset);                             // direct.py:138
             return radiance;
         }
         const Ray r2 = make_ray(offset_ray_origin(it.p, it.ng), wi, 0.0f, 1e30f);
@@ -117,7 +119,7 @@ ZDR_DEV float3 direct_walk(CTX& c, const Ray& ray, Sampler& sampler, float3 le_g
             const Interaction it2 = surface_interact(sc, hit2);
             if (backfacing(r2.d, it2)) {
                 // direct.py:152 scatters at `it.uv` after `it` was rebound to the second hit
-                if (BWD) c.scatter(it2.uv, mat_grad);
+                if (BWD) c.scatter(it2.uv, mat_grad, mset);
                 return radiance;
             }
             emission = inst_emission(sc, hit2.inst);
@@ -135,7 +137,7 @@ ZDR_DEV float3 direct_walk(CTX& c, const Ray& ray, Sampler& sampler, float3 le_g
             }
         }
     }
-    if (BWD) c.scatter(it.uv, mat_grad);                                           // direct.py:167
+    if (BWD) c.scatter(it.uv, mat_grad, mset);                                     // direct.py:167
     return radiance;
 }
 
@@ -285,12 +287,13 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
                         const float3 contrib = (beta * mis_weight) * emission;
                         L = (phase == 0) ? L + contrib : L - contrib;
                         end = true;
-                    } else if ((phase == 0 || corrected) && hit.inst > 0) {        // prb.py:45-46 (forward only upstream)
+                    } else if ((phase == 0 || corrected) && inst_material_set(sc, hit.inst) < 0) {   // prb.py:45-46 (forward only upstream)
                         end = true;
                     } else {
                         tl.shaded++;
                         float4 mat_grad = make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float4 mat = read_bsdf(a.tex, itx.uv);
+                        const int mset = inst_texture_set(sc, hit.inst);
+                        const float4 mat = read_bsdf(a.tex, itx.uv, mset);
                         const float3 diffuse = f3(mat.x, mat.y, mat.z);
                         const float roughness = mat.w;
                         const Onb onb = make_onb(itx.ns);
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
                         }
                         if (BWD && phase == 1) {                                                        // prb.py:178-187
                             if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad))
-                                c.scatter(itx.uv, mat_grad);
+                                c.scatter(itx.uv, mat_grad, mset);
                         }
                         ++depth;
                     }
@@ -734,7 +737,7 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_A_MINB) k_wf_shade_a(
                     const float3 contrib = (p.beta * mis_weight) * emission;
                     p.L = (phase == 0) ? p.L + contrib : p.L - contrib;
                     end = true;
-                } else if ((phase == 0 || corrected) && hit.inst > 0) {          // prb.py:45-46
+                } else if ((phase == 0 || corrected) && inst_material_set(sc, hit.inst) < 0) {          // prb.py:45-46
                     wf_load_throughput(a, p);
                     end = true;
                 } else {
@@ -787,7 +790,8 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
                     if (any_nan(le_grad)) le_grad = zero;
                 }
                 const Interaction itx = surface_interact(sc, hit);
-                const float4 mat = read_bsdf(a.tex, itx.uv);
+                const int mset = inst_texture_set(sc, hit.inst);
+                const float4 mat = read_bsdf(a.tex, itx.uv, mset);
                 const float3 diffuse = f3(mat.x, mat.y, mat.z);
                 const float roughness = mat.w;
                 const Onb onb = make_onb(itx.ns);
@@ -846,7 +850,7 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
                 }
                 if (ADJ) {                                                          // prb.py:178-187
                     if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad))
-                        c.scatter(itx.uv, mat_grad);
+                        c.scatter(itx.uv, mat_grad, mset);
                 }
                 ++p.depth;
                 if (p.depth >= a.max_depth) end = true;                                             // prb.py:23

@@ -22,7 +22,9 @@ struct InstData {            // 64 B
     float emission[3];       // heap slot 23333 (render.py:120)
     int tri_base;            // first gid of the instance
     int tri_count;           // heap slot 23335 (render.py:126)
-    int pad[2];
+    int material_set;        // texture set that shades this instance, or -1: a light / terminal surface ("everything but the
+                             // first object", direct.py:30, prb.py:45).  Default: instance 0 -> set 0, all others -1 (upstream)
+    int pad;
 };
 
 struct SceneView {

@@ -51,19 +51,27 @@ struct TexView {
     float4* __restrict__ dmat;        // gradient accumulator (backward only)
     int rx, ry;
     int bilinear;
+    int set_texels;                   // texels of one texture set (rx * ry): set k starts at k * set_texels ("polymorphic materials")
 };
+// Material sets (README.md:5 "currently only one set of material"): the texture buffer holds K sets of (ry, rx) texels; an
+// instance is shaded with the set its InstData names.  -1 = the reference's "treat everything as light other than the first
+// object" (direct.py:30, prb.py:45); stages that upstream shade any instance (collocated.py:22, the literal PRB adjoint)
+// fall back to set 0.
+ZDR_DEV int inst_material_set(const SceneView& sc, int inst) { return sc.inst[inst].material_set; }
+ZDR_DEV int inst_texture_set(const SceneView& sc, int inst) { const int m = sc.inst[inst].material_set; return m < 0 ? 0 : m; }
 
-ZDR_DEV float4 read_single_bsdf(const TexView& t, int cx, int cy) {      // interaction.py:35-44
+ZDR_DEV float4 read_single_bsdf(const TexView& t, int cx, int cy, int base) {      // interaction.py:35-44
     cx = clampi(cx, 0, t.rx - 1); cy = clampi(cy, 0, t.ry - 1);
-    return __ldg(t.mat + (cx + t.rx * cy));
+    return __ldg(t.mat + (base + cx + t.rx * cy));
 }
-ZDR_DEV float4 read_bsdf(const TexView& t, float2 uv) {                    // interaction.py:46-60
+ZDR_DEV float4 read_bsdf(const TexView& t, float2 uv, int set = 0) {       // interaction.py:46-60
+    const int base = set * t.set_texels;
     const float px = uv.x * (float)(t.rx - 1), py = (1.0f - uv.y) * (float)(t.ry - 1);
-    if (!t.bilinear) return read_single_bsdf(t, f2i(px + 0.4999f), f2i(py + 0.4999f));
+    if (!t.bilinear) return read_single_bsdf(t, f2i(px + 0.4999f), f2i(py + 0.4999f), base);
     const int ix = f2i(px), iy = f2i(py);
     const float ox = px - (float)ix, oy = py - (float)iy;
-    const float4 c00 = read_single_bsdf(t, ix, iy), c01 = read_single_bsdf(t, ix, iy + 1);
-    const float4 c10 = read_single_bsdf(t, ix + 1, iy), c11 = read_single_bsdf(t, ix + 1, iy + 1);
+    const float4 c00 = read_single_bsdf(t, ix, iy, base), c01 = read_single_bsdf(t, ix, iy + 1, base);
+    const float4 c10 = read_single_bsdf(t, ix + 1, iy, base), c11 = read_single_bsdf(t, ix + 1, iy + 1, base);
     return lerp(lerp(c00, c01, oy), lerp(c10, c11, oy), ox);
 }
 
@@ -163,7 +171,7 @@ ZDR_DEV unsigned scatter_one(const GradCache& c, float4* dmat, int texel, float4
     return 1u;
 }
 static __device__ __noinline__ unsigned write_bsdf_grad_agg_nl(float4* __restrict__ dmat, int rx, int ry, int bilinear, float uvx, float uvy,
-                                                            float dx, float dy, float dz, float dw, int* cache_key, float* cache_acc) {  // interaction.py:62-89
+                                                            float dx, float dy, float dz, float dw, int* cache_key, float* cache_acc, int base) {  // interaction.py:62-89
     TexView t;
     t.mat = nullptr; t.dmat = dmat; t.rx = rx; t.ry = ry; t.bilinear = bilinear;
     GradCache cache;
@@ -176,16 +184,16 @@ static __device__ __noinline__ unsigned write_bsdf_grad_agg_nl(float4* __restric
     int n;
     if (!t.bilinear) {
         n = 1;
-        idx[0] = texel_index(t, f2i(px + 0.4999f), f2i(py + 0.4999f));
+        idx[0] = base + texel_index(t, f2i(px + 0.4999f), f2i(py + 0.4999f));
         v[0] = d;
     } else {
         n = 4;
         const int ix = f2i(px), iy = f2i(py);
         const float ox = px - (float)ix, oy = py - (float)iy;
-        idx[0] = texel_index(t, ix, iy);         v[0] = scale4((1.0f - ox) * (1.0f - oy), d);
-        idx[1] = texel_index(t, ix, iy + 1);     v[1] = scale4((1.0f - ox) * oy, d);
-        idx[2] = texel_index(t, ix + 1, iy);     v[2] = scale4(ox * (1.0f - oy), d);
-        idx[3] = texel_index(t, ix + 1, iy + 1); v[3] = scale4(ox * oy, d);
+        idx[0] = base + texel_index(t, ix, iy);         v[0] = scale4((1.0f - ox) * (1.0f - oy), d);
+        idx[1] = base + texel_index(t, ix, iy + 1);     v[1] = scale4((1.0f - ox) * oy, d);
+        idx[2] = base + texel_index(t, ix + 1, iy);     v[2] = scale4(ox * (1.0f - oy), d);
+        idx[3] = base + texel_index(t, ix + 1, iy + 1); v[3] = scale4(ox * oy, d);
     }
     const unsigned active = __activemask();
     // lanes with equal first texel and equal far-corner texel have identical footprints
@@ -210,22 +218,23 @@ static __device__ __noinline__ unsigned write_bsdf_grad_agg_nl(float4* __restric
     return issued;
 }
 
-ZDR_DEV unsigned write_bsdf_grad_aggregated(const TexView& t, float2 uv, float4 d, GradCache cache = grad_cache_null()) {
-    return write_bsdf_grad_agg_nl(t.dmat, t.rx, t.ry, t.bilinear, uv.x, uv.y, d.x, d.y, d.z, d.w, cache.key, cache.acc);
+ZDR_DEV unsigned write_bsdf_grad_aggregated(const TexView& t, float2 uv, float4 d, GradCache cache = grad_cache_null(), int set = 0) {
+    return write_bsdf_grad_agg_nl(t.dmat, t.rx, t.ry, t.bilinear, uv.x, uv.y, d.x, d.y, d.z, d.w, cache.key, cache.acc, set * t.set_texels);
 }
 // Plain scatter: one red.v4 per texel of the footprint (the reference issues four scalar atomics per
 // texel, interaction.py:67-70).  Used when the footprints of a warp are spread over the texture
 // (uv-mapped mesh, high-resolution texture): measured on C3, 3.81 of 4 reductions per scatter
 // survive aggregation, so the match + shuffle work is pure overhead there.
-ZDR_DEV unsigned write_bsdf_grad(const TexView& t, float2 uv, float4 d) {
+ZDR_DEV unsigned write_bsdf_grad(const TexView& t, float2 uv, float4 d, int set = 0) {
+    float4* dm = t.dmat + set * t.set_texels;
     const float px = uv.x * (float)(t.rx - 1), py = (1.0f - uv.y) * (float)(t.ry - 1);
-    if (!t.bilinear) { red_add_f4(t.dmat + texel_index(t, f2i(px + 0.4999f), f2i(py + 0.4999f)), d); return 1u; }
+    if (!t.bilinear) { red_add_f4(dm + texel_index(t, f2i(px + 0.4999f), f2i(py + 0.4999f)), d); return 1u; }
     const int ix = f2i(px), iy = f2i(py);
     const float ox = px - (float)ix, oy = py - (float)iy;
-    red_add_f4(t.dmat + texel_index(t, ix, iy), scale4((1.0f - ox) * (1.0f - oy), d));
-    red_add_f4(t.dmat + texel_index(t, ix, iy + 1), scale4((1.0f - ox) * oy, d));
-    red_add_f4(t.dmat + texel_index(t, ix + 1, iy), scale4(ox * (1.0f - oy), d));
-    red_add_f4(t.dmat + texel_index(t, ix + 1, iy + 1), scale4(ox * oy, d));
+    red_add_f4(dm + texel_index(t, ix, iy), scale4((1.0f - ox) * (1.0f - oy), d));
+    red_add_f4(dm + texel_index(t, ix, iy + 1), scale4((1.0f - ox) * oy, d));
+    red_add_f4(dm + texel_index(t, ix + 1, iy), scale4(ox * (1.0f - oy), d));
+    red_add_f4(dm + texel_index(t, ix + 1, iy + 1), scale4(ox * oy, d));
     return 4u;
 }
 

@@ -142,6 +142,18 @@ class Scene:
         self.env_count = 0
         self.emissions = emissions
         self.light_count = lib.zdr_scene_light_count(self._handle)
+        self.material_sets = [0] + [-1] * (self.inst_count - 1)        # direct.py:30: only the first object is textured
+
+    def set_material_sets(self, sets):
+        """Several texture sets ("polymorphic materials", listed as not implemented upstream, README.md:5).  ``sets[i]`` is
+        the texture set that shades instance ``i`` or ``-1`` for a light / terminal surface; ``render`` then takes a
+        ``(K, Ht, Wt, 4)`` material tensor and returns gradients of the same shape.  The default ``[0, -1, -1, ...]`` is the
+        reference's rule "treat everything as light other than the first object" (``direct.py:30``, ``prb.py:45``)."""
+        sets = [int(x) for x in sets]
+        assert len(sets) == self.inst_count
+        a = np.asarray(sets, dtype=np.int32)
+        check(self._lib.zdr_scene_set_material_sets(self._handle, np_ptr(a, C.c_int32), a.shape[0]), "zdr_scene_set_material_sets")
+        self.material_sets = sets
 
     def update_lights(self, emissions):
         """Rewrite the emission of every instance (``render.py:130-148``)."""
@@ -171,7 +183,8 @@ class Scene:
 
     # ------------------------------------------------------------------ operator launches
     def _params(self, material, res, spp, seed, rows=None):
-        p = make_params(self.camera, res, material.shape[0:2], spp, seed, use_tent_filter=self.use_tent_filter,
+        tex_shape = material.shape if material.ndim == 4 else material.shape[0:2]      # (K, Ht, Wt, 4): K texture sets
+        p = make_params(self.camera, res, tex_shape, spp, seed, use_tent_filter=self.use_tent_filter,
                         max_depth=self.max_depth, rr_depth=self.rr_depth, use_mis=self.use_mis, bilinear=self.bilinear,
                         prb_mode=PRB_MODES[self.prb_mode] if isinstance(self.prb_mode, str) else int(self.prb_mode),
                         rows=rows if rows is not None else self.shard_rows, its=self.shard_samples, shard=self.shard, stats=self.collect_stats, scatter=self.scatter_mode, schedule=self.schedule,
@@ -179,7 +192,11 @@ class Scene:
         return p
 
     def _check_material(self, material):
-        assert material.ndim == 3 and material.shape[2] == 4                          # render.py:160
+        # render.py:160: (Ht, Wt, 4); with material sets (set_material_sets) also (K, Ht, Wt, 4)
+        assert (material.ndim == 3 and material.shape[2] == 4) or (material.ndim == 4 and material.shape[3] == 4)
+        if (material.shape[0] if material.ndim == 4 else 1) <= max(self.material_sets):
+            raise ValueError(f"instance material sets {self.material_sets} need {max(self.material_sets) + 1} texture sets, "
+                             f"the material tensor {tuple(material.shape)} holds {material.shape[0] if material.ndim == 4 else 1}")
         if not material.is_cuda or material.device.index != self.device_index:
             raise ValueError(f"material must live on cuda:{self.device_index}")
         if material.dtype != torch.float32:
