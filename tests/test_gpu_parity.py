@@ -3,6 +3,7 @@ seeded inputs.  Bars (BASELINE.json north_star): sampler values and primitive id
 images rel-L2 <= 1e-4, gradients rel-L2 <= 1e-3.  The forward pass shares the oracle's numeric
 contract, so per-sample radiance is additionally compared bit-for-bit."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
