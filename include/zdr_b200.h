@@ -150,6 +150,19 @@ int zdr_scene_set_envmap(zdr_scene* s, const float* rgba_host, int w, int h, int
  * -1: the instance is a light / terminal surface.  The default (instance 0 -> 0, all others -1) is the reference's rule
  * "treat everything as light other than the first object" (direct.py:30, prb.py:45). n must equal the instance count. */
 int zdr_scene_set_material_sets(zdr_scene* s, const int32_t* set_of_instance_host, int n);
+/* Workspace of the path-integrator schedules (no counterpart upstream: LuisaCompute's per-pixel kernels keep their paths in
+ * registers).  HBM wavefront: 152 B per resident path, by default as many samples of every pixel as fit a quarter of the free
+ * memory (up to 2^28 paths = 41 GB); persistent schedule: 16 B per camera sample of a forward batch (up to 2 GiB).  Allocated
+ * with cudaMalloc on first use and kept, unless the caller
+ *   - bounds it:            zdr_scene_set_workspace_limit(bytes)   (0 = default policy; batches shrink to fit),
+ *   - provides it:          zdr_scene_set_workspace(ptr, bytes)    (256-byte aligned device buffer the CALLER owns, e.g. a torch
+ *                           tensor, so that the caller's allocator accounts for it; NULL, 0 = back to the library's own),
+ *   - or releases it:       zdr_scene_trim()                       (re-allocated on demand).
+ * A launch that does not fit fails with ZDR_ERR_LIMIT. */
+int zdr_scene_set_workspace_limit(zdr_scene* s, uint64_t bytes);
+int zdr_scene_set_workspace(zdr_scene* s, void* workspace_dev, uint64_t bytes);
+int zdr_scene_trim(zdr_scene* s);
+uint64_t zdr_scene_workspace_bytes(const zdr_scene* s);
 int zdr_scene_instance_count(const zdr_scene* s);
 int zdr_scene_light_count(const zdr_scene* s);
 int zdr_scene_triangle_count(const zdr_scene* s);

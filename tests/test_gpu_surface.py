@@ -343,3 +343,40 @@ def test_material_sets_through_the_torch_surface():
     img[..., :3].sum().backward()
     assert two.grad.shape == two.shape and float(two.grad[0].abs().sum()) > 0 and float(two.grad[1].abs().sum()) > 0
     sc.close()
+
+
+@pytest.mark.parametrize("schedule,res,spp", [("wavefront", (256, 256), 16), ("persistent", (256, 256), 16)])
+def test_workspace_limit_external_buffer_and_trim(schedule, res, spp):
+    """The path schedules' device workspace can be bounded, provided by the caller (a torch tensor: torch's allocator then
+    accounts for it) or released; the image does not depend on how it was batched."""
+    from zdr_b200 import Scene
+    from zdr_b200._abi import ZdrError
+    sc = Scene(scenes.cbox_path_models(), integrator="path")
+    sc.camera = scenes.CBOX_CAMERA.copy()
+    sc.max_depth = 4
+    sc.schedule = schedule
+    mat = torch.from_numpy(scenes.random_material((64, 64), 3)).cuda().requires_grad_()
+    ref = sc.render(mat, res=res, spp=spp, seed=1)
+    ref[..., :3].sum().backward()
+    g_ref, mat.grad = mat.grad.clone(), None
+    big = sc.workspace_bytes
+    assert big > 0
+    sc.trim()
+    assert sc.workspace_bytes == 0
+    sc.set_workspace_limit(24 << 20)                                   # forces several batches
+    img = sc.render(mat, res=res, spp=spp, seed=1)
+    img[..., :3].sum().backward()
+    assert torch.equal(img, ref) and 0 < sc.workspace_bytes <= (24 << 20)
+    assert rel_l2(mat.grad.cpu().numpy(), g_ref.cpu().numpy()) < 1e-5
+    mat.grad = None
+    sc.set_workspace_limit(0)
+    buf = torch.empty(32 << 20, dtype=torch.uint8, device="cuda")
+    sc.set_workspace(buf)
+    img = sc.render(mat, res=res, spp=spp, seed=1)
+    assert torch.equal(img, ref) and sc.workspace_bytes == buf.numel()
+    sc.set_workspace(torch.empty(1 << 16, dtype=torch.uint8, device="cuda"))      # cannot hold one sample per pixel
+    with pytest.raises(ZdrError):
+        sc.render(mat, res=res, spp=spp, seed=1)
+    sc.set_workspace(None)
+    assert torch.equal(sc.render(mat, res=res, spp=spp, seed=1), ref)
+    sc.close()

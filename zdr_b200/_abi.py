@@ -98,6 +98,10 @@ SIGNATURES = {
     "zdr_scene_set_emissions": (C.c_int, [_vp, _f32p, C.c_int]),
     "zdr_scene_set_envmap": (C.c_int, [_vp, _f32p, C.c_int, C.c_int, C.c_int]),
     "zdr_scene_set_material_sets": (C.c_int, [_vp, _i32p, C.c_int]),
+    "zdr_scene_set_workspace_limit": (C.c_int, [_vp, C.c_uint64]),
+    "zdr_scene_set_workspace": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "zdr_scene_trim": (C.c_int, [_vp]),
+    "zdr_scene_workspace_bytes": (C.c_uint64, [_vp]),
     "zdr_scene_instance_count": (C.c_int, [_vp]),
     "zdr_scene_light_count": (C.c_int, [_vp]),
     "zdr_scene_triangle_count": (C.c_int, [_vp]),

@@ -74,18 +74,20 @@ void normal_matrix(const float* M, float* N) {
 }
 
 template <typename T>
-struct DevBuf {   // grow-only device scratch
+struct DevBuf {   // grow-only device scratch; `external`: a buffer the caller owns (zdr_scene_set_workspace), never reallocated
     T* p = nullptr;
     size_t cap = 0;
+    bool external = false;
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
+        if (external) return cudaErrorMemoryAllocation;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         cudaError_t e = cudaMalloc(&p, sizeof(T) * n);
         if (e == cudaSuccess) cap = n;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && !external) cudaFree(p); p = nullptr; cap = 0; external = false; }
 };
 
 }  // namespace
@@ -106,7 +108,8 @@ struct zdr_scene {
     cudaStream_t side_streams[kWfMaxSets - 1] = {};      // further lanes of the wavefront schedule (launch_path_wavefront)
     cudaEvent_t wf_events[kWfMaxSets + 2] = {};
     DevBuf<float> s_mat, s_img, s_dimg, s_dmat, s_misc, s_misc2;
-    DevBuf<char> s_wf;                       // wavefront path state (render.cuh WfState)
+    DevBuf<char> s_wf;                       // workspace of the path schedules: wavefront path state (render.cuh WfState) / persistent sample buffer
+    size_t ws_limit = 0;                     // zdr_scene_set_workspace_limit: upper bound of that workspace in bytes (0: default policy)
     int num_sms = 148;
     DevBuf<int> s_int, s_int2;
 };
@@ -282,7 +285,14 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
         set_bytes = (slots * wf_bytes_per_slot() + 256 + 255) & ~(size_t)255;
         bytes = set_bytes * sets;
     };
-    if (const char* slots_env = getenv("ZDR_WF_SLOTS_LOG2")) {
+    const size_t ws_cap = s->s_wf.external ? s->s_wf.cap : s->ws_limit;      // caller-provided buffer / caller-set bound
+    if (ws_cap) {
+        long long fit = (long long)((ws_cap > 512 ? ws_cap - 512 : 0) / wf_bytes_per_slot());
+        if (fit < pixels) return fail(ZDR_ERR_LIMIT, "workspace of %zu MiB cannot hold one sample per pixel of this launch (%lld MiB needed)",
+                                      ws_cap >> 20, (long long)(pixels * wf_bytes_per_slot() + 512) >> 20);
+        plan(fit < (1ll << 28) ? fit : (1ll << 28));
+        while (bytes > ws_cap && S > 1) { plan((long long)(slots - pixels)); }
+    } else if (const char* slots_env = getenv("ZDR_WF_SLOTS_LOG2")) {
         plan(1ll << atoi(slots_env));
     } else {
         plan(1ll << 28);
@@ -340,7 +350,14 @@ int setup_persistent(zdr_scene* s, int integrator, const zdr_params* p, RenderAr
     if (!(p->flags & ZDR_FLAG_PERSISTENT) && (pixels * its < auto_lo || pixels * its >= auto_hi)) return ZDR_OK;
     cudaError_t e = pw_plan(a->sc, s->bvh.max_depth, s->num_sms, plan);
     if (e != cudaSuccess) return fail(ZDR_ERR_CUDA, "persistent schedule: %s", cudaGetErrorString(e));
-    static const long long r_cap = getenv("ZDR_PW_R_BYTES") ? atoll(getenv("ZDR_PW_R_BYTES")) : (2ll << 30);
+    static const long long r_cap_default = getenv("ZDR_PW_R_BYTES") ? atoll(getenv("ZDR_PW_R_BYTES")) : (2ll << 30);
+    long long r_cap = r_cap_default;
+    const size_t ws_cap = s->s_wf.external ? s->s_wf.cap : s->ws_limit;
+    if (ws_cap) {
+        const long long room = (long long)ws_cap - (long long)kPwHeaderBytes - (long long)plan->gstate_bytes;
+        if (room < (backward ? 0 : pixels * 16)) return fail(ZDR_ERR_LIMIT, "workspace of %zu MiB is too small for this launch", ws_cap >> 20);
+        if (room < r_cap) r_cap = room;
+    }
     size_t slots = 0;
     if (!backward) {
         long long smax = r_cap / 16 / pixels;
@@ -599,6 +616,42 @@ ZDR_EXPORT int zdr_scene_set_envmap(zdr_scene* s, const float* rgba, int w, int 
     if (e != cudaSuccess) return fail(ZDR_ERR_CUDA, "set_envmap: %s", cudaGetErrorString(e));
     return ZDR_OK;
 }
+
+// Workspace of the path-integrator schedules (wavefront path state: up to 152 B per resident path; persistent: 16 B per
+// camera sample of a forward batch).  By default the library allocates it with cudaMalloc, outside the caller's allocator:
+//   zdr_scene_set_workspace_limit  bounds it (batches shrink to fit);
+//   zdr_scene_set_workspace        makes the scene use a buffer the CALLER owns (a torch tensor: the caching allocator then
+//                                  accounts for it); NULL / 0 goes back to the library's own allocation;
+//   zdr_scene_trim                 frees what the library allocated (it is re-allocated on demand).
+ZDR_EXPORT int zdr_scene_set_workspace_limit(zdr_scene* s, uint64_t bytes) {
+    if (!s) return fail(ZDR_ERR_ARG, "set_workspace_limit: null");
+    s->ws_limit = (size_t)bytes;
+    return ZDR_OK;
+}
+ZDR_EXPORT int zdr_scene_set_workspace(zdr_scene* s, void* workspace_dev, uint64_t bytes) {
+    if (!s) return fail(ZDR_ERR_ARG, "set_workspace: null");
+    if ((workspace_dev == nullptr) != (bytes == 0)) return fail(ZDR_ERR_ARG, "set_workspace: pointer and size must both be given or both be zero");
+    if (((uintptr_t)workspace_dev & 255) != 0) return fail(ZDR_ERR_ARG, "set_workspace: the buffer must be 256-byte aligned");
+    DevGuard dev_guard;
+    int rc = use_device(s->device, dev_guard);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    s->s_wf.release();
+    if (workspace_dev) { s->s_wf.p = static_cast<char*>(workspace_dev); s->s_wf.cap = (size_t)bytes; s->s_wf.external = true; }
+    return ZDR_OK;
+}
+ZDR_EXPORT int zdr_scene_trim(zdr_scene* s) {
+    if (!s) return fail(ZDR_ERR_ARG, "scene_trim: null");
+    DevGuard dev_guard;
+    int rc = use_device(s->device, dev_guard);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    if (!s->s_wf.external) s->s_wf.release();
+    s->s_mat.release(); s->s_img.release(); s->s_dimg.release(); s->s_dmat.release(); s->s_misc.release(); s->s_misc2.release();
+    s->s_int.release(); s->s_int2.release();
+    return ZDR_OK;
+}
+ZDR_EXPORT uint64_t zdr_scene_workspace_bytes(const zdr_scene* s) { return s ? (uint64_t)s->s_wf.cap : 0; }
 
 ZDR_EXPORT int zdr_scene_instance_count(const zdr_scene* s) { return s ? (int)s->meshes.size() : 0; }
 ZDR_EXPORT int zdr_scene_light_count(const zdr_scene* s) {

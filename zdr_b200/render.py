@@ -324,6 +324,31 @@ class Scene:
                 (sc.shard, sc.shard_samples), sc.camera = old, old_cam
         return sharded_render(material, fwd, bwd, res=res, spp=spp, seed=seed, group=self._dist_group, axis=self._dist_axis)
 
+    # ------------------------------------------------------------------ workspace of the path schedules
+    def set_workspace_limit(self, nbytes: int):
+        """Upper bound (bytes) of the scene's device workspace (wavefront path state / persistent sample buffer); 0 = the
+        library's default policy (up to a quarter of the free memory).  Batches shrink to fit."""
+        check(self._lib.zdr_scene_set_workspace_limit(self._handle, int(nbytes)), "zdr_scene_set_workspace_limit")
+
+    def set_workspace(self, buffer: Optional[torch.Tensor]):
+        """Use a torch tensor (any dtype, contiguous, on this scene's device) as the workspace instead of memory the library
+        allocates with cudaMalloc behind torch's caching allocator; ``None`` goes back to the library's own allocation.  The
+        scene keeps a reference to the tensor."""
+        if buffer is None:
+            check(self._lib.zdr_scene_set_workspace(self._handle, None, 0), "zdr_scene_set_workspace")
+        else:
+            assert buffer.is_cuda and buffer.device.index == self.device_index and buffer.is_contiguous()
+            check(self._lib.zdr_scene_set_workspace(self._handle, buffer.data_ptr(), buffer.numel() * buffer.element_size()), "zdr_scene_set_workspace")
+        self._workspace = buffer
+
+    def trim(self):
+        """Free the device scratch the library allocated for this scene (re-allocated on demand)."""
+        check(self._lib.zdr_scene_trim(self._handle), "zdr_scene_trim")
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self._lib.zdr_scene_workspace_bytes(self._handle))
+
     # ------------------------------------------------------------------ instrumentation
     def counters(self) -> dict:
         out = (C.c_uint64 * _abi.ZDR_NUM_COUNTERS)()
