@@ -461,6 +461,19 @@ constexpr int kWfRefill = ZDR_WF_REFILL;
 #ifndef ZDR_WF_FETCH_CHUNK
 #define ZDR_WF_FETCH_CHUNK 128
 #endif
+// Staged ray fetch of the traversal kernels: a warp claims list entries a chunk AHEAD (the cursor atomic's round trip is off
+// the critical path), reads the chunk's list entries once, and copies the chunk's ray records from HBM into its own
+// shared-memory staging buffer with cp.async while it is still traversing the previous chunk; refills then take rays from
+// shared memory.  profiles/r01w (ncu source page of k_wf_trace): 24 % of the warps' time went to the refill path — cursor
+// atomic -> list entry -> ray record, three dependent trips to L2 / HBM per refill.
+// Measured (profiles/r02l): correct, but C3 7081 -> 6718 Mrays/s and the C5-shaped scene 1587 -> 1492: the 18 KB of staging per
+// block cost more L1 and issue slots than the hidden latency was worth (the other resident warps already covered it).  Off.
+#ifndef ZDR_WF_STAGE_RAYS
+#define ZDR_WF_STAGE_RAYS 0
+#endif
+#ifndef ZDR_WF_STAGE_CHUNK
+#define ZDR_WF_STAGE_CHUNK 64
+#endif
 #ifndef ZDR_WF_TRACE_PREFETCH      // measured r02h: 6917 (on) vs 6936 (off) Mrays/s on C3 at 64 spp — no gain, off
 #define ZDR_WF_TRACE_PREFETCH 0
 #endif
@@ -491,7 +504,37 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
     float3 id = f3(0.f, 0.f, 0.f), oid = id;
     RayPre rp = {};
     int stack[kStackSize];
-#if ZDR_WF_FETCH_CHUNK
+#if ZDR_WF_STAGE_RAYS
+    constexpr int CH = BIG ? ZDR_WF_STAGE_CHUNK / 2 : ZDR_WF_STAGE_CHUNK;      // large scenes keep more of the SM's memory as L1 for the tree
+    __shared__ float4 s_ray[kWfThreads / 32][2][CH][2];      // per warp: two chunks of ray records (current / being staged)
+    __shared__ int s_slot[kWfThreads / 32][2][CH];
+    const int wid = threadIdx.x >> 5;
+    const int total_warps = gridDim.x * (kWfThreads / 32);
+    const int chunk = max(32, min(CH, (n / (4 * total_warps)) & ~31));     // shrinks with the list so that short lists spread over all warps
+    int cb = 1, c_n = 0, c_pos = 0, n_n = 0;              // warp-uniform: current buffer, its entries, next unread entry; entries of the staged chunk
+    int pend = 0;                                        // lane 0: base of the chunk claimed ahead (atomicAdd issued, result not yet consumed)
+    bool claims_done = false;
+    // stage the chunk whose base lane 0 holds in `pend` into buffer `b`, then claim the chunk after it
+    auto stage_next = [&](int b) -> int {
+        if (claims_done) return 0;
+        const int base = __shfl_sync(0xffffffffu, pend, 0);
+        const int cnt = min(max(n - base, 0), chunk);
+        if (cnt <= 0) { claims_done = true; return 0; }
+        for (int k = lane; k < cnt; k += 32) {
+            const int sl = list[base + k];
+            const float4* rec = ANY ? w.SAB + 2 * (size_t)sl : w.AB + 2 * (size_t)sl;
+            s_slot[wid][b][k] = sl;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_ray[wid][b][k][0]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rec) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(rec + 1) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (lane == 0) pend = atomicAdd(cursor, chunk);
+        return cnt;
+    };
+    if (lane == 0) pend = atomicAdd(cursor, chunk);
+    n_n = stage_next(0);                                 // chunk 0 -> buffer 0 (the "staged" one while cb == 1)
+#elif ZDR_WF_FETCH_CHUNK
     // A warp takes list entries from the shared cursor a chunk at a time and hands them to its lanes over several
     // refills: every refill hitting ONE address with an atomic is what a same-address atomic unit serialises
     // (tools/microbench: ~1-2 G/s).  The chunk shrinks with the list so that short lists still spread over all warps.
@@ -503,6 +546,31 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
         // ---- refill idle lanes
         const unsigned idle = __ballot_sync(0xffffffffu, !has_ray && !exhausted);
         if (idle) {
+            const bool mine = !has_ray && !exhausted;
+            const int rank = __popc(idle & ((1u << lane) - 1u));
+            float4 RA = make_float4(0.f, 0.f, 0.f, 0.f), RB = RA;      // the lane's new ray record
+            bool got = false;
+#if ZDR_WF_STAGE_RAYS
+            const int need = __popc(idle), have = c_n - c_pos;
+            if (mine && rank < have) {                   // from the current chunk
+                const int e = c_pos + rank;
+                RA = s_ray[wid][cb][e][0]; RB = s_ray[wid][cb][e][1]; slot = s_slot[wid][cb][e];
+                got = true;
+            }
+            if (have < need) {                           // switch to the staged chunk, stage the one after it into the freed buffer
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                cb ^= 1; c_n = n_n; c_pos = min(need - have, c_n);
+                if (mine && rank >= have) {
+                    const int e = rank - have;
+                    if (e < c_n) { RA = s_ray[wid][cb][e][0]; RB = s_ray[wid][cb][e][1]; slot = s_slot[wid][cb][e]; got = true; }
+                }
+                __syncwarp();
+                n_n = stage_next(cb ^ 1);
+            } else {
+                c_pos += need;
+            }
+#else
 #if ZDR_WF_FETCH_CHUNK
             const int need = __popc(idle), have = chunk_end - chunk_next;
             int base = 0;
@@ -510,13 +578,10 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
                 if (lane == 0) base = atomicAdd(cursor, chunk);
                 base = __shfl_sync(0xffffffffu, base, 0);
             }
-            const int rank = __popc(idle & ((1u << lane) - 1u));
             const int i_next = rank < have ? chunk_next + rank : base + (rank - have);
             if (have < need) {
 #if ZDR_WF_TRACE_PREFETCH
-                // The chunk's ray records are 128 random 32-byte sectors of HBM that the lanes will ask for one refill at a
-                // time over the next thousands of cycles: ask L2 for all of them now (profiles/r01w: long_scoreboard 12
-                // warps per issue in this kernel = the two dependent HBM round trips of every refill).
+                // ask L2 for the chunk's ray records at claim time (measured r02h: no gain; off)
                 for (int k = lane; k < chunk; k += 32) {
                     const int j = base + k;
                     if (j < n) {
@@ -532,35 +597,31 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
             int base = 0;
             if (lane == __ffs(idle) - 1) base = atomicAdd(cursor, __popc(idle));
             base = __shfl_sync(0xffffffffu, base, __ffs(idle) - 1);
-            const int i_next = base + __popc(idle & ((1u << lane) - 1u));
+            const int i_next = base + rank;
 #endif
-            if (!has_ray && !exhausted) {
-                const int i = i_next;
-                if (i >= n) {
+            if (mine && i_next < n) {
+                slot = list[i_next];
+                const float4* rec = ANY ? w.SAB + 2 * (size_t)slot : w.AB + 2 * (size_t)slot;
+                RA = rec[0]; RB = rec[1];
+                got = true;
+            }
+#endif
+            if (mine) {
+                if (!got) {
                     exhausted = true;
                 } else {
-                    slot = list[i];
-                    {
-                        float3 o, d;
-                        if (ANY) {
-                            const float4 SA = w.SAB[2 * (size_t)(slot)], SB = w.SAB[2 * (size_t)(slot) + 1];
-                            o = f3(SA.x, SA.y, SA.z); d = f3(SB.x, SB.y, SB.z); tmin = 1e-4f; tmax = SA.w;
-                            tl.any++;
-                        } else {
-                            const float4 A = w.AB[2 * (size_t)(slot)], B = w.AB[2 * (size_t)(slot) + 1];
-                            o = f3(A.x, A.y, A.z); d = f3(B.x, B.y, B.z); tmin = 0.0f; tmax = 1e30f;
-                            tl.closest++;
-                        }
-                        rp = ray_pre(o, d);
-                        id = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                        if (!(fabsf(id.x) <= 1e30f)) id.x = copysignf(1e30f, d.x);
-                        if (!(fabsf(id.y) <= 1e30f)) id.y = copysignf(1e30f, d.y);
-                        if (!(fabsf(id.z) <= 1e30f)) id.z = copysignf(1e30f, d.z);
-                        oid = f3(o.x * id.x, o.y * id.y, o.z * id.z);
-                        best = tmax; best_gid = 0x7fffffff; hit_slot = -1; hit_u = hit_v = hit_t = 0.0f;
-                        sp = 0; stack[sp++] = kLinkSentinel; link = a.sc.root_link;
-                        has_ray = true;
-                    }
+                    const float3 o = f3(RA.x, RA.y, RA.z), d = f3(RB.x, RB.y, RB.z);
+                    if (ANY) { tmin = 1e-4f; tmax = RA.w; tl.any++; }           // SAB: origin | light.dist, light.wi | light.pdf
+                    else { tmin = 0.0f; tmax = 1e30f; tl.closest++; }           // AB: origin | pdf_bsdf, direction | packed state
+                    rp = ray_pre(o, d);
+                    id = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                    if (!(fabsf(id.x) <= 1e30f)) id.x = copysignf(1e30f, d.x);
+                    if (!(fabsf(id.y) <= 1e30f)) id.y = copysignf(1e30f, d.y);
+                    if (!(fabsf(id.z) <= 1e30f)) id.z = copysignf(1e30f, d.z);
+                    oid = f3(o.x * id.x, o.y * id.y, o.z * id.z);
+                    best = tmax; best_gid = 0x7fffffff; hit_slot = -1; hit_u = hit_v = hit_t = 0.0f;
+                    sp = 0; stack[sp++] = kLinkSentinel; link = a.sc.root_link;
+                    has_ray = true;
                 }
             }
         }
