@@ -142,10 +142,14 @@ ZDR_DEV float3 direct_walk(CTX& c, const Ray& ray, Sampler& sampler, float3 le_g
 }
 
 // AGG kernels: declare, clear and (at the end, by every thread of the CTA) fold the shared-memory gradient duplicate
+// (dynamic shared memory, kGradCacheBytes, passed by the launcher only in block-scatter mode: the default launches carry none)
 #define ZDR_GRAD_CACHE_BEGIN(c)                                               \
-    __shared__ int gc_key_[AGG ? kGradCacheSlots : 1];                       \
-    __shared__ float gc_acc_[AGG ? 4 * kGradCacheSlots : 1];                 \
-    if (AGG && a.block_scatter) { (c).gc.key = gc_key_; (c).gc.acc = gc_acc_; grad_cache_init((c).gc); }
+    extern __shared__ __align__(16) unsigned char gc_dyn_[];                 \
+    if (AGG && a.block_scatter) {                                            \
+        (c).gc.key = reinterpret_cast<int*>(gc_dyn_);                        \
+        (c).gc.acc = reinterpret_cast<float*>(gc_dyn_ + 4 * kGradCacheSlots); \
+        grad_cache_init((c).gc);                                             \
+    }
 #define ZDR_GRAD_CACHE_END(c, a, tl) \
     if (AGG && (a).block_scatter) (tl).red += grad_cache_flush((c).gc, (a).tex.dmat);
 
@@ -158,6 +162,12 @@ ZDR_DEV void flush_tally(const RenderArgs& a, const Tally& t) {
     }
 }
 
+// Resident blocks per SM the per-pixel kernels (collocated, direct) are compiled for.  Round 1 left them uncapped (128
+// registers, 16 warps per SM); at 8 blocks (64 registers, 32 warps) C2 4 861 -> 5 182, C4 7 268 -> 8 734, C4d 7 201 -> 7 638 Mrays/s
+// (profiles/r02n_pixel_kernel_occupancy.txt; 6 and 10 blocks are in between).
+#ifndef ZDR_PIXEL_MINB
+#define ZDR_PIXEL_MINB 8
+#endif
 // block = 128 threads = 4 warps; each warp owns an 8x4 pixel tile, the block a 16x8 tile
 constexpr int kBlockThreads = 128;
 ZDR_DEV void pixel_of_thread(const RenderArgs& a, int& x, int& y) {
@@ -167,7 +177,7 @@ ZDR_DEV void pixel_of_thread(const RenderArgs& a, int& x, int& y) {
 }
 
 template <int INTEGRATOR, bool STATS>
-__global__ void __launch_bounds__(kBlockThreads) k_forward(const __grid_constant__ RenderArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, ZDR_PIXEL_MINB) k_forward(const __grid_constant__ RenderArgs a) {
     int x, y;
     pixel_of_thread(a, x, y);
     Tally tl = {};
@@ -195,7 +205,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_forward(const __grid_constant
 }
 
 template <int INTEGRATOR, bool STATS, bool AGG>
-__global__ void __launch_bounds__(kBlockThreads) k_backward(const __grid_constant__ RenderArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, ZDR_PIXEL_MINB) k_backward(const __grid_constant__ RenderArgs a) {
     int x, y;
     pixel_of_thread(a, x, y);
     Tally tl = {};
@@ -1093,8 +1103,9 @@ template <int I>
 cudaError_t launch_bwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
     ++g_kernel_launches;
     if (a.aggregate_scatter) {
-        if (stats) k_backward<I, true, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
-        else k_backward<I, false, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+        const size_t gc = a.block_scatter ? kGradCacheBytes : 0;
+        if (stats) k_backward<I, true, true><<<render_grid(a), kBlockThreads, gc, s>>>(a);
+        else k_backward<I, false, true><<<render_grid(a), kBlockThreads, gc, s>>>(a);
     } else {
         if (stats) k_backward<I, true, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
         else k_backward<I, false, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
@@ -1118,7 +1129,8 @@ void launch_wf_round(bool stats, bool agg, bool env, int grid, cudaStream_t s, c
     else { if (big) k_wf_trace<true, false, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<true, false, false><<<tgrid, kWfThreads, 0, s>>>(a); }
     if constexpr (MODE == 2) {
         if (agg) {
-            if (stats) k_wf_shade_b<MODE, true, true><<<grid, kWfThreads, 0, s>>>(a); else k_wf_shade_b<MODE, false, true><<<grid, kWfThreads, 0, s>>>(a);
+            const size_t gc = a.block_scatter ? kGradCacheBytes : 0;
+            if (stats) k_wf_shade_b<MODE, true, true><<<grid, kWfThreads, gc, s>>>(a); else k_wf_shade_b<MODE, false, true><<<grid, kWfThreads, gc, s>>>(a);
             return;
         }
     }
@@ -1127,8 +1139,9 @@ void launch_wf_round(bool stats, bool agg, bool env, int grid, cudaStream_t s, c
 template <bool BWD, bool STATS, bool AGG>
 void launch_path3(bool env, const RenderArgs& a, cudaStream_t s) {
     ++g_kernel_launches;
-    if (env) k_path<BWD, STATS, AGG, true><<<render_grid(a), kBlockThreads, 0, s>>>(a);
-    else k_path<BWD, STATS, AGG, false><<<render_grid(a), kBlockThreads, 0, s>>>(a);
+    const size_t gc = (BWD && AGG && a.block_scatter) ? kGradCacheBytes : 0;
+    if (env) k_path<BWD, STATS, AGG, true><<<render_grid(a), kBlockThreads, gc, s>>>(a);
+    else k_path<BWD, STATS, AGG, false><<<render_grid(a), kBlockThreads, gc, s>>>(a);
 }
 }  // namespace
 

@@ -122,6 +122,7 @@ ZDR_DEV float4 scale4(float k, float4 d) { return make_float4(k * d.x, k * d.y, 
 // literally a per-SM duplicate buffer.  A full table (more than ~kGradCacheSlots distinct texels in one CTA) falls back to
 // the direct reduction.
 constexpr int kGradCacheSlots = 256;
+constexpr int kGradCacheBytes = kGradCacheSlots * 20;      // keys (int) + 4 floats per slot
 struct GradCache {
     int* key;        // texel index, -1 = empty
     float* acc;      // 4 floats per slot
