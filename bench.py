@@ -62,6 +62,9 @@ def parse_args():
     ap.add_argument("--ref-spp", type=int, default=None, help="samples per pixel (of --spp) one reference step renders")
     ap.add_argument("--cpu-spp", type=int, default=None, help="samples per pixel of the cpu_baseline sample")
     ap.add_argument("--schedule", default="auto", choices=["auto", "persistent", "wavefront", "megakernel"])
+    ap.add_argument("--math", default="exact", choices=["exact", "fast"],
+                    help="exact (default): IEEE arithmetic of the numeric contract, images bit-identical to the oracle; fast: ZDR_FLAG_FAST_MATH")
+    ap.add_argument("--no-fast-line", action="store_true", help="skip the extra measurement of the fast build that an exact run reports in config.fast_math")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-multi-gpu-check", action="store_true")
@@ -268,6 +271,7 @@ def run_ours(args):
     scene.camera = w.camera.copy()
     scene.max_depth = w.depth
     scene.schedule = args.schedule
+    scene.math = args.math
     lib, h = scene._lib, scene._handle
     integ = INTEGRATORS[w.integrator]
     res = w.res
@@ -275,8 +279,8 @@ def run_ours(args):
     loops = max(1, w.lights)
     shard = (rank, world) if world > 1 else None
 
-    def params(seed, shard_=shard, stats=False):
-        return make_params(w.camera, res, mat_np.shape, w.spp, seed, max_depth=w.depth, shard=shard_, stats=stats, schedule=args.schedule)
+    def params(seed, shard_=shard, stats=False, math=args.math):
+        return make_params(w.camera, res, mat_np.shape, w.spp, seed, max_depth=w.depth, shard=shard_, stats=stats, schedule=args.schedule, math=math)
     pf, pb = params(0), params(1)
     material = torch.from_numpy(mat_np).to(dev)
     image = torch.zeros((res[1], res[0], 4), dtype=torch.float32, device=dev)
@@ -360,6 +364,34 @@ def run_ours(args):
                         "ok": bool(bits and g_rel <= GRAD_TOL),
                         "what": f"{world}-rank tile-sharded render, all_reduce(image) and all_reduce(d_material), against rank 0 rendering the whole job alone"}
         barrier()
+
+    # ---- the fast build on the same workload (outside the timed region): its throughput and its deviation from the exact build
+    fast_rec = None
+    if args.math == "exact" and world == 1 and not args.no_fast_line:
+        d_material.zero_()
+        render_pair(pf, pb, image, d_material)
+        img_x, g_x = image.clone(), d_material.clone()
+        pff, pbf = params(0, math="fast"), params(1, math="fast")
+        img_f, g_f = torch.zeros_like(image), torch.zeros_like(d_material)
+        render_pair(pff, pbf, img_f, g_f)                       # also the warm-up of the fast kernels
+        torch.cuda.synchronize(dev)
+        ev_f = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        n_f = max(1, min(args.steps, 3))
+        t_f = 0.0
+        for k in range(n_f):
+            flush.fill_(k & 0xFF)
+            g_f.zero_()
+            ev_f[0].record(stream)
+            render_pair(pff, pbf, img_f, g_f)
+            ev_f[1].record(stream)
+            torch.cuda.synchronize(dev)
+            t_f += ev_f[0].elapsed_time(ev_f[1])
+        fast_rec = {"value": round(rays_local / (t_f / n_f * 1e-3) / 1e6, 2), "unit": UNIT, "ms_per_step": round(t_f / n_f, 3), "steps": n_f,
+                    "image_rel_l2_vs_exact": float((img_f - img_x).norm() / img_x.norm().clamp_min(1e-30)),
+                    "grad_rel_l2_vs_exact": float((g_f - g_x).norm() / g_x.norm().clamp_min(1e-30)),
+                    "what": "ZDR_FLAG_FAST_MATH (Scene.math = 'fast'): approximate division / sqrt / sin / cos + contraction in the shading "
+                            "arithmetic; sampler and ray / triangle test bit-exact in both builds; same workload, device-resident inputs"}
+        del img_x, g_x, img_f, g_f
 
     # ---- e2e: torch surface, host buffers in the timed region
     t_e2e = 0.0
@@ -445,7 +477,7 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w.name(), "config": w.key, "schedule": args.schedule,
+        "config": {"workload": w.name(), "config": w.key, "schedule": args.schedule, "math": args.math,
                    "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": f"tile-dp{world}",
                    "sampler_tables": scene.sampler_tables_provenance, "prb_mode": scene.prb_mode,
                    "rays_per_step": int(rays_total), "camera_samples_per_step": 2 * res[0] * res[1] * w.spp * loops,
@@ -460,6 +492,8 @@ def run_ours(args):
     }
     if mg_check is not None:
         out["multi_gpu_check"] = mg_check
+    if fast_rec is not None:
+        out["config"]["fast_math"] = fast_rec
     if not args.no_e2e:
         out["e2e"] = {"value": round(rays_total / t_e2e / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(mat_np.nbytes),
                       "d2h_bytes_per_step": int(mat_np.nbytes) + 4 * loops, "ms_per_step": round(t_e2e * 1e3, 3),

@@ -2,6 +2,7 @@
 seeded inputs.  Bars (BASELINE.json north_star): sampler values and primitive ids bit-exact,
 images rel-L2 <= 1e-4, gradients rel-L2 <= 1e-3.  The forward pass shares the oracle's numeric
 contract, so per-sample radiance is additionally compared bit-for-bit."""
+import contextlib
 import ctypes as C
 import os
 
@@ -233,6 +234,13 @@ CASES = {
     "c3_path_small_wavefront": (scenes.cbox_path_models, ZDR_PATH, (96, 96), 8, lambda: scenes.random_material((1024, 1024), 0), {"max_depth": 8, "schedule": "wavefront"}),
     "path_literal_wavefront": (scenes.cbox_path_models, ZDR_PATH, (64, 64), 4, lambda: scenes.random_material((128, 128), 4), {"max_depth": 5, "prb_mode": _abi.ZDR_PRB_LITERAL, "schedule": "wavefront"}),
     "path_depth1_wavefront": (scenes.cbox_path_models, ZDR_PATH, (40, 24), 3, lambda: scenes.random_material((64, 64), 6), {"max_depth": 1, "schedule": "wavefront"}),
+    # ... with the rays of the traversal stages binned by (origin cell, direction octant) from the second bounce on (k_wf_bin), and
+    # on the general traversal kernel instead of the shared-memory / register-stack one small scenes get (k_wf_trace_tiny)
+    "c3_path_small_wavefront_binned": (scenes.cbox_path_models, ZDR_PATH, (96, 96), 8, lambda: scenes.random_material((1024, 1024), 0), {"max_depth": 8, "schedule": "wavefront", "env": {"ZDR_WF_BIN": "3"}}),
+    "path_literal_wavefront_binned": (scenes.cbox_path_models, ZDR_PATH, (64, 64), 4, lambda: scenes.random_material((128, 128), 4), {"max_depth": 5, "prb_mode": _abi.ZDR_PRB_LITERAL, "schedule": "wavefront", "env": {"ZDR_WF_BIN": "1"}}),
+    "path_wavefront_binned_shadow_only": (scenes.cbox_path_models, ZDR_PATH, (64, 64), 4, lambda: scenes.random_material((128, 128), 4), {"max_depth": 5, "schedule": "wavefront", "env": {"ZDR_WF_BIN": "2"}}),
+    "c3_path_small_wavefront_general": (scenes.cbox_path_models, ZDR_PATH, (96, 96), 8, lambda: scenes.random_material((1024, 1024), 0), {"max_depth": 8, "schedule": "wavefront", "env": {"ZDR_WF_TINY_OFF": "1", "ZDR_WF_BIN": "0"}}),
+    "c3_path_small_wavefront_general_binned": (scenes.cbox_path_models, ZDR_PATH, (96, 96), 8, lambda: scenes.random_material((1024, 1024), 0), {"max_depth": 8, "schedule": "wavefront", "env": {"ZDR_WF_TINY_OFF": "1", "ZDR_WF_BIN": "3"}}),
     # the persistent schedule (path state and ray queues in shared memory; persistent.cu)
     "c3_path_small_persistent": (scenes.cbox_path_models, ZDR_PATH, (96, 96), 8, lambda: scenes.random_material((1024, 1024), 0), {"max_depth": 8, "schedule": "persistent"}),
     "path_literal_persistent": (scenes.cbox_path_models, ZDR_PATH, (64, 64), 4, lambda: scenes.random_material((128, 128), 4), {"max_depth": 5, "prb_mode": _abi.ZDR_PRB_LITERAL, "schedule": "persistent"}),
@@ -248,13 +256,30 @@ def case_cache():
     return {}
 
 
+@contextlib.contextmanager
+def _env(env):
+    """Library switches that are read per launch (ZDR_WF_BIN, ZDR_WF_TINY_OFF), set for the duration of a case."""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def _run_case(oracle, name, cache):
     if name in cache:
         return cache[name]
     models_fn, integ, res, spp, mat_fn, kw = CASES[name]
     models, mat = models_fn(), mat_fn()
     g, o = GpuScene(models), oracle.OracleScene(models)
-    out = {"integ": integ, "mat": mat, "g": g, "o": o, "res": res, "spp": spp, "kw": kw}
+    kw = dict(kw)
+    env = kw.pop("env", {})
+    out = {"integ": integ, "mat": mat, "g": g, "o": o, "res": res, "spp": spp, "kw": kw, "env": env}
     cache[name] = out
     return out
 
@@ -263,10 +288,13 @@ def _run_case(oracle, name, cache):
 def test_forward_parity(oracle, case_cache, name):
     c = _run_case(oracle, name, case_cache)
     p = make_params(scenes.CBOX_CAMERA, c["res"], c["mat"].shape, c["spp"], 0, **c["kw"])
-    s_g, s_o = c["g"].samples(c["integ"], p, c["mat"]), c["o"].render_samples(c["integ"], p, c["mat"])
+    with _env(c["env"]):
+        s_g = c["g"].samples(c["integ"], p, c["mat"])
+        img_g = c["g"].forward(c["integ"], p, c["mat"])
+    s_o = c["o"].render_samples(c["integ"], p, c["mat"])
     same = bits(s_g) == bits(s_o)
     assert same.all(), f"{(~same).sum()} of {same.size} per-sample radiance values differ; max abs {np.nanmax(np.abs(s_g - s_o))}"
-    img_g, img_o = c["g"].forward(c["integ"], p, c["mat"]), c["o"].render_forward(c["integ"], p, c["mat"])
+    img_o = c["o"].render_forward(c["integ"], p, c["mat"])
     assert np.array_equal(bits(img_g), bits(img_o))
     assert rel_l2(img_g, img_o) <= IMG_TOL
     assert (img_o[..., 3] == 1).all() and img_o[..., :3].max() > 0
@@ -280,7 +308,9 @@ def test_backward_parity(oracle, case_cache, name):
     dimg = rng.normal(size=(c["res"][1], c["res"][0], 4)).astype(np.float32)
     c["g"].reset_counters()
     c["o"].reset_ray_counters()
-    dm_g, dm_o = c["g"].backward(c["integ"], p, c["mat"], dimg), c["o"].render_backward(c["integ"], p, c["mat"], dimg)
+    with _env(c["env"]):
+        dm_g = c["g"].backward(c["integ"], p, c["mat"], dimg)
+    dm_o = c["o"].render_backward(c["integ"], p, c["mat"], dimg)
     assert np.abs(dm_o).max() > 0
     assert rel_l2(dm_g, dm_o) <= GRAD_TOL, rel_l2(dm_g, dm_o)
     # the same texels are touched

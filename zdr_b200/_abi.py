@@ -20,6 +20,8 @@ ZDR_FLAG_LIGHT_PDF_COUNTS_ENV = 32
 ZDR_FLAG_PERSISTENT = 64
 SCHEDULES = {"auto": 0, "wavefront": ZDR_FLAG_WAVEFRONT, "megakernel": ZDR_FLAG_MEGAKERNEL, "persistent": ZDR_FLAG_PERSISTENT}
 ZDR_FLAG_SCATTER_BLOCK = 128
+ZDR_FLAG_FAST_MATH = 256
+MATH_MODES = {"exact": 0, "fast": ZDR_FLAG_FAST_MATH}
 SCATTER_MODES = {"auto": 0, "aggregate": ZDR_FLAG_SCATTER_AGGREGATE, "plain": ZDR_FLAG_SCATTER_PLAIN,
                  "block": ZDR_FLAG_SCATTER_AGGREGATE | ZDR_FLAG_SCATTER_BLOCK}
 COUNTER_NAMES = ("closest_rays", "any_rays", "nodes_visited", "tris_tested",
@@ -52,7 +54,7 @@ def wrap_i32(x: int) -> int:
 
 def make_params(camera, res, tex_shape, spp, seed, *, use_tent_filter=True, max_depth=16, rr_depth=2,
                 use_mis=True, bilinear=True, prb_mode=ZDR_PRB_CORRECTED, rows=None, its=None, shard=None,
-                stats=False, scatter="auto", schedule="auto", light_pdf_counts_env=False, num_material_sets=1) -> ZdrParams:
+                stats=False, scatter="auto", schedule="auto", light_pdf_counts_env=False, num_material_sets=1, math="exact") -> ZdrParams:
     p = ZdrParams()
     p.cam_fov = float(camera.fov)
     p.cam_origin[:] = list(camera.origin)
@@ -71,7 +73,7 @@ def make_params(camera, res, tex_shape, spp, seed, *, use_tent_filter=True, max_
     p.it0, p.it1 = (0, p.spp) if its is None else (int(its[0]), int(its[1]))
     p.shard_index, p.shard_count = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
     p.flags = ((ZDR_FLAG_STATS if stats else 0) | SCATTER_MODES[scatter] | SCHEDULES[schedule]
-               | (ZDR_FLAG_LIGHT_PDF_COUNTS_ENV if light_pdf_counts_env else 0))
+               | (ZDR_FLAG_LIGHT_PDF_COUNTS_ENV if light_pdf_counts_env else 0) | MATH_MODES[math])
     return p
 
 

@@ -104,6 +104,7 @@ struct zdr_scene {
     EnvMap env = {};
     unsigned long long* d_counters = nullptr;
     float uv_lo[2] = {0.f, 0.f}, uv_hi[2] = {0.f, 0.f};   // uv bounds of instance 0, the textured object (direct.py:30)
+    float3 bounds_lo = {0.f, 0.f, 0.f}, bounds_hi = {1.f, 1.f, 1.f};      // world-space bounds of the committed geometry
     cudaStream_t own_stream = nullptr;       // for the *_host entry points and the probes
     cudaStream_t side_streams[kWfMaxSets - 1] = {};      // further lanes of the wavefront schedule (launch_path_wavefront)
     cudaEvent_t wf_events[kWfMaxSets + 2] = {};
@@ -282,14 +283,15 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
         while (sets < lanes && sets < kWfMaxSets && S >= 2 * (sets + 1) && pixels * S >= (long long)(sets + 1) << 22) ++sets;
         S = (S + sets - 1) / sets;
         slots = (size_t)(pixels * S);
-        set_bytes = (slots * wf_bytes_per_slot() + 256 + 255) & ~(size_t)255;
+        set_bytes = (slots * wf_bytes_per_slot() + wf_fixed_bytes() + 255) & ~(size_t)255;
         bytes = set_bytes * sets;
     };
     const size_t ws_cap = s->s_wf.external ? s->s_wf.cap : s->ws_limit;      // caller-provided buffer / caller-set bound
     if (ws_cap) {
-        long long fit = (long long)((ws_cap > 512 ? ws_cap - 512 : 0) / wf_bytes_per_slot());
+        const size_t fixed = 2 * (wf_fixed_bytes() + 256);      // up to two state sets
+        long long fit = (long long)((ws_cap > fixed ? ws_cap - fixed : 0) / wf_bytes_per_slot());
         if (fit < pixels) return fail(ZDR_ERR_LIMIT, "workspace of %zu MiB cannot hold one sample per pixel of this launch (%lld MiB needed)",
-                                      ws_cap >> 20, (long long)(pixels * wf_bytes_per_slot() + 512) >> 20);
+                                      ws_cap >> 20, (long long)(pixels * wf_bytes_per_slot() + fixed) >> 20);
         plan(fit < (1ll << 28) ? fit : (1ll << 28));
         while (bytes > ws_cap && S > 1) { plan((long long)(slots - pixels)); }
     } else if (const char* slots_env = getenv("ZDR_WF_SLOTS_LOG2")) {
@@ -318,7 +320,28 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
     w.SC = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
     w.list[0] = reinterpret_cast<int*>(base); base += slots * sizeof(int);
     w.list[1] = reinterpret_cast<int*>(base); base += slots * sizeof(int);
-    w.counts = reinterpret_cast<int*>(base);
+    w.blist = reinterpret_cast<int*>(base); base += slots * sizeof(int);
+    w.keys[0] = reinterpret_cast<unsigned short*>(base); base += slots * sizeof(unsigned short);
+    w.keys[1] = reinterpret_cast<unsigned short*>(base); base += slots * sizeof(unsigned short);
+    base = s->s_wf.p + (((base - s->s_wf.p) + 15) & ~(size_t)15);
+    w.counts = reinterpret_cast<int*>(base); base += 64;
+    w.hist[0] = reinterpret_cast<int*>(base); base += kWfBins * sizeof(int);      // hist[0], hist[1], cur: contiguous (k_wf_generate zeroes them)
+    w.hist[1] = reinterpret_cast<int*>(base); base += kWfBins * sizeof(int);
+    w.cur = reinterpret_cast<int*>(base);
+    // ray binning: origin cells over the scene's bounds; which traversal stages read binned lists (ZDR_WF_BIN: bit 0 extension
+    // rays, bit 1 shadow rays; default from the measurements in DESIGN.md)
+    const int bin_env = getenv("ZDR_WF_BIN") ? atoi(getenv("ZDR_WF_BIN")) : ZDR_WF_BIN_DEFAULT;      // read per call: tests switch it
+    w.bin_mask = bin_env & 3;
+    w.bin_in = w.bin_out = 0;
+    w.key_lo = s->bounds_lo;
+    w.key_scale = f3((float)kWfCells / fmaxf(s->bounds_hi.x - s->bounds_lo.x, 1e-30f), (float)kWfCells / fmaxf(s->bounds_hi.y - s->bounds_lo.y, 1e-30f),
+                     (float)kWfCells / fmaxf(s->bounds_hi.z - s->bounds_lo.z, 1e-30f));
+    // shared-memory traversal with a register stack (k_wf_trace_tiny): scenes of at most 8 KB whose links fit 16 bits and whose
+    // tree leaves at most 12 pending links (ZDR_WF_TINY_OFF=1: off)
+    const bool tiny_off = getenv("ZDR_WF_TINY_OFF") != nullptr;
+    const int pending = s->bvh.max_depth - 1;
+    w.tiny_regs = 0;
+    if (!tiny_off && 64 * (size_t)s->bvh.num_nodes + 48 * (size_t)s->num_tris <= 8192 && pending <= 12) w.tiny_regs = pending <= 8 ? 4 : 6;
     w.S = (int)S;
     w.num_sms = s->num_sms;
     w.num_sets = sets;
@@ -377,6 +400,7 @@ int setup_persistent(zdr_scene* s, int integrator, const zdr_params* p, RenderAr
 }
 
 inline bool want_stats(const zdr_params* p) { return (p->flags & ZDR_FLAG_STATS) != 0; }
+inline bool fast_math(const zdr_params* p) { return (p->flags & ZDR_FLAG_FAST_MATH) != 0; }      // the render_fast.cu / persistent_fast.cu twins
 
 }  // namespace
 
@@ -537,6 +561,7 @@ ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
             }
         }
         if (!(finite && lo.x <= hi.x)) return fail(ZDR_ERR_ARG, "commit: non-finite geometry");
+        s->bounds_lo = lo; s->bounds_hi = hi;
         e = build_bvh_sah_host(tri.data(), shade.data(), (int)nt, lo, hi, s->own_stream, &s->bvh);
     } else {
         // large scene: the same records are produced on the GPU (k_flatten), then the GPU build
@@ -554,6 +579,7 @@ ZDR_EXPORT int zdr_scene_commit(zdr_scene* s) {
             return fail(ZDR_ERR_ARG, "commit: non-finite geometry");
         }
         const double t_flat = seconds_since(t_start);
+        if (e == cudaSuccess) { s->bounds_lo = lo; s->bounds_hi = hi; }
         if (e == cudaSuccess) e = build_bvh(d_tri, d_shade, (int)nt, lo, hi, s->own_stream, &s->bvh, !lbvh);
         cudaFree(d_tri); cudaFree(d_shade);
         if (verbose)
@@ -685,12 +711,12 @@ ZDR_EXPORT int zdr_render_forward(zdr_scene* s, int integrator, const zdr_params
     unsigned* pw_counters = nullptr;
     if ((rc = setup_persistent(s, integrator, p, &a, false, &persistent, &plan, &r_slots, &pw_counters))) return rc;
     if (persistent) {
-        CK(launch_path_persistent(false, a, want_stats(p), plan, r_slots, pw_counters, kPwMaxBatches, (cudaStream_t)stream));
+        CK((fast_math(p) ? launch_path_persistent_fast : launch_path_persistent)(false, a, want_stats(p), plan, r_slots, pw_counters, kPwMaxBatches, (cudaStream_t)stream));
         return ZDR_OK;
     }
     if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;
-    if (wavefront) CK(launch_path_wavefront(false, a, want_stats(p), (cudaStream_t)stream, s->side_streams, s->wf_events));
-    else CK(launch_forward(integrator, a, want_stats(p), (cudaStream_t)stream));
+    if (wavefront) CK((fast_math(p) ? launch_path_wavefront_fast : launch_path_wavefront)(false, a, want_stats(p), (cudaStream_t)stream, s->side_streams, s->wf_events));
+    else CK((fast_math(p) ? launch_forward_fast : launch_forward)(integrator, a, want_stats(p), (cudaStream_t)stream));
     return ZDR_OK;
 }
 
@@ -712,12 +738,12 @@ ZDR_EXPORT int zdr_render_backward(zdr_scene* s, int integrator, const zdr_param
     unsigned* pw_counters = nullptr;
     if ((rc = setup_persistent(s, integrator, p, &a, true, &persistent, &plan, &r_slots, &pw_counters))) return rc;
     if (persistent) {
-        CK(launch_path_persistent(true, a, want_stats(p), plan, 0, pw_counters, kPwMaxBatches, (cudaStream_t)stream));
+        CK((fast_math(p) ? launch_path_persistent_fast : launch_path_persistent)(true, a, want_stats(p), plan, 0, pw_counters, kPwMaxBatches, (cudaStream_t)stream));
         return ZDR_OK;
     }
     if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;
-    if (wavefront) CK(launch_path_wavefront(true, a, want_stats(p), (cudaStream_t)stream, s->side_streams, s->wf_events));
-    else CK(launch_backward(integrator, a, want_stats(p), (cudaStream_t)stream));
+    if (wavefront) CK((fast_math(p) ? launch_path_wavefront_fast : launch_path_wavefront)(true, a, want_stats(p), (cudaStream_t)stream, s->side_streams, s->wf_events));
+    else CK((fast_math(p) ? launch_backward_fast : launch_backward)(integrator, a, want_stats(p), (cudaStream_t)stream));
     return ZDR_OK;
 }
 
@@ -901,11 +927,11 @@ ZDR_EXPORT int zdr_probe_render_samples(zdr_scene* s, int integrator, const zdr_
     unsigned* pw_counters = nullptr;
     if ((rc = setup_persistent(s, integrator, p, &a, false, &persistent, &plan, &r_slots, &pw_counters))) return rc;
     if (persistent) {
-        CK(launch_path_persistent(false, a, want_stats(p), plan, r_slots, pw_counters, kPwMaxBatches, st));
+        CK((fast_math(p) ? launch_path_persistent_fast : launch_path_persistent)(false, a, want_stats(p), plan, r_slots, pw_counters, kPwMaxBatches, st));
     } else {
         if ((rc = setup_wavefront(s, integrator, p, &a, &wavefront))) return rc;
-        if (wavefront) CK(launch_path_wavefront(false, a, want_stats(p), st, s->side_streams, s->wf_events));
-        else CK(launch_forward(integrator, a, want_stats(p), st));
+        if (wavefront) CK((fast_math(p) ? launch_path_wavefront_fast : launch_path_wavefront)(false, a, want_stats(p), st, s->side_streams, s->wf_events));
+        else CK((fast_math(p) ? launch_forward_fast : launch_forward)(integrator, a, want_stats(p), st));
     }
     CK(cudaMemcpyAsync(out_host, s->s_misc.p, sizeof(float) * nout, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

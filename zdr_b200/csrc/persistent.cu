@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(kPwThreads, kPwBlocks) k_pw(const __grid_const
                         }
                     }
                     if (ADJ) {                                                          // prb.py:178-187
-                        if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad)) {
+                        if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && grad_ok(mat_grad)) {
                             scatters++;
                             reds += a.aggregate_scatter ? write_bsdf_grad_aggregated(a.tex, itx.uv, mat_grad, gcache, mset) : write_bsdf_grad(a.tex, itx.uv, mat_grad, mset);
                         }
@@ -656,6 +656,7 @@ cudaError_t launch_k_pw(const RenderArgs& a, const PwPlan& plan, cudaStream_t s)
 
 }  // namespace
 
+#ifndef ZDR_FAST_MATH      // exists once (exact build): depends on constants only
 // Pool size, traversal-stack placement and shared-memory footprint of the persistent kernel for a scene.
 cudaError_t pw_plan(const SceneView& sc, int bvh_depth, int num_sms, PwPlan* out) {
     int dev = 0, max_smem = 0;
@@ -682,6 +683,7 @@ cudaError_t pw_plan(const SceneView& sc, int bvh_depth, int num_sms, PwPlan* out
     *out = p;
     return cudaSuccess;
 }
+#endif
 
 // Host side: batches of S consecutive samples of every pixel of the shard; per batch ONE persistent launch (+ the ordered
 // accumulation of the forward pass).  The adjoint pass needs no buffer and runs as one batch.

@@ -9,7 +9,11 @@
 
 namespace zdr {
 
+#ifdef ZDR_FAST_MATH
+extern std::atomic<unsigned long long> g_kernel_launches;      // one counter, defined by the exact build
+#else
 std::atomic<unsigned long long> g_kernel_launches{0};
+#endif
 
 namespace {
 
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
                             }
                         }
                         if (BWD && phase == 1) {                                                        // prb.py:178-187
-                            if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad))
+                            if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && grad_ok(mat_grad))
                                 c.scatter(itx.uv, mat_grad, mset);
                         }
                         ++depth;
@@ -455,6 +459,7 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_generate(const __grid_constan
         w.list[0][slot] = slot;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { w.counts[0] = a.max_depth > 0 ? w.nslots : 0; w.counts[1] = 0; w.counts[2] = 0; w.counts[3] = 0; }
+    if (w.bin_mask) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * kWfBins; i += wf_stride()) w.hist[0][i] = 0;   // hist[0], hist[1], cur
     flush_tally(a, tl);
 }
 
@@ -490,6 +495,10 @@ constexpr int kWfRefill = ZDR_WF_REFILL;
 #ifndef ZDR_WF_REFILL_ANY_SMALL      // shadow rays of small scenes also refill idle lanes (cheap once the records are prefetched)
 #define ZDR_WF_REFILL_ANY_SMALL 0
 #endif
+// the stage that consumed a binned list leaves the list's bin counters and the cursors zero for their next use
+ZDR_DEV void wf_bins_reset(const WfState& w, int which) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kWfBins; i += wf_stride()) { w.hist[which][i] = 0; w.cur[i] = 0; }
+}
 constexpr int kWfNodeBudget = 12;
 constexpr int kWfBigSceneNodes = 1024;
 template <bool ANY, bool STATS, bool BIG>      // BIG: scene with more than kWfBigSceneNodes nodes (launch_wf_round)
@@ -501,7 +510,8 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
         if (ANY) { w.counts[0] = 0; w.counts[2] = 0; }       // shade B appends to list[0]; cursor of the next extend
         else { w.counts[1] = 0; w.counts[3] = 0; }           // shade A appends to list[1]; cursor of the next shadow stage
     }
-    const int* __restrict__ list = w.list[ANY ? 1 : 0];
+    const int* __restrict__ list = w.bin_in ? w.blist : w.list[ANY ? 1 : 0];
+    if (w.bin_in) wf_bins_reset(w, ANY ? 1 : 0);
     const float4* __restrict__ nodes = a.sc.nodes;
     const float4* __restrict__ tris = a.sc.tris;
     Tally tl = {};
@@ -698,6 +708,148 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(con
     flush_tally(a, tl);
 }
 
+// The traversal stages for scenes of a few kilobytes (the Cornell box: 35 nodes + 36 triangles = 4 KB): every block keeps the
+// tree and the triangles in SHARED memory (LDS with 32-bit addresses instead of L1-cached global loads) and every lane its
+// traversal stack in NREG registers (traverse.cuh RegStack: links fit 16 bits, the tree is at most 2 * NREG levels deep) — the
+// pop -> node load -> box test chain no longer goes through local memory and L1.  Same fetch policy and the same arithmetic as
+// k_wf_trace (tri_test_vals, box_test): bit-identical hits.
+#ifndef ZDR_WF_TINY
+#define ZDR_WF_TINY 1
+#endif
+#ifndef ZDR_WF_TINY_LOCAL_STACK      // measured (profiles/r02q): the PRMT register stack costs +3-6 % warp instructions (its predicated push / pop
+#define ZDR_WF_TINY_LOCAL_STACK 1      // sequences issue every node step) and is 0.6 % slower than the local-memory stack on C3: local stack shipped
+#endif
+template <bool ANY, bool STATS, int NREG>
+__global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace_tiny(const __grid_constant__ RenderArgs a) {
+    extern __shared__ __align__(16) float4 s_scene[];
+    const WfState& w = a.wf;
+    const int n = *(volatile int*)(w.counts + (ANY ? 1 : 0));
+    int* cursor = w.counts + (ANY ? 3 : 2);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (ANY) { w.counts[0] = 0; w.counts[2] = 0; }
+        else { w.counts[1] = 0; w.counts[3] = 0; }
+    }
+    const int* __restrict__ list = w.bin_in ? w.blist : w.list[ANY ? 1 : 0];
+    if (w.bin_in) wf_bins_reset(w, ANY ? 1 : 0);
+    const int n_node4 = 4 * a.sc.num_nodes, n_tri4 = 3 * a.sc.num_tris;
+    for (int i = threadIdx.x; i < n_node4; i += kWfThreads) s_scene[i] = __ldg(a.sc.nodes + i);
+    for (int i = threadIdx.x; i < n_tri4; i += kWfThreads) s_scene[n_node4 + i] = __ldg(a.sc.tris + i);
+    __syncthreads();
+    unsigned s_nodes = (unsigned)__cvta_generic_to_shared(s_scene), s_tris = s_nodes + 16u * (unsigned)n_node4;
+    asm volatile("" : "+r"(s_nodes), "+r"(s_tris));      // keep both bases in registers (ptxas otherwise recomputes the shared window base,
+                                                         // an S2R, inside the node loop)
+    Tally tl = {};
+    const int lane = threadIdx.x & 31;
+    bool has_ray = false, exhausted = false;
+    int slot = 0, link = kShortSentinel, hit_slot = -1, best_gid = 0x7fffffff;
+    float tmin = 0.f, tmax = 0.f, best = 0.f, hit_u = 0.f, hit_v = 0.f, hit_t = 0.f;
+    float3 id = f3(0.f, 0.f, 0.f), oid = id;
+    RayPre rp = {};
+#if ZDR_WF_TINY_LOCAL_STACK
+    LocalStack16 stack;
+#else
+    RegStack<NREG> stack;
+#endif
+    stack.clear();
+    const int total_warps = gridDim.x * (kWfThreads / 32);
+    const int chunk = max(32, min(ZDR_WF_FETCH_CHUNK, (n / (4 * total_warps)) & ~31));
+    int chunk_next = 0, chunk_end = 0;                  // warp-uniform
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !has_ray && !exhausted);
+        if (idle) {
+            const bool mine = !has_ray && !exhausted;
+            const int rank = __popc(idle & ((1u << lane) - 1u));
+            const int need = __popc(idle), have = chunk_end - chunk_next;
+            int base = 0;
+            if (have < need) {
+                if (lane == 0) base = atomicAdd(cursor, chunk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+            }
+            const int i_next = rank < have ? chunk_next + rank : base + (rank - have);
+            if (have < need) { chunk_next = base + (need - have); chunk_end = base + chunk; }
+            else chunk_next += need;
+            if (mine) {
+                if (i_next >= n) {
+                    exhausted = true;
+                } else {
+                    slot = list[i_next];
+                    const float4* rec = ANY ? w.SAB + 2 * (size_t)slot : w.AB + 2 * (size_t)slot;
+                    const float4 RA = rec[0], RB = rec[1];
+                    const float3 o = f3(RA.x, RA.y, RA.z), d = f3(RB.x, RB.y, RB.z);
+                    if (ANY) { tmin = 1e-4f; tmax = RA.w; tl.any++; }
+                    else { tmin = 0.0f; tmax = 1e30f; tl.closest++; }
+                    rp = ray_pre(o, d);
+                    id = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                    if (!(fabsf(id.x) <= 1e30f)) id.x = copysignf(1e30f, d.x);
+                    if (!(fabsf(id.y) <= 1e30f)) id.y = copysignf(1e30f, d.y);
+                    if (!(fabsf(id.z) <= 1e30f)) id.z = copysignf(1e30f, d.z);
+                    oid = f3(o.x * id.x, o.y * id.y, o.z * id.z);
+                    best = tmax; best_gid = 0x7fffffff; hit_slot = -1; hit_u = hit_v = hit_t = 0.0f;
+                    stack.clear(); link = a.sc.root_link;
+                    has_ray = true;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, !has_ray)) {
+            if (__all_sync(0xffffffffu, exhausted)) break;
+            continue;
+        }
+        while (has_ray) {
+            while (link >= 0) {                                  // inner nodes
+                const unsigned nd = s_nodes + 64u * (unsigned)link;
+                const float4 n0 = lds_f4(nd), n1 = lds_f4(nd + 16u), n2 = lds_f4(nd + 32u);
+                const float2 n3 = lds_f2(nd + 48u);
+                if (STATS) tl.ts.nodes++;
+                float t0, t1;
+                const bool h0 = box_test(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, id, oid, tmin, best, t0);
+                const bool h1 = box_test(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, id, oid, tmin, best, t1);
+                const int l0 = __float_as_int(n3.x), l1 = __float_as_int(n3.y);
+                if (h0 && h1) {
+                    const bool swap = t1 < t0;
+                    stack.push(swap ? l0 : l1);
+                    link = swap ? l1 : l0;
+                } else if (h0 || h1) {
+                    link = h0 ? l0 : l1;
+                } else {
+                    link = stack.pop();
+                }
+            }
+            bool done = link == kShortSentinel;
+            if (!done) {                                         // leaf
+                const int code = ~link;
+                const int first = code >> 2, count = (code & 3) + 1;
+                for (int k = 0; k < count; ++k) {
+                    const unsigned tp = s_tris + 48u * (unsigned)(first + k);
+                    const unsigned ax = tp + 4u * (unsigned)rp.kx, ay = tp + 4u * (unsigned)rp.ky, az = tp + 4u * (unsigned)rp.kz;
+                    if (STATS) tl.ts.tris++;
+                    float t, u, v;
+                    if (tri_test_vals(rp, lds_f(ax), lds_f(ay), lds_f(az), lds_f(ax + 16u), lds_f(ay + 16u), lds_f(az + 16u), lds_f(ax + 32u),
+                                      lds_f(ay + 32u), lds_f(az + 32u), tmin, t, u, v)) {
+                        if (ANY) {
+                            if (t < tmax) { hit_slot = first + k; done = true; break; }
+                            continue;
+                        }
+                        const int gid = __float_as_int(lds_f(tp + 12u));
+                        if (t < best || (hit_slot >= 0 && t == best && gid < best_gid)) {
+                            best = t; best_gid = gid;
+                            hit_t = t; hit_u = u; hit_v = v; hit_slot = first + k;
+                        }
+                    }
+                }
+                if (!done) { link = stack.pop(); done = link == kShortSentinel; }
+            }
+            if (done) {
+                if (ANY) w.SC[slot].w = hit_slot >= 0 ? 1.0f : 0.0f;
+                else w.H[slot] = make_float4(__int_as_float(hit_slot), hit_u, hit_v, hit_t);
+                has_ray = false;
+                break;
+            }
+            if (!ANY && __popc(__activemask()) < kWfRefill) break;
+        }
+    }
+    flush_tally(a, tl);
+}
+
 // survivors of a warp are appended to `list` with one atomic
 ZDR_DEV void wf_append(int* __restrict__ list, int* counter, bool keep, int value) {
     const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -707,6 +859,71 @@ ZDR_DEV void wf_append(int* __restrict__ list, int* counter, bool keep, int valu
     if (lane == 0) base = atomicAdd(counter, __popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (keep) list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+// Ray binning (WfState): bin of a ray = (cell of its origin in a kWfCells^3 grid over the scene, octant of its direction).
+ZDR_DEV int wf_key(const WfState& w, float3 o, float3 d) {
+    const int cx = min(max((int)((o.x - w.key_lo.x) * w.key_scale.x), 0), kWfCells - 1);
+    const int cy = min(max((int)((o.y - w.key_lo.y) * w.key_scale.y), 0), kWfCells - 1);
+    const int cz = min(max((int)((o.z - w.key_lo.z) * w.key_scale.z), 0), kWfCells - 1);
+    const int oct = (d.x < 0.0f ? 1 : 0) | (d.y < 0.0f ? 2 : 0) | (d.z < 0.0f ? 4 : 0);
+    return ((cx * kWfCells + cy) * kWfCells + cz) * 8 + oct;
+}
+// wf_append that also records the bin of every appended entry and counts the bins (one reduction per distinct bin of the warp)
+ZDR_DEV void wf_append_binned(const WfState& w, int which, bool keep, int value, int key) {
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(w.counts + which, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const unsigned same = __match_any_sync(0xffffffffu, keep ? key : -1 - lane);
+    if (keep) {
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        w.list[which][pos] = value;
+        w.keys[which][pos] = (unsigned short)key;
+        if (lane == __ffs(same) - 1) atomicAdd(w.hist[which] + key, __popc(same));
+    }
+}
+
+// The binned list of a traversal stage: blist = list[WHICH] grouped by bin (counting sort; the order inside a bin is
+// whatever the cursor atomics give — the image is summed per pixel in sample order by k_wf_accumulate, so no result
+// depends on the order rays are traced in).  Every block scans the kWfBins counters itself (16 KB from L2).
+constexpr int kWfBinThreads = 256;
+template <int WHICH>
+__global__ void __launch_bounds__(kWfBinThreads) k_wf_bin(const __grid_constant__ RenderArgs a) {
+    const WfState& w = a.wf;
+    __shared__ int s_base[kWfBins];
+    __shared__ int s_part[kWfBinThreads];
+    const int n = *(volatile int*)(w.counts + WHICH);
+    constexpr int per = kWfBins / kWfBinThreads;
+    int loc[per], sum = 0;
+#pragma unroll
+    for (int k = 0; k < per; ++k) { loc[k] = sum; sum += w.hist[WHICH][threadIdx.x * per + k]; }
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < kWfBinThreads; o <<= 1) {          // inclusive scan of the per-thread sums
+        const int v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const int before = s_part[threadIdx.x] - sum;
+#pragma unroll
+    for (int k = 0; k < per; ++k) s_base[threadIdx.x * per + k] = before + loc[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int n_round = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += wf_stride()) {
+        const bool on = i < n;
+        const int key = on ? (int)w.keys[WHICH][i] : -1 - lane;
+        const int slot = on ? w.list[WHICH][i] : 0;
+        const unsigned same = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(same) - 1;
+        int at = 0;
+        if (on && lane == leader) at = atomicAdd(w.cur + key, __popc(same));
+        at = __shfl_sync(0xffffffffu, at, leader);
+        if (on) w.blist[s_base[key] + at + __popc(same & ((1u << lane) - 1u))] = slot;
+    }
 }
 
 struct WfPath {        // registers of one path inside a stage
@@ -782,7 +999,7 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_A_MINB) k_wf_shade_a(
     Tally tl = {};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += wf_stride()) {
         bool keep = false;
-        int entry = 0;
+        int entry = 0, key = 0;
         if (i < n) {
             WfPath p = wf_load(a, w.list[0][i], false);       // beta / L are only needed when the path ends here
             const Hit hit = wf_hit(a, p.slot);
@@ -820,11 +1037,13 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_SHADE_A_MINB) k_wf_shade_a(
                     w.AB[2 * (size_t)(p.slot) + 1].w = __uint_as_float(wf_pack(p.depth, phase, p.sampler.dimension));
                     keep = true;
                     entry = p.slot;
+                    if (w.bin_out) key = wf_key(w, itx.p, light.wi);
                 }
             }
             if (end) wf_finish<MODE>(a, p);
         }
-        wf_append(w.list[1], w.counts + 1, keep, entry);
+        if (w.bin_out) wf_append_binned(w, 1, keep, entry, key);
+        else wf_append(w.list[1], w.counts + 1, keep, entry);
     }
     flush_tally(a, tl);
 }
@@ -848,7 +1067,7 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
     constexpr bool ADJ = MODE == 2;      // adjoint walk: BRDF adjoints + scatter
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += wf_stride()) {
         bool survive = false;
-        int slot = 0;
+        int slot = 0, key = 0;
         if (i < n) {
             slot = w.list[1][i];
             {
@@ -920,7 +1139,7 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
                     }
                 }
                 if (ADJ) {                                                          // prb.py:178-187
-                    if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && !any_nan(mat_grad))
+                    if ((mat_grad.x != 0.0f || mat_grad.y != 0.0f || mat_grad.z != 0.0f || mat_grad.w != 0.0f) && grad_ok(mat_grad))
                         c.scatter(itx.uv, mat_grad, mset);
                 }
                 ++p.depth;
@@ -933,10 +1152,12 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
                     w.AB[2 * (size_t)(slot) + 1] = make_float4(p.ray.d.x, p.ray.d.y, p.ray.d.z, __uint_as_float(wf_pack(p.depth, ADJ ? 1 : 0, p.sampler.dimension)));
                     w.CD[2 * (size_t)(slot)] = make_float4(p.beta.x, p.beta.y, p.beta.z, 0.f);
                     w.CD[2 * (size_t)(slot) + 1] = make_float4(p.L.x, p.L.y, p.L.z, 0.f);
+                    if (w.bin_out) key = wf_key(w, p.ray.o, p.ray.d);
                 }
             }
         }
-        wf_append(w.list[0], w.counts + 0, survive, slot);
+        if (w.bin_out) wf_append_binned(w, 0, survive, slot, key);
+        else wf_append(w.list[0], w.counts + 0, survive, slot);
     }
     if constexpr (MODE == 2) { ZDR_GRAD_CACHE_END(c, a, tl) }
     flush_tally(a, tl);
@@ -1116,17 +1337,40 @@ cudaError_t launch_bwd_i(const RenderArgs& a, bool stats, cudaStream_t s) {
 }  // namespace
 
 namespace {
-template <int MODE>
-void launch_wf_round(bool stats, bool agg, bool env, int grid, cudaStream_t s, const RenderArgs& a) {
-    g_kernel_launches += 4;
+template <bool ANY>
+void launch_wf_trace(bool stats, int tgrid, cudaStream_t s, const RenderArgs& a) {
     const bool big = a.sc.num_nodes > kWfBigSceneNodes;
+    if (ZDR_WF_TINY && a.wf.tiny_regs > 0) {
+        const size_t sm = 64 * (size_t)a.sc.num_nodes + 48 * (size_t)a.sc.num_tris;
+        if (a.wf.tiny_regs <= 4) { if (stats) k_wf_trace_tiny<ANY, true, 4><<<tgrid, kWfThreads, sm, s>>>(a); else k_wf_trace_tiny<ANY, false, 4><<<tgrid, kWfThreads, sm, s>>>(a); }
+        else { if (stats) k_wf_trace_tiny<ANY, true, 6><<<tgrid, kWfThreads, sm, s>>>(a); else k_wf_trace_tiny<ANY, false, 6><<<tgrid, kWfThreads, sm, s>>>(a); }
+        return;
+    }
+    if (stats) { if (big) k_wf_trace<ANY, true, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<ANY, true, false><<<tgrid, kWfThreads, 0, s>>>(a); }
+    else { if (big) k_wf_trace<ANY, false, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<ANY, false, false><<<tgrid, kWfThreads, 0, s>>>(a); }
+}
+// One bounce (round r of a pass).  From the second bounce on the rays of a traversal stage are binned first (WfState): the
+// first bounce's rays are coherent as they come (camera rays / shadow rays of neighbouring pixels).
+template <int MODE>
+void launch_wf_round(int r, bool stats, bool agg, bool env, int grid, cudaStream_t s, const RenderArgs& a0) {
+    RenderArgs a = a0;
     const int tgrid = min(grid, a.wf.num_sms * ZDR_WF_TRACE_GRID_MULT);
-    if (stats) { if (big) k_wf_trace<false, true, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<false, true, false><<<tgrid, kWfThreads, 0, s>>>(a); }
-    else { if (big) k_wf_trace<false, false, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<false, false, false><<<tgrid, kWfThreads, 0, s>>>(a); }
+    const int bgrid = min(grid, a.wf.num_sms * 8);
+    const bool bin_closest = (a.wf.bin_mask & 1) && r >= 1, bin_any = (a.wf.bin_mask & 2) && r >= 1;
+    const bool bin_next = (a.wf.bin_mask & 1) && r + 1 < a.max_depth;      // stage B feeds the next bounce's extension rays
+    g_kernel_launches += 4 + (bin_closest ? 1 : 0) + (bin_any ? 1 : 0);
+    a.wf.bin_out = 0;
+    if (bin_closest) k_wf_bin<0><<<bgrid, kWfBinThreads, 0, s>>>(a);
+    a.wf.bin_in = bin_closest ? 1 : 0;
+    launch_wf_trace<false>(stats, tgrid, s, a);
+    a.wf.bin_in = 0; a.wf.bin_out = bin_any ? 1 : 0;
     if (env) k_wf_shade_a<MODE, true><<<grid, kWfThreads, 0, s>>>(a);
     else k_wf_shade_a<MODE, false><<<grid, kWfThreads, 0, s>>>(a);
-    if (stats) { if (big) k_wf_trace<true, true, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<true, true, false><<<tgrid, kWfThreads, 0, s>>>(a); }
-    else { if (big) k_wf_trace<true, false, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<true, false, false><<<tgrid, kWfThreads, 0, s>>>(a); }
+    a.wf.bin_out = 0;
+    if (bin_any) k_wf_bin<1><<<bgrid, kWfBinThreads, 0, s>>>(a);
+    a.wf.bin_in = bin_any ? 1 : 0;
+    launch_wf_trace<true>(stats, tgrid, s, a);
+    a.wf.bin_in = 0; a.wf.bin_out = bin_next ? 1 : 0;
     if constexpr (MODE == 2) {
         if (agg) {
             const size_t gc = a.block_scatter ? kGradCacheBytes : 0;
@@ -1172,6 +1416,7 @@ cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cud
             return cudaGetLastError();
     }
 }
+#ifndef ZDR_FAST_MATH      // exist once (exact build): uv Jacobian, counters, workspace sizes
 cudaError_t launch_duvdxy(const RenderArgs& a, cudaStream_t s) {
     if (a.row1 <= a.row0 || a.it1 <= a.it0 || render_grid(a).y == 0) return cudaSuccess;
     ++g_kernel_launches;
@@ -1181,7 +1426,9 @@ cudaError_t launch_duvdxy(const RenderArgs& a, cudaStream_t s) {
 
 unsigned long long kernel_launch_count() { return g_kernel_launches.load(); }
 
-size_t wf_bytes_per_slot() { return 9 * sizeof(float4) + 2 * sizeof(int); }
+size_t wf_bytes_per_slot() { return 9 * sizeof(float4) + 3 * sizeof(int) + 2 * sizeof(unsigned short); }      // + list[2], blist, keys[2]
+size_t wf_fixed_bytes() { return 256 + 3 * kWfBins * sizeof(int); }                                       // counts, hist[2], cur
+#endif
 
 // Host side of the wavefront path tracer: batches of S consecutive samples of every pixel of the
 // shard; per batch generate, then max_depth (forward) or 2*max_depth (adjoint: replay + adjoint
@@ -1191,6 +1438,7 @@ namespace {
 void wf_shift_set(WfState& w, size_t bytes) {
     auto sh = [bytes](auto*& p) { p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(reinterpret_cast<char*>(p) + bytes); };
     sh(w.AB); sh(w.CD); sh(w.H); sh(w.R); sh(w.SAB); sh(w.SC); sh(w.list[0]); sh(w.list[1]); sh(w.counts);
+    sh(w.blist); sh(w.keys[0]); sh(w.keys[1]); sh(w.hist[0]); sh(w.hist[1]); sh(w.cur);
 }
 }  // namespace
 
@@ -1241,12 +1489,12 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
         else k_wf_generate<false><<<grid, kWfThreads, 0, s>>>(ab);
         const bool env = a.sc.env_count > 0;
         if (!backward) {
-            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<0>(stats, false, env, grid, s, ab);
+            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<0>(r, stats, false, env, grid, s, ab);
         } else {
-            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<1>(stats, false, env, grid, s, ab);      // replay: Le of every sample
+            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<1>(r, stats, false, env, grid, s, ab);      // replay: Le of every sample
             ++g_kernel_launches;
             k_wf_restart<<<grid, kWfThreads, 0, s>>>(ab);
-            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<2>(stats, a.aggregate_scatter != 0, env, grid, s, ab);   // adjoint walk
+            for (int r = 0; r < a.max_depth; ++r) launch_wf_round<2>(r, stats, a.aggregate_scatter != 0, env, grid, s, ab);   // adjoint walk
         }
         if (!backward && a.image) {
             if (K > 1 && b > 0) { cudaError_t e = cudaStreamWaitEvent(s, ev[1 + (b - 1) % K], 0); if (e != cudaSuccess) return e; }
@@ -1262,6 +1510,7 @@ cudaError_t launch_path_wavefront(bool backward, RenderArgs a, bool stats, cudaS
     return cudaGetLastError();
 }
 
+#ifndef ZDR_FAST_MATH      // the probes exist once (exact build)
 cudaError_t launch_probe_trace(const SceneView& sc, const float* rays, int n, bool any, int* ip, float* uvt, int* occ,
                                cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
@@ -1282,5 +1531,6 @@ cudaError_t launch_probe_ggx(const float* in, int n, float* out, cudaStream_t s)
     k_probe_ggx<<<(n + 127) / 128, 128, 0, s>>>(in, n, out);
     return cudaGetLastError();
 }
+#endif
 
 }  // namespace zdr

@@ -28,7 +28,24 @@ struct WfState {
     int num_sms;
     int num_sets;           // 1..kWfMaxSets copies of the state (set k = set 0 + k * set_bytes), one stream each
     size_t set_bytes;
+    // Ray binning (k_wf_bin): the rays of a traversal stage are grouped by (origin cell, direction octant) so that the 32 rays
+    // of a warp walk the same part of the tree.  The producing stage writes a key per list entry and counts the bins; one
+    // kernel per stage turns that into the binned list the traversal reads.  Shade stages keep the slot-ordered list.
+    unsigned short* keys[2];   // bin of list[k][i]
+    int* blist;             // binned copy of the list the next traversal stage reads
+    int* hist[2];           // kWfBins counters per list, zero between uses
+    int* cur;               // kWfBins cursors of k_wf_bin, zero between uses
+    float3 key_lo, key_scale;   // origin cell = (o - key_lo) * key_scale, clamped to [0, kWfCells)
+    int bin_mask;           // scene-level switch: bit 0 = extension rays, bit 1 = shadow rays (from bounce 1 on)
+    int bin_in;             // this launch (traversal): read blist instead of list[k]
+    int bin_out;            // this launch (generate / shade): write keys + hist for the list it appends to
+    int tiny_regs;          // > 0: scene fits the shared-memory traversal kernel with a register stack of 2 * tiny_regs entries
 };
+#ifndef ZDR_WF_BIN_DEFAULT      // which traversal stages read binned lists when ZDR_WF_BIN is not set (bit 0 extension, bit 1 shadow)
+#define ZDR_WF_BIN_DEFAULT 0
+#endif
+constexpr int kWfCells = 8;                                     // origin cells per axis
+constexpr int kWfBins = kWfCells * kWfCells * kWfCells * 8;     // x 8 direction octants
 
 // Persistent per-SM wavefront (persistent.cu, k_pw): one resident CTA per SM keeps a pool of paths in SHARED memory and
 // runs the stages of the wavefront as barrier-separated phases over shared-memory queues.  Nothing but finished samples
@@ -75,6 +92,7 @@ cudaError_t launch_forward(int integrator, const RenderArgs& a, bool stats, cuda
 cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cudaStream_t stream);
 // wavefront variant of the path integrator / PRB adjoint; `wf` buffers sized for wf_slot_capacity() slots
 size_t wf_bytes_per_slot();
+size_t wf_fixed_bytes();      // per state set, on top of the slots
 // side / events: the scene's kWfMaxSets - 1 extra streams and kWfMaxSets + 2 timing-less events, used when
 // wf.num_sets > 1 to run consecutive batches from several streams (the tail of every stage kernel overlaps the other
 // streams' work); both may be null otherwise
@@ -92,6 +110,16 @@ cudaError_t pw_plan(const SceneView& sc, int bvh_depth, int num_sms, PwPlan* out
 cudaError_t launch_path_persistent(bool backward, RenderArgs a, bool stats, const PwPlan& plan, size_t r_capacity_slots,
                                    unsigned* counters_dev, int max_batches, cudaStream_t stream);
 cudaError_t launch_duvdxy(const RenderArgs& a, cudaStream_t stream);
+// The "fast" build of the render kernels (ZDR_FLAG_FAST_MATH): render_fast.cu / persistent_fast.cu are the same sources
+// compiled with --use_fast_math and ZDR_FAST_MATH (approximate division / square root / sin / cos, contraction, denormals
+// flushed) — except the sampler and the ray / triangle test, which are written with explicit IEEE operations and stay
+// bit-exact.  Same arguments as their exact twins.
+cudaError_t launch_forward_fast(int integrator, const RenderArgs& a, bool stats, cudaStream_t stream);
+cudaError_t launch_backward_fast(int integrator, const RenderArgs& a, bool stats, cudaStream_t stream);
+cudaError_t launch_path_wavefront_fast(bool backward, RenderArgs a, bool stats, cudaStream_t stream, cudaStream_t* side,
+                                       cudaEvent_t* events);
+cudaError_t launch_path_persistent_fast(bool backward, RenderArgs a, bool stats, const PwPlan& plan, size_t r_capacity_slots,
+                                        unsigned* counters_dev, int max_batches, cudaStream_t stream);
 cudaError_t launch_probe_trace(const SceneView& sc, const float* rays_dev, int n, bool any, int* ip_dev,
                                float* uvt_dev, int* occ_dev, cudaStream_t stream);
 cudaError_t launch_probe_sampler(const SceneView& sc, const int* state_dev, int n, const char* prog_dev, int prog_len,

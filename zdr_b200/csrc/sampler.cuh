@@ -125,7 +125,7 @@ static __device__ __noinline__ float sampler_next_v(const float* __restrict__ bn
     const uint32_t h = hash_dim(h_xy, dimension);
     const int index = permutation_element(sample_index, spp, w, h);
     const float delta = blue_noise(bn, ntex, res, bn_k, bn_cy, dimension);
-    const float u = ((float)index + delta) / (float)spp;
+    const float u = __fdiv_rn(__fadd_rn((float)index, delta), (float)spp);      // explicit IEEE operations: the sampler is bit-exact in every build
     return clampf(u, 0.0f, kOneMinusEps);
 }
 // pmj02bn.py:114-126
@@ -136,10 +136,10 @@ static __device__ __noinline__ float2 sampler_next2f_v(const float2* __restrict_
     const int pmj_instance = dimension / 2;
     if (pmj_instance >= sets) index = permutation_element(sample_index, spp, w, hash_dim(h_xy, dimension));
     float2 u = pmj02bn_sample(pmj, sets, n, pmj_instance, index);
-    u.x = u.x + blue_noise(bn, ntex, res, bn_k, bn_cy, dimension);
-    u.y = u.y + blue_noise(bn, ntex, res, bn_k, bn_cy, dimension + 1);
-    u.x = u.x - floorf(u.x);
-    u.y = u.y - floorf(u.y);
+    u.x = __fadd_rn(u.x, blue_noise(bn, ntex, res, bn_k, bn_cy, dimension));
+    u.y = __fadd_rn(u.y, blue_noise(bn, ntex, res, bn_k, bn_cy, dimension + 1));
+    u.x = __fsub_rn(u.x, floorf(u.x));
+    u.y = __fsub_rn(u.y, floorf(u.y));
     return u;
 }
 ZDR_DEV float sampler_next(const SceneView& sc, Sampler& s) {

@@ -49,9 +49,9 @@ ZDR_DEV RayPre ray_pre(float3 o, float3 d) {
     r.kx = r.kz + 1; if (r.kx == 3) r.kx = 0;
     r.ky = r.kx + 1; if (r.ky == 3) r.ky = 0;
     const float dz = comp(d, r.kz);
-    r.Sx = comp(d, r.kx) / dz;
-    r.Sy = comp(d, r.ky) / dz;
-    r.Sz = 1.0f / dz;
+    r.Sx = __fdiv_rn(comp(d, r.kx), dz);      // explicit IEEE divisions: part of the triangle test's contract in every build
+    r.Sy = __fdiv_rn(comp(d, r.ky), dz);
+    r.Sz = __fdiv_rn(1.0f, dz);
     r.okx = comp(o, r.kx); r.oky = comp(o, r.ky); r.okz = comp(o, r.kz);
     return r;
 }
@@ -63,23 +63,12 @@ ZDR_DEV RayPre ray_pre(float3 o, float3 d) {
 // Every product and sum below is written with an explicit round-to-nearest intrinsic (or fmaf): the expression is part of
 // the numeric contract (it decides primitive ids), so it must not change when the rest of the library is built with
 // floating-point contraction (the "fma" performance build, Makefile).
-ZDR_DEV bool tri_test(const RayPre& rp, const float* __restrict__ tp, float tmin, float& t_out, float& u_out, float& v_out) {
-#if ZDR_TRI_VECTOR_LOADS
-    // three 16-byte loads + selects: a third of the L1 / shared-memory wavefronts of nine scalar loads at lane-dependent
-    // offsets (the traversal stages are bound by load wavefronts, not by issue slots: DESIGN.md)
-    const float4 va = ld_scene(reinterpret_cast<const float4*>(tp)), vb = ld_scene(reinterpret_cast<const float4*>(tp) + 1),
-                 vc = ld_scene(reinterpret_cast<const float4*>(tp) + 2);
-    const float Akx = __fsub_rn(comp(f3(va.x, va.y, va.z), rp.kx), rp.okx), Aky = __fsub_rn(comp(f3(va.x, va.y, va.z), rp.ky), rp.oky),
-                Akz = __fsub_rn(comp(f3(va.x, va.y, va.z), rp.kz), rp.okz);
-    const float Bkx = __fsub_rn(comp(f3(vb.x, vb.y, vb.z), rp.kx), rp.okx), Bky = __fsub_rn(comp(f3(vb.x, vb.y, vb.z), rp.ky), rp.oky),
-                Bkz = __fsub_rn(comp(f3(vb.x, vb.y, vb.z), rp.kz), rp.okz);
-    const float Ckx = __fsub_rn(comp(f3(vc.x, vc.y, vc.z), rp.kx), rp.okx), Cky = __fsub_rn(comp(f3(vc.x, vc.y, vc.z), rp.ky), rp.oky),
-                Ckz = __fsub_rn(comp(f3(vc.x, vc.y, vc.z), rp.kz), rp.okz);
-#else
-    const float Akx = __fsub_rn(ld_scene(tp + rp.kx), rp.okx), Aky = __fsub_rn(ld_scene(tp + rp.ky), rp.oky), Akz = __fsub_rn(ld_scene(tp + rp.kz), rp.okz);
-    const float Bkx = __fsub_rn(ld_scene(tp + 4 + rp.kx), rp.okx), Bky = __fsub_rn(ld_scene(tp + 4 + rp.ky), rp.oky), Bkz = __fsub_rn(ld_scene(tp + 4 + rp.kz), rp.okz);
-    const float Ckx = __fsub_rn(ld_scene(tp + 8 + rp.kx), rp.okx), Cky = __fsub_rn(ld_scene(tp + 8 + rp.ky), rp.oky), Ckz = __fsub_rn(ld_scene(tp + 8 + rp.kz), rp.okz);
-#endif
+// The arithmetic of the test, given the (kx, ky, kz) components of the three vertices (callers differ only in where they load them from).
+ZDR_DEV bool tri_test_vals(const RayPre& rp, float akx, float aky, float akz, float bkx, float bky, float bkz, float ckx, float cky, float ckz,
+                           float tmin, float& t_out, float& u_out, float& v_out) {
+    const float Akx = __fsub_rn(akx, rp.okx), Aky = __fsub_rn(aky, rp.oky), Akz = __fsub_rn(akz, rp.okz);
+    const float Bkx = __fsub_rn(bkx, rp.okx), Bky = __fsub_rn(bky, rp.oky), Bkz = __fsub_rn(bkz, rp.okz);
+    const float Ckx = __fsub_rn(ckx, rp.okx), Cky = __fsub_rn(cky, rp.oky), Ckz = __fsub_rn(ckz, rp.okz);
     const float Ax = fmaf(-rp.Sx, Akz, Akx), Ay = fmaf(-rp.Sy, Akz, Aky);
     const float Bx = fmaf(-rp.Sx, Bkz, Bkx), By = fmaf(-rp.Sy, Bkz, Bky);
     const float Cx = fmaf(-rp.Sx, Ckz, Ckx), Cy = fmaf(-rp.Sy, Ckz, Cky);
@@ -104,6 +93,70 @@ ZDR_DEV bool tri_test(const RayPre& rp, const float* __restrict__ tp, float tmin
     if (!(t > tmin)) return false;
     t_out = t; u_out = __fmul_rn(V, rcp); v_out = __fmul_rn(W, rcp);
     return true;
+}
+ZDR_DEV bool tri_test(const RayPre& rp, const float* __restrict__ tp, float tmin, float& t_out, float& u_out, float& v_out) {
+#if ZDR_TRI_VECTOR_LOADS
+    // three 16-byte loads + selects: a third of the L1 / shared-memory wavefronts of nine scalar loads at lane-dependent
+    // offsets (measured slower, see above)
+    const float4 va = ld_scene(reinterpret_cast<const float4*>(tp)), vb = ld_scene(reinterpret_cast<const float4*>(tp) + 1),
+                 vc = ld_scene(reinterpret_cast<const float4*>(tp) + 2);
+    const float3 a3 = f3(va.x, va.y, va.z), b3 = f3(vb.x, vb.y, vb.z), c3 = f3(vc.x, vc.y, vc.z);
+    return tri_test_vals(rp, comp(a3, rp.kx), comp(a3, rp.ky), comp(a3, rp.kz), comp(b3, rp.kx), comp(b3, rp.ky), comp(b3, rp.kz),
+                         comp(c3, rp.kx), comp(c3, rp.ky), comp(c3, rp.kz), tmin, t_out, u_out, v_out);
+#else
+    return tri_test_vals(rp, ld_scene(tp + rp.kx), ld_scene(tp + rp.ky), ld_scene(tp + rp.kz), ld_scene(tp + 4 + rp.kx), ld_scene(tp + 4 + rp.ky),
+                         ld_scene(tp + 4 + rp.kz), ld_scene(tp + 8 + rp.kx), ld_scene(tp + 8 + rp.ky), ld_scene(tp + 8 + rp.kz), tmin, t_out, u_out, v_out);
+#endif
+}
+
+// Traversal stack of scenes whose links fit 16 bits and whose tree is at most 2 * NREG levels deep below the root (the Cornell
+// box: 35 nodes, 36 triangles): 2 * NREG entries held in NREG registers and moved with byte permutes (PRMT) — no local-memory
+// round trip on the pop -> node-load chain.  An empty stack pops kShortSentinel.
+constexpr int kShortSentinel = (int)0xffff8000;     // (short)0x8000 sign-extended; as a leaf code it is slot 8191 x 4 triangles: never built
+template <int NREG>
+struct RegStack {
+    unsigned r[NREG];
+    ZDR_DEV void clear() {
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) r[i] = 0x80008000u;
+    }
+    ZDR_DEV void push(int link) {
+#pragma unroll
+        for (int i = NREG - 1; i > 0; --i) r[i] = __byte_perm(r[i - 1], r[i], 0x5432);     // (r[i] << 16) | (r[i-1] >> 16)
+        r[0] = __byte_perm((unsigned)link, r[0], 0x5410);                                  // (r[0] << 16) | (link & 0xffff)
+    }
+    ZDR_DEV int pop() {
+        int link;                                                                           // sign-extended low half: selector bit 3
+        asm("prmt.b32 %0, %1, %2, 0x9910;" : "=r"(link) : "r"(r[0]), "r"(0u));             // replicates the byte's sign (__byte_perm ignores it)
+#pragma unroll
+        for (int i = 0; i < NREG - 1; ++i) r[i] = __byte_perm(r[i], r[i + 1], 0x5432);     // (r[i] >> 16) | (r[i+1] << 16)
+        r[NREG - 1] = __byte_perm(r[NREG - 1], 0x80008000u, 0x5432);
+        return link;
+    }
+};
+
+// a local-memory stack with the same interface (comparison build of k_wf_trace_tiny, -DZDR_WF_TINY_LOCAL_STACK=1)
+struct LocalStack16 {
+    int s[16], sp;
+    ZDR_DEV void clear() { sp = 1; s[0] = kShortSentinel; }
+    ZDR_DEV void push(int link) { s[sp++] = link; }
+    ZDR_DEV int pop() { return s[--sp]; }
+};
+// shared-memory loads at 32-bit shared-window addresses (the scene of k_wf_trace_tiny is read-only after its first barrier)
+ZDR_DEV float4 lds_f4(unsigned addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+ZDR_DEV float2 lds_f2(unsigned addr) {
+    float2 v;
+    asm("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+ZDR_DEV float lds_f(unsigned addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
 
 // One 64-byte node record.  sm_100 has 256-bit global loads (LDG.E.256): two instead of four load instructions per node step,

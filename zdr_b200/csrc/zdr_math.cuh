@@ -10,6 +10,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef ZDR_FAST_SINCOS
+#define ZDR_FAST_SINCOS 0
+#endif
 #define ZDR_DEV __device__ __forceinline__
 #define ZDR_HD __host__ __device__ __forceinline__
 
@@ -34,7 +37,10 @@ ZDR_HD float3 cross(float3 a, float3 b) {
 // v * (1/sqrt(v.v)).  On the device the IEEE sqrt + divide expand to ~45 instructions with their slow
 // paths; ~20 call sites per path vertex made this the largest single contributor to the render
 // kernels' code size (ncu source page, profiles/r01g), so the device version is ONE out-of-line copy.
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && defined(ZDR_FAST_MATH)
+// "fast" build of the shading code (Makefile: --use_fast_math): one MUFU.RSQ, inline
+ZDR_HD float3 normalize(float3 v) { return v * rsqrtf(fmaf(v.z, v.z, fmaf(v.y, v.y, v.x * v.x))); }
+#elif defined(__CUDA_ARCH__)
 static __device__ __noinline__ float rcp_length(float x, float y, float z) { return 1.0f / sqrtf(fmaf(z, z, fmaf(y, y, x * x))); }
 ZDR_HD float3 normalize(float3 v) { return v * rcp_length(v.x, v.y, v.z); }
 #else
@@ -57,6 +63,15 @@ ZDR_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi
 ZDR_HD int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
 ZDR_HD bool any_nan(float3 a) { return (a.x != a.x) || (a.y != a.y) || (a.z != a.z); }
 ZDR_HD bool any_nan(float4 a) { return (a.x != a.x) || (a.y != a.y) || (a.z != a.z) || (a.w != a.w); }
+// May this texel gradient be scattered?  The reference drops NaN (prb.py:178-187); the "fast" build also drops +-inf, which
+// approximate divisions by nearly-zero BRDF values produce where the IEEE ones give huge finite numbers.
+ZDR_HD bool grad_ok(float4 g) {
+#ifdef ZDR_FAST_MATH
+    return fabsf(g.x) <= 3.0e38f && fabsf(g.y) <= 3.0e38f && fabsf(g.z) <= 3.0e38f && fabsf(g.w) <= 3.0e38f;
+#else
+    return !any_nan(g);
+#endif
+}
 ZDR_HD bool any_pos(float3 a) { return a.x > 0.0f || a.y > 0.0f || a.z > 0.0f; }
 
 // float -> int, saturating, NaN -> 0 (cvt.rzi.s32.f32)
@@ -83,6 +98,14 @@ static __device__ __noinline__
 inline
 #endif
 void sincos_contract(float phi, float* s_out, float* c_out) {
+#if defined(__CUDA_ARCH__) && defined(ZDR_FAST_MATH) && ZDR_FAST_SINCOS
+    // MUFU.SIN / MUFU.COS (absolute error ~2^-21 on [0, 2 pi]).  Measured (profiles/r02u): the 5e-7 rad this puts on every
+    // sampled direction moves the next hit by ~1e-4 units, which a white-noise texture turns into ~1e-4 relative changes of
+    // the material — the path integrator's samples then differ from the oracle's by > 1e-3 in 10 % of the cases.  Off: the
+    // fast build keeps the binary64 polynomial below (3 % of the shade stage).
+    __sincosf(phi, s_out, c_out);
+    return;
+#endif
     double x = (double)phi;
     double kd = rint(x * 0.63661977236758134308);
     double r = fma(-kd, 1.57079632679489655800e+00, x);
