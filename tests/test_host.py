@@ -35,6 +35,20 @@ def test_library_loads_and_exports_every_symbol():
     assert lib.zdr_abi_version() == 1
 
 
+def test_header_flags_match_the_python_constants():
+    """Every ZDR_FLAG_* of the header has the same value in zdr_b200/_abi.py (the flags select schedules, scatter modes, the build)."""
+    src = open(os.path.join(ROOT, "include", "zdr_b200.h")).read()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(ZDR_FLAG_[A-Z_0-9]+)\s+(\d+)", src)}
+    assert len(flags) >= 9 and "ZDR_FLAG_FAST_MATH" in flags
+    for name, value in flags.items():
+        assert getattr(_abi, name) == value, name
+    assert len(set(flags.values())) == len(flags) and all(v & (v - 1) == 0 for v in flags.values())      # distinct single bits
+    p = _abi.make_params(scenes.CBOX_CAMERA, (8, 8), (4, 4, 4), 1, 0, math="fast", schedule="wavefront")
+    assert p.flags == _abi.ZDR_FLAG_FAST_MATH | _abi.ZDR_FLAG_WAVEFRONT
+    with pytest.raises(KeyError):
+        _abi.make_params(scenes.CBOX_CAMERA, (8, 8), (4, 4, 4), 1, 0, math="sloppy")
+
+
 def test_params_struct_layout():
     """zdr_params is ABI: field order / size must match the header (27 x 4 bytes + 10 floats)."""
     src = open(os.path.join(ROOT, "include", "zdr_b200.h")).read()

@@ -532,7 +532,9 @@ __global__ void __launch_bounds__(kPwThreads, kPwBlocks) k_pw(const __grid_const
                     float3 ray_o = zero, ray_nd = zero;
                     const float3 wi_light_local = to_local(onb, light_wi);
                     if (!occluded && wi_light_local.z >= 1e-4f) {                                       // prb.py:61-66
-                        const float4 ev = ggx_eval(wo_local, wi_light_local, diffuse, specular, roughness);
+                        float2 gb = make_float2(0.f, 0.f);      // adjoint: (dk, common) of ggx_brdf_grad, computed with the value (shading.cuh ggx_eval_adj)
+                        const float4 ev = ADJ ? ggx_eval_adj(wo_local, wi_light_local, diffuse, specular, roughness, gb)
+                                              : ggx_eval(wo_local, wi_light_local, diffuse, specular, roughness);
                         const float3 bsdf = f3(ev.x, ev.y, ev.z);
                         const float mis_weight = balanced_heuristic(light_pdf, ev.w);
                         const float dn = fmaxf(light_pdf, 1e-4f);
@@ -541,12 +543,13 @@ __global__ void __launch_bounds__(kPwThreads, kPwBlocks) k_pw(const __grid_const
                             L = L + contrib;
                         } else {
                             const float3 cot = (((beta * mis_weight) * light_eval) / dn) * le_grad;     // prb.py:145
-                            mat_grad = mat_grad + ggx_brdf_grad_nl(wo_local, wi_light_local, specular, roughness, cot);
+                            mat_grad = mat_grad + ggx_grad_from_basis(gb, cot);
                             L = L - contrib;                                                        // prb.py:147
                         }
                     }
                     const float3 wi_local = ggx_sample(a.sc, wo_local, roughness, sampler);             // prb.py:69
-                    const float4 ev = ggx_eval(wo_local, wi_local, diffuse, specular, roughness);
+                    float2 gb = make_float2(0.f, 0.f);
+                    const float4 ev = ADJ ? ggx_eval_adj(wo_local, wi_local, diffuse, specular, roughness, gb) : ggx_eval(wo_local, wi_local, diffuse, specular, roughness);
                     pdf_bsdf = ev.w;
                     const float3 wi = to_world(onb, wi_local);
                     if (dot(wi, itx.ng) < 1e-4f || wi_local.z < 1e-4f) {                                // prb.py:73-74
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(kPwThreads, kPwBlocks) k_pw(const __grid_const
                                          bsdf.z != 0.0f ? L.z / bsdf.z * le_grad.z : 0.0f);
                             else
                                 cot = ((beta / pdf_bsdf) * L) * le_grad;                                // prb.py:162
-                            mat_grad = mat_grad + ggx_brdf_grad_nl(wo_local, wi_local, specular, roughness, cot);
+                            mat_grad = mat_grad + ggx_grad_from_basis(gb, cot);
                         }
                         beta = beta * (bsdf / pdf_bsdf);                                                // prb.py:76
                         if (depth >= a.rr_depth) {                                                      // prb.py:78-87

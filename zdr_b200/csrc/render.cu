@@ -1094,7 +1094,9 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
                 bool end = false;
                 const float3 wi_light_local = to_local(onb, light_wi);
                 if (!occluded && wi_light_local.z >= 1e-4f) {                                       // prb.py:61-66
-                    const float4 ev = ggx_eval(wo_local, wi_light_local, diffuse, specular, roughness);
+                    float2 gb = make_float2(0.f, 0.f);      // adjoint: (dk, common) of ggx_brdf_grad, computed with the value (shading.cuh ggx_eval_adj)
+                    const float4 ev = ADJ ? ggx_eval_adj(wo_local, wi_light_local, diffuse, specular, roughness, gb)
+                                          : ggx_eval(wo_local, wi_light_local, diffuse, specular, roughness);
                     const float3 bsdf = f3(ev.x, ev.y, ev.z);
                     const float mis_weight = balanced_heuristic(light_pdf, ev.w);
                     const float dn = fmaxf(light_pdf, 1e-4f);
@@ -1103,12 +1105,13 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
                         p.L = p.L + contrib;
                     } else {
                         const float3 cot = (((p.beta * mis_weight) * light_eval) / dn) * le_grad;     // prb.py:145
-                        mat_grad = mat_grad + ggx_brdf_grad_nl(wo_local, wi_light_local, specular, roughness, cot);
+                        mat_grad = mat_grad + ggx_grad_from_basis(gb, cot);
                         p.L = p.L - contrib;                                                        // prb.py:147
                     }
                 }
                 const float3 wi_local = ggx_sample(sc, wo_local, roughness, p.sampler);             // prb.py:69
-                const float4 ev = ggx_eval(wo_local, wi_local, diffuse, specular, roughness);
+                float2 gb = make_float2(0.f, 0.f);
+                const float4 ev = ADJ ? ggx_eval_adj(wo_local, wi_local, diffuse, specular, roughness, gb) : ggx_eval(wo_local, wi_local, diffuse, specular, roughness);
                 p.pdf_bsdf = ev.w;
                 const float3 wi = to_world(onb, wi_local);
                 if (dot(wi, itx.ng) < 1e-4f || wi_local.z < 1e-4f) {                                // prb.py:73-74
@@ -1123,7 +1126,7 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
                                      bsdf.z != 0.0f ? p.L.z / bsdf.z * le_grad.z : 0.0f);
                         else
                             cot = ((p.beta / p.pdf_bsdf) * p.L) * le_grad;                          // prb.py:162
-                        mat_grad = mat_grad + ggx_brdf_grad_nl(wo_local, wi_local, specular, roughness, cot);
+                        mat_grad = mat_grad + ggx_grad_from_basis(gb, cot);
                     }
                     p.beta = p.beta * (bsdf / p.pdf_bsdf);                                          // prb.py:76
                     if (p.depth >= a.rr_depth) {                                                    // prb.py:78-87

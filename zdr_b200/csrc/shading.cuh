@@ -342,11 +342,64 @@ ZDR_DEV float ggx_sample_pdf(float3 wo, float3 wi, float roughness) {    // micr
     return 0.5f * diffuse_pdf + 0.5f * glossy_pdf;
 }
 
+// The terms ggx_brdf and ggx_sample_pdf (and the adjoint) share for one direction pair, each computed ONCE: the half vector
+// (one normalize), D, the Fresnel term, both Smith terms and dot(wo, h).  Same operations on the same inputs as the separate
+// functions above, so every value has the same bits — the out-of-line normalize is simply no longer called twice (the compiler
+// cannot merge calls of a __noinline__ function) and D no longer evaluated twice.
+struct GgxTerms { float nh, voh, d, f, gi, go; };
+ZDR_DEV GgxTerms ggx_terms(float3 wo, float3 wi, float specular, float alpha) {
+    GgxTerms t;
+    const float3 h = normalize(wi + wo);
+    t.nh = h.z;
+    t.d = ggx_distribution(h, alpha);
+    t.voh = dot(wo, h);
+    t.f = fresnel_schlick(clampf(t.voh, 0.00001f, 1.0f), specular);
+    t.gi = smith_geometry(wi, alpha);
+    t.go = smith_geometry(wo, alpha);
+    return t;
+}
+ZDR_DEV float4 ggx_eval_from_terms(const GgxTerms& t, float3 wo, float3 wi, float3 diffuse) {
+    const float g = t.gi * t.go;                                                              // ggx_brdf, microfacet.py:23-30
+    const float spec = (t.d * t.f * g) / (4.0f * fmaxf(0.00001f, wi.z) * fmaxf(0.00001f, wo.z));
+    const float diffuse_pdf = wi.z / kPi;                                                     // ggx_sample_pdf, microfacet.py:51-58
+    const float glossy_pdf = (t.go / fabsf(wo.z) * t.d * fabsf(t.voh)) / (4.0f * fabsf(t.voh));   // pdf_wm(wo, h) / (4 |wo . h|)
+    return make_float4((spec + diffuse.x / kPi) * wi.z, (spec + diffuse.y / kPi) * wi.z, (spec + diffuse.z / kPi) * wi.z,
+                       0.5f * diffuse_pdf + 0.5f * glossy_pdf);
+}
 static __device__ __noinline__ float4 ggx_eval(float wox, float woy, float woz, float wix, float wiy, float wiz, float dr, float dg, float db,
                                         float specular, float roughness) {
     const float3 wo = f3(wox, woy, woz), wi = f3(wix, wiy, wiz);
-    const float3 f = ggx_brdf(wo, wi, f3(dr, dg, db), specular, roughness);
-    return make_float4(f.x, f.y, f.z, ggx_sample_pdf(wo, wi, roughness));
+    const GgxTerms t = ggx_terms(wo, wi, specular, roughness * roughness);
+    return ggx_eval_from_terms(t, wo, wi, f3(dr, dg, db));
+}
+// (ggx_brdf, ggx_sample_pdf) AND the basis of the adjoint of one direction pair in one call (adjoint kernels): the adjoint is
+// linear in the cotangent g, ggx_brdf_grad(.., g) = (g.x dk, g.y dk, g.z dk, (g.x + g.y + g.z) common), so (dk, common) can be
+// computed next to the BRDF value, before the caller knows g, from the terms the value already needed (half vector, D, F, both
+// Smith terms — the separate ggx_brdf_grad computes all of them again).  Gradients are compared at 1e-3 (float atomics are
+// unordered anyway); the Smith terms reused here differ from ggx_brdf_grad's own by the rounding of a2 * k.
+static __device__ __noinline__ float4 ggx_eval_adj(float wox, float woy, float woz, float wix, float wiy, float wiz, float dr, float dg, float db,
+                                            float specular, float roughness, float2* basis) {
+    const float3 wo = f3(wox, woy, woz), wi = f3(wix, wiy, wiz);
+    const float alpha = roughness * roughness, a2 = alpha * alpha;
+    const GgxTerms t = ggx_terms(wo, wi, specular, alpha);
+    const float nh = fmaxf(0.00001f, t.nh), nh2 = nh * nh;
+    const float tt = nh2 * (a2 - 1.0f) + 1.0f;
+    const float dD = (tt - 2.0f * a2 * nh2) / (kPi * (tt * tt * tt));
+    const float nvi = fmaxf(0.00001f, wi.z), nvo = fmaxf(0.00001f, wo.z);
+    const float ki = (1.0f - nvi * nvi) / (nvi * nvi), ko = (1.0f - nvo * nvo) / (nvo * nvo);
+    const float si = sqrtf(1.0f + a2 * ki), so = sqrtf(1.0f + a2 * ko);
+    const float dGi = -ki / (si * ((1.0f + si) * (1.0f + si)));
+    const float dGo = -ko / (so * ((1.0f + so) * (1.0f + so)));
+    const float dDGG = dD * t.gi * t.go + t.d * dGi * t.go + t.d * t.gi * dGo;
+    const float da2_dr = 4.0f * roughness * roughness * roughness;
+    *basis = make_float2(wi.z / kPi, wi.z * t.f / (4.0f * nvi * nvo) * dDGG * da2_dr);
+    return ggx_eval_from_terms(t, wo, wi, f3(dr, dg, db));
+}
+ZDR_DEV float4 ggx_eval_adj(float3 wo, float3 wi, float3 diffuse, float specular, float roughness, float2& basis) {
+    return ggx_eval_adj(wo.x, wo.y, wo.z, wi.x, wi.y, wi.z, diffuse.x, diffuse.y, diffuse.z, specular, roughness, &basis);
+}
+ZDR_DEV float4 ggx_grad_from_basis(float2 basis, float3 g) {
+    return make_float4(g.x * basis.x, g.y * basis.x, g.z * basis.x, (g.x + g.y + g.z) * basis.y);
 }
 static __device__ __noinline__ float4 ggx_brdf_grad_nl(float wox, float woy, float woz, float wix, float wiy, float wiz, float specular,
                                                 float roughness, float gx, float gy, float gz) {
