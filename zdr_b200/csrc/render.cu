@@ -416,6 +416,12 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_path(const __grid_constant
 // paths, each kernel is small (64 registers), and the state traffic (~1.5 kB of DRAM per path) is what the
 // 7.7 TB/s of HBM3e are for.  Arithmetic per sample is unchanged (same device functions), so images stay
 // bit-identical to the oracle.
+#ifndef ZDR_WF_EARLY_SHADOW_LOADS      // stage B: load the light-sample records right after the list entry, with the rest of the
+#define ZDR_WF_EARLY_SHADOW_LOADS 1      // slot's state (measured r02y: C3 at 64 spp 7067 -> 7103 Mrays/s, reproducible; 256 spp: +0.1 %)
+#endif
+#ifndef ZDR_WF_EARLY_TEXELS      // stage B: texel loads issued before the shading frame is built.  Measured r02y: C3 7115 -> 6730 Mrays/s
+#define ZDR_WF_EARLY_TEXELS 0      // (16 more live registers at the 64-register cap: spills); off
+#endif
 #ifndef ZDR_WF_SHADE_A_MINB
 #define ZDR_WF_SHADE_A_MINB 8
 #endif
@@ -1071,6 +1077,9 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
         if (i < n) {
             slot = w.list[1][i];
             {
+#if ZDR_WF_EARLY_SHADOW_LOADS
+                const float4 SB = w.SAB[2 * (size_t)(slot) + 1], SC = w.SC[slot];      // issued with the other state loads of the slot
+#endif
                 WfPath p = wf_load(a, slot, true);
                 const Hit hit = wf_hit(a, slot);
                 float3 le_grad = zero;
@@ -1081,12 +1090,24 @@ __global__ void __launch_bounds__(kWfThreads, MODE == 2 ? ZDR_WF_SHADE_BB_MINB :
                 }
                 const Interaction itx = surface_interact(sc, hit);
                 const int mset = inst_texture_set(sc, hit.inst);
+#if ZDR_WF_EARLY_TEXELS
+                BsdfTexels tx;
+                if (a.tex.bilinear) tx = fetch_bsdf(a.tex, itx.uv, mset);      // texel loads in flight while the frame is built
+                const Onb onb = make_onb(itx.ns);
+                const float3 wo_local = to_local(onb, -p.ray.d);
+                const float4 mat = a.tex.bilinear ? combine_bsdf(tx) : read_bsdf(a.tex, itx.uv, mset);
+                const float3 diffuse = f3(mat.x, mat.y, mat.z);
+                const float roughness = mat.w;
+#else
                 const float4 mat = read_bsdf(a.tex, itx.uv, mset);
                 const float3 diffuse = f3(mat.x, mat.y, mat.z);
                 const float roughness = mat.w;
                 const Onb onb = make_onb(itx.ns);
                 const float3 wo_local = to_local(onb, -p.ray.d);
+#endif
+#if !ZDR_WF_EARLY_SHADOW_LOADS
                 const float4 SB = w.SAB[2 * (size_t)(slot) + 1], SC = w.SC[slot];
+#endif
                 const float3 light_wi = f3(SB.x, SB.y, SB.z), light_eval = f3(SC.x, SC.y, SC.z);
                 const float light_pdf = SB.w;
                 const bool occluded = SC.w != 0.0f;

@@ -28,11 +28,7 @@ ZDR_DEV Ray camera_sample(const RenderArgs& a, int x, int y, Sampler& sampler) {
     return make_ray(a.cam_o, normalize(d), 0.0f, 1e30f);
 }
 
-ZDR_DEV unsigned warp_sum(unsigned v) {
-#pragma unroll 1
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+ZDR_DEV unsigned warp_sum(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }      // one REDUX (was a 5-step shuffle loop: 3 % of a shade stage's instructions)
 constexpr unsigned kWfPhaseBit = 1u << 8;
 
 ZDR_DEV unsigned wf_pack(int depth, int phase, int dimension) { return (unsigned)depth | (phase ? kWfPhaseBit : 0u) | ((unsigned)dimension << 12); }

@@ -75,6 +75,21 @@ ZDR_DEV float4 read_bsdf(const TexView& t, float2 uv, int set = 0) {       // in
     return lerp(lerp(c00, c01, oy), lerp(c10, c11, oy), ox);
 }
 
+// read_bsdf in two halves (bilinear only): the four texel loads, and their interpolation — a stage can put independent work
+// between them (experiment ZDR_WF_EARLY_TEXELS)
+struct BsdfTexels { float4 c00, c01, c10, c11; float ox, oy; };
+ZDR_DEV BsdfTexels fetch_bsdf(const TexView& t, float2 uv, int set = 0) {
+    const int base = set * t.set_texels;
+    const float px = uv.x * (float)(t.rx - 1), py = (1.0f - uv.y) * (float)(t.ry - 1);
+    const int ix = f2i(px), iy = f2i(py);
+    BsdfTexels r;
+    r.ox = px - (float)ix; r.oy = py - (float)iy;
+    r.c00 = read_single_bsdf(t, ix, iy, base); r.c01 = read_single_bsdf(t, ix, iy + 1, base);
+    r.c10 = read_single_bsdf(t, ix + 1, iy, base); r.c11 = read_single_bsdf(t, ix + 1, iy + 1, base);
+    return r;
+}
+ZDR_DEV float4 combine_bsdf(const BsdfTexels& r) { return lerp(lerp(r.c00, r.c01, r.oy), lerp(r.c10, r.c11, r.oy), r.ox); }
+
 // one 16-byte vector reduction per texel instead of the reference's four scalar
 // atomic_fetch_add (interaction.py:67-70): red.global.add.v4.f32 (sm_90+)
 ZDR_DEV void red_add_f4(float4* addr, float4 v) {
