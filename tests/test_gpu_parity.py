@@ -349,6 +349,32 @@ def test_shard_rows_and_samples(oracle, case_cache, case):
     assert rel_l2(g_sum, g_full) < 1e-5
 
 
+def test_scenes_of_one_or_two_leaves_all_schedules(oracle):
+    """Scenes whose tree is a single leaf or one node (root link negative / no stack traffic): a turned-over, enlarged copy of the
+    light quad as the textured floor under the light, and the floor alone; every schedule (the wavefront one takes the
+    shared-memory traversal kernel here), binned and not."""
+    from zdr_b200.mathtypes import float4x4
+    floor = float4x4(-3, 0, 0, 0, 0, -1, 0, 0, 0, 0, 3, 0, -0.936, 6.319, 6.08, 1)      # half turn about z, x and z enlarged
+    light = scenes.asset("cbox-light.obj")
+    mat = scenes.random_material((64, 64), 12)
+    for models in ([(light, floor, scenes.float3(0.0)), (light, None, scenes.float3(17, 12, 4))], [(light, floor, scenes.float3(0.5, 0.4, 0.3))]):
+        g, o = GpuScene(models), oracle.OracleScene(models)
+        for sched, env in (("megakernel", {}), ("wavefront", {}), ("wavefront", {"ZDR_WF_BIN": "3"}), ("wavefront", {"ZDR_WF_TINY_OFF": "1"}), ("persistent", {})):
+            p = make_params(scenes.CBOX_CAMERA, (64, 48), mat.shape, 4, 0, max_depth=4, schedule=sched)
+            with _env(env):
+                s_g = g.samples(ZDR_PATH, p, mat)
+            s_o = o.render_samples(ZDR_PATH, p, mat)
+            assert np.array_equal(bits(s_g), bits(s_o)), (len(models), sched, env)
+            pb = make_params(scenes.CBOX_CAMERA, (64, 48), mat.shape, 4, 1, max_depth=4, schedule=sched)
+            dimg = np.ones((48, 64, 4), np.float32)
+            with _env(env):
+                dm_g = g.backward(ZDR_PATH, pb, mat, dimg)
+            dm_o = o.render_backward(ZDR_PATH, pb, mat, dimg)
+            assert rel_l2(dm_g, dm_o) <= GRAD_TOL or not dm_o.any(), (len(models), sched, env, rel_l2(dm_g, dm_o))
+        assert s_o.max() > 0 or len(models) == 1
+        g.close()
+
+
 def test_transformed_instances_and_update_lights(oracle):
     """test_lightstage.py shape: transformed instances, lights toggled with update_lights."""
     models = scenes.sphere_grid_models(6, seed=2)

@@ -10,7 +10,7 @@ name=$1; shift
 mkdir -p variants
 make -s -j4 > /dev/null
 objs=""
-for o in api render persistent render_fast persistent_fast bvh_build envmap obj_loader; do
+for o in api render wavefront persistent render_fast wavefront_fast persistent_fast bvh_build envmap obj_loader; do
   if [[ " ${FILE:=render} " == *" $o "* ]]; then
     math="-fmad=${FMAD:-false}"
     [[ $o == *_fast ]] && math="${FAST_FLAGS:---use_fast_math}"

@@ -269,8 +269,12 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
     // (41 GB at 152 B per slot: all 256 samples of a 1024^2 image in one batch); ZDR_WF_SLOTS_LOG2 overrides.
     // Larger batches amortise the ~4*depth launches per batch and the thin tail rounds (measured: 2^24 -> 2^28
     // slots = 4.9 -> 5.5 Grays/s on C3).
-    // Several state sets of a fraction of the samples each, worked on from as many streams (render.cu
+    // Several state sets of a fraction of the samples each, worked on from as many streams (wavefront.cu
     // launch_path_wavefront), once the job is large enough for the parts to fill the GPU; ZDR_WF_LANES=1 keeps one.
+    // ray binning (render.cuh WfState): which traversal stages read binned lists (ZDR_WF_BIN: bit 0 extension rays, bit 1 shadow
+    // rays; read per call: tests switch it).  Its arrays are part of the workspace only when it is on.
+    const int bin_mask = (getenv("ZDR_WF_BIN") ? atoi(getenv("ZDR_WF_BIN")) : ZDR_WF_BIN_DEFAULT) & 3;
+    const bool binned = bin_mask != 0;
     static const int lanes = getenv("ZDR_WF_LANES") ? atoi(getenv("ZDR_WF_LANES")) : 2;
     long long S = 0;
     int sets = 1;
@@ -283,15 +287,15 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
         while (sets < lanes && sets < kWfMaxSets && S >= 2 * (sets + 1) && pixels * S >= (long long)(sets + 1) << 22) ++sets;
         S = (S + sets - 1) / sets;
         slots = (size_t)(pixels * S);
-        set_bytes = (slots * wf_bytes_per_slot() + wf_fixed_bytes() + 255) & ~(size_t)255;
+        set_bytes = (slots * wf_bytes_per_slot(binned) + wf_fixed_bytes(binned) + 255) & ~(size_t)255;
         bytes = set_bytes * sets;
     };
     const size_t ws_cap = s->s_wf.external ? s->s_wf.cap : s->ws_limit;      // caller-provided buffer / caller-set bound
     if (ws_cap) {
-        const size_t fixed = 2 * (wf_fixed_bytes() + 256);      // up to two state sets
-        long long fit = (long long)((ws_cap > fixed ? ws_cap - fixed : 0) / wf_bytes_per_slot());
+        const size_t fixed = 2 * (wf_fixed_bytes(binned) + 256);      // up to two state sets
+        long long fit = (long long)((ws_cap > fixed ? ws_cap - fixed : 0) / wf_bytes_per_slot(binned));
         if (fit < pixels) return fail(ZDR_ERR_LIMIT, "workspace of %zu MiB cannot hold one sample per pixel of this launch (%lld MiB needed)",
-                                      ws_cap >> 20, (long long)(pixels * wf_bytes_per_slot() + fixed) >> 20);
+                                      ws_cap >> 20, (long long)(pixels * wf_bytes_per_slot(binned) + fixed) >> 20);
         plan(fit < (1ll << 28) ? fit : (1ll << 28));
         while (bytes > ws_cap && S > 1) { plan((long long)(slots - pixels)); }
     } else if (const char* slots_env = getenv("ZDR_WF_SLOTS_LOG2")) {
@@ -303,7 +307,7 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
         if (bytes > s->s_wf.cap) {
             size_t free_b = 0, total_b = 0;
             if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-                const long long fit = (long long)((free_b + s->s_wf.cap) / 4 / wf_bytes_per_slot());
+                const long long fit = (long long)((free_b + s->s_wf.cap) / 4 / wf_bytes_per_slot(binned));
                 if (fit < (1ll << 28)) plan(fit);
             }
         }
@@ -320,24 +324,26 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
     w.SC = reinterpret_cast<float4*>(base); base += slots * sizeof(float4);
     w.list[0] = reinterpret_cast<int*>(base); base += slots * sizeof(int);
     w.list[1] = reinterpret_cast<int*>(base); base += slots * sizeof(int);
-    w.blist = reinterpret_cast<int*>(base); base += slots * sizeof(int);
-    w.keys[0] = reinterpret_cast<unsigned short*>(base); base += slots * sizeof(unsigned short);
-    w.keys[1] = reinterpret_cast<unsigned short*>(base); base += slots * sizeof(unsigned short);
+    w.blist = nullptr; w.keys[0] = w.keys[1] = nullptr; w.hist[0] = w.hist[1] = w.cur = nullptr;
+    if (binned) {
+        w.blist = reinterpret_cast<int*>(base); base += slots * sizeof(int);
+        w.keys[0] = reinterpret_cast<unsigned short*>(base); base += slots * sizeof(unsigned short);
+        w.keys[1] = reinterpret_cast<unsigned short*>(base); base += slots * sizeof(unsigned short);
+    }
     base = s->s_wf.p + (((base - s->s_wf.p) + 15) & ~(size_t)15);
     w.counts = reinterpret_cast<int*>(base); base += 64;
-    w.hist[0] = reinterpret_cast<int*>(base); base += kWfBins * sizeof(int);      // hist[0], hist[1], cur: contiguous (k_wf_generate zeroes them)
-    w.hist[1] = reinterpret_cast<int*>(base); base += kWfBins * sizeof(int);
-    w.cur = reinterpret_cast<int*>(base);
-    // ray binning: origin cells over the scene's bounds; which traversal stages read binned lists (ZDR_WF_BIN: bit 0 extension
-    // rays, bit 1 shadow rays; default from the measurements in DESIGN.md)
-    const int bin_env = getenv("ZDR_WF_BIN") ? atoi(getenv("ZDR_WF_BIN")) : ZDR_WF_BIN_DEFAULT;      // read per call: tests switch it
-    w.bin_mask = bin_env & 3;
+    if (binned) {
+        w.hist[0] = reinterpret_cast<int*>(base); base += kWfBins * sizeof(int);      // hist[0], hist[1], cur: contiguous (k_wf_generate zeroes them)
+        w.hist[1] = reinterpret_cast<int*>(base); base += kWfBins * sizeof(int);
+        w.cur = reinterpret_cast<int*>(base);
+    }
+    w.bin_mask = bin_mask;
     w.bin_in = w.bin_out = 0;
     w.key_lo = s->bounds_lo;
     w.key_scale = f3((float)kWfCells / fmaxf(s->bounds_hi.x - s->bounds_lo.x, 1e-30f), (float)kWfCells / fmaxf(s->bounds_hi.y - s->bounds_lo.y, 1e-30f),
                      (float)kWfCells / fmaxf(s->bounds_hi.z - s->bounds_lo.z, 1e-30f));
-    // shared-memory traversal with a register stack (k_wf_trace_tiny): scenes of at most 8 KB whose links fit 16 bits and whose
-    // tree leaves at most 12 pending links (ZDR_WF_TINY_OFF=1: off)
+    // shared-memory traversal (k_wf_trace_tiny): scenes of at most 8 KB whose links fit 16 bits and whose tree leaves at most 12
+    // pending links (its stack: 16 local-memory entries, or 8 / 12 entries in registers); ZDR_WF_TINY_OFF=1: the general kernel
     const bool tiny_off = getenv("ZDR_WF_TINY_OFF") != nullptr;
     const int pending = s->bvh.max_depth - 1;
     w.tiny_regs = 0;

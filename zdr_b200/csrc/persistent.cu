@@ -17,7 +17,7 @@
 // stages' code runs with the whole CTA in the same phase (instruction-cache friendly, unlike a one-kernel state machine),
 // and nothing but finished samples (forward: 16 bytes per sample, summed per pixel IN SAMPLE ORDER by k_pw_accumulate,
 // integrator.py:15-28, so images stay bit-identical to the oracle's) ever leaves the SM.  Against the HBM wavefront of
-// render.cu (k_wf_*: ~100 launches and ~1.7 kB of DRAM traffic per path and pass) a pass is 1 launch (+1 accumulate).
+// wavefront.cu (k_wf_*: ~100 launches and ~1.7 kB of DRAM traffic per path and pass) a pass is 1 launch (+1 accumulate).
 // Replay and adjoint-walk paths of the adjoint pass share the pool but never a warp of stage B: L1 is filled from both
 // ends (replay paths bottom-up, adjoint paths top-down).
 //
@@ -27,6 +27,8 @@
 //
 // Arithmetic per sample is unchanged (the device functions of shading.cuh / sampler.cuh / traverse.cuh).
 #define ZDR_SCENE_GENERIC_LOADS 1
+#define ZDR_INLINE_RCP_LENGTH 1      // normalize() inline: 5 277 -> 5 440 Mrays/s on C3 at 64 spp (profiles/r03b)
+#define ZDR_INLINE_GGX_EVAL 1
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
@@ -121,7 +123,7 @@ struct TStack<false> {
 };
 
 // Stage E (ANY = false: closest hit of queue `lo` -> pool.hit) and stage S (ANY = true: occlusion of the two-ended queue
-// `lo` / `hi` -> pool.le.w): the persistent dynamic-fetch traversal of render.cu's k_wf_trace with the queue, its cursor,
+// `lo` / `hi` -> pool.le.w): the persistent dynamic-fetch traversal of wavefront.cu's k_wf_trace with the queue, its cursor,
 // the rays and (small scenes) the tree, the triangles and the stack in shared memory.  A lane that finishes its ray takes the
 // next queue entry; lanes still traversing leave the inner loop to let idle ones refill once fewer than `refill` are left.
 template <bool ANY, bool STATS, bool SMALL>

@@ -1,4 +1,4 @@
-// render.cuh — kernel argument block shared by render.cu and api.cu.
+// render.cuh — kernel argument block shared by the render kernels (render.cu, wavefront.cu, persistent.cu) and api.cu.
 #pragma once
 #include "scene.cuh"
 #include "shading.cuh"
@@ -6,7 +6,7 @@
 
 namespace zdr {
 
-// Global-memory path state of the wavefront path tracer (render.cu, k_wf_*): one slot per
+// Global-memory path state of the wavefront path tracer (wavefront.cu, k_wf_*): one slot per
 // (sample-in-batch j, pixel pix), slot = j * P + pix, so a warp works on 32 neighbouring pixels.
 struct WfState {
     // pairs of records that are always read together share one 32-byte sector (slots of a compacted list are
@@ -87,12 +87,12 @@ struct RenderArgs {
 
 // number of kernels this library has launched (render kernels and probes), for bench.py's gpu_launches
 unsigned long long kernel_launch_count();
-// launchers (render.cu)
+// launchers (render.cu; the wavefront schedule: wavefront.cu)
 cudaError_t launch_forward(int integrator, const RenderArgs& a, bool stats, cudaStream_t stream);
 cudaError_t launch_backward(int integrator, const RenderArgs& a, bool stats, cudaStream_t stream);
 // wavefront variant of the path integrator / PRB adjoint; `wf` buffers sized for wf_slot_capacity() slots
-size_t wf_bytes_per_slot();
-size_t wf_fixed_bytes();      // per state set, on top of the slots
+size_t wf_bytes_per_slot(bool binned);      // binned: with the arrays of the ray binning (WfState)
+size_t wf_fixed_bytes(bool binned);         // per state set, on top of the slots
 // side / events: the scene's kWfMaxSets - 1 extra streams and kWfMaxSets + 2 timing-less events, used when
 // wf.num_sets > 1 to run consecutive batches from several streams (the tail of every stage kernel overlaps the other
 // streams' work); both may be null otherwise

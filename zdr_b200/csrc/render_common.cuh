@@ -1,4 +1,4 @@
-// render_common.cuh — device functions shared by the render kernels of render.cu and persistent.cu: camera sample
+// render_common.cuh — device functions shared by the render kernels of render.cu, wavefront.cu and persistent.cu: camera sample
 // (integrator.py:17-25, camera.py:5-31), envmap emission on a miss, the packing of (depth, phase, sampler dimension), the
 // pixel order of a shard.
 #pragma once

@@ -4,5 +4,4 @@
 #define ZDR_FAST_MATH 1
 #define launch_forward launch_forward_fast
 #define launch_backward launch_backward_fast
-#define launch_path_wavefront launch_path_wavefront_fast
 #include "render.cu"

@@ -309,7 +309,15 @@ ZDR_DEV float4 ggx_brdf_grad(float3 wo, float3 wi, float specular, float roughne
 }
 // (ggx_brdf, ggx_sample_pdf) of one direction pair; one out-of-line copy shared by the
 // light-sample and BSDF-sample evaluations (instruction-cache budget, see traverse.cuh)
-static __device__ __noinline__ float4 ggx_eval(float wox, float woy, float woz, float wix, float wiy, float wiz, float dr, float dg, float db,
+#ifndef ZDR_INLINE_GGX_EVAL
+#define ZDR_INLINE_GGX_EVAL 0
+#endif
+#if ZDR_INLINE_GGX_EVAL
+#define ZDR_GGX_LINKAGE static __device__ __forceinline__
+#else
+#define ZDR_GGX_LINKAGE static __device__ __noinline__
+#endif
+ZDR_GGX_LINKAGE float4 ggx_eval(float wox, float woy, float woz, float wix, float wiy, float wiz, float dr, float dg, float db,
                                         float specular, float roughness);
 // out-of-line ggx_brdf_grad (adjoint kernels)
 static __device__ __noinline__ float4 ggx_brdf_grad_nl(float wox, float woy, float woz, float wix, float wiy, float wiz, float specular,
@@ -381,7 +389,7 @@ ZDR_DEV float4 ggx_eval_from_terms(const GgxTerms& t, float3 wo, float3 wi, floa
     return make_float4((spec + diffuse.x / kPi) * wi.z, (spec + diffuse.y / kPi) * wi.z, (spec + diffuse.z / kPi) * wi.z,
                        0.5f * diffuse_pdf + 0.5f * glossy_pdf);
 }
-static __device__ __noinline__ float4 ggx_eval(float wox, float woy, float woz, float wix, float wiy, float wiz, float dr, float dg, float db,
+ZDR_GGX_LINKAGE float4 ggx_eval(float wox, float woy, float woz, float wix, float wiy, float wiz, float dr, float dg, float db,
                                         float specular, float roughness) {
     const float3 wo = f3(wox, woy, woz), wi = f3(wix, wiy, wiz);
     const GgxTerms t = ggx_terms(wo, wi, specular, roughness * roughness);
@@ -392,7 +400,7 @@ static __device__ __noinline__ float4 ggx_eval(float wox, float woy, float woz, 
 // computed next to the BRDF value, before the caller knows g, from the terms the value already needed (half vector, D, F, both
 // Smith terms — the separate ggx_brdf_grad computes all of them again).  Gradients are compared at 1e-3 (float atomics are
 // unordered anyway); the Smith terms reused here differ from ggx_brdf_grad's own by the rounding of a2 * k.
-static __device__ __noinline__ float4 ggx_eval_adj(float wox, float woy, float woz, float wix, float wiy, float wiz, float dr, float dg, float db,
+ZDR_GGX_LINKAGE float4 ggx_eval_adj(float wox, float woy, float woz, float wix, float wiy, float wiz, float dr, float dg, float db,
                                             float specular, float roughness, float2* basis) {
     const float3 wo = f3(wox, woy, woz), wi = f3(wix, wiy, wiz);
     const float alpha = roughness * roughness, a2 = alpha * alpha;

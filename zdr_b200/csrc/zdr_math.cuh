@@ -41,7 +41,15 @@ ZDR_HD float3 cross(float3 a, float3 b) {
 // "fast" build of the shading code (Makefile: --use_fast_math): one MUFU.RSQ, inline
 ZDR_HD float3 normalize(float3 v) { return v * rsqrtf(fmaf(v.z, v.z, fmaf(v.y, v.y, v.x * v.x))); }
 #elif defined(__CUDA_ARCH__)
-static __device__ __noinline__ float rcp_length(float x, float y, float z) { return 1.0f / sqrtf(fmaf(z, z, fmaf(y, y, x * x))); }
+#ifndef ZDR_INLINE_RCP_LENGTH      // 1: the IEEE sqrt + divide inline at every call site (no call / register saves, more code).  Set per
+#define ZDR_INLINE_RCP_LENGTH 0      // translation unit: the wavefront / persistent stages gain 0.8 / 3 % inline, the per-pixel kernels lose 2-3 % (r03b)
+#endif
+#if ZDR_INLINE_RCP_LENGTH
+static __device__ __forceinline__
+#else
+static __device__ __noinline__
+#endif
+float rcp_length(float x, float y, float z) { return 1.0f / sqrtf(fmaf(z, z, fmaf(y, y, x * x))); }
 ZDR_HD float3 normalize(float3 v) { return v * rcp_length(v.x, v.y, v.z); }
 #else
 ZDR_HD float3 normalize(float3 v) {
@@ -92,7 +100,12 @@ ZDR_HD float3 mat3_mul(const float* N, float3 v) {
 // sin/cos of a binary32 angle evaluated in binary64: Cody-Waite reduction by pi/2 and Taylor
 // polynomials in fma-Horner form, rounded once.  Identical operation sequence on host and
 // device, so the sampled directions do not depend on a vendor libm.
-#ifdef __CUDA_ARCH__
+#ifndef ZDR_INLINE_SINCOS
+#define ZDR_INLINE_SINCOS 0
+#endif
+#if defined(__CUDA_ARCH__) && ZDR_INLINE_SINCOS
+static __device__ __forceinline__
+#elif defined(__CUDA_ARCH__)
 static __device__ __noinline__
 #else
 inline
