@@ -136,8 +136,11 @@ struct RegStack {
 };
 
 // a local-memory stack with the same interface (comparison build of k_wf_trace_tiny, -DZDR_WF_TINY_LOCAL_STACK=1)
+// (the entries live in an array of the kernel, the stack pointer in this struct: a struct holding both is indexed dynamically
+// and so lives in local memory as a whole — stack pointer included, one more dependent local load on every pop)
 struct LocalStack16 {
-    int s[16], sp;
+    int* s;
+    int sp;
     ZDR_DEV void clear() { sp = 1; s[0] = kShortSentinel; }
     ZDR_DEV void push(int link) { s[sp++] = link; }
     ZDR_DEV int pop() { return s[--sp]; }
@@ -180,8 +183,14 @@ ZDR_DEV void ld_node(const float4* nd, float4& n0, float4& n1, float4& n2, float
 #endif
 }
 
-// Conservative slab test (entry distance in tn).  Not part of the numeric contract: the boxes are
-// inflated at build time and the comparison is widened, so it may fuse (t = lo*id - o*id).
+// Conservative slab test (entry distance in tn).  Not part of the numeric contract, it only has to be conservative: the
+// boxes are inflated at build time by 1e-5 x the scene's magnitude (bvh_build.cu inflate_eps), the slab distances
+// t = lo*id - o*id carry at most ~2e-7 x that magnitude of rounding error in position units (id = RN(1/d), o*id rounded, one
+// fma), i.e. 50 x less.  Rounds 1-2 also widened the comparison by 1e-6 relative (ZDR_BOX_WIDEN=1): four FMUL per node step of
+// kernels that ncu shows issue-bound (80-84 % issue-active, profiles/r02s) for a margin the inflation already gives.
+#ifndef ZDR_BOX_WIDEN
+#define ZDR_BOX_WIDEN 0
+#endif
 ZDR_DEV bool box_test(float lox, float hix, float loy, float hiy, float loz, float hiz, float3 id, float3 oid,
                       float tmin, float tmax, float& tn) {
     const float x0 = fmaf(lox, id.x, -oid.x), x1 = fmaf(hix, id.x, -oid.x);
@@ -190,7 +199,11 @@ ZDR_DEV bool box_test(float lox, float hix, float loy, float hiy, float loz, flo
     const float tnear = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
     const float tfar = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
     tn = tnear;
+#if ZDR_BOX_WIDEN
     return tnear * 0.999999f <= tfar * 1.000001f;
+#else
+    return tnear <= tfar;
+#endif
 }
 
 // Closest hit (any == 0) or occlusion query (any != 0).  Returns (slot, u, v, t) packed in a

@@ -368,7 +368,8 @@ __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace_tin
     float3 id = f3(0.f, 0.f, 0.f), oid = id;
     RayPre rp = {};
 #if ZDR_WF_TINY_LOCAL_STACK
-    LocalStack16 stack;
+    int stack_entries[16];
+    LocalStack16 stack{stack_entries, 0};
 #else
     RegStack<NREG> stack;
 #endif
