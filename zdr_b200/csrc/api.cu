@@ -272,8 +272,8 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
     // Several state sets of a fraction of the samples each, worked on from as many streams (wavefront.cu
     // launch_path_wavefront), once the job is large enough for the parts to fill the GPU; ZDR_WF_LANES=1 keeps one.
     // ray binning (render.cuh WfState): which traversal stages read binned lists (ZDR_WF_BIN: bit 0 extension rays, bit 1 shadow
-    // rays; read per call: tests switch it).  Its arrays are part of the workspace only when it is on.
-    const int bin_mask = (getenv("ZDR_WF_BIN") ? atoi(getenv("ZDR_WF_BIN")) : ZDR_WF_BIN_DEFAULT) & 3;
+    // rays; read per call: tests switch it; default: on for large scenes).  Its arrays are part of the workspace only when it is on.
+    const int bin_mask = (getenv("ZDR_WF_BIN") ? atoi(getenv("ZDR_WF_BIN")) : (s->bvh.num_nodes > kWfBigSceneNodes ? ZDR_WF_BIN_DEFAULT_BIG : ZDR_WF_BIN_DEFAULT)) & 3;
     const bool binned = bin_mask != 0;
     static const int lanes = getenv("ZDR_WF_LANES") ? atoi(getenv("ZDR_WF_LANES")) : 2;
     long long S = 0;

@@ -41,9 +41,17 @@ struct WfState {
     int bin_out;            // this launch (generate / shade): write keys + hist for the list it appends to
     int tiny_regs;          // > 0: scene fits the shared-memory traversal kernel with a register stack of 2 * tiny_regs entries
 };
-#ifndef ZDR_WF_BIN_DEFAULT      // which traversal stages read binned lists when ZDR_WF_BIN is not set (bit 0 extension, bit 1 shadow)
+// Which traversal stages read binned lists when ZDR_WF_BIN is not set (bit 0 extension rays, bit 1 shadow rays), for scenes of at
+// most / more than kWfBigSceneNodes nodes.  Measured (profiles/r03j, r03k): the Cornell box loses (C3 7 360 -> 6 859 Mrays/s: its
+// traversal is short, the binned traversal gathers ray records at random from a 4 GB array), the 9.6 M-triangle scene gains
+// (C5 1 974 -> 2 085: rays that start in the same cell and octant share the top of a deep tree and its cache lines).
+#ifndef ZDR_WF_BIN_DEFAULT
 #define ZDR_WF_BIN_DEFAULT 0
 #endif
+#ifndef ZDR_WF_BIN_DEFAULT_BIG
+#define ZDR_WF_BIN_DEFAULT_BIG 3
+#endif
+constexpr int kWfBigSceneNodes = 1024;
 constexpr int kWfCells = 8;                                     // origin cells per axis
 constexpr int kWfBins = kWfCells * kWfCells * kWfCells * 8;     // x 8 direction octants
 

@@ -122,7 +122,6 @@ ZDR_DEV void wf_bins_reset(const WfState& w, int which) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kWfBins; i += wf_stride()) { w.hist[which][i] = 0; w.cur[i] = 0; }
 }
 constexpr int kWfNodeBudget = 12;
-constexpr int kWfBigSceneNodes = 1024;
 template <bool ANY, bool STATS, bool BIG>      // BIG: scene with more than kWfBigSceneNodes nodes (launch_wf_round)
 __global__ void __launch_bounds__(kWfThreads, ZDR_WF_EXTEND_MINB) k_wf_trace(const __grid_constant__ RenderArgs a) {
     const WfState& w = a.wf;
@@ -508,45 +507,48 @@ ZDR_DEV void wf_append_binned(const WfState& w, int which, bool keep, int value,
     }
 }
 
-// The binned list of a traversal stage: blist = list[WHICH] grouped by bin (counting sort; the order inside a bin is
-// whatever the cursor atomics give — the image is summed per pixel in sample order by k_wf_accumulate, so no result
-// depends on the order rays are traced in).  Every block scans the kWfBins counters itself (16 KB from L2).
+// The binned list of a traversal stage: blist = list[WHICH] grouped by bin (counting sort; the order inside a bin is whatever
+// the atomics give — the image is summed per pixel in sample order by k_wf_accumulate, so no result depends on the order rays
+// are traced in).  Every block owns one contiguous tile of the list: it counts the tile's keys in shared memory, reserves the
+// tile's share of every bin it touches with ONE global atomic per bin (against the global prefix of the stage's histogram,
+// which each thread holds for its own 16 bins), and places the entries with shared-memory atomics.  (The first version placed
+// every entry with a global atomic on its bin's cursor: a Cornell box fills a few hundred bins and the atomics of a hot bin
+// serialise — 200 us for 3.3 M entries, profiles/r02r; this one is a streaming pass.)
 constexpr int kWfBinThreads = 256;
 template <int WHICH>
 __global__ void __launch_bounds__(kWfBinThreads) k_wf_bin(const __grid_constant__ RenderArgs a) {
     const WfState& w = a.wf;
-    __shared__ int s_base[kWfBins];
+    __shared__ int s_pos[kWfBins];      // count of the tile's entries per bin, then the next free position of the bin's reserved range
     __shared__ int s_part[kWfBinThreads];
     const int n = *(volatile int*)(w.counts + WHICH);
     constexpr int per = kWfBins / kWfBinThreads;
+    const int tid = threadIdx.x;
+    // global exclusive prefix of this thread's bins [tid * per, tid * per + per)
     int loc[per], sum = 0;
 #pragma unroll
-    for (int k = 0; k < per; ++k) { loc[k] = sum; sum += w.hist[WHICH][threadIdx.x * per + k]; }
-    s_part[threadIdx.x] = sum;
+    for (int k = 0; k < per; ++k) { loc[k] = sum; sum += w.hist[WHICH][tid * per + k]; s_pos[tid * per + k] = 0; }
+    s_part[tid] = sum;
     __syncthreads();
     for (int o = 1; o < kWfBinThreads; o <<= 1) {          // inclusive scan of the per-thread sums
-        const int v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+        const int v = tid >= o ? s_part[tid - o] : 0;
         __syncthreads();
-        s_part[threadIdx.x] += v;
+        s_part[tid] += v;
         __syncthreads();
     }
-    const int before = s_part[threadIdx.x] - sum;
-#pragma unroll
-    for (int k = 0; k < per; ++k) s_base[threadIdx.x * per + k] = before + loc[k];
+    const int before = s_part[tid] - sum;
+    // the tile of this block
+    const long long t0 = (long long)n * blockIdx.x / gridDim.x, t1 = (long long)n * (blockIdx.x + 1) / gridDim.x;
+    const unsigned short* __restrict__ keys = w.keys[WHICH];
+    const int* __restrict__ list = w.list[WHICH];
+    for (long long i = t0 + tid; i < t1; i += kWfBinThreads) atomicAdd(&s_pos[keys[i]], 1);
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int n_round = (n + 31) & ~31;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += wf_stride()) {
-        const bool on = i < n;
-        const int key = on ? (int)w.keys[WHICH][i] : -1 - lane;
-        const int slot = on ? w.list[WHICH][i] : 0;
-        const unsigned same = __match_any_sync(0xffffffffu, key);
-        const int leader = __ffs(same) - 1;
-        int at = 0;
-        if (on && lane == leader) at = atomicAdd(w.cur + key, __popc(same));
-        at = __shfl_sync(0xffffffffu, at, leader);
-        if (on) w.blist[s_base[key] + at + __popc(same & ((1u << lane) - 1u))] = slot;
+#pragma unroll
+    for (int k = 0; k < per; ++k) {
+        const int bin = tid * per + k, c = s_pos[bin];
+        if (c) s_pos[bin] = before + loc[k] + atomicAdd(w.cur + bin, c);
     }
+    __syncthreads();
+    for (long long i = t0 + tid; i < t1; i += kWfBinThreads) w.blist[atomicAdd(&s_pos[keys[i]], 1)] = list[i];
 }
 
 struct WfPath {        // registers of one path inside a stage
@@ -867,7 +869,7 @@ template <int MODE>
 void launch_wf_round(int r, bool stats, bool agg, bool env, int grid, cudaStream_t s, const RenderArgs& a0) {
     RenderArgs a = a0;
     const int tgrid = min(grid, a.wf.num_sms * ZDR_WF_TRACE_GRID_MULT);
-    const int bgrid = min(grid, a.wf.num_sms * 8);
+    const int bgrid = min(grid, a.wf.num_sms * 2);      // k_wf_bin: one tile of the list per block
     const bool bin_closest = (a.wf.bin_mask & 1) && r >= 1, bin_any = (a.wf.bin_mask & 2) && r >= 1;
     const bool bin_next = (a.wf.bin_mask & 1) && r + 1 < a.max_depth;      // stage B feeds the next bounce's extension rays
     g_kernel_launches += 4 + (bin_closest ? 1 : 0) + (bin_any ? 1 : 0);
