@@ -340,8 +340,9 @@ int setup_wavefront(zdr_scene* s, int integrator, const zdr_params* p, RenderArg
     w.bin_mask = bin_mask;
     w.bin_in = w.bin_out = 0;
     w.key_lo = s->bounds_lo;
-    w.key_scale = f3((float)kWfCells / fmaxf(s->bounds_hi.x - s->bounds_lo.x, 1e-30f), (float)kWfCells / fmaxf(s->bounds_hi.y - s->bounds_lo.y, 1e-30f),
-                     (float)kWfCells / fmaxf(s->bounds_hi.z - s->bounds_lo.z, 1e-30f));
+    w.key_cells = s->bvh.num_nodes > kWfBigSceneNodes ? 16 : 8;
+    w.key_scale = f3((float)w.key_cells / fmaxf(s->bounds_hi.x - s->bounds_lo.x, 1e-30f), (float)w.key_cells / fmaxf(s->bounds_hi.y - s->bounds_lo.y, 1e-30f),
+                     (float)w.key_cells / fmaxf(s->bounds_hi.z - s->bounds_lo.z, 1e-30f));
     // shared-memory traversal (k_wf_trace_tiny): scenes of at most 8 KB whose links fit 16 bits and whose tree leaves at most 12
     // pending links (its stack: 16 local-memory entries, or 8 / 12 entries in registers); ZDR_WF_TINY_OFF=1: the general kernel
     const bool tiny_off = getenv("ZDR_WF_TINY_OFF") != nullptr;

@@ -35,7 +35,8 @@ struct WfState {
     int* blist;             // binned copy of the list the next traversal stage reads
     int* hist[2];           // kWfBins counters per list, zero between uses
     int* cur;               // kWfBins cursors of k_wf_bin, zero between uses
-    float3 key_lo, key_scale;   // origin cell = (o - key_lo) * key_scale, clamped to [0, kWfCells)
+    float3 key_lo, key_scale;   // origin cell = (o - key_lo) * key_scale, clamped to [0, key_cells)
+    int key_cells;              // 8: bin = (8^3 origin cells, direction octant); 16: bin = 16^3 origin cells (large scenes: +1.6 % on C5, r03m)
     int bin_mask;           // scene-level switch: bit 0 = extension rays, bit 1 = shadow rays (from bounce 1 on)
     int bin_in;             // this launch (traversal): read blist instead of list[k]
     int bin_out;            // this launch (generate / shade): write keys + hist for the list it appends to
@@ -52,8 +53,7 @@ struct WfState {
 #define ZDR_WF_BIN_DEFAULT_BIG 3
 #endif
 constexpr int kWfBigSceneNodes = 1024;
-constexpr int kWfCells = 8;                                     // origin cells per axis
-constexpr int kWfBins = kWfCells * kWfCells * kWfCells * 8;     // x 8 direction octants
+constexpr int kWfBins = 4096;      // 8^3 origin cells x 8 direction octants, or 16^3 origin cells (WfState.key_cells)
 
 // Persistent per-SM wavefront (persistent.cu, k_pw): one resident CTA per SM keeps a pool of paths in SHARED memory and
 // runs the stages of the wavefront as barrier-separated phases over shared-memory queues.  Nothing but finished samples

@@ -482,13 +482,17 @@ ZDR_DEV void wf_append(int* __restrict__ list, int* counter, bool keep, int valu
     base = __shfl_sync(0xffffffffu, base, 0);
     if (keep) list[base + __popc(m & ((1u << lane) - 1u))] = value;
 }
-// Ray binning (WfState): bin of a ray = (cell of its origin in a kWfCells^3 grid over the scene, octant of its direction).
+// Ray binning (WfState): bin of a ray = (cell of its origin in an 8^3 grid over the scene, octant of its direction), or for large
+// scenes the cell of its origin in a 16^3 grid.
 ZDR_DEV int wf_key(const WfState& w, float3 o, float3 d) {
-    const int cx = min(max((int)((o.x - w.key_lo.x) * w.key_scale.x), 0), kWfCells - 1);
-    const int cy = min(max((int)((o.y - w.key_lo.y) * w.key_scale.y), 0), kWfCells - 1);
-    const int cz = min(max((int)((o.z - w.key_lo.z) * w.key_scale.z), 0), kWfCells - 1);
+    const int nc = w.key_cells;
+    const int cx = min(max((int)((o.x - w.key_lo.x) * w.key_scale.x), 0), nc - 1);
+    const int cy = min(max((int)((o.y - w.key_lo.y) * w.key_scale.y), 0), nc - 1);
+    const int cz = min(max((int)((o.z - w.key_lo.z) * w.key_scale.z), 0), nc - 1);
+    const int cell = (cx * nc + cy) * nc + cz;
+    if (nc == 16) return cell;
     const int oct = (d.x < 0.0f ? 1 : 0) | (d.y < 0.0f ? 2 : 0) | (d.z < 0.0f ? 4 : 0);
-    return ((cx * kWfCells + cy) * kWfCells + cz) * 8 + oct;
+    return cell * 8 + oct;
 }
 // wf_append that also records the bin of every appended entry and counts the bins (one reduction per distinct bin of the warp)
 ZDR_DEV void wf_append_binned(const WfState& w, int which, bool keep, int value, int key) {
