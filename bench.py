@@ -473,6 +473,15 @@ def run_ours(args):
                      "hbm": {"achieved": round(dram / (ms_render * 1e-3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
                              "frac": round(dram / (ms_render * 1e-3) / 1e9 / hbm_peak, 4), "peak_source": peak_src},
                      "source": os.path.relpath(path, ROOT), "scaled_by_rays": round(scale, 4)})
+        kern = rec.get("kernels") or {}
+        if kern:      # the dominant kernel of the step, from the same committed launch list (ncu per-launch times: serialised, cold)
+            name, k = max(kern.items(), key=lambda kv: kv[1]["ms_under_ncu"])
+            k_ach = k["warp_inst"] / (k["ms_under_ncu"] * 1e-3) / 1e9
+            roof["dominant_kernel"] = {"name": name, "share_of_step_under_ncu": round(k["ms_under_ncu"] / rec["ms_under_ncu"], 3),
+                                       "achieved": round(k_ach, 1), "unit": "Gwarp-inst/s", "frac": round(k_ach / issue_peak, 4),
+                                       "lanes_per_warp_inst": k.get("lanes"), "dram_gb_per_s": round(k["dram_bytes"] / (k["ms_under_ncu"] * 1e-3) / 1e9, 1),
+                                       "note": "ncu --set full of one large launch of this kernel: profiles/r02s_stage_ncu_summary.txt (issue-active 81-84 %)"
+                                       if "trace" in name else "profiles/r02s_stage_ncu_summary.txt"}
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -860,8 +860,12 @@ void launch_wf_trace(bool stats, int tgrid, cudaStream_t s, const RenderArgs& a)
     const bool big = a.sc.num_nodes > kWfBigSceneNodes;
     if (ZDR_WF_TINY && a.wf.tiny_regs > 0) {
         const size_t sm = 64 * (size_t)a.sc.num_nodes + 48 * (size_t)a.sc.num_tris;
+#if ZDR_WF_TINY_LOCAL_STACK
+        if (stats) k_wf_trace_tiny<ANY, true, 4><<<tgrid, kWfThreads, sm, s>>>(a); else k_wf_trace_tiny<ANY, false, 4><<<tgrid, kWfThreads, sm, s>>>(a);
+#else      // the register-stack build has a second instantiation for deeper trees
         if (a.wf.tiny_regs <= 4) { if (stats) k_wf_trace_tiny<ANY, true, 4><<<tgrid, kWfThreads, sm, s>>>(a); else k_wf_trace_tiny<ANY, false, 4><<<tgrid, kWfThreads, sm, s>>>(a); }
         else { if (stats) k_wf_trace_tiny<ANY, true, 6><<<tgrid, kWfThreads, sm, s>>>(a); else k_wf_trace_tiny<ANY, false, 6><<<tgrid, kWfThreads, sm, s>>>(a); }
+#endif
         return;
     }
     if (stats) { if (big) k_wf_trace<ANY, true, true><<<tgrid, kWfThreads, 0, s>>>(a); else k_wf_trace<ANY, true, false><<<tgrid, kWfThreads, 0, s>>>(a); }
