@@ -480,8 +480,8 @@ def run_ours(args):
             roof["dominant_kernel"] = {"name": name, "share_of_step_under_ncu": round(k["ms_under_ncu"] / rec["ms_under_ncu"], 3),
                                        "achieved": round(k_ach, 1), "unit": "Gwarp-inst/s", "frac": round(k_ach / issue_peak, 4),
                                        "lanes_per_warp_inst": k.get("lanes"), "dram_gb_per_s": round(k["dram_bytes"] / (k["ms_under_ncu"] * 1e-3) / 1e9, 1),
-                                       "note": "ncu --set full of one large launch of this kernel: profiles/r02s_stage_ncu_summary.txt (issue-active 81-84 %)"
-                                       if "trace" in name else "profiles/r02s_stage_ncu_summary.txt"}
+                                       "note": "ncu --set full of one large launch of this kernel: profiles/r04e_stage_ncu_summary.txt (issue-active 80-83 %)"
+                                       if "trace" in name else "profiles/r04e_stage_ncu_summary.txt"}
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -187,7 +187,7 @@ ZDR_DEV void ld_node(const float4* nd, float4& n0, float4& n1, float4& n2, float
 // boxes are inflated at build time by 1e-5 x the scene's magnitude (bvh_build.cu inflate_eps), the slab distances
 // t = lo*id - o*id carry at most ~2e-7 x that magnitude of rounding error in position units (id = RN(1/d), o*id rounded, one
 // fma), i.e. 50 x less.  Rounds 1-2 also widened the comparison by 1e-6 relative (ZDR_BOX_WIDEN=1): four FMUL per node step of
-// kernels that ncu shows issue-bound (80-84 % issue-active, profiles/r02s) for a margin the inflation already gives.
+// kernels that ncu shows issue-bound (80-83 % issue-active, profiles/r04e) for a margin the inflation already gives.
 #ifndef ZDR_BOX_WIDEN
 #define ZDR_BOX_WIDEN 0
 #endif
