@@ -3,14 +3,14 @@
 cases' random material as it is (roughness down to 0.02: binary32 GGX is ill conditioned there) and with the roughness clamped
 from below: per case image rel-L2 (bar 1e-4), gradient rel-L2 (bar 1e-3), fraction of per-sample radiance values that differ
 bitwise / by more than 1e-3, ray counts.
-usage (GPU box): python tools/fast_parity.py out.json [case ...]"""
+usage (GPU box): python tests/fast_parity_report.py out.json [case ...]"""
 import json
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))      # repo root
 from oracle import oracle  # noqa: E402
 from tests import scenes  # noqa: E402
 from tests.test_gpu_parity import CASES, GpuScene, bits, rel_l2  # noqa: E402

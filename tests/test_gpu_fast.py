@@ -4,7 +4,7 @@ oracle bit for bit elsewhere; here the bars are BASELINE.json's tolerances (imag
 well-conditioned material — roughness >= 0.3, the restriction under which the oracle itself is pinned to the reference's sources
 (tests/golden/gen_golden.py), and a texture that is smooth at the scale of a float32 rounding error of the hit point.  On a
 1024^2 white-noise texture a 1e-7 change of a bounce direction already changes the fetched material by ~1e-4, so any two
-float32 implementations differ there (measured: tools/fast_parity.py, profiles/r02v_*)."""
+float32 implementations differ there (measured: tests/fast_parity_report.py, profiles/r02v_*)."""
 import numpy as np
 import pytest
 

@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 R=${1:-r02u}
 mkdir -p gpurun_out
 timeout 2400 python -m pytest tests -q -m gpu -x > gpurun_out/${R}_pytest.log 2>&1; tail -3 gpurun_out/${R}_pytest.log
-timeout 1200 python tools/fast_parity.py gpurun_out/${R}_fast_parity.json > gpurun_out/${R}_fast_parity.log 2>&1; grep -v Warning gpurun_out/${R}_fast_parity.log | cut -c1-330 | tail -20
+timeout 1200 python tests/fast_parity_report.py gpurun_out/${R}_fast_parity.json > gpurun_out/${R}_fast_parity.log 2>&1; grep -v Warning gpurun_out/${R}_fast_parity.log | cut -c1-330 | tail -20
 for c in c3 c2 c4 c4d c1; do
   python bench.py --config $c --no-cpu-baseline > gpurun_out/${R}_bench_$c.json 2>> gpurun_out/${R}_bench.err
   python - <<PY

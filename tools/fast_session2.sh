@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 for lib in default zdr_b200/csrc/variants/lib_fast*.so; do
   n=$(basename $lib .so); n=${n#lib_}
   if [ $lib != default ]; then export ZDR_B200_LIB=$PWD/$lib; else unset ZDR_B200_LIB; fi
-  timeout 900 python tools/fast_parity.py gpurun_out/${R}_fast_parity_$n.json c3_path_small_wavefront path_literal_wavefront c1_collocated > gpurun_out/${R}_fast_parity_$n.log 2>&1
+  timeout 900 python tests/fast_parity_report.py gpurun_out/${R}_fast_parity_$n.json c3_path_small_wavefront path_literal_wavefront c1_collocated > gpurun_out/${R}_fast_parity_$n.log 2>&1
   grep -v Warning gpurun_out/${R}_fast_parity_$n.log | cut -c1-230 | tail -9
   for c in c3 c2; do
     python bench.py --config $c --no-cpu-baseline --no-e2e > gpurun_out/${R}_bench_${c}_$n.json 2>> gpurun_out/${R}_bench.err

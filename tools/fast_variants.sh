@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU-box: the "fast" shading builds (variants/lib_fast*.so) against the exact build: what stays bit-exact (sampler, hits), the
-# deviation from the oracle (tools/fast_parity.py), and the bench lines.  usage: tools/fast_variants.sh <tag>
+# deviation from the oracle (tests/fast_parity_report.py), and the bench lines.  usage: tools/fast_variants.sh <tag>
 cd "$(dirname "$0")/.."
 R=${1:-r02t}
 mkdir -p gpurun_out
@@ -14,7 +14,7 @@ for lib in default zdr_b200/csrc/variants/lib_fast*.so; do
   if [ $lib != default ]; then export ZDR_B200_LIB=$PWD/$lib; else unset ZDR_B200_LIB; fi
   if [ $lib != default ]; then
     timeout 600 python -m pytest tests/test_gpu_parity.py -q -k "sampler or trace or large or degenerate" > gpurun_out/${R}_pytest_exact_$n.log 2>&1; tail -1 gpurun_out/${R}_pytest_exact_$n.log | tee -a $O
-    timeout 900 python tools/fast_parity.py gpurun_out/${R}_parity_$n.json > gpurun_out/${R}_parity_$n.log 2>&1; tail -8 gpurun_out/${R}_parity_$n.log | cut -c1-400
+    timeout 900 python tests/fast_parity_report.py gpurun_out/${R}_parity_$n.json > gpurun_out/${R}_parity_$n.log 2>&1; tail -8 gpurun_out/${R}_parity_$n.log | cut -c1-400
   fi
   echo "$n C3@64 wavefront: $(b --spp 64 --schedule wavefront)" | tee -a $O
   echo "$n C3@64 persistent: $(b --spp 64 --schedule persistent)" | tee -a $O
