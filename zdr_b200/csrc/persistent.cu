@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(kPwThreads, kPwBlocks) k_pw(const __grid_const
                 if (!ADJ) { act = i < n1a; if (act) slot = l1[i]; }
                 else { const int k = i - ra; act = k < n1b; if (act) slot = l1[N - 1 - k]; }
                 if (act) {
-                    const float4 RO = pool.ro[slot], RD = pool.rd[slot], H = pool.hit[slot], B4 = pool.bi[slot], L4 = pool.Ls[slot];
+                    const float4 RD = pool.rd[slot], H = pool.hit[slot], B4 = pool.bi[slot], L4 = pool.Ls[slot];
                     const float4 LW = pool.lw[slot], LE = pool.le[slot];
                     const unsigned packed = __float_as_uint(RD.w);
                     int depth = (int)(packed & 0xffu);
