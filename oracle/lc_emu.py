@@ -45,6 +45,17 @@ for _n in ("tanf", "acosf", "expf"):
     getattr(_libm, _n).argtypes = [ctypes.c_float]
 _libm.atan2f.restype = ctypes.c_float
 _libm.atan2f.argtypes = [ctypes.c_float, ctypes.c_float]
+_libm.fmaf.restype = ctypes.c_float
+_libm.fmaf.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_float]
+
+# Arithmetic of the CLOSED builtins (dot, cross, lerp, hit.interpolate, matrix * vector).  LuisaCompute lowers them to CUDA
+# that nvcc is free to contract into fused multiply-adds; which it does is not knowable here.  False (default, every committed
+# fixture but the *_large ones): one rounded product and one rounded sum per term.  True: the fmaf chains of the numeric
+# contract in oracle/zdr_oracle.c (dot3 / cross3 / lincomb3 / lerpf / xform_point / mat3_mul).  The two agree to an ulp per
+# call; on 10+-bounce paths over a white-noise texture that ulp is amplified into visibly different paths (chaos, not logic),
+# so the large path fixtures, which exist to exercise every branch of the reference's source thousands of times, are generated
+# with the builtins in the contract's arithmetic.  Everything the reference's own source spells out stays as it spells it.
+CONTRACT_BUILTINS = False
 
 _py_max, _py_min, _py_abs, _py_any, _py_all = max, min, abs, any, all
 
@@ -391,6 +402,18 @@ class Mat:
         return Mat(self.cols)
 
     def __mul__(self, v):
+        if isinstance(v, Vec) and CONTRACT_BUILTINS:
+            # xform_point / mat3_mul: a (point, 1) vector starts the chain at the translation column
+            rows = []
+            for r in range(self.n):
+                if self.n == 4 and float(F._c(v.c[3]).v) == 1.0 and F._c(v.c[3]).node is None:
+                    acc = F._c(self.cols[3].c[r])
+                    for c in range(3):
+                        acc = _fma(self.cols[c].c[r], v.c[c], acc)
+                else:
+                    acc = _lincomb([(self.cols[c].c[r], v.c[c]) for c in range(self.n)])
+                rows.append(acc)
+            return type(v)(*rows)
         if isinstance(v, Vec):
             # sum over columns of column * v[c], plain binary32 operations in column order
             acc = self.cols[0] * v.c[0]
@@ -448,6 +471,31 @@ def inverse(m: Mat) -> Mat:
 
 
 # ------------------------------------------------------------------------------------ builtins
+def _fma(a, b, c):
+    """fmaf(a, b, c): one rounding; taped like a * b + c."""
+    a, b, c = F._c(a), F._c(b), F._c(c)
+    out = F(_libm.fmaf(float(a.v), float(b.v), float(c.v)))
+    if _tape is not None and (a.node is not None or b.node is not None or c.node is not None):
+        out.node = _tape.new()
+        ins = []
+        if a.node is not None:
+            ins.append((a.node, float(b.v)))
+        if b.node is not None:
+            ins.append((b.node, float(a.v)))
+        if c.node is not None:
+            ins.append((c.node, 1.0))
+        _tape.ops.append((out.node, ins))
+    return out
+
+
+def _lincomb(terms):
+    """sum of w * x over (w, x) pairs, contract order: fmaf(w_k, x_k, ... fmaf(w_1, x_1, w_0 * x_0))"""
+    acc = F._c(terms[0][0]) * terms[0][1]
+    for w, x in terms[1:]:
+        acc = _fma(w, x, acc)
+    return acc
+
+
 def _map(fn, x):
     if isinstance(x, Vec):
         return type(x)(*[fn(a) for a in x.c])
@@ -535,10 +583,16 @@ def clamp(x, lo, hi):
 
 
 def lerp(a, b, t):
+    if CONTRACT_BUILTINS and not isinstance(t, Vec):      # lerpf: fmaf(t, b - a, a)
+        if isinstance(a, Vec):
+            return type(a)(*[_fma(t, y - x, x) for x, y in zip(a.c, b.c)])
+        return _fma(t, F._c(b) - a, a)
     return a + (b - a) * t if not isinstance(t, Vec) else a + (b - a) * t
 
 
 def dot(a, b):
+    if CONTRACT_BUILTINS:                                 # dot3
+        return _lincomb(list(zip(a.c, b.c)))
     r = a.c[0] * b.c[0]
     for i in range(1, a.n):
         r = r + a.c[i] * b.c[i]
@@ -546,13 +600,30 @@ def dot(a, b):
 
 
 def cross(a, b):
+    if CONTRACT_BUILTINS:                                 # cross3: fmaf(a.y, b.z, -(a.z * b.y)), ...
+        return float3(_fma(a.y, b.z, -(a.z * b.y)), _fma(a.z, b.x, -(a.x * b.z)), _fma(a.x, b.y, -(a.y * b.x)))
     return float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x)
 
 
 def length_squared(a): return dot(a, a)
 def length(a): return sqrt(dot(a, a))
 def normalize(a): return a * (1.0 / sqrt(dot(a, a)))
-def reflect(i, n): return i - n * (2.0 * dot(n, i))
+def reflect(i, n):
+    if CONTRACT_BUILTINS:                                 # k = 2 dot(n, i); fmaf(-k, n, i)
+        k = 2.0 * dot(n, i)
+        return type(i)(*[_fma(-k, b, a) for a, b in zip(i.c, n.c)])
+    return i - n * (2.0 * dot(n, i))
+
+
+def _sum3(a, x, b, y, c, z):
+    """`a * x + b * y + c * z` as written in DSL source.  With CONTRACT_BUILTINS a VECTOR-valued sum of three scalar-weighted
+    vectors (onb.py:11, microfacet.py:89, light.py:64 — the only three in the reference) is evaluated as the contract's
+    lincomb3, the contraction nvcc applies to exactly this shape; scalar sums (envmap.py:111) stay in source order."""
+    pairs = [(a, x), (b, y), (c, z)]
+    if CONTRACT_BUILTINS and all(isinstance(p, Vec) != isinstance(q, Vec) for p, q in pairs):
+        pairs = [(p, q) if isinstance(q, Vec) else (q, p) for p, q in pairs]
+        return type(pairs[0][1])(*[_lincomb([(w, v.c[i]) for w, v in pairs]) for i in range(pairs[0][1].n)])
+    return a * x + b * y + c * z
 
 
 def lc_any(x):
@@ -896,6 +967,9 @@ class Hit:
 
     def interpolate(self, a, b, c):
         u, v = self.bary.x, self.bary.y
+        if CONTRACT_BUILTINS:                             # interp3 = lincomb3(1 - u - v, a, u, b, v, c)
+            w = 1.0 - u - v
+            return type(a)(*[_lincomb([(w, x), (u, y), (v, z)]) for x, y, z in zip(a.c, b.c, c.c)])
         return a * (1.0 - u - v) + b * u + c * v
 
 
@@ -946,6 +1020,16 @@ class _IfExpToSelect(ast.NodeTransformer):
         self.generic_visit(node)
         if isinstance(node.value, ast.Name):
             node.value = ast.copy_location(ast.Call(func=ast.Name(id="__lc_copy", ctx=ast.Load()), args=[node.value], keywords=[]), node.value)
+        return node
+
+    def visit_BinOp(self, node):
+        self.generic_visit(node)
+        is_mul = lambda n: isinstance(n, ast.BinOp) and isinstance(n.op, ast.Mult)
+        if (isinstance(node.op, ast.Add) and is_mul(node.right) and isinstance(node.left, ast.BinOp) and isinstance(node.left.op, ast.Add)
+                and is_mul(node.left.left) and is_mul(node.left.right)):
+            m = [node.left.left, node.left.right, node.right]
+            return ast.copy_location(ast.Call(func=ast.Name(id="__lc_sum3", ctx=ast.Load()),
+                                              args=[e for t in m for e in (t.left, t.right)], keywords=[]), node)
         return node
 
     def visit_IfExp(self, node):
@@ -1003,7 +1087,7 @@ def func(fn):
 
 
 _BUILTINS.update(dict(
-    __lc_select=_select, __lc_copy=_copy, sqrt=sqrt, sin=sin, cos=cos, tan=tan, acos=acos, atan2=atan2, exp=exp, floor=floor, ceil=ceil, fract=fract,
+    __lc_select=_select, __lc_copy=_copy, __lc_sum3=_sum3, sqrt=sqrt, sin=sin, cos=cos, tan=tan, acos=acos, atan2=atan2, exp=exp, floor=floor, ceil=ceil, fract=fract,
     isnan=isnan, abs=lc_abs, max=lc_max, min=lc_min, clamp=clamp, lerp=lerp, dot=dot, cross=cross, length=length,
     length_squared=length_squared, normalize=normalize, reflect=reflect, any=lc_any, all=lc_all,
     make_float2=float2, make_float3=float3, make_float4=float4, make_int2=int2, make_int3=int3, make_int4=int4,

@@ -511,6 +511,38 @@ if __name__ == "__main__":
                    (20, 20), 2, 64, 5, 4)
     if "material_sets" in which:
         gen_material_sets()
+    # larger fixtures (64 x 64 pixels, 8 spp, 128^2 texture: 32 768 samples per pass instead of 512-1 152; minutes under the
+    # emulator, so they are not in the default list): every bounce depth, Russian-roulette branch and light-sampling case of the
+    # reference's direct.py / prb.py occurs thousands of times in them.  Generated with lc_emu.CONTRACT_BUILTINS: the closed
+    # builtins (dot, cross, lerp, reflect, hit.interpolate, matrix * vector) and the three vector sums a X + b Y + c Z evaluate
+    # in the numeric contract's fmaf arithmetic.  With the plain-arithmetic builtins the same source gives an image 1.7e-3 away
+    # (237 of 4 096 pixels hold a 10+-bounce path that an ulp in hit.interpolate sends elsewhere on the white-noise texture);
+    # with them, the reference's source reproduces the oracle to 1e-7, path by path.
+    LARGE = ("direct_large", "path_large", "collocated_large", "direct_env_large", "path_env_large", "path_large_smooth")
+    if any(w in which for w in LARGE):
+        E.CONTRACT_BUILTINS = True
+        if "collocated_large" in which:
+            gen_render("collocated_large", scenes.cbox_collocated_models(), R_collocated.render_collocated_kernel,
+                       R_collocated.render_collocated_backward_kernel, (64, 64), 8, 128, 25, 16)
+        if "direct_env_large" in which:
+            gen_render("direct_env_large", scenes.cbox_path_models(), R_direct.render_direct_kernel, R_direct.render_direct_backward_kernel,
+                       (48, 48), 8, 128, 27, 17, envmap=scenes.procedural_envmap(64, 32, seed=2) * np.float32(0.2))
+        if "path_env_large" in which:
+            prb = load_patched_prb()
+            gen_render("path_literal_env_large", scenes.cbox_path_models(), prb.render_path_kernel, prb.render_path_backward_kernel, (48, 48), 4, 128, 29, 18,
+                       envmap=scenes.procedural_envmap(64, 32, seed=2) * np.float32(0.2))
+        if "path_large_smooth" in which:       # the full roughness range [0, 1] (the plain-arithmetic path fixtures keep roughness >= 0.3)
+            prb = load_patched_prb()
+            gen_render("path_literal_large_smooth", scenes.cbox_path_models(), prb.render_path_kernel, prb.render_path_backward_kernel, (48, 48), 4, 128, 31, 19)
+        if "direct_large" in which:
+            gen_render("direct_large", scenes.cbox_path_models(), R_direct.render_direct_kernel, R_direct.render_direct_backward_kernel,
+                       (64, 64), 8, 128, 23, 15)
+        if "path_large" in which:
+            prb = load_patched_prb()
+            assert prb.max_depth == 16 and prb.rr_depth == 2
+            gen_render("path_literal_large", scenes.cbox_path_models(), prb.render_path_kernel, prb.render_path_backward_kernel, (64, 64), 8, 128, 21, 14,
+                       rough_min=0.3)
+        E.CONTRACT_BUILTINS = False
     if "path" in which:
         prb = load_patched_prb()
         assert prb.max_depth == 16 and prb.rr_depth == 2

@@ -375,6 +375,32 @@ def test_scenes_of_one_or_two_leaves_all_schedules(oracle):
         g.close()
 
 
+@pytest.mark.parametrize("name", ["collocated_large", "direct_large", "path_literal_large", "path_literal_large_smooth",
+                                  "direct_env_large", "path_literal_env_large"])
+def test_cuda_vs_reference_source_fixtures(name):
+    """The CUDA path directly against the large committed fixtures that tests/golden/gen_golden.py produced by running the
+    REFERENCE'S OWN collocated.py / direct.py / prb.py under the LuisaCompute emulator (48^2-64^2 pixels, 4-8 spp, 128^2 white-noise
+    texture, depth 16, roughness down to 0; no oracle in between).  Without an envmap the image is the reference source's BIT FOR BIT
+    on every schedule (tests/test_golden.py: so is the oracle's) and the gradient within 1e-5; with one, the north-star bars 1e-4 / 1e-3."""
+    from .test_golden import LARGE_FIXTURES, load_large_fixture
+    _, models, integ, extra, bit_exact = next(f for f in LARGE_FIXTURES if f[0] == name)
+    z, res, spp, seed, mat = load_large_fixture(name)
+    g = GpuScene(models())
+    if "envmap" in z:
+        g.set_envmap(z["envmap"], True)
+    kws = [{"schedule": s_} for s_ in ("megakernel", "wavefront", "persistent")] if integ == ZDR_PATH else [{}]
+    for kw in kws:
+        img = g.forward(integ, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed, **extra, **kw), mat)
+        if bit_exact:
+            assert np.array_equal(img.view(np.uint32), z["image"].view(np.uint32)), (kw, rel_l2(img, z["image"]))
+        # envmap: acosf / atan2f of direction_to_uv are CUDA's here and libm's in the fixture (a pdf cell can flip): the north-star bars
+        assert rel_l2(img, z["image"]) <= (1e-6 if bit_exact else IMG_TOL), (kw, rel_l2(img, z["image"]))
+        dm = g.backward(integ, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed + 1, **extra, **kw), mat, z["d_image"])
+        assert np.abs(z["d_material"]).max() > 0
+        assert rel_l2(dm, z["d_material"]) <= (1e-5 if bit_exact else GRAD_TOL), (kw, rel_l2(dm, z["d_material"]))
+    g.close()
+
+
 def test_transformed_instances_and_update_lights(oracle):
     """test_lightstage.py shape: transformed instances, lights toggled with update_lights."""
     models = scenes.sphere_grid_models(6, seed=2)
