@@ -357,7 +357,7 @@ def _load_patched(module, patches, new_name):
     return mod
 
 
-def gen_material_sets():
+def gen_material_sets(name="direct_material_sets", res=(24, 24), spp=2, tex=32, seed=21):
     """Cornell box (set 0) + light + a textured sphere inside the box (set 1) + a second, untextured quad (set -1): direct.py
     with the material-set patch above, forward and adjoint."""
     _load_patched("interaction", MS_INTERACTION_PATCHES, "interaction_ms")
@@ -367,7 +367,6 @@ def gen_material_sets():
     sc.heap.emplace(23336, E.buffer([int(x) for x in sets]))
     cam = R_render.Camera(fov=50 / 180 * 3.1415926, origin=E.float3(-0.2, 2.6, 6.0), target=E.float3(-0.2, 2.6, -2.5),
                           up=E.float3(0.0, 1.0, 0.0))
-    res, spp, tex, seed = (24, 24), 2, 32, 21
     W, H = res
     mat = np.stack([scenes.random_material((tex, tex), 12), scenes.random_material((tex, tex), 13)])
     image = E.Buffer(dtype=E.float4, size=W * H, data=np.zeros((W * H, 4), np.float32))
@@ -378,9 +377,9 @@ def gen_material_sets():
     dmat = E.Buffer(dtype=float, size=mat.size, data=np.zeros(mat.size, np.float64))
     dms.render_direct_backward_kernel(dbuf, sc.heap, sc.accel, sc.light_count, 0, dmat, mbuf, E.int2(tex, tex), cam, spp, seed + 1, True, dispatch_size=(W, H))
     dm = dmat.data.reshape(2, tex, tex, 4).astype(np.float32)
-    np.savez_compressed(os.path.join(OUT, "render_direct_material_sets.npz"), res=np.asarray(res), spp=spp, tex=tex, seed=seed, sets=np.asarray(sets, np.int32),
+    np.savez_compressed(os.path.join(OUT, f"render_{name}.npz"), res=np.asarray(res), spp=spp, tex=tex, seed=seed, sets=np.asarray(sets, np.int32),
                         material=mat, image=image.data.reshape(H, W, 4).astype(np.float32), d_image=d_image, d_material=dm)
-    print(f"render_direct_material_sets.npz: image mean {image.data[:, :3].mean():.5f}, |d_material| per set {np.abs(dm).sum(axis=(1, 2, 3))}")
+    print(f"render_{name}.npz: image mean {image.data[:, :3].mean():.5f}, |d_material| per set {np.abs(dm).sum(axis=(1, 2, 3))}")
 
 
 # ------------------------------------------------------------------------------------ envmap.py
@@ -518,9 +517,15 @@ if __name__ == "__main__":
     # in the numeric contract's fmaf arithmetic.  With the plain-arithmetic builtins the same source gives an image 1.7e-3 away
     # (237 of 4 096 pixels hold a 10+-bounce path that an ulp in hit.interpolate sends elsewhere on the white-noise texture);
     # with them, the reference's source reproduces the oracle to 1e-7, path by path.
-    LARGE = ("direct_large", "path_large", "collocated_large", "direct_env_large", "path_env_large", "path_large_smooth")
+    LARGE = ("direct_large", "path_large", "collocated_large", "direct_env_large", "path_env_large", "path_large_smooth",
+             "direct_xform_large", "material_sets_large")
     if any(w in which for w in LARGE):
         E.CONTRACT_BUILTINS = True
+        if "direct_xform_large" in which:
+            gen_render("direct_xform_large", scenes.cbox_sheared_models(), R_direct.render_direct_kernel, R_direct.render_direct_backward_kernel,
+                       (48, 48), 8, 128, 33, 20)
+        if "material_sets_large" in which:
+            gen_material_sets("direct_material_sets_large", (48, 48), 8, 64, 35)
         if "collocated_large" in which:
             gen_render("collocated_large", scenes.cbox_collocated_models(), R_collocated.render_collocated_kernel,
                        R_collocated.render_collocated_backward_kernel, (64, 64), 8, 128, 25, 16)
