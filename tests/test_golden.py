@@ -93,6 +93,8 @@ LARGE_FIXTURES = [
     # name, models, integrator, params, image bit-identical to the oracle's
     ("collocated_large", scenes.cbox_collocated_models, ZDR_COLLOCATED, {}, True),
     ("direct_large", scenes.cbox_path_models, ZDR_DIRECT, {}, True),
+    # one non-rigid transform on box and light (interaction.py:19-28: p = M v, normals by inverse(transpose(M3x3)))
+    ("direct_xform_large", scenes.cbox_sheared_models, ZDR_DIRECT, {}, True),
     ("path_literal_large", scenes.cbox_path_models, ZDR_PATH, {"prb_mode": ZDR_PRB_LITERAL, "max_depth": 16, "rr_depth": 2}, True),
     # the full roughness range [0, 1] (the plain-arithmetic path fixtures above keep roughness >= 0.3)
     ("path_literal_large_smooth", scenes.cbox_path_models, ZDR_PATH, {"prb_mode": ZDR_PRB_LITERAL, "max_depth": 16, "rr_depth": 2}, True),
@@ -153,6 +155,24 @@ def test_material_sets_vs_patched_reference_source(oracle):
     assert dm.shape == mat.shape and np.abs(z["d_material"][0]).max() > 0 and np.abs(z["d_material"][1]).max() > 0
     for k in range(2):
         assert rel_l2(dm[k], z["d_material"][k]) <= 1e-3, (k, rel_l2(dm[k], z["d_material"][k]))
+
+
+def test_material_sets_large_fixture(oracle):
+    """The same patched direct.py / interaction.py on 48 x 48 pixels at 8 spp with two 64^2 texture sets, builtins in the contract's
+    arithmetic (gen_golden.py material_sets_large): image bit-identical, both sets' gradients to 1e-7."""
+    z = np.load(os.path.join(G, "render_direct_material_sets_large.npz"))
+    res, spp, seed = tuple(int(x) for x in z["res"]), int(z["spp"]), int(z["seed"])
+    models, sets = scenes.cbox_material_sets_models()
+    assert sets == [int(x) for x in z["sets"]]
+    mat = z["material"]
+    sc = oracle.OracleScene(models)
+    sc.set_material_sets(sets)
+    img = sc.render_forward(ZDR_DIRECT, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed), mat)
+    assert np.array_equal(bits(img), bits(z["image"]))
+    dm = sc.render_backward(ZDR_DIRECT, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed + 1), mat, z["d_image"])
+    for k in range(2):
+        assert np.abs(z["d_material"][k]).max() > 0
+        assert rel_l2(dm[k], z["d_material"][k]) <= 1e-5, (k, rel_l2(dm[k], z["d_material"][k]))
 
 
 def test_duvdxy_vs_reference_source(oracle):

@@ -375,7 +375,7 @@ def test_scenes_of_one_or_two_leaves_all_schedules(oracle):
         g.close()
 
 
-@pytest.mark.parametrize("name", ["collocated_large", "direct_large", "path_literal_large", "path_literal_large_smooth",
+@pytest.mark.parametrize("name", ["collocated_large", "direct_large", "direct_xform_large", "path_literal_large", "path_literal_large_smooth",
                                   "direct_env_large", "path_literal_env_large"])
 def test_cuda_vs_reference_source_fixtures(name):
     """The CUDA path directly against the large committed fixtures that tests/golden/gen_golden.py produced by running the
@@ -398,6 +398,23 @@ def test_cuda_vs_reference_source_fixtures(name):
         dm = g.backward(integ, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed + 1, **extra, **kw), mat, z["d_image"])
         assert np.abs(z["d_material"]).max() > 0
         assert rel_l2(dm, z["d_material"]) <= (1e-5 if bit_exact else GRAD_TOL), (kw, rel_l2(dm, z["d_material"]))
+    g.close()
+
+
+def test_cuda_vs_reference_source_material_sets_fixture():
+    """... and against the large material-set fixture (the reference's direct.py / interaction.py with the set-index patch, two 64^2
+    texture sets, 48 x 48 pixels at 8 spp): image bit for bit, both sets' gradients within 1e-5."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render_direct_material_sets_large.npz"))
+    res, spp, seed = tuple(int(x) for x in z["res"]), int(z["spp"]), int(z["seed"])
+    models, sets = scenes.cbox_material_sets_models()
+    mat = z["material"]
+    g = GpuScene(models)
+    g.set_material_sets(sets)
+    img = g.forward(ZDR_DIRECT, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed), mat)
+    assert np.array_equal(img.view(np.uint32), z["image"].view(np.uint32)), rel_l2(img, z["image"])
+    dm = g.backward(ZDR_DIRECT, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed + 1), mat, z["d_image"])
+    for k in range(2):
+        assert rel_l2(dm[k], z["d_material"][k]) <= 1e-5, (k, rel_l2(dm[k], z["d_material"][k]))
     g.close()
 
 
