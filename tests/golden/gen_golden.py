@@ -285,19 +285,28 @@ PRB_PATCHES = [
 ]
 
 
-def load_patched_prb():
+# The ONE further line that turns prb.py into prb_mode = "corrected" on a scene without envmap (DESIGN.md §2 "PRB adjoint weighting"):
+# the cotangent of the BSDF-sample vertex.  prb.py:162 seeds it with beta / pdf * Le; Path Replay Backpropagation needs
+# d(Le_remaining) / d(bsdf) = Le_remaining / bsdf per channel (0 where bsdf is 0).  Nothing else of the adjoint walk changes.
+PRB_CORRECTED_PATCH = [
+    ("backward(bsdf, beta / pdf_bsdf * Le * le_grad)",
+     "backward(bsdf, float3(0.0) if bsdf == float3(0.0) else Le / bsdf * le_grad)"),
+]
+
+
+def load_patched_prb(extra=(), name="prb_patched"):
     import importlib.util
     import tempfile
     src = open("/root/reference/prb.py").read()
-    for a, b in PRB_PATCHES:
+    for a, b in list(PRB_PATCHES) + list(extra):
         assert a in src, a
         src = src.replace(a, b)
     d = tempfile.mkdtemp()
-    path = os.path.join(d, "prb_patched.py")
+    path = os.path.join(d, f"{name}.py")
     open(path, "w").write(src)
-    spec = importlib.util.spec_from_file_location("zdr_ref.prb_patched", path)
+    spec = importlib.util.spec_from_file_location(f"zdr_ref.{name}", path)
     mod = importlib.util.module_from_spec(spec)
-    sys.modules["zdr_ref.prb_patched"] = mod
+    sys.modules[f"zdr_ref.{name}"] = mod
     spec.loader.exec_module(mod)
     return mod
 
@@ -518,9 +527,12 @@ if __name__ == "__main__":
     # (237 of 4 096 pixels hold a 10+-bounce path that an ulp in hit.interpolate sends elsewhere on the white-noise texture);
     # with them, the reference's source reproduces the oracle to 1e-7, path by path.
     LARGE = ("direct_large", "path_large", "collocated_large", "direct_env_large", "path_env_large", "path_large_smooth",
-             "direct_xform_large", "material_sets_large")
+             "direct_xform_large", "material_sets_large", "path_corrected_large")
     if any(w in which for w in LARGE):
         E.CONTRACT_BUILTINS = True
+        if "path_corrected_large" in which:    # prb.py + the arity substitutions + PRB_CORRECTED_PATCH: pins prb_mode = corrected
+            prb = load_patched_prb(PRB_CORRECTED_PATCH, "prb_corrected")
+            gen_render("path_corrected_large", scenes.cbox_path_models(), prb.render_path_kernel, prb.render_path_backward_kernel, (48, 48), 4, 128, 37, 22)
         if "direct_xform_large" in which:
             gen_render("direct_xform_large", scenes.cbox_sheared_models(), R_direct.render_direct_kernel, R_direct.render_direct_backward_kernel,
                        (48, 48), 8, 128, 33, 20)

