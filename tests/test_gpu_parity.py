@@ -397,8 +397,8 @@ def test_cuda_vs_reference_source_fixtures(name):
         assert rel_l2(img, z["image"]) <= (1e-6 if bit_exact else IMG_TOL), (kw, rel_l2(img, z["image"]))
         dm = g.backward(integ, make_params(scenes.CBOX_CAMERA, res, mat.shape, spp, seed + 1, **extra, **kw), mat, z["d_image"])
         assert np.abs(z["d_material"]).max() > 0
-        # (path_corrected_large was added after the last GPU session of the round: ten times the bar of its siblings, still a tenth
-        # of the north star's; the oracle sits 9e-8 from it and the CUDA path ~4e-8 from the oracle in this mode)
+        # (path_corrected_large: a tenth of the north star's bar; the oracle sits 9e-8 from the fixture and the CUDA path ~4e-8 from
+        # the oracle in this mode — profiles/r05f_corrected_fixture.log)
         grad_tol = GRAD_TOL if not bit_exact else 1e-4 if name == "path_corrected_large" else 1e-5
         assert rel_l2(dm, z["d_material"]) <= grad_tol, (kw, rel_l2(dm, z["d_material"]))
     g.close()
