@@ -294,6 +294,23 @@ PRB_CORRECTED_PATCH = [
 ]
 
 
+# ... and on a scene WITH an envmap one more: prb.py:28 multiplies the envmap radiance of a miss by the throughput and :31 multiplies
+# by it again (SURVEY.md 8a defect 2); corrected mode applies it once.
+PRB_CORRECTED_ENV_PATCH = [
+    ("emission = beta * heap.texture2d_sample(23332, direction_to_uv(ray.get_dir())).xyz",
+     "emission = heap.texture2d_sample(23332, direction_to_uv(ray.get_dir())).xyz"),
+]
+
+
+# ... and on a scene with NON-EMISSIVE instances other than the first: the forward walk stops at them (prb.py:45 "treat everything as
+# light other than the first object"), the adjoint walk lacks that line and shades them with the first object's texture
+# (SURVEY.md 8a defect 2; literal mode reproduces it); corrected mode stops where the forward walk stopped.
+PRB_CORRECTED_TERMINAL_PATCH = [
+    ("            Le -= beta * mis_weight * emission\n            break\n",
+     "            Le -= beta * mis_weight * emission\n            break\n        if hit.inst > 0:\n            break\n"),
+]
+
+
 def load_patched_prb(extra=(), name="prb_patched"):
     import importlib.util
     import tempfile
@@ -527,9 +544,19 @@ if __name__ == "__main__":
     # (237 of 4 096 pixels hold a 10+-bounce path that an ulp in hit.interpolate sends elsewhere on the white-noise texture);
     # with them, the reference's source reproduces the oracle to 1e-7, path by path.
     LARGE = ("direct_large", "path_large", "collocated_large", "direct_env_large", "path_env_large", "path_large_smooth",
-             "direct_xform_large", "material_sets_large", "path_corrected_large")
+             "direct_xform_large", "material_sets_large", "path_corrected_large", "path_corrected_env_large", "path_terminal_large")
     if any(w in which for w in LARGE):
         E.CONTRACT_BUILTINS = True
+        if "path_corrected_env_large" in which:
+            prb = load_patched_prb(PRB_CORRECTED_PATCH + PRB_CORRECTED_ENV_PATCH, "prb_corrected_env")
+            gen_render("path_corrected_env_large", scenes.cbox_path_models(), prb.render_path_kernel, prb.render_path_backward_kernel, (48, 48), 4, 128, 39, 23,
+                       envmap=scenes.procedural_envmap(64, 32, seed=2) * np.float32(0.2))
+        if "path_terminal_large" in which:     # Cornell box + light + two non-emissive instances (sphere, dark quad): both weightings
+            models = scenes.cbox_material_sets_models()[0]
+            prb = load_patched_prb(PRB_CORRECTED_PATCH + PRB_CORRECTED_TERMINAL_PATCH, "prb_corrected_terminal")
+            gen_render("path_corrected_terminal_large", models, prb.render_path_kernel, prb.render_path_backward_kernel, (48, 48), 4, 128, 41, 24)
+            prb = load_patched_prb()
+            gen_render("path_literal_terminal_large", models, prb.render_path_kernel, prb.render_path_backward_kernel, (48, 48), 4, 128, 41, 24)
         if "path_corrected_large" in which:    # prb.py + the arity substitutions + PRB_CORRECTED_PATCH: pins prb_mode = corrected
             prb = load_patched_prb(PRB_CORRECTED_PATCH, "prb_corrected")
             gen_render("path_corrected_large", scenes.cbox_path_models(), prb.render_path_kernel, prb.render_path_backward_kernel, (48, 48), 4, 128, 37, 22)

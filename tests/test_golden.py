@@ -102,11 +102,19 @@ LARGE_FIXTURES = [
     # Le_remaining / bsdf instead of prb.py:162's beta / pdf * Le) = prb_mode "corrected", the surface's and bench.py's default;
     # the literal mode is 64 % away from this fixture's gradient
     ("path_corrected_large", scenes.cbox_path_models, ZDR_PATH, {"prb_mode": ZDR_PRB_CORRECTED, "max_depth": 16, "rr_depth": 2}, True),
+    # Cornell box + light + two NON-EMISSIVE other instances (sphere, dark quad).  The forward walk stops at them (prb.py:45); the
+    # reference's adjoint walk lacks that line and shades them with the first object's texture (SURVEY.md 8a defect 2): literal mode
+    # reproduces the source as it is, corrected mode the source with PRB_CORRECTED_PATCH + the missing `if hit.inst > 0: break`
+    ("path_literal_terminal_large", lambda: scenes.cbox_material_sets_models()[0], ZDR_PATH, {"prb_mode": ZDR_PRB_LITERAL, "max_depth": 16, "rr_depth": 2}, True),
+    ("path_corrected_terminal_large", lambda: scenes.cbox_material_sets_models()[0], ZDR_PATH, {"prb_mode": ZDR_PRB_CORRECTED, "max_depth": 16, "rr_depth": 2}, True),
     # envmap: ~200 pixels differ in the last bit, 1e-8 overall — the pdf table comes out of envmap.py's numpy host pipeline (sums in
     # numpy's order; 2.4e-6 relative to the oracle's, see envmap.npz), and `2 * pi * pi` (envmap.py:236,248) is one binary64 constant
     # under the emulator's Python but two binary32 products in the oracle (as LuisaCompute's DSL would evaluate it)
     ("direct_env_large", scenes.cbox_path_models, ZDR_DIRECT, {}, False),
     ("path_literal_env_large", scenes.cbox_path_models, ZDR_PATH, {"prb_mode": ZDR_PRB_LITERAL, "max_depth": 16, "rr_depth": 2}, False),
+    # corrected mode with an envmap = the source with PRB_CORRECTED_PATCH + PRB_CORRECTED_ENV_PATCH (the miss term's throughput once,
+    # prb.py:28-31); literal is 6 % (image) / 85 % (gradient) away from this fixture
+    ("path_corrected_env_large", scenes.cbox_path_models, ZDR_PATH, {"prb_mode": ZDR_PRB_CORRECTED, "max_depth": 16, "rr_depth": 2}, False),
 ]
 
 
