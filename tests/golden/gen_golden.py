@@ -17,6 +17,11 @@ What is recorded
                   env_sampled_light_pdf, uv <-> direction, create_alias_table
   render_*.npz    integrator.py kernels built from collocated.py / direct.py on the Cornell box:
                   image, and d_material for a fixed d_image, at fixture sizes
+  render_*_large.npz   NOT in the default list (2-15 minutes each): the same kernels and prb.py on 48^2-64^2 pixels at 4-8 spp with
+                  lc_emu.CONTRACT_BUILTINS (closed builtins in the numeric contract's fmaf arithmetic) — images bit-identical to
+                  the oracle's.  Names: collocated_large direct_large direct_xform_large material_sets_large path_large
+                  path_large_smooth direct_env_large path_env_large, and prb.py with the one-line patches that make up
+                  prb_mode = corrected: path_corrected_large path_corrected_env_large path_terminal_large
 """
 import os
 import sys
