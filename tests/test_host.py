@@ -203,3 +203,13 @@ def test_ref_luisa_hook_reports_unavailable_without_luisa():
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and "luisa" in d["unavailable"]
+
+
+@pytest.mark.parametrize("script", ["benchmark.py", "lightstage.py", "fd_validate.py", "inverse_cornell.py"])
+def test_example_scripts_import_and_parse_arguments(script):
+    """examples/ = the reference's caller scripts (benchmark.py, test_lightstage.py, fd_validate.py, example.py) on this package.
+    They need a GPU to run (profiles/r05b_examples.log); here: they import the package and get as far as their argument parser."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", script), "--help"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("usage: " + script), out.stderr[-2000:]
